@@ -1,0 +1,413 @@
+// SPPF pooling cascade: three chained stride-1 "same" max-pools + the 4-way channel concat, computed from ONE
+// shared-memory-staged tile per (image, channel chunk).  Replaces block.py:224-226 of the reference.
+//
+// Layout: NHWC.  A CTA owns image b, channels [c0, c0 + LP*EPL) over the WHOLE H x W plane (the reference only
+// uses SPPF at P5 = 20x20; larger planes shrink LP so the plane still fits in shared memory).  One 32-bit word
+// per lane = EPL elements (1 f32 / 2 bf16|f16), LP lanes per pixel, so a pixel's chunk is LP*4 contiguous bytes.
+// Each max-pool is separable: a row pass (threads walk rows) into `tmp`, a column pass (threads walk columns)
+// back into `cur` + straight to the concat slice in global memory.  Both passes use ATen's exact update rule
+// "take iff (v > best) || isnan(v)", scanning left->right / top->bottom, which composes to the row-major
+// first-occurrence argmax of max_pool2d_with_indices (and "last NaN wins").
+//
+// Backward: the per-stage winners (row offset, col offset: 4+4 bits) are recomputed from y0 with the same rule,
+// then gradients are routed stage 3 -> 1 by two 1-D scatters per stage.  Every strip (row / column, channel)
+// is owned by exactly one thread, so the scatter is race-free and summation order is fixed: deterministic.
+#include "common.cuh"
+
+namespace b200 {
+namespace {
+
+template <typename T> struct Word;  // 32-bit lane word <-> EPL elements
+template <> struct Word<float> {
+  static constexpr int EPL = 1;
+  __device__ static __forceinline__ float get(uint32_t w, int) { return __uint_as_float(w); }
+  __device__ static __forceinline__ uint32_t neg_inf() { return 0xff800000u; }
+  __device__ static __forceinline__ uint32_t put(uint32_t w, int, uint32_t bits) { return bits; }
+  __device__ static __forceinline__ uint32_t bits(uint32_t w, int) { return w; }
+  __device__ static __forceinline__ float bits_to_f(uint32_t b) { return __uint_as_float(b); }
+  __device__ static __forceinline__ uint32_t f_to_bits(float f) { return __float_as_uint(f); }
+};
+template <> struct Word<__nv_bfloat16> {
+  static constexpr int EPL = 2;
+  __device__ static __forceinline__ uint32_t neg_inf() { return 0xff80ff80u; }
+  __device__ static __forceinline__ uint32_t bits(uint32_t w, int e) { return (w >> (16 * e)) & 0xffffu; }
+  __device__ static __forceinline__ float bits_to_f(uint32_t b) { return __uint_as_float(b << 16); }
+  __device__ static __forceinline__ uint32_t put(uint32_t w, int e, uint32_t b) {
+    return e ? ((w & 0x0000ffffu) | (b << 16)) : ((w & 0xffff0000u) | b);
+  }
+  __device__ static __forceinline__ uint32_t f_to_bits(float f) {
+    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f));
+  }
+};
+template <> struct Word<__half> {
+  static constexpr int EPL = 2;
+  __device__ static __forceinline__ uint32_t neg_inf() { return 0xfc00fc00u; }
+  __device__ static __forceinline__ uint32_t bits(uint32_t w, int e) { return (w >> (16 * e)) & 0xffffu; }
+  __device__ static __forceinline__ float bits_to_f(uint32_t b) { return __half2float(__ushort_as_half((unsigned short)b)); }
+  __device__ static __forceinline__ uint32_t put(uint32_t w, int e, uint32_t b) {
+    return e ? ((w & 0x0000ffffu) | (b << 16)) : ((w & 0xffff0000u) | b);
+  }
+  __device__ static __forceinline__ uint32_t f_to_bits(float f) {
+    return (uint32_t)__half_as_ushort(__float2half_rn(f));
+  }
+};
+
+// One 1-D max pass over a strip for one lane word.  src/dst are strided smem word arrays.
+//   len    : strip length,  K: window, r = K/2
+//   win_out: if non-null, receives the winner's OFFSET in the window [0,K) per element (4 bits each, packed
+//            as (e*4) nibbles in a byte... one byte per element stored in a uint8 array with its own stride).
+// Returns nothing; writes dst[i*dstride] for i in [0,len).
+template <typename T, int K>
+__device__ __forceinline__ void pass1d(const uint32_t* __restrict__ src, int sstride, uint32_t* __restrict__ dst,
+                                       int dstride, int len, uint8_t* __restrict__ win_out, int wstride) {
+  using WD = Word<T>;
+  constexpr int R = K / 2;
+  constexpr int EPL = WD::EPL;
+  uint32_t win[K];  // sliding window of words, win[j] = src[i - R + j] (or -inf outside)
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    int s = j - R - 1 + 1;  // position for i = 0 is j - R; we pre-load then shift at loop top
+    win[j] = (s >= 0 && s < len) ? src[s * sstride] : WD::neg_inf();
+  }
+  for (int i = 0; i < len; ++i) {
+    uint32_t outw = 0;
+    uint32_t wsel = 0;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      uint32_t bb = WD::bits(WD::neg_inf(), e);
+      float bf = -INFINITY;
+      int lo = i - R < 0 ? R - i : 0;  // first in-bounds window slot (ATen's initial index)
+      int bj = lo;
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        uint32_t vb = WD::bits(win[j], e);
+        float vf = WD::bits_to_f(vb);
+        bool take = (vf > bf) || (vf != vf);
+        // out-of-range slots hold -inf and can never be taken (-inf > x is false, not NaN)
+        bb = take ? vb : bb;
+        bf = take ? vf : bf;
+        bj = take ? j : bj;
+      }
+      outw = WD::put(outw, e, bb);
+      wsel |= (uint32_t)bj << (4 * e);
+    }
+    dst[i * dstride] = outw;
+    if (win_out) win_out[i * wstride] = (uint8_t)wsel;
+    // slide
+#pragma unroll
+    for (int j = 0; j < K - 1; ++j) win[j] = win[j + 1];
+    int s = i + 1 + R;
+    win[K - 1] = (s < len) ? src[s * sstride] : WD::neg_inf();
+  }
+}
+
+struct PoolGeom {
+  int B, C, H, W, Wp;  // Wp: padded pitch in pixels (odd -> consecutive rows land 16 banks apart for LP=16)
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int K, int LP, bool WITH_IDX>
+__global__ void __launch_bounds__(512) sppf_pool_fwd_kernel(const T* __restrict__ y0, T* __restrict__ cat,
+                                                            int32_t* __restrict__ idx, PoolGeom g) {
+  using WD = Word<T>;
+  constexpr int EPL = WD::EPL;
+  constexpr int CC = LP * EPL;
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int plane = g.H * g.Wp;
+  uint32_t* cur = smem;               // [H][Wp][LP]
+  uint32_t* tmp = smem + plane * LP;  // [H][Wp][LP]
+  uint8_t* wrow = reinterpret_cast<uint8_t*>(smem + 2 * plane * LP);  // [H][Wp][LP] (WITH_IDX only)
+
+  const int chunks = (g.C + CC - 1) / CC;
+  const int b = blockIdx.x / chunks;
+  const int c0 = (blockIdx.x % chunks) * CC;
+  const int lane = threadIdx.x % LP;
+  const int sid = threadIdx.x / LP;
+  const int nstrips = blockDim.x / LP;
+  const int c = c0 + lane * EPL;
+  const bool cvalid = c < g.C;  // C % EPL == 0 is enforced on the host
+  const size_t in_img = (size_t)b * g.H * g.W * g.C;
+  const size_t out_img = (size_t)b * g.H * g.W * 4 * g.C;
+
+  // stage the tile (word loads: LP*4 contiguous bytes per pixel) and emit concat slice 0
+  for (int p = sid; p < g.H * g.W; p += nstrips) {
+    const int y = p / g.W, x = p - y * g.W;
+    uint32_t w = WD::neg_inf();
+    if (cvalid) {
+      w = *reinterpret_cast<const uint32_t*>(y0 + in_img + (size_t)p * g.C + c);
+      *reinterpret_cast<uint32_t*>(cat + out_img + (size_t)p * 4 * g.C + c) = w;
+    }
+    cur[(y * g.Wp + x) * LP + lane] = w;
+  }
+  __syncthreads();
+
+  for (int st = 0; st < 3; ++st) {
+    // row pass: cur -> tmp
+    for (int y = sid; y < g.H; y += nstrips)
+      pass1d<T, K>(cur + (y * g.Wp) * LP + lane, LP, tmp + (y * g.Wp) * LP + lane, LP, g.W,
+                   WITH_IDX ? wrow + (y * g.Wp) * LP + lane : nullptr, LP);
+    __syncthreads();
+    // column pass: tmp -> cur, and out to global
+    for (int x = sid; x < g.W; x += nstrips) {
+      if (!WITH_IDX) {
+        pass1d<T, K>(tmp + x * LP + lane, g.Wp * LP, cur + x * LP + lane, g.Wp * LP, g.H, nullptr, 0);
+      } else {
+        // need the column winners too: reuse pass1d with a private winner strip in registers is awkward for
+        // runtime H, so write winners into the (now free) low byte lanes of a second byte plane
+        uint8_t* wcol = wrow + plane * LP;
+        pass1d<T, K>(tmp + x * LP + lane, g.Wp * LP, cur + x * LP + lane, g.Wp * LP, g.H,
+                     wcol + x * LP + lane, g.Wp * LP);
+      }
+    }
+    __syncthreads();
+    // emit slice st+1 (+ indices)
+    for (int p = sid; p < g.H * g.W; p += nstrips) {
+      const int y = p / g.W, x = p - y * g.W;
+      if (!cvalid) continue;
+      const int sp = (y * g.Wp + x) * LP + lane;
+      *reinterpret_cast<uint32_t*>(cat + out_img + (size_t)p * 4 * g.C + (size_t)(st + 1) * g.C + c) = cur[sp];
+      if (WITH_IDX) {
+        const uint8_t* wcol = wrow + plane * LP;
+        const uint32_t wc = wcol[sp];
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          const int yy = y - K / 2 + (int)((wc >> (4 * e)) & 15u);
+          const uint32_t wr = wrow[(yy * g.Wp + x) * LP + lane];
+          const int xx = x - K / 2 + (int)((wr >> (4 * e)) & 15u);
+          idx[(((size_t)st * g.B + b) * g.H * g.W + p) * g.C + c + e] = yy * g.W + xx;
+        }
+      }
+    }
+    if (WITH_IDX) __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------------
+// scatter one strip of gradients through a 1-D max pass: dst[i + off(i) - R] += src[i]; strips are thread-private.
+template <int K, int EPL>
+__device__ __forceinline__ void scatter1d(const float* __restrict__ src, int sstride, float* __restrict__ dst,
+                                          int dstride, int len, const uint8_t* __restrict__ win, int wstride) {
+  constexpr int R = K / 2;
+  for (int i = 0; i < len; ++i) {
+    const uint32_t ws = win[i * wstride];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const int t = i - R + (int)((ws >> (4 * e)) & 15u);
+      dst[t * dstride + e] += src[i * sstride + e];
+    }
+  }
+}
+
+template <typename T, int K, int LP>
+__global__ void __launch_bounds__(512) sppf_pool_bwd_kernel(const T* __restrict__ gcat, const T* __restrict__ y0,
+                                                            T* __restrict__ gy0, PoolGeom g) {
+  using WD = Word<T>;
+  constexpr int EPL = WD::EPL;
+  constexpr int CC = LP * EPL;
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int plane = g.H * g.Wp;
+  // gradient ping-pong buffers (f32, EPL per lane) double as the value buffers of the recompute phase
+  float* ga = reinterpret_cast<float*>(smem);                   // [plane][LP][EPL]
+  float* gb = ga + (size_t)plane * LP * EPL;                    // [plane][LP][EPL]
+  uint8_t* wrow = reinterpret_cast<uint8_t*>(gb + (size_t)plane * LP * EPL);  // [3][plane][LP]
+  uint8_t* wcol = wrow + (size_t)3 * plane * LP;                // [3][plane][LP]
+  uint32_t* cur = reinterpret_cast<uint32_t*>(ga);              // [plane][LP] words (fits: EPL*4 >= 4)
+  uint32_t* tmp = reinterpret_cast<uint32_t*>(gb);
+
+  const int chunks = (g.C + CC - 1) / CC;
+  const int b = blockIdx.x / chunks;
+  const int c0 = (blockIdx.x % chunks) * CC;
+  const int lane = threadIdx.x % LP;
+  const int sid = threadIdx.x / LP;
+  const int nstrips = blockDim.x / LP;
+  const int c = c0 + lane * EPL;
+  const bool cvalid = c < g.C;
+  const size_t in_img = (size_t)b * g.H * g.W * g.C;
+  const size_t cat_img = (size_t)b * g.H * g.W * 4 * g.C;
+
+  for (int p = sid; p < g.H * g.W; p += nstrips) {
+    const int y = p / g.W, x = p - y * g.W;
+    uint32_t w = WD::neg_inf();
+    if (cvalid) w = *reinterpret_cast<const uint32_t*>(y0 + in_img + (size_t)p * g.C + c);
+    cur[(y * g.Wp + x) * LP + lane] = w;
+  }
+  __syncthreads();
+  // recompute winners of the three stages
+  for (int st = 0; st < 3; ++st) {
+    for (int y = sid; y < g.H; y += nstrips)
+      pass1d<T, K>(cur + (y * g.Wp) * LP + lane, LP, tmp + (y * g.Wp) * LP + lane, LP, g.W,
+                   wrow + ((size_t)st * plane + y * g.Wp) * LP + lane, LP);
+    __syncthreads();
+    for (int x = sid; x < g.W; x += nstrips)
+      pass1d<T, K>(tmp + x * LP + lane, g.Wp * LP, cur + x * LP + lane, g.Wp * LP, g.H,
+                   wcol + ((size_t)st * plane + x) * LP + lane, g.Wp * LP);
+    __syncthreads();
+  }
+  // G3 = g3
+  auto load_slice = [&](float* dstbuf, int slice, bool accumulate) {
+    for (int p = sid; p < g.H * g.W; p += nstrips) {
+      const int y = p / g.W, x = p - y * g.W;
+      uint32_t w = 0;
+      if (cvalid) w = *reinterpret_cast<const uint32_t*>(gcat + cat_img + (size_t)p * 4 * g.C + (size_t)slice * g.C + c);
+      float* d = dstbuf + ((size_t)(y * g.Wp + x) * LP + lane) * EPL;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const float v = cvalid ? WD::bits_to_f(WD::bits(w, e)) : 0.f;
+        d[e] = accumulate ? d[e] + v : v;
+      }
+    }
+  };
+  auto zero = [&](float* buf) {
+    for (int i = threadIdx.x; i < plane * LP * EPL; i += blockDim.x) buf[i] = 0.f;
+  };
+  load_slice(ga, 3, false);
+  __syncthreads();
+  for (int st = 2; st >= 0; --st) {
+    // column-pass backward: ga (grad of stage output) -> gb (grad of row-pass output)
+    zero(gb);
+    __syncthreads();
+    for (int x = sid; x < g.W; x += nstrips)
+      scatter1d<K, EPL>(ga + ((size_t)x * LP + lane) * EPL, g.Wp * LP * EPL, gb + ((size_t)x * LP + lane) * EPL,
+                        g.Wp * LP * EPL, g.H, wcol + ((size_t)st * plane + x) * LP + lane, g.Wp * LP);
+    __syncthreads();
+    // row-pass backward: gb -> ga (grad of stage input), then add the concat slice gradient g_st
+    zero(ga);
+    __syncthreads();
+    for (int y = sid; y < g.H; y += nstrips)
+      scatter1d<K, EPL>(gb + ((size_t)(y * g.Wp) * LP + lane) * EPL, LP * EPL,
+                        ga + ((size_t)(y * g.Wp) * LP + lane) * EPL, LP * EPL, g.W,
+                        wrow + ((size_t)st * plane + y * g.Wp) * LP + lane, LP);
+    __syncthreads();
+    load_slice(ga, st, true);
+    __syncthreads();
+  }
+  for (int p = sid; p < g.H * g.W; p += nstrips) {
+    if (!cvalid) continue;
+    const int y = p / g.W, x = p - y * g.W;
+    const float* s = ga + ((size_t)(y * g.Wp + x) * LP + lane) * EPL;
+    uint32_t w = 0;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) w = WD::put(w, e, WD::f_to_bits(s[e]));
+    *reinterpret_cast<uint32_t*>(gy0 + in_img + (size_t)p * g.C + c) = w;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int K, int LP>
+int launch_fwd(const void* y0, void* cat, int32_t* idx, PoolGeom g, cudaStream_t st, bool* done) {
+  constexpr int EPL = Word<T>::EPL;
+  const size_t plane = (size_t)g.H * g.Wp;
+  const size_t smem = plane * LP * 4 * 2 + (idx ? plane * LP * 2 : 0);
+  if (smem > (size_t)max_smem_optin()) return B200_OK;  // try a smaller LP
+  *done = true;
+  const int chunks = (g.C + LP * EPL - 1) / (LP * EPL);
+  int strips = g.H > g.W ? g.H : g.W;
+  int threads = ((strips * LP + 31) / 32) * 32;
+  if (threads > 512) threads = 512;
+  if (threads < 64) threads = 64;
+  dim3 grid(g.B * chunks);
+  if (idx) {
+    auto kern = sppf_pool_fwd_kernel<T, K, LP, true>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, threads, smem, st>>>((const T*)y0, (T*)cat, idx, g);
+  } else {
+    auto kern = sppf_pool_fwd_kernel<T, K, LP, false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, threads, smem, st>>>((const T*)y0, (T*)cat, idx, g);
+  }
+  return check_launch("sppf_pool_fwd");
+}
+
+template <typename T, int K, int LP>
+int launch_bwd(const void* gcat, const void* y0, void* gy0, PoolGeom g, cudaStream_t st, bool* done) {
+  constexpr int EPL = Word<T>::EPL;
+  const size_t plane = (size_t)g.H * g.Wp;
+  const size_t smem = plane * LP * EPL * 4 * 2 + plane * LP * 6;
+  if (smem > (size_t)max_smem_optin()) return B200_OK;
+  *done = true;
+  const int chunks = (g.C + LP * EPL - 1) / (LP * EPL);
+  int strips = g.H > g.W ? g.H : g.W;
+  int threads = ((strips * LP + 31) / 32) * 32;
+  if (threads > 512) threads = 512;
+  if (threads < 64) threads = 64;
+  auto kern = sppf_pool_bwd_kernel<T, K, LP>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<dim3(g.B * chunks), threads, smem, st>>>((const T*)gcat, (const T*)y0, (T*)gy0, g);
+  return check_launch("sppf_pool_bwd");
+}
+
+template <typename T, int K>
+int fwd_k(const void* y0, void* cat, int32_t* idx, PoolGeom g, cudaStream_t st) {
+  bool done = false;
+  int rc = launch_fwd<T, K, 16>(y0, cat, idx, g, st, &done);
+  if (!done) rc = launch_fwd<T, K, 8>(y0, cat, idx, g, st, &done);
+  if (!done) rc = launch_fwd<T, K, 4>(y0, cat, idx, g, st, &done);
+  if (!done) rc = launch_fwd<T, K, 2>(y0, cat, idx, g, st, &done);
+  if (!done) rc = launch_fwd<T, K, 1>(y0, cat, idx, g, st, &done);
+  B200_REQUIRE(done, B200_ERR_UNSUPPORTED, "sppf_pool_fwd: %dx%d plane does not fit in shared memory", g.H, g.W);
+  return rc;
+}
+template <typename T, int K>
+int bwd_k(const void* gcat, const void* y0, void* gy0, PoolGeom g, cudaStream_t st) {
+  bool done = false;
+  int rc = launch_bwd<T, K, 8>(gcat, y0, gy0, g, st, &done);
+  if (!done) rc = launch_bwd<T, K, 4>(gcat, y0, gy0, g, st, &done);
+  if (!done) rc = launch_bwd<T, K, 2>(gcat, y0, gy0, g, st, &done);
+  if (!done) rc = launch_bwd<T, K, 1>(gcat, y0, gy0, g, st, &done);
+  B200_REQUIRE(done, B200_ERR_UNSUPPORTED, "sppf_pool_bwd: %dx%d plane does not fit in shared memory", g.H, g.W);
+  return rc;
+}
+
+int check_args(const void* a, const void* b, int B, int C, int H, int W, int k, int dtype) {
+  B200_REQUIRE(a && b, B200_ERR_SHAPE, "sppf_pool: null tensor pointer");
+  B200_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, B200_ERR_SHAPE, "sppf_pool: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
+  B200_REQUIRE(k >= 3 && k <= 13 && (k & 1), B200_ERR_SHAPE, "sppf_pool: k must be odd in [3,13], got %d", k);
+  B200_REQUIRE(H < 4096 && W < 4096, B200_ERR_SHAPE, "sppf_pool: plane too large");
+  if (dtype != B200_F32) B200_REQUIRE(C % 2 == 0, B200_ERR_ALIGN, "sppf_pool: C must be even for 16-bit dtypes (C=%d)", C);
+  B200_REQUIRE(((uintptr_t)a & 3) == 0 && ((uintptr_t)b & 3) == 0, B200_ERR_ALIGN, "sppf_pool: pointers must be 4-byte aligned");
+  return B200_OK;
+}
+
+#define B200_DISPATCH_K(k, ...)                                           \
+  [&]() -> int {                                                          \
+    switch (k) {                                                          \
+      case 3: { constexpr int K = 3; return __VA_ARGS__(); }              \
+      case 5: { constexpr int K = 5; return __VA_ARGS__(); }              \
+      case 7: { constexpr int K = 7; return __VA_ARGS__(); }              \
+      case 9: { constexpr int K = 9; return __VA_ARGS__(); }              \
+      case 11: { constexpr int K = 11; return __VA_ARGS__(); }            \
+      default: { constexpr int K = 13; return __VA_ARGS__(); }            \
+    }                                                                     \
+  }()
+
+}  // namespace
+}  // namespace b200
+
+extern "C" B200_API int b200_sppf_pool_fwd(const void* y0, void* cat, int32_t* idx, int32_t B, int32_t C, int32_t H,
+                                  int32_t W, int32_t k, int32_t dtype, void* stream) {
+  using namespace b200;
+  if (int rc = check_args(y0, cat, B, C, H, W, k, dtype)) return rc;
+  PoolGeom g{B, C, H, W, (W & 1) ? W : W + 1};
+  cudaStream_t st = (cudaStream_t)stream;
+  return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
+    return B200_DISPATCH_K(k, [&]() -> int { return fwd_k<T, K>(y0, cat, idx, g, st); });
+  });
+}
+
+extern "C" B200_API int b200_sppf_pool_bwd(const void* gcat, const void* y0, void* gy0, int32_t B, int32_t C, int32_t H,
+                                  int32_t W, int32_t k, int32_t dtype, void* stream) {
+  using namespace b200;
+  if (int rc = check_args(gcat, y0, B, C, H, W, k, dtype)) return rc;
+  B200_REQUIRE(gy0, B200_ERR_SHAPE, "sppf_pool_bwd: null output");
+  PoolGeom g{B, C, H, W, (W & 1) ? W : W + 1};
+  cudaStream_t st = (cudaStream_t)stream;
+  return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
+    return B200_DISPATCH_K(k, [&]() -> int { return bwd_k<T, K>(gcat, y0, gy0, g, st); });
+  });
+}

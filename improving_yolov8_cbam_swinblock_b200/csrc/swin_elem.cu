@@ -1,0 +1,414 @@
+// SwinBlock: the non-GEMM stages (window partition / reverse folded into the loads and stores, LayerNorm,
+// residuals, GELU) forward and backward.  Replaces the data-movement and normalisation ops of
+// swin_block.py:37-58 (F.pad, rearrange, window_partition, norm1, residual adds, norm2, GELU, window_reverse,
+// crop) and their autograd backward.
+//
+// Token order: t = ((b*nWh + wh)*nWw + ww)*L + r*ws + c  <->  pixel (y, x) = (wh*ws + r, ww*ws + c); tokens with
+// y >= H or x >= W are the zero padding of swin_block.py:41-43 (they become norm1.bias after LN1 and still act
+// as keys/values -- SURVEY D3).  Activations are NHWC so a token's C channels are contiguous on both sides:
+// partition / reverse is pure address arithmetic in the kernels below, never a separate copy.
+#include "common.cuh"
+
+namespace b200 {
+namespace {
+
+struct WinGeom {
+  int B, C, H, W, ws, nWh, nWw, L;
+  long long T;  // padded token count
+};
+
+__device__ __forceinline__ long long token_pixel(const WinGeom& g, long long t, bool* real) {
+  const int l = (int)(t % g.L);
+  long long w = t / g.L;
+  const int ww = (int)(w % g.nWw);
+  w /= g.nWw;
+  const int wh = (int)(w % g.nWh);
+  const int b = (int)(w / g.nWh);
+  const int y = wh * g.ws + l / g.ws, x = ww * g.ws + l % g.ws;
+  *real = (y < g.H) && (x < g.W);
+  return ((long long)b * g.H + y) * g.W + x;
+}
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p) { return DT<T>::to_f(*p); }
+
+// ---- warp-per-token LayerNorm statistics over a register-resident row ------------------------------------------
+// Each lane holds elements c = lane + 32*i (i < NPL).  Two-pass (mean, then centred variance) for fp32 parity.
+template <int MAXPL>
+__device__ __forceinline__ void row_stats(const float (&v)[MAXPL], int npl, int C, int lane, float* mean, float* rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXPL; ++i)
+    if (i < npl && lane + 32 * i < C) s += v[i];
+  s = warp_sum(s);
+  const float mu = s / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXPL; ++i)
+    if (i < npl && lane + 32 * i < C) { const float d = v[i] - mu; q += d * d; }
+  q = warp_sum(q);
+  *mean = mu;
+  *rstd = rsqrtf(q / (float)C + 1e-5f);
+}
+
+constexpr int kMaxPL = 32;  // C <= 1024
+
+// n1[t,:] = LN1(token t of x) (padded tokens: LN(0) = beta).  Saves mean / rstd per token for the backward.
+template <typename T>
+__global__ void __launch_bounds__(256) swin_ln1_partition_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, T* __restrict__ n1,
+                                                                float* __restrict__ mean, float* __restrict__ rstd,
+                                                                WinGeom g) {
+  const int lane = threadIdx.x & 31;
+  const long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= g.T) return;
+  bool real;
+  const long long pix = token_pixel(g, t, &real);
+  const int npl = (g.C + 31) / 32;
+  float v[kMaxPL];
+#pragma unroll
+  for (int i = 0; i < kMaxPL; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = (i < npl && c < g.C && real) ? ldf(x + pix * g.C + c) : 0.f;
+  }
+  float mu, rs;
+  row_stats<kMaxPL>(v, npl, g.C, lane, &mu, &rs);
+#pragma unroll
+  for (int i = 0; i < kMaxPL; ++i) {
+    const int c = lane + 32 * i;
+    if (i < npl && c < g.C) n1[t * g.C + c] = DT<T>::from_f((v[i] - mu) * rs * gamma[c] + beta[c]);
+  }
+  if (lane == 0) { mean[t] = mu; rstd[t] = rs; }
+}
+
+// y1 = n1 + a (a = out_proj output incl. bias);  u = LN2(y1).  Saves mean / rstd.
+template <typename T>
+__global__ void __launch_bounds__(256) swin_res_ln2_kernel(const T* __restrict__ n1, const T* __restrict__ a,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          T* __restrict__ y1, T* __restrict__ u, float* __restrict__ mean,
+                                                          float* __restrict__ rstd, long long Ttok, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= Ttok) return;
+  const int npl = (C + 31) / 32;
+  float v[kMaxPL];
+#pragma unroll
+  for (int i = 0; i < kMaxPL; ++i) {
+    const int c = lane + 32 * i;
+    if (i < npl && c < C) {
+      // the residual sum is rounded to the activation dtype first: LN2 must see exactly the stored y1
+      const T s = DT<T>::from_f(ldf(n1 + t * C + c) + ldf(a + t * C + c));
+      y1[t * C + c] = s;
+      v[i] = DT<T>::to_f(s);
+    } else v[i] = 0.f;
+  }
+  float mu, rs;
+  row_stats<kMaxPL>(v, npl, C, lane, &mu, &rs);
+#pragma unroll
+  for (int i = 0; i < kMaxPL; ++i) {
+    const int c = lane + 32 * i;
+    if (i < npl && c < C) u[t * C + c] = DT<T>::from_f((v[i] - mu) * rs * gamma[c] + beta[c]);
+  }
+  if (lane == 0) { mean[t] = mu; rstd[t] = rs; }
+}
+
+__device__ __forceinline__ float gelu_erf(float a) { return 0.5f * a * (1.f + erff(a * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_erf_grad(float a) {
+  const float cdf = 0.5f * (1.f + erff(a * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * a * a);
+  return cdf + a * pdf;
+}
+
+// h = gelu(a)   /   ga = gh * gelu'(a)        (elementwise, 16-byte vectorised when aligned)
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(256) swin_gelu_kernel(const T* __restrict__ a, const T* __restrict__ gh, T* __restrict__ out,
+                                                       long long n) {
+  constexpr int V = 16 / sizeof(T);
+  const long long nv = n / V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+    uint4 av = *reinterpret_cast<const uint4*>(a + i * V);
+    uint4 gv = BWD ? *reinterpret_cast<const uint4*>(gh + i * V) : make_uint4(0, 0, 0, 0);
+    uint4 ov;
+    const T* ap = reinterpret_cast<const T*>(&av);
+    const T* gp = reinterpret_cast<const T*>(&gv);
+    T* op = reinterpret_cast<T*>(&ov);
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const float f = DT<T>::to_f(ap[e]);
+      op[e] = DT<T>::from_f(BWD ? DT<T>::to_f(gp[e]) * gelu_erf_grad(f) : gelu_erf(f));
+    }
+    *reinterpret_cast<uint4*>(out + i * V) = ov;
+  }
+  if (blockIdx.x == 0)
+    for (long long i = nv * V + threadIdx.x; i < n; i += blockDim.x) {
+      const float f = DT<T>::to_f(a[i]);
+      out[i] = DT<T>::from_f(BWD ? DT<T>::to_f(gh[i]) * gelu_erf_grad(f) : gelu_erf(f));
+    }
+}
+
+// out[b,y,x,:] = y1[t,:] + m[t,:] for real tokens (window_reverse + crop folded into the store address)
+template <typename T>
+__global__ void __launch_bounds__(256) swin_res_reverse_kernel(const T* __restrict__ y1, const T* __restrict__ m,
+                                                              T* __restrict__ out, WinGeom g) {
+  const int lane = threadIdx.x & 31;
+  const long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= g.T) return;
+  bool real;
+  const long long pix = token_pixel(g, t, &real);
+  if (!real) return;
+  for (int c = lane; c < g.C; c += 32) out[pix * g.C + c] = DT<T>::from_f(ldf(y1 + t * g.C + c) + ldf(m + t * g.C + c));
+}
+
+// gy2[t,:] = g[b,y,x,:] for real tokens, 0 for padded ones (they are cropped, swin_block.py:58)
+template <typename T>
+__global__ void __launch_bounds__(256) swin_partition_kernel(const T* __restrict__ gsrc, T* __restrict__ gtok, WinGeom g) {
+  const int lane = threadIdx.x & 31;
+  const long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= g.T) return;
+  bool real;
+  const long long pix = token_pixel(g, t, &real);
+  for (int c = lane; c < g.C; c += 32) gtok[t * g.C + c] = real ? gsrc[pix * g.C + c] : DT<T>::from_f(0.f);
+}
+
+// LayerNorm backward for a block of tokens + column partials of gamma / beta gradients.
+//   gin[t,:] = (ghat - mean(ghat) - xhat*mean(ghat*xhat)) * rstd (+ gres[t,:]),  ghat = gout*gamma
+// MODE 0 (LN2): xin = y1 tokens, output token-major, adds the residual gradient gres (= g_y2).
+// MODE 1 (LN1): xin = x in NHWC (gathered through the window map; padded tokens are all-zero rows), output is
+//               scattered back to NHWC gx for real tokens only; gres = nullptr.
+// gamma/beta partials: one row of [2][C] per CTA in `part` (folded by a second tiny kernel: deterministic).
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) swin_ln_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ xin,
+                                                         const T* __restrict__ gres, const float* __restrict__ gamma,
+                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                         T* __restrict__ gin, float* __restrict__ part, WinGeom g,
+                                                         int tokens_per_cta) {
+  extern __shared__ float sm[];  // [warps][2][C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int C = g.C, npl = (C + 31) / 32;
+  float accg[kMaxPL], accb[kMaxPL];
+#pragma unroll
+  for (int i = 0; i < kMaxPL; ++i) { accg[i] = 0.f; accb[i] = 0.f; }
+  const long long t0 = (long long)blockIdx.x * tokens_per_cta;
+  for (int k = warp; k < tokens_per_cta; k += nwarp) {
+    const long long t = t0 + k;
+    if (t >= g.T) break;
+    bool real = true;
+    long long src = t;
+    if (MODE == 1) src = token_pixel(g, t, &real);
+    const float mu = mean[t], rs = rstd[t];
+    float go[kMaxPL], xh[kMaxPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxPL; ++i) {
+      const int c = lane + 32 * i;
+      if (i < npl && c < C) {
+        const float gv = ldf(gout + t * C + c);
+        const float xv = (MODE == 1 && !real) ? 0.f : ldf(xin + src * C + c);
+        xh[i] = (xv - mu) * rs;
+        go[i] = gv * gamma[c];
+        s1 += go[i];
+        s2 += go[i] * xh[i];
+        accg[i] += gv * xh[i];
+        accb[i] += gv;
+      } else { go[i] = 0.f; xh[i] = 0.f; }
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+    if (MODE == 0 || real) {
+#pragma unroll
+      for (int i = 0; i < kMaxPL; ++i) {
+        const int c = lane + 32 * i;
+        if (i < npl && c < C) {
+          float r = (go[i] - s1 - xh[i] * s2) * rs;
+          if (MODE == 0) r += ldf(gres + t * C + c);
+          gin[src * C + c] = DT<T>::from_f(r);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kMaxPL; ++i) {
+    const int c = lane + 32 * i;
+    if (i < npl && c < C) { sm[(warp * 2 + 0) * C + c] = accg[i]; sm[(warp * 2 + 1) * C + c] = accb[i]; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nwarp; ++w) s += sm[w * 2 * C + i];
+    part[(size_t)blockIdx.x * 2 * C + i] = s;
+  }
+}
+
+// [rows][2][C] partials -> ggamma[C], gbeta[C]   (fixed order)
+__global__ void fold_ln_kernel(const float* __restrict__ part, float* __restrict__ gg, float* __restrict__ gb, int rows, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * C) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += part[(size_t)r * 2 * C + i];
+  if (i < C) gg[i] = s; else gb[i - C] = s;
+}
+
+// out[i] = sum_r part[r][i]   (fixed order)
+__global__ void fold_rows_kernel(const float* __restrict__ part, float* __restrict__ out, int rows, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += part[(size_t)r * n + i];
+  out[i] = s;
+}
+
+// column sums of a [rows, n] activation matrix -> f32 [n] (bias gradients); two-stage, deterministic
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ a, float* __restrict__ part, long long rows,
+                                                            int n, int rows_per_cta) {
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float s = 0.f;
+  const long long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
+  for (long long r = r0; r < r1; ++r) s += ldf(a + r * n + c);
+  part[(size_t)blockIdx.y * n + c] = s;
+}
+
+int make_geom(WinGeom* g, int B, int C, int H, int W, int ws) {
+  B200_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && ws > 0, B200_ERR_SHAPE, "swin: bad shape B=%d C=%d H=%d W=%d ws=%d", B, C, H, W, ws);
+  B200_REQUIRE(C <= 32 * kMaxPL, B200_ERR_UNSUPPORTED, "swin: C=%d > %d unsupported", C, 32 * kMaxPL);
+  g->B = B; g->C = C; g->H = H; g->W = W; g->ws = ws;
+  g->nWh = (H + ws - 1) / ws; g->nWw = (W + ws - 1) / ws; g->L = ws * ws;
+  g->T = (long long)B * g->nWh * g->nWw * g->L;
+  return B200_OK;
+}
+
+inline unsigned warps_grid(long long tokens) { return (unsigned)((tokens + 7) / 8); }
+
+}  // namespace
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" B200_API long long b200_swin_num_tokens(int32_t B, int32_t H, int32_t W, int32_t ws) {
+  if (B <= 0 || H <= 0 || W <= 0 || ws <= 0) return 0;
+  return (long long)B * ((H + ws - 1) / ws) * ((W + ws - 1) / ws) * ws * ws;
+}
+
+extern "C" B200_API int b200_swin_ln1_partition(const void* x, const float* gamma, const float* beta, void* n1, float* mean,
+                                                float* rstd, int32_t B, int32_t C, int32_t H, int32_t W, int32_t ws,
+                                                int32_t dtype, void* stream) {
+  WinGeom g;
+  if (int rc = make_geom(&g, B, C, H, W, ws)) return rc;
+  B200_REQUIRE(x && gamma && beta && n1 && mean && rstd, B200_ERR_SHAPE, "swin_ln1_partition: null pointer");
+  return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
+    swin_ln1_partition_kernel<T><<<warps_grid(g.T), 256, 0, (cudaStream_t)stream>>>((const T*)x, gamma, beta, (T*)n1, mean, rstd, g);
+    return check_launch("swin_ln1_partition");
+  });
+}
+
+extern "C" B200_API int b200_swin_res_ln2(const void* n1, const void* a, const float* gamma, const float* beta, void* y1,
+                                          void* u, float* mean, float* rstd, int64_t tokens, int32_t C, int32_t dtype,
+                                          void* stream) {
+  B200_REQUIRE(n1 && a && gamma && beta && y1 && u && mean && rstd, B200_ERR_SHAPE, "swin_res_ln2: null pointer");
+  B200_REQUIRE(tokens > 0 && C > 0 && C <= 32 * kMaxPL, B200_ERR_SHAPE, "swin_res_ln2: bad shape");
+  return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
+    swin_res_ln2_kernel<T><<<warps_grid(tokens), 256, 0, (cudaStream_t)stream>>>((const T*)n1, (const T*)a, gamma, beta, (T*)y1,
+                                                                                 (T*)u, mean, rstd, tokens, C);
+    return check_launch("swin_res_ln2");
+  });
+}
+
+extern "C" B200_API int b200_swin_gelu(const void* a, const void* gh, void* out, int64_t n, int32_t dtype, int32_t backward,
+                                       void* stream) {
+  B200_REQUIRE(a && out && n > 0 && (!backward || gh), B200_ERR_SHAPE, "swin_gelu: bad arguments");
+  B200_REQUIRE((((uintptr_t)a | (uintptr_t)out | (uintptr_t)gh) & 15) == 0, B200_ERR_ALIGN, "swin_gelu: pointers must be 16-byte aligned");
+  return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
+    const long long nv = n / (16 / sizeof(T));
+    unsigned grid = (unsigned)((nv + 255) / 256);
+    const unsigned cap = (unsigned)sm_count() * 16;
+    if (grid > cap) grid = cap;
+    if (grid == 0) grid = 1;
+    if (backward) swin_gelu_kernel<T, true><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)gh, (T*)out, n);
+    else swin_gelu_kernel<T, false><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)a, nullptr, (T*)out, n);
+    return check_launch("swin_gelu");
+  });
+}
+
+extern "C" B200_API int b200_swin_res_reverse(const void* y1, const void* m, void* out, int32_t B, int32_t C, int32_t H,
+                                              int32_t W, int32_t ws, int32_t dtype, void* stream) {
+  WinGeom g;
+  if (int rc = make_geom(&g, B, C, H, W, ws)) return rc;
+  B200_REQUIRE(y1 && m && out, B200_ERR_SHAPE, "swin_res_reverse: null pointer");
+  return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
+    swin_res_reverse_kernel<T><<<warps_grid(g.T), 256, 0, (cudaStream_t)stream>>>((const T*)y1, (const T*)m, (T*)out, g);
+    return check_launch("swin_res_reverse");
+  });
+}
+
+extern "C" B200_API int b200_swin_partition(const void* src, void* tok, int32_t B, int32_t C, int32_t H, int32_t W,
+                                            int32_t ws, int32_t dtype, void* stream) {
+  WinGeom g;
+  if (int rc = make_geom(&g, B, C, H, W, ws)) return rc;
+  B200_REQUIRE(src && tok, B200_ERR_SHAPE, "swin_partition: null pointer");
+  return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
+    swin_partition_kernel<T><<<warps_grid(g.T), 256, 0, (cudaStream_t)stream>>>((const T*)src, (T*)tok, g);
+    return check_launch("swin_partition");
+  });
+}
+
+static const int kLnTokensPerCta = 64;
+
+extern "C" B200_API size_t b200_swin_ln_bwd_workspace_bytes(int64_t tokens, int32_t C) {
+  const long long ctas = (tokens + kLnTokensPerCta - 1) / kLnTokensPerCta;
+  return (size_t)ctas * 2 * C * sizeof(float);
+}
+
+// mode 0: LN2 backward (token-major in/out, + residual);  mode 1: LN1 backward (gathers x / scatters gx in NHWC)
+extern "C" B200_API int b200_swin_ln_bwd(const void* gout, const void* xin, const void* gres, const float* gamma,
+                                         const float* mean, const float* rstd, void* gin, float* ggamma, float* gbeta,
+                                         void* workspace, size_t workspace_bytes, int32_t B, int32_t C, int32_t H,
+                                         int32_t W, int32_t ws, int32_t dtype, int32_t mode, void* stream) {
+  WinGeom g;
+  if (int rc = make_geom(&g, B, C, H, W, ws)) return rc;
+  B200_REQUIRE(gout && xin && gamma && mean && rstd && gin && ggamma && gbeta, B200_ERR_SHAPE, "swin_ln_bwd: null pointer");
+  B200_REQUIRE(mode == 1 || gres, B200_ERR_SHAPE, "swin_ln_bwd: LN2 mode needs the residual gradient");
+  const size_t need = b200_swin_ln_bwd_workspace_bytes(g.T, C);
+  B200_REQUIRE(workspace && workspace_bytes >= need, B200_ERR_WORKSPACE, "swin_ln_bwd: workspace %zu < %zu", workspace_bytes, need);
+  const unsigned ctas = (unsigned)((g.T + kLnTokensPerCta - 1) / kLnTokensPerCta);
+  const size_t smem = (size_t)8 * 2 * C * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = B200_DISPATCH_DTYPE(dtype, [&]() -> int {
+    if (mode == 0) {
+      auto k = swin_ln_bwd_kernel<T, 0>;
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      k<<<ctas, 256, smem, st>>>((const T*)gout, (const T*)xin, (const T*)gres, gamma, mean, rstd, (T*)gin, (float*)workspace, g, kLnTokensPerCta);
+    } else {
+      auto k = swin_ln_bwd_kernel<T, 1>;
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      k<<<ctas, 256, smem, st>>>((const T*)gout, (const T*)xin, nullptr, gamma, mean, rstd, (T*)gin, (float*)workspace, g, kLnTokensPerCta);
+    }
+    return check_launch("swin_ln_bwd");
+  });
+  if (rc) return rc;
+  fold_ln_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>((const float*)workspace, ggamma, gbeta, (int)ctas, C);
+  return check_launch("swin_ln_bwd_fold");
+}
+
+static const int kColsumRows = 512;
+
+extern "C" B200_API size_t b200_colsum_workspace_bytes(int64_t rows, int32_t n) {
+  return (size_t)((rows + kColsumRows - 1) / kColsumRows) * n * sizeof(float);
+}
+
+// out[n] (f32) = column sums of a [rows, n] (bias gradients: attn.in_proj_bias, out_proj.bias, mlp.{0,2}.bias)
+extern "C" B200_API int b200_colsum(const void* a, float* out, void* workspace, size_t workspace_bytes, int64_t rows,
+                                    int32_t n, int32_t dtype, void* stream) {
+  B200_REQUIRE(a && out && rows > 0 && n > 0, B200_ERR_SHAPE, "colsum: bad arguments");
+  const size_t need = b200_colsum_workspace_bytes(rows, n);
+  B200_REQUIRE(workspace && workspace_bytes >= need, B200_ERR_WORKSPACE, "colsum: workspace %zu < %zu", workspace_bytes, need);
+  const unsigned rblocks = (unsigned)((rows + kColsumRows - 1) / kColsumRows);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = B200_DISPATCH_DTYPE(dtype, [&]() -> int {
+    colsum_partial_kernel<T><<<dim3((n + 255) / 256, rblocks), 256, 0, st>>>((const T*)a, (float*)workspace, rows, n, kColsumRows);
+    return check_launch("colsum_partial");
+  });
+  if (rc) return rc;
+  fold_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>((const float*)workspace, out, (int)rblocks, n);
+  return check_launch("colsum_fold");
+}

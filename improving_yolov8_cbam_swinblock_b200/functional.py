@@ -1,0 +1,301 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels (include/b200_yolo_blocks.h).
+
+PyTorch is plumbing here: it owns device memory, streams and the autograd graph; every number on the CBAM /
+SwinBlock / SPPF path is produced by ``libb200yolo.so``.  Tensors are logical NCHW (what the callers in
+``ultralytics/nn/tasks.py:171`` pass) held in channels_last memory = the NHWC layout the kernels address; an
+NCHW-contiguous input is converted once on entry (run the model ``channels_last`` to avoid that copy).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check, dtype_code, lib, ptr, stream_ptr
+
+_I64, _I32, _VP, _SZ = C.c_int64, C.c_int32, C.c_void_p, C.c_size_t
+_lib.register("b200_swin_num_tokens", C.c_longlong, [_I32] * 4)
+_lib.register("b200_swin_ln1_partition", C.c_int, [_VP] * 6 + [_I32] * 6 + [_VP])
+_lib.register("b200_swin_attn_fwd", C.c_int, [_VP] * 3 + [_I64] + [_I32] * 4 + [_VP])
+_lib.register("b200_swin_attn_bwd", C.c_int, [_VP] * 5 + [_I64] + [_I32] * 4 + [_VP])
+_lib.register("b200_swin_res_ln2", C.c_int, [_VP] * 8 + [_I64] + [_I32] * 2 + [_VP])
+_lib.register("b200_swin_gelu", C.c_int, [_VP] * 3 + [_I64] + [_I32] * 2 + [_VP])
+_lib.register("b200_swin_res_reverse", C.c_int, [_VP] * 3 + [_I32] * 6 + [_VP])
+_lib.register("b200_swin_partition", C.c_int, [_VP] * 2 + [_I32] * 6 + [_VP])
+_lib.register("b200_swin_ln_bwd_workspace_bytes", _SZ, [_I64, _I32])
+_lib.register("b200_swin_ln_bwd", C.c_int, [_VP] * 10 + [_SZ] + [_I32] * 7 + [_VP])
+_lib.register("b200_colsum_workspace_bytes", _SZ, [_I64, _I32])
+_lib.register("b200_colsum", C.c_int, [_VP] * 3 + [_SZ] + [_I64] + [_I32] * 2 + [_VP])
+
+
+def _nhwc(x: torch.Tensor) -> torch.Tensor:
+    """Return x (logical [B,C,H,W]) in dense channels_last memory."""
+    if x.dim() != 4:
+        raise RuntimeError(f"expected a 4-D [B,C,H,W] tensor, got shape {tuple(x.shape)}")
+    if not x.is_cuda:
+        raise RuntimeError("B200 kernels need a CUDA tensor (there is no CPU compute path in this package)")
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+def _empty_nhwc(B, Cc, H, W, dtype, device):
+    return torch.empty((B, Cc, H, W), dtype=dtype, device=device, memory_format=torch.channels_last)
+
+
+def _f32(w: torch.Tensor) -> torch.Tensor:
+    return w.detach().to(torch.float32).contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# SPPF pooling cascade + concat   (block.py:224-226)
+# --------------------------------------------------------------------------------------------------
+def sppf_pool_forward_raw(y0: torch.Tensor, k: int, want_idx: bool = False):
+    y0 = _nhwc(y0)
+    B, Cc, H, W = y0.shape
+    cat = _empty_nhwc(B, 4 * Cc, H, W, y0.dtype, y0.device)
+    idx = torch.empty((3, B, H, W, Cc), dtype=torch.int32, device=y0.device) if want_idx else None
+    with torch.cuda.device(y0.device):
+        check(lib().b200_sppf_pool_fwd(ptr(y0), ptr(cat), ptr(idx), B, Cc, H, W, int(k), dtype_code(y0.dtype),
+                                       stream_ptr(y0.device)), "b200_sppf_pool_fwd")
+    return cat, idx
+
+
+class SPPFPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y0, k):
+        y0 = _nhwc(y0)
+        cat, _ = sppf_pool_forward_raw(y0, k)
+        ctx.save_for_backward(y0)
+        ctx.k = int(k)
+        return cat
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gcat):
+        (y0,) = ctx.saved_tensors
+        B, Cc, H, W = y0.shape
+        gcat = _nhwc(gcat.to(y0.dtype))
+        gy0 = _empty_nhwc(B, Cc, H, W, y0.dtype, y0.device)
+        with torch.cuda.device(y0.device):
+            check(lib().b200_sppf_pool_bwd(ptr(gcat), ptr(y0), ptr(gy0), B, Cc, H, W, ctx.k, dtype_code(y0.dtype),
+                                           stream_ptr(y0.device)), "b200_sppf_pool_bwd")
+        return gy0, None
+
+
+def sppf_pool(y0: torch.Tensor, k: int) -> torch.Tensor:
+    """[B,c,H,W] -> [B,4c,H,W] = cat[y0, m(y0), m(m(y0)), m(m(m(y0)))], m = MaxPool2d(k,1,k//2)."""
+    return SPPFPoolFn.apply(y0, k)
+
+
+# --------------------------------------------------------------------------------------------------
+# CBAM   (cbam.py:29-38, :48-53, :62-71)
+# --------------------------------------------------------------------------------------------------
+class CBAMFn(torch.autograd.Function):
+    """mode 0: x*ca*sa;  mode 1: ca map [B,C,1,1];  mode 2: sa map [B,1,H,W]."""
+
+    @staticmethod
+    def forward(ctx, x, w1, w2, wsa, mode):
+        x = _nhwc(x)
+        B, Cc, H, W = x.shape
+        dev = x.device
+        r = w1.shape[0] if w1 is not None else 1
+        ksa = wsa.shape[-1] if wsa is not None else 3
+        w1f = _f32(w1).view(r, Cc) if w1 is not None else None
+        w2f = _f32(w2).view(Cc, r) if w2 is not None else None
+        wsf = _f32(wsa).view(2, ksa, ksa) if wsa is not None else None
+        need_grad = any(ctx.needs_input_grad)
+        ca = torch.empty((B, Cc), dtype=torch.float32, device=dev) if (mode == 1 or (need_grad and mode == 0)) else None
+        sa = torch.empty((B, H * W), dtype=torch.float32, device=dev) if (mode == 2 or (need_grad and mode == 0)) else None
+        out = _empty_nhwc(B, Cc, H, W, x.dtype, dev) if mode == 0 else None
+        with torch.cuda.device(dev):
+            check(lib().b200_cbam_fwd(ptr(x), ptr(w1f), ptr(w2f), ptr(wsf), ptr(out), ptr(ca), ptr(sa), B, Cc, H, W, r,
+                                      ksa, dtype_code(x.dtype), mode, stream_ptr(dev)), "b200_cbam_fwd")
+        ctx.mode, ctx.dims = mode, (B, Cc, H, W, r, ksa)
+        ctx.wshapes = tuple(None if w is None else (w.shape, w.dtype) for w in (w1, w2, wsa))
+        ctx.save_for_backward(x, w1f, w2f, wsf, ca, sa)
+        if mode == 0:
+            return out
+        if mode == 1:
+            return ca.view(B, Cc, 1, 1).to(x.dtype)
+        return sa.view(B, 1, H, W).to(x.dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, w1f, w2f, wsf, ca, sa = ctx.saved_tensors
+        B, Cc, H, W, r, ksa = ctx.dims
+        dev, mode = x.device, ctx.mode
+        if mode == 0:
+            g = _nhwc(g.to(x.dtype))
+        else:
+            g = g.to(torch.float32).contiguous().view(B, -1)
+        gx = _empty_nhwc(B, Cc, H, W, x.dtype, dev)
+        gw1 = torch.empty((r, Cc), dtype=torch.float32, device=dev) if mode != 2 else None
+        gw2 = torch.empty((Cc, r), dtype=torch.float32, device=dev) if mode != 2 else None
+        gws = torch.empty((2, ksa, ksa), dtype=torch.float32, device=dev) if mode != 1 else None
+        L = lib()
+        nbytes = L.b200_cbam_bwd_workspace_bytes(B, Cc, H, W, r, ksa)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(L.b200_cbam_bwd(ptr(g), ptr(x), ptr(w1f), ptr(w2f), ptr(wsf), ptr(ca), ptr(sa), ptr(gx), ptr(gw1),
+                                  ptr(gw2), ptr(gws), ptr(ws), nbytes, B, Cc, H, W, r, ksa, dtype_code(x.dtype), mode,
+                                  stream_ptr(dev)), "b200_cbam_bwd")
+        outs = []
+        for gw, meta in zip((gw1, gw2, gws), ctx.wshapes):
+            outs.append(None if (gw is None or meta is None) else gw.view(meta[0]).to(meta[1]))
+        return gx, outs[0], outs[1], outs[2], None
+
+
+def cbam(x, w1, w2, wsa):
+    return CBAMFn.apply(x, w1, w2, wsa, _lib.CBAM_FULL)
+
+
+def cbam_channel_attention(x, w1, w2):
+    return CBAMFn.apply(x, w1, w2, None, _lib.CBAM_CA)
+
+
+def cbam_spatial_attention(x, wsa):
+    return CBAMFn.apply(x, None, None, wsa, _lib.CBAM_SA)
+
+
+# --------------------------------------------------------------------------------------------------
+# SwinBlock   (swin_block.py:37-58)
+# --------------------------------------------------------------------------------------------------
+def _gemm_nt(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None) -> torch.Tensor:
+    """a[M,K] @ w[N,K]^T (+ bias) -> [M,N] in a's dtype."""
+    from . import gemm
+
+    return gemm.linear(a, w, bias)
+
+
+def _colsum(a: torch.Tensor) -> torch.Tensor:
+    rows, n = a.shape
+    L = lib()
+    nbytes = L.b200_colsum_workspace_bytes(rows, n)
+    ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=a.device)
+    out = torch.empty(n, dtype=torch.float32, device=a.device)
+    check(L.b200_colsum(ptr(a), ptr(out), ptr(ws), nbytes, rows, n, dtype_code(a.dtype), stream_ptr(a.device)),
+          "b200_colsum")
+    return out
+
+
+class SwinBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, *args):
+        with torch.autocast("cuda", enabled=False):  # dtype is decided by the caller (swin_block), not by autocast
+            return SwinBlockFn._forward(ctx, *args)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        with torch.autocast("cuda", enabled=False):
+            return SwinBlockFn._backward(ctx, gout)
+
+    @staticmethod
+    def _forward(ctx, x, g1, b1, win, bin_, wo, bo, g2, b2, w1, bb1, w2, bb2, num_heads, ws):
+        from . import gemm
+
+        x = _nhwc(x)
+        B, Cc, H, W = x.shape
+        dev, dt = x.device, x.dtype
+        code = dtype_code(dt)
+        L = lib()
+        T = int(L.b200_swin_num_tokens(B, H, W, ws))
+        Lw = ws * ws
+        st = stream_ptr(dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        g1f, b1f, g2f, b2f = _f32(g1), _f32(b1), _f32(g2), _f32(b2)
+        with torch.cuda.device(dev):
+            n1 = torch.empty((T, Cc), dtype=dt, device=dev)
+            mean1, rstd1 = torch.empty(T, **f32), torch.empty(T, **f32)
+            check(L.b200_swin_ln1_partition(ptr(x), ptr(g1f), ptr(b1f), ptr(n1), ptr(mean1), ptr(rstd1), B, Cc, H, W, ws,
+                                            code, st), "b200_swin_ln1_partition")
+            qkv = gemm.linear(n1, win, bin_)
+            o = torch.empty((T, Cc), dtype=dt, device=dev)
+            lse = torch.empty((T, num_heads), **f32)
+            check(L.b200_swin_attn_fwd(ptr(qkv), ptr(o), ptr(lse), T, Lw, Cc, num_heads, code, st), "b200_swin_attn_fwd")
+            a = gemm.linear(o, wo, bo)
+            y1, u = torch.empty_like(n1), torch.empty_like(n1)
+            mean2, rstd2 = torch.empty(T, **f32), torch.empty(T, **f32)
+            check(L.b200_swin_res_ln2(ptr(n1), ptr(a), ptr(g2f), ptr(b2f), ptr(y1), ptr(u), ptr(mean2), ptr(rstd2), T, Cc,
+                                      code, st), "b200_swin_res_ln2")
+            del a
+            hpre = gemm.linear(u, w1, bb1)
+            h = torch.empty_like(hpre)
+            check(L.b200_swin_gelu(ptr(hpre), None, ptr(h), hpre.numel(), code, 0, st), "b200_swin_gelu")
+            m = gemm.linear(h, w2, bb2)
+            out = _empty_nhwc(B, Cc, H, W, dt, dev)
+            check(L.b200_swin_res_reverse(ptr(y1), ptr(m), ptr(out), B, Cc, H, W, ws, code, st), "b200_swin_res_reverse")
+        ctx.save_for_backward(x, g1f, g2f, win, wo, w1, w2, n1, mean1, rstd1, qkv, o, lse, y1, u, mean2, rstd2, hpre, h)
+        ctx.cfg = (B, Cc, H, W, ws, num_heads, T)
+        ctx.pdtypes = tuple(p.dtype for p in (g1, b1, win, bin_, wo, bo, g2, b2, w1, bb1, w2, bb2))
+        return out
+
+    @staticmethod
+    def _backward(ctx, gout):
+        from . import gemm
+
+        (x, g1f, g2f, win, wo, w1, w2, n1, mean1, rstd1, qkv, o, lse, y1, u, mean2, rstd2, hpre, h) = ctx.saved_tensors
+        B, Cc, H, W, ws, nh, T = ctx.cfg
+        dev, dt = x.device, x.dtype
+        code = dtype_code(dt)
+        L = lib()
+        st = stream_ptr(dev)
+        Lw = ws * ws
+        with torch.cuda.device(dev):
+            gout = _nhwc(gout.to(dt))
+            gy2 = torch.empty((T, Cc), dtype=dt, device=dev)
+            check(L.b200_swin_partition(ptr(gout), ptr(gy2), B, Cc, H, W, ws, code, st), "b200_swin_partition")
+            # MLP
+            gw2 = gemm.matmul_tn(gy2, h)          # [C, 4C] = gy2^T h
+            gb2 = _colsum(gy2)
+            gh = gemm.matmul_nn(gy2, w2)          # [T, 4C] = gy2 W2
+            check(L.b200_swin_gelu(ptr(hpre), ptr(gh), ptr(gh), gh.numel(), code, 1, st), "b200_swin_gelu(bwd)")
+            ga = gh
+            gw1 = gemm.matmul_tn(ga, u)           # [4C, C]
+            gb1 = _colsum(ga)
+            gu = gemm.matmul_nn(ga, w1)           # [T, C]
+            del ga, gh
+            # LN2 + residual
+            nbytes = L.b200_swin_ln_bwd_workspace_bytes(T, Cc)
+            wsb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            gy1 = torch.empty_like(gy2)
+            gg2 = torch.empty(Cc, dtype=torch.float32, device=dev)
+            gbt2 = torch.empty(Cc, dtype=torch.float32, device=dev)
+            check(L.b200_swin_ln_bwd(ptr(gu), ptr(y1), ptr(gy2), ptr(g2f), ptr(mean2), ptr(rstd2), ptr(gy1), ptr(gg2),
+                                     ptr(gbt2), ptr(wsb), nbytes, B, Cc, H, W, ws, code, 0, st), "b200_swin_ln_bwd(2)")
+            del gu, gy2
+            # attention
+            gwo = gemm.matmul_tn(gy1, o)          # [C, C]
+            gbo = _colsum(gy1)
+            go = gemm.matmul_nn(gy1, wo)          # [T, C]
+            gqkv = torch.empty_like(qkv)
+            check(L.b200_swin_attn_bwd(ptr(qkv), ptr(o), ptr(lse), ptr(go), ptr(gqkv), T, Lw, Cc, nh, code, st),
+                  "b200_swin_attn_bwd")
+            del go
+            gwin = gemm.matmul_tn(gqkv, n1)       # [3C, C]
+            gbin = _colsum(gqkv)
+            gn1 = gemm.matmul_nn(gqkv, win, add=gy1)  # [T, C] = gy1 + gqkv Win
+            del gqkv, gy1
+            # LN1 + un-partition
+            gx = _empty_nhwc(B, Cc, H, W, dt, dev)
+            gg1 = torch.empty(Cc, dtype=torch.float32, device=dev)
+            gbt1 = torch.empty(Cc, dtype=torch.float32, device=dev)
+            check(L.b200_swin_ln_bwd(ptr(gn1), ptr(x), None, ptr(g1f), ptr(mean1), ptr(rstd1), ptr(gx), ptr(gg1),
+                                     ptr(gbt1), ptr(wsb), nbytes, B, Cc, H, W, ws, code, 1, st), "b200_swin_ln_bwd(1)")
+        grads = [gg1, gbt1, gwin, gbin, gwo, gbo, gg2, gbt2, gw1, gb1, gw2, gb2]
+        grads = [g.to(d) for g, d in zip(grads, ctx.pdtypes)]
+        return (gx, *grads, None, None)
+
+
+def swin_block(x, p: dict, num_heads: int, ws: int):
+    """p: parameters keyed like the reference state_dict (norm1.weight, attn.in_proj_weight, ...).
+
+    Compute dtype = the autocast dtype when autocast is on (the reference runs its GEMMs there; trainer.py:383),
+    else x.dtype."""
+    if torch.is_autocast_enabled("cuda") and x.dtype == torch.float32:
+        x = x.to(torch.get_autocast_dtype("cuda"))
+    return SwinBlockFn.apply(
+        x, p["norm1.weight"], p["norm1.bias"], p["attn.in_proj_weight"], p["attn.in_proj_bias"],
+        p["attn.out_proj.weight"], p["attn.out_proj.bias"], p["norm2.weight"], p["norm2.bias"],
+        p["mlp.0.weight"], p["mlp.0.bias"], p["mlp.2.weight"], p["mlp.2.bias"], num_heads, ws)

@@ -1,0 +1,57 @@
+"""Bind the B200 blocks into an (unmodified) Ultralytics checkout of the reference fork.
+
+``parse_model`` resolves yaml strings with ``globals()[m]`` in ``ultralytics.nn.tasks`` (tasks.py:1438) and builds
+its ``base_modules`` set from the same globals at call time (tasks.py:1375-1412), so rebinding three names there
+(and in ``ultralytics.nn.modules`` for ``from ... import`` users / pickles) IS the integration:
+
+    import improving_yolov8_cbam_swinblock_b200.ultralytics_plugin as plugin
+    plugin.install()            # before building DetectionModel / YOLO(...)
+    ...
+    plugin.uninstall()
+
+Classes are created once at import (bound to the reference's own ``Conv`` so ``fuse()`` still sees Conv
+instances) and live at module level here, so whole-model pickles (trainer.py:531-562) resolve them by path.
+"""
+from __future__ import annotations
+
+import importlib
+
+from . import modules as _m
+
+_TARGETS = ("ultralytics.nn.tasks", "ultralytics.nn.modules", "ultralytics.nn.modules.cbam",
+            "ultralytics.nn.modules.swin_block", "ultralytics.nn.modules.block")
+_saved: dict = {}
+
+CBAM = _m.CBAM
+ChannelAttentionMap = _m.ChannelAttention
+SpatialAttentionMap = _m.SpatialAttention
+SwinBlock = _m.SwinBlock
+SPPF = None  # created by install() against ultralytics' Conv
+
+
+def install():
+    """Rebind CBAM / SwinBlock / SPPF in the reference's namespaces.  Returns the {name: class} table."""
+    global SPPF
+    conv_mod = importlib.import_module("ultralytics.nn.modules.conv")
+    if SPPF is None:
+        SPPF = _m.make_sppf(conv_mod.Conv, module=__name__)
+    table = {"CBAM": CBAM, "SwinBlock": SwinBlock, "SPPF": SPPF}
+    for modname in _TARGETS:
+        mod = importlib.import_module(modname)
+        for name, cls in table.items():
+            if hasattr(mod, name):
+                _saved.setdefault((modname, name), getattr(mod, name))
+                setattr(mod, name, cls)
+    # cbam.py's own ChannelAttention / SpatialAttention (maps only).  NOTE: ultralytics.nn.modules exports the
+    # *stock* conv.py classes under these names (modules/__init__.py:66,78) -- those are left alone.
+    cb = importlib.import_module("ultralytics.nn.modules.cbam")
+    for name, cls in (("ChannelAttention", ChannelAttentionMap), ("SpatialAttention", SpatialAttentionMap)):
+        _saved.setdefault((cb.__name__, name), getattr(cb, name))
+        setattr(cb, name, cls)
+    return table
+
+
+def uninstall():
+    for (modname, name), cls in list(_saved.items()):
+        setattr(importlib.import_module(modname), name, cls)
+    _saved.clear()

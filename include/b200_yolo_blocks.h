@@ -1,0 +1,139 @@
+/*
+ * b200_yolo_blocks.h -- C-ABI of the B200 (sm_100a) kernels behind the CBAM / SwinBlock / SPPF drop-ins.
+ *
+ * The reference (mazouziwissem/improving_yolov8_CBAM_SwinBlock, an Ultralytics 8.3.108 fork) is pure Python:
+ * its "operator interface" for this path is the nn.Module.forward of three classes that parse_model binds by
+ * name (ultralytics/nn/tasks.py:1438).  Each entry point below replaces the ATen op sequence of one of those
+ * forwards (or of its autograd backward) and is what a ctypes / cffi stub on the reference side binds
+ * (INTEGRATION.md shows the stub).  Conventions:
+ *
+ *   - plain pointers + sizes only; device pointers unless stated; no torch types.
+ *   - activations are NHWC-dense ("channels_last"): element (b,c,h,w) lives at ((b*H+h)*W+w)*C+c.
+ *   - dtype codes: 0=f32, 1=bf16, 2=f16 for activations; parameters and parameter gradients are always f32.
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*) of the current device;
+ *     no hidden synchronisation, no allocation: scratch memory is passed in as `workspace`.
+ *   - return 0 on success, a B200_ERR_* code otherwise (message via b200_last_error(), thread-local);
+ *     nothing throws or exits across the ABI.  Stateless and re-entrant.
+ */
+#ifndef B200_YOLO_BLOCKS_H_
+#define B200_YOLO_BLOCKS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+#if defined(__GNUC__)
+#define B200_API __attribute__((visibility("default")))
+#else
+#define B200_API
+#endif
+
+enum { B200_F32 = 0, B200_BF16 = 1, B200_F16 = 2 };
+enum {
+  B200_OK = 0,
+  B200_ERR_SHAPE = 1,
+  B200_ERR_DTYPE = 2,
+  B200_ERR_ALIGN = 3,
+  B200_ERR_LAUNCH = 4,
+  B200_ERR_WORKSPACE = 5,
+  B200_ERR_UNSUPPORTED = 6
+};
+
+B200_API int b200_abi_version(void);
+B200_API const char* b200_last_error(void);
+/* number of kernel launches enqueued through this library by the calling process so far (bench bookkeeping) */
+B200_API uint64_t b200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * SPPF pooling cascade -- replaces `y = [cv1(x)]; y.extend(self.m(y[-1]) for _ in range(3)); torch.cat(y, 1)`
+ * (ultralytics/nn/modules/block.py:224-226; self.m = MaxPool2d(k, 1, k//2), block.py:220).
+ *   y0  [B,H,W,C]   in
+ *   cat [B,H,W,4C]  out: channel slices [y0 | m(y0) | m(m(y0)) | m(m(m(y0)))]
+ *   idx [3,B,H,W,C] optional (NULL to skip): per-stage argmax as torch's flat h*W+w index into the previous
+ *                   stage's plane, with ATen's rule (row-major window scan, replace iff val>max or isnan(val)).
+ * k odd, 3 <= k <= 13.  Values are exact selections: bit-exact in every dtype.
+ * ------------------------------------------------------------------------------------------------------ */
+B200_API int b200_sppf_pool_fwd(const void* y0, void* cat, int32_t* idx, int32_t B, int32_t C, int32_t H, int32_t W,
+                       int32_t k, int32_t dtype, void* stream);
+/* backward of the cascade + concat w.r.t. y0 (autograd of block.py:224-226):
+ *   gcat [B,H,W,4C] in, y0 [B,H,W,C] in (argmax maps are recomputed from it with the same rule),
+ *   gy0 [B,H,W,C] out.  Deterministic (no atomics); accumulation in f32. */
+B200_API int b200_sppf_pool_bwd(const void* gcat, const void* y0, void* gy0, int32_t B, int32_t C, int32_t H, int32_t W,
+                       int32_t k, int32_t dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * CBAM -- replaces CBAM.forward / ChannelAttention.forward / SpatialAttention.forward
+ * (ultralytics/nn/modules/cbam.py:62-71, :29-38, :48-53).
+ *   mode B200_CBAM_FULL : out[B,H,W,C] = x * ca * sa        (cbam.py:62-71)
+ *   mode B200_CBAM_CA   : ca_out[B,C]  = sigmoid(MLP(avg)+MLP(max))   only (cbam.py:29-38), `out` unused
+ *   mode B200_CBAM_SA   : sa_out[B,H*W] = sigmoid(conv(cat[mean_c x, max_c x])) only (cbam.py:48-53)
+ *   w1 [r,C], w2 [C,r]  shared_MLP.{0,2}.weight (no bias, cbam.py:24-26); wsa [2,ksa,ksa] sa.conv.weight,
+ *   ksa in {3,7} (cbam.py:43).  ca_out / sa_out (f32) may be NULL in FULL mode when no backward is needed.
+ * ------------------------------------------------------------------------------------------------------ */
+enum { B200_CBAM_FULL = 0, B200_CBAM_CA = 1, B200_CBAM_SA = 2 };
+B200_API int b200_cbam_fwd(const void* x, const float* w1, const float* w2, const float* wsa, void* out, float* ca_out,
+                  float* sa_out, int32_t B, int32_t C, int32_t H, int32_t W, int32_t r, int32_t ksa,
+                  int32_t dtype, int32_t mode, void* stream);
+/* backward (autograd of the same forwards).
+ *   FULL: g = dL/dout [B,H,W,C];  CA: g = dL/dca [B,C] (f32);  SA: g = dL/dsa [B,H*W] (f32).
+ *   ca/sa: the maps saved by the forward (f32).  gx [B,H,W,C] out (activation dtype).
+ *   gw1 [r,C], gw2 [C,r], gwsa [2,ksa,ksa]: f32, OVERWRITTEN (not accumulated).
+ *   workspace: b200_cbam_bwd_workspace_bytes(...) bytes of device scratch. */
+B200_API size_t b200_cbam_bwd_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W, int32_t r, int32_t ksa);
+B200_API int b200_cbam_bwd(const void* g, const void* x, const float* w1, const float* w2, const float* wsa,
+                  const float* ca, const float* sa, void* gx, float* gw1, float* gw2, float* gwsa,
+                  void* workspace, size_t workspace_bytes, int32_t B, int32_t C, int32_t H, int32_t W,
+                  int32_t r, int32_t ksa, int32_t dtype, int32_t mode, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * SwinBlock stages -- replace SwinBlock.forward (ultralytics/nn/modules/swin_block.py:37-58) and its autograd
+ * backward.  x is NHWC [B,H,W,C]; "tokens" are the zero-padded, window-partitioned rows
+ *   t = ((b*nWh + wh)*nWw + ww)*L + r*ws + c,   L = ws*ws,  nWh = ceil(H/ws), nWw = ceil(W/ws)
+ * (swin_block.py:8-13,41-47).  T = b200_swin_num_tokens(...).  The dense contractions between the stages
+ * (in_proj / out_proj / mlp.0 / mlp.2, torch F.linear in the reference) are b200_gemm_* below.
+ * ------------------------------------------------------------------------------------------------------ */
+B200_API long long b200_swin_num_tokens(int32_t B, int32_t H, int32_t W, int32_t ws);
+/* n1[T,C] = LayerNorm_1(partition(pad(x)))  (swin_block.py:41-50); mean/rstd [T] f32 saved for the backward */
+B200_API int b200_swin_ln1_partition(const void* x, const float* gamma, const float* beta, void* n1, float* mean,
+                                     float* rstd, int32_t B, int32_t C, int32_t H, int32_t W, int32_t ws,
+                                     int32_t dtype, void* stream);
+/* windowed multi-head attention on packed rows qkv[T,3C] (q|k|v) -> o[T,C]; lse[T,nh] f32 (swin_block.py:51,
+ * torch F.multi_head_attention_forward: q*hd^-0.5, softmax over the window's L keys, heads concatenated) */
+B200_API int b200_swin_attn_fwd(const void* qkv, void* o, float* lse, int64_t tokens, int32_t L, int32_t C,
+                                int32_t nh, int32_t dtype, void* stream);
+B200_API int b200_swin_attn_bwd(const void* qkv, const void* o, const float* lse, const void* go, void* gqkv,
+                                int64_t tokens, int32_t L, int32_t C, int32_t nh, int32_t dtype, void* stream);
+/* y1 = n1 + a (post-norm residual, swin_block.py:52);  u = LayerNorm_2(y1) (swin_block.py:53) */
+B200_API int b200_swin_res_ln2(const void* n1, const void* a, const float* gamma, const float* beta, void* y1,
+                               void* u, float* mean, float* rstd, int64_t tokens, int32_t C, int32_t dtype,
+                               void* stream);
+/* GELU(erf) forward (backward=0: out = gelu(a)) / backward (backward=1: out = gh * gelu'(a)), swin_block.py:33 */
+B200_API int b200_swin_gelu(const void* a, const void* gh, void* out, int64_t n, int32_t dtype, int32_t backward,
+                            void* stream);
+/* out[B,H,W,C] = reverse(crop(y1 + m))  (swin_block.py:53-58) */
+B200_API int b200_swin_res_reverse(const void* y1, const void* m, void* out, int32_t B, int32_t C, int32_t H,
+                                   int32_t W, int32_t ws, int32_t dtype, void* stream);
+/* tok[T,C] = partition(pad(src)) without normalisation (used for the upstream gradient) */
+B200_API int b200_swin_partition(const void* src, void* tok, int32_t B, int32_t C, int32_t H, int32_t W,
+                                 int32_t ws, int32_t dtype, void* stream);
+/* LayerNorm backward.  mode 0 (LN2): token-major, gin = LN^T(gout) + gres.  mode 1 (LN1): xin = x (NHWC, gathered
+ * through the window map), gin = gx scattered back to NHWC; ggamma/gbeta [C] f32 overwritten; norm1.bias receives
+ * gradient from padded tokens too. */
+B200_API size_t b200_swin_ln_bwd_workspace_bytes(int64_t tokens, int32_t C);
+B200_API int b200_swin_ln_bwd(const void* gout, const void* xin, const void* gres, const float* gamma,
+                              const float* mean, const float* rstd, void* gin, float* ggamma, float* gbeta,
+                              void* workspace, size_t workspace_bytes, int32_t B, int32_t C, int32_t H,
+                              int32_t W, int32_t ws, int32_t dtype, int32_t mode, void* stream);
+/* out[n] f32 = column sums of a[rows,n]  (bias gradients) */
+B200_API size_t b200_colsum_workspace_bytes(int64_t rows, int32_t n);
+B200_API int b200_colsum(const void* a, float* out, void* workspace, size_t workspace_bytes, int64_t rows,
+                         int32_t n, int32_t dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_YOLO_BLOCKS_H_ */

@@ -1,0 +1,79 @@
+"""-m gpu: SwinBlock (C-ABI kernels + GEMMs) vs the reference-generated fixtures and the oracle.
+Bars: fp32 rtol 1e-5 (checked as <=1e-5 relative error + elementwise), bf16/f16 <= 2e-2 relative error vs fp32."""
+import pytest
+import torch
+
+from util import assert_close_f32, load_golden, rel_err, state_dict_of, to_cl
+
+pytestmark = pytest.mark.gpu
+
+GOLD = ["swin_c16_pad", "swin_c32_exact", "swin_c32_ws8_h4", "swin_c16_tiny", "swin_c128_p4"]
+
+
+@pytest.mark.parametrize("name", GOLD)
+def test_golden_fp32(name):
+    import improving_yolov8_cbam_swinblock_b200.modules as M
+
+    g = load_golden(name)
+    dim, heads, ws = (int(v) for v in g["args"])
+    mod = M.SwinBlock(dim, heads, ws)
+    mod.load_state_dict(state_dict_of(g))
+    mod = mod.cuda()
+    x = to_cl(torch.from_numpy(g["x"]).cuda()).requires_grad_(True)
+    y = mod(x)
+    y.backward(torch.from_numpy(g["gy"]).cuda())
+    assert_close_f32(y, torch.from_numpy(g["y"]), name + " y", rtol=1e-5, atol=4e-6)
+    assert_close_f32(x.grad, torch.from_numpy(g["gx"]), name + " gx", rtol=1e-5, atol=4e-6)
+    for k, p in mod.named_parameters():
+        want = torch.from_numpy(g["gw." + k])
+        assert rel_err(p.grad.cpu(), want) <= 1e-5, f"{name} grad {k}: {rel_err(p.grad.cpu(), want):.2e}"
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 2e-2), (torch.float16, 4e-3), (torch.float32, 1e-5)])
+@pytest.mark.parametrize("cfg", [((2, 128, 40, 40), 2, 7), ((1, 256, 20, 20), 2, 7), ((2, 64, 16, 24), 2, 8),
+                                 ((1, 384, 14, 14), 2, 7), ((2, 128, 23, 9), 4, 7)])
+def test_vs_oracle(dtype, tol, cfg):
+    import improving_yolov8_cbam_swinblock_b200.modules as M
+    from oracle import blocks as ob
+
+    shape, heads, ws = cfg
+    torch.manual_seed(sum(shape) + ws)
+    mod = M.SwinBlock(shape[1], heads, ws)
+    with torch.no_grad():
+        for k, p in mod.named_parameters():
+            if "norm" in k or "bias" in k:
+                p.add_(0.2 * torch.randn_like(p))
+    po = {k: v.detach().double().requires_grad_(True) for k, v in mod.named_parameters()}
+    x = torch.randn(shape).to(dtype)
+    gy = torch.randn(shape).to(dtype)
+    xo = x.double().requires_grad_(True)
+    yo = ob.swin_forward(xo, po, heads, ws)
+    yo.backward(gy.double())
+    mod = mod.cuda()
+    xc = to_cl(x.cuda()).requires_grad_(True)
+    with torch.autocast("cuda", dtype=dtype, enabled=dtype != torch.float32):
+        y = mod(xc)
+    y.backward(to_cl(gy.cuda()))
+    assert y.shape == x.shape
+    assert rel_err(y.cpu(), yo) <= tol, f"y {rel_err(y.cpu(), yo):.2e}"
+    assert rel_err(xc.grad.cpu(), xo.grad) <= tol, f"gx {rel_err(xc.grad.cpu(), xo.grad):.2e}"
+    for k, p in mod.named_parameters():
+        e = rel_err(p.grad.cpu(), po[k].grad)
+        assert e <= tol, f"grad {k}: {e:.2e}"
+
+
+def test_padded_tokens_feed_norm1_bias():
+    """padded tokens equal norm1.bias, act as keys/values and send gradient to norm1.bias."""
+    import improving_yolov8_cbam_swinblock_b200.modules as M
+
+    torch.manual_seed(0)
+    mod = M.SwinBlock(32, 2, 7).cuda()
+    with torch.no_grad():
+        mod.norm1.bias.normal_()
+    x = to_cl(torch.randn(1, 32, 9, 9, device="cuda"))
+    y0 = mod(x)
+    with torch.no_grad():
+        mod.norm1.bias.mul_(2.0)
+    y1 = mod(x)
+    assert not torch.allclose(y0, y1)
+    assert y0.shape == (1, 32, 9, 9)
