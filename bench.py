@@ -1,0 +1,235 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: training images/s of the custom YOLOv8n-CBAM-Swin model at 640^2,
+batch 64 per GPU, data-parallel (DDP / NCCL gradient all-reduce) on synthetic COCO-shaped batches, bf16 autocast,
+plus the per-module roofline numbers of the hand-written kernels.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Prints ONE JSON line on rank 0.  Keys beyond the base contract: ``e2e`` (same metric through the user-facing
+``Trainer.step_from_host``: pinned host batch in, host loss out), ``roofline`` (dominant hand-written kernel, timed
+with CUDA events on the launching stream inside the timed region), ``modules`` (per-kernel % of roofline, standalone,
+L2 flushed between launches), ``cpu_baseline`` (the oracle port of the reference blocks inside the same graph on the
+host cores, bounded sample), ``clocks``, ``gpu_launches``.
+
+``--impl reference`` times the reference's CPU implementation of the path (the oracle port: the reference package
+cannot travel to the GPU box) with all host threads on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SCALE, NC, IMGSZ, PER_GPU_BATCH = "n", 80, 640, 64
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc, self.idx = None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_leg(steps, warmup, batch=2):
+    """Reference blocks (oracle port) inside the same graph, training step on the host cores, fp32."""
+    import torch
+
+    from improving_yolov8_cbam_swinblock_b200.harness import graph, synthetic, train
+    from oracle import modules as om
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    blocks = {"CBAM": om.CBAM, "SwinBlock": om.SwinBlock, "SPPF": om.make_sppf(graph.Conv)}
+    tr = train.Trainer(blocks, SCALE, NC, device="cpu", amp_dtype=None, ema=True)
+    tr.max_boxes = synthetic.BOXES_PER_IMAGE
+    host = synthetic.make_batch(batch, IMGSZ, NC, seed=1234)
+    for _ in range(warmup):
+        tr.step_from_host(host)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.step_from_host(host)
+    dt = time.perf_counter() - t0
+    return {"value": batch * steps / dt, "unit": "img/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} fp32 training steps (fwd+loss+bwd+SGD+EMA) of YOLOv8{SCALE}-CBAM-Swin at {IMGSZ}^2, batch {batch}, "
+                      f"oracle/modules.py blocks (CPU restatement of cbam.py/swin_block.py/block.py SPPF) in the harness graph, "
+                      f"{cores} torch threads", "ms_per_step": 1e3 * dt / steps}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (default = BASELINE config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    config = {"workload": f"configs[2]: YOLOv8{SCALE}-CBAM-Swin (yolov8.yaml:734-776, SwinBlock [128]) training fwd+bwd+SGD+EMA, "
+                          f"synthetic COCO-shaped batches {IMGSZ}x{IMGSZ}, nc={NC}, 8 boxes/img",
+              "per_gpu_batch": args.batch, "global_batch": args.batch * world, "parallelism": f"dp{world}",
+              "amp": "bf16 autocast", "memory_format": "channels_last",
+              "l2": "each step touches >1 GB of activations (> 126 MB L2); module sweep flushes L2 between launches"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_reference_leg(max(1, min(args.steps, 8)), max(1, min(args.warmup, 2)))
+        line = {"impl": "reference", "metric": "train_images_per_sec", "value": cb["value"], "unit": "img/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import improving_yolov8_cbam_swinblock_b200 as P
+    from improving_yolov8_cbam_swinblock_b200 import _lib
+    from improving_yolov8_cbam_swinblock_b200.harness import sweep, synthetic, train
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the B200 kernels have no CPU path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    _lib.lib()  # fail loudly here if libb200yolo.so is missing
+    tr = train.Trainer(P.BLOCKS, SCALE, NC, device=f"cuda:{local_rank}", amp_dtype=torch.bfloat16, world_size=world,
+                       local_rank=local_rank, channels_last=True)
+    tr.max_boxes = synthetic.BOXES_PER_IMAGE
+    host = [synthetic.make_batch(args.batch, IMGSZ, NC, seed=1234 + rank + 100 * i, pin=True) for i in range(2)]
+    dev = [tr.to_device(h) for h in host]
+    h2d = synthetic.batch_nbytes(host[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            fn(i)
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=f"cuda:{local_rank}")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # max over ranks
+        return float(ms.item())
+
+    for i in range(args.warmup):
+        tr.step(dev[i % 2])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    _lib.enable_timing(True)
+    ms_dev = timed(lambda i: tr.step(dev[i % 2]), args.steps)
+    ktimes = _lib.timing_summary()
+    _lib.enable_timing(False)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    for i in range(2):
+        tr.step_from_host(host[i % 2])
+    last = {}
+
+    def e2e_step(i):
+        last["loss"] = tr.step_from_host(host[i % 2])
+
+    ms_e2e = timed(e2e_step, args.steps)
+    imgs = args.batch * world * args.steps
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = _peaks()
+    # dominant hand-written kernel inside the timed region -> roofline (algorithmic work from SURVEY section 8(d))
+    work = sweep.algorithmic_work(SCALE, args.batch)
+    roof = None
+    if ktimes:
+        tot = {k: n * ms for k, (n, ms) in ktimes.items()}
+        top = max(tot, key=tot.get)
+        n, ms = ktimes[top]
+        w = work.get(top)
+        if w:
+            achieved = w["amount"] / (ms * 1e-3) / (1e9 if w["bound"] == "hbm" else 1e12)
+            peak = peaks["hbm_gbs"] if w["bound"] == "hbm" else peaks["bf16_tflops_sustained"]
+            roof = {"kernel": top, "bound": w["bound"], "achieved": achieved, "peak": peak, "unit": "GB/s" if w["bound"] == "hbm" else "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None, "avg_ms": ms, "calls": n, "peak_source": peaks["source"] + " (sustained)",
+                    "algorithmic": w["note"],
+                    "share_of_step": tot[top] / ms_dev, "kernels_ms_per_step": {k: v / args.steps for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
+    line = {"metric": "train_images_per_sec", "value": imgs / (ms_dev * 1e-3), "unit": "img/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
+                    "ms_per_step": ms_e2e / args.steps, "loss_items": [float(v) for v in last["loss"]]},
+            "roofline": roof}
+    if not args.no_sweep:
+        line["modules"] = sweep.run(SCALE, args.batch, peaks, iters=10)
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = {k: v for k, v in cpu_reference_leg(6, 2).items() if k != "ms_per_step"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -73,6 +73,44 @@ def check(rc: int, what: str):
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
 
 
+_timers = None  # name -> [(start_event, end_event)] while kernel timing is enabled (bench.py roofline leg)
+
+
+def enable_timing(flag: bool = True):
+    """Bracket every C-ABI call with CUDA events on the launching stream (bench.py reads them back)."""
+    global _timers
+    _timers = {} if flag else None
+
+
+def timing_summary():
+    """-> {entry point: (calls, mean ms)}; synchronises."""
+    import torch
+
+    out = {}
+    if _timers:
+        torch.cuda.synchronize()
+        for name, evs in _timers.items():
+            ms = [s.elapsed_time(e) for s, e in evs]
+            out[name] = (len(ms), sum(ms) / max(len(ms), 1))
+    return out
+
+
+def call(name: str, *args):
+    """Invoke one C-ABI entry point; raise RuntimeError(b200_last_error()) on a non-zero return code."""
+    fn = getattr(lib(), name)
+    if _timers is None:
+        rc = fn(*args)
+    else:
+        import torch
+
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*args)
+        e.record()
+        _timers.setdefault(name, []).append((s, e))
+    check(rc, name)
+
+
 def launch_count() -> int:
     return int(lib().b200_launch_count())
 

@@ -12,7 +12,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import check, dtype_code, lib, ptr, stream_ptr
+from ._lib import call, dtype_code, lib, ptr, stream_ptr
 
 _I64, _I32, _VP, _SZ = C.c_int64, C.c_int32, C.c_void_p, C.c_size_t
 _lib.register("b200_swin_num_tokens", C.c_longlong, [_I32] * 4)
@@ -55,8 +55,8 @@ def sppf_pool_forward_raw(y0: torch.Tensor, k: int, want_idx: bool = False):
     cat = _empty_nhwc(B, 4 * Cc, H, W, y0.dtype, y0.device)
     idx = torch.empty((3, B, H, W, Cc), dtype=torch.int32, device=y0.device) if want_idx else None
     with torch.cuda.device(y0.device):
-        check(lib().b200_sppf_pool_fwd(ptr(y0), ptr(cat), ptr(idx), B, Cc, H, W, int(k), dtype_code(y0.dtype),
-                                       stream_ptr(y0.device)), "b200_sppf_pool_fwd")
+        call("b200_sppf_pool_fwd", ptr(y0), ptr(cat), ptr(idx), B, Cc, H, W, int(k), dtype_code(y0.dtype),
+                                       stream_ptr(y0.device))
     return cat, idx
 
 
@@ -77,8 +77,8 @@ class SPPFPoolFn(torch.autograd.Function):
         gcat = _nhwc(gcat.to(y0.dtype))
         gy0 = _empty_nhwc(B, Cc, H, W, y0.dtype, y0.device)
         with torch.cuda.device(y0.device):
-            check(lib().b200_sppf_pool_bwd(ptr(gcat), ptr(y0), ptr(gy0), B, Cc, H, W, ctx.k, dtype_code(y0.dtype),
-                                           stream_ptr(y0.device)), "b200_sppf_pool_bwd")
+            call("b200_sppf_pool_bwd", ptr(gcat), ptr(y0), ptr(gy0), B, Cc, H, W, ctx.k, dtype_code(y0.dtype),
+                                           stream_ptr(y0.device))
         return gy0, None
 
 
@@ -108,8 +108,8 @@ class CBAMFn(torch.autograd.Function):
         sa = torch.empty((B, H * W), dtype=torch.float32, device=dev) if (mode == 2 or (need_grad and mode == 0)) else None
         out = _empty_nhwc(B, Cc, H, W, x.dtype, dev) if mode == 0 else None
         with torch.cuda.device(dev):
-            check(lib().b200_cbam_fwd(ptr(x), ptr(w1f), ptr(w2f), ptr(wsf), ptr(out), ptr(ca), ptr(sa), B, Cc, H, W, r,
-                                      ksa, dtype_code(x.dtype), mode, stream_ptr(dev)), "b200_cbam_fwd")
+            call("b200_cbam_fwd", ptr(x), ptr(w1f), ptr(w2f), ptr(wsf), ptr(out), ptr(ca), ptr(sa), B, Cc, H, W, r,
+                                      ksa, dtype_code(x.dtype), mode, stream_ptr(dev))
         ctx.mode, ctx.dims = mode, (B, Cc, H, W, r, ksa)
         ctx.wshapes = tuple(None if w is None else (w.shape, w.dtype) for w in (w1, w2, wsa))
         ctx.save_for_backward(x, w1f, w2f, wsf, ca, sa)
@@ -137,9 +137,9 @@ class CBAMFn(torch.autograd.Function):
         nbytes = L.b200_cbam_bwd_workspace_bytes(B, Cc, H, W, r, ksa)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            check(L.b200_cbam_bwd(ptr(g), ptr(x), ptr(w1f), ptr(w2f), ptr(wsf), ptr(ca), ptr(sa), ptr(gx), ptr(gw1),
+            call("b200_cbam_bwd", ptr(g), ptr(x), ptr(w1f), ptr(w2f), ptr(wsf), ptr(ca), ptr(sa), ptr(gx), ptr(gw1),
                                   ptr(gw2), ptr(gws), ptr(ws), nbytes, B, Cc, H, W, r, ksa, dtype_code(x.dtype), mode,
-                                  stream_ptr(dev)), "b200_cbam_bwd")
+                                  stream_ptr(dev))
         outs = []
         for gw, meta in zip((gw1, gw2, gws), ctx.wshapes):
             outs.append(None if (gw is None or meta is None) else gw.view(meta[0]).to(meta[1]))
@@ -174,8 +174,7 @@ def _colsum(a: torch.Tensor) -> torch.Tensor:
     nbytes = L.b200_colsum_workspace_bytes(rows, n)
     ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=a.device)
     out = torch.empty(n, dtype=torch.float32, device=a.device)
-    check(L.b200_colsum(ptr(a), ptr(out), ptr(ws), nbytes, rows, n, dtype_code(a.dtype), stream_ptr(a.device)),
-          "b200_colsum")
+    call("b200_colsum", ptr(a), ptr(out), ptr(ws), nbytes, rows, n, dtype_code(a.dtype), stream_ptr(a.device))
     return out
 
 
@@ -208,24 +207,24 @@ class SwinBlockFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             n1 = torch.empty((T, Cc), dtype=dt, device=dev)
             mean1, rstd1 = torch.empty(T, **f32), torch.empty(T, **f32)
-            check(L.b200_swin_ln1_partition(ptr(x), ptr(g1f), ptr(b1f), ptr(n1), ptr(mean1), ptr(rstd1), B, Cc, H, W, ws,
-                                            code, st), "b200_swin_ln1_partition")
+            call("b200_swin_ln1_partition", ptr(x), ptr(g1f), ptr(b1f), ptr(n1), ptr(mean1), ptr(rstd1), B, Cc, H, W, ws,
+                                            code, st)
             qkv = gemm.linear(n1, win, bin_)
             o = torch.empty((T, Cc), dtype=dt, device=dev)
             lse = torch.empty((T, num_heads), **f32)
-            check(L.b200_swin_attn_fwd(ptr(qkv), ptr(o), ptr(lse), T, Lw, Cc, num_heads, code, st), "b200_swin_attn_fwd")
+            call("b200_swin_attn_fwd", ptr(qkv), ptr(o), ptr(lse), T, Lw, Cc, num_heads, code, st)
             a = gemm.linear(o, wo, bo)
             y1, u = torch.empty_like(n1), torch.empty_like(n1)
             mean2, rstd2 = torch.empty(T, **f32), torch.empty(T, **f32)
-            check(L.b200_swin_res_ln2(ptr(n1), ptr(a), ptr(g2f), ptr(b2f), ptr(y1), ptr(u), ptr(mean2), ptr(rstd2), T, Cc,
-                                      code, st), "b200_swin_res_ln2")
+            call("b200_swin_res_ln2", ptr(n1), ptr(a), ptr(g2f), ptr(b2f), ptr(y1), ptr(u), ptr(mean2), ptr(rstd2), T, Cc,
+                                      code, st)
             del a
             hpre = gemm.linear(u, w1, bb1)
             h = torch.empty_like(hpre)
-            check(L.b200_swin_gelu(ptr(hpre), None, ptr(h), hpre.numel(), code, 0, st), "b200_swin_gelu")
+            call("b200_swin_gelu", ptr(hpre), None, ptr(h), hpre.numel(), code, 0, st)
             m = gemm.linear(h, w2, bb2)
             out = _empty_nhwc(B, Cc, H, W, dt, dev)
-            check(L.b200_swin_res_reverse(ptr(y1), ptr(m), ptr(out), B, Cc, H, W, ws, code, st), "b200_swin_res_reverse")
+            call("b200_swin_res_reverse", ptr(y1), ptr(m), ptr(out), B, Cc, H, W, ws, code, st)
         ctx.save_for_backward(x, g1f, g2f, win, wo, w1, w2, n1, mean1, rstd1, qkv, o, lse, y1, u, mean2, rstd2, hpre, h)
         ctx.cfg = (B, Cc, H, W, ws, num_heads, T)
         ctx.pdtypes = tuple(p.dtype for p in (g1, b1, win, bin_, wo, bo, g2, b2, w1, bb1, w2, bb2))
@@ -245,12 +244,12 @@ class SwinBlockFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             gout = _nhwc(gout.to(dt))
             gy2 = torch.empty((T, Cc), dtype=dt, device=dev)
-            check(L.b200_swin_partition(ptr(gout), ptr(gy2), B, Cc, H, W, ws, code, st), "b200_swin_partition")
+            call("b200_swin_partition", ptr(gout), ptr(gy2), B, Cc, H, W, ws, code, st)
             # MLP
             gw2 = gemm.matmul_tn(gy2, h)          # [C, 4C] = gy2^T h
             gb2 = _colsum(gy2)
             gh = gemm.matmul_nn(gy2, w2)          # [T, 4C] = gy2 W2
-            check(L.b200_swin_gelu(ptr(hpre), ptr(gh), ptr(gh), gh.numel(), code, 1, st), "b200_swin_gelu(bwd)")
+            call("b200_swin_gelu", ptr(hpre), ptr(gh), ptr(gh), gh.numel(), code, 1, st)
             ga = gh
             gw1 = gemm.matmul_tn(ga, u)           # [4C, C]
             gb1 = _colsum(ga)
@@ -262,16 +261,15 @@ class SwinBlockFn(torch.autograd.Function):
             gy1 = torch.empty_like(gy2)
             gg2 = torch.empty(Cc, dtype=torch.float32, device=dev)
             gbt2 = torch.empty(Cc, dtype=torch.float32, device=dev)
-            check(L.b200_swin_ln_bwd(ptr(gu), ptr(y1), ptr(gy2), ptr(g2f), ptr(mean2), ptr(rstd2), ptr(gy1), ptr(gg2),
-                                     ptr(gbt2), ptr(wsb), nbytes, B, Cc, H, W, ws, code, 0, st), "b200_swin_ln_bwd(2)")
+            call("b200_swin_ln_bwd", ptr(gu), ptr(y1), ptr(gy2), ptr(g2f), ptr(mean2), ptr(rstd2), ptr(gy1), ptr(gg2),
+                                     ptr(gbt2), ptr(wsb), nbytes, B, Cc, H, W, ws, code, 0, st)
             del gu, gy2
             # attention
             gwo = gemm.matmul_tn(gy1, o)          # [C, C]
             gbo = _colsum(gy1)
             go = gemm.matmul_nn(gy1, wo)          # [T, C]
             gqkv = torch.empty_like(qkv)
-            check(L.b200_swin_attn_bwd(ptr(qkv), ptr(o), ptr(lse), ptr(go), ptr(gqkv), T, Lw, Cc, nh, code, st),
-                  "b200_swin_attn_bwd")
+            call("b200_swin_attn_bwd", ptr(qkv), ptr(o), ptr(lse), ptr(go), ptr(gqkv), T, Lw, Cc, nh, code, st)
             del go
             gwin = gemm.matmul_tn(gqkv, n1)       # [3C, C]
             gbin = _colsum(gqkv)
@@ -281,8 +279,8 @@ class SwinBlockFn(torch.autograd.Function):
             gx = _empty_nhwc(B, Cc, H, W, dt, dev)
             gg1 = torch.empty(Cc, dtype=torch.float32, device=dev)
             gbt1 = torch.empty(Cc, dtype=torch.float32, device=dev)
-            check(L.b200_swin_ln_bwd(ptr(gn1), ptr(x), None, ptr(g1f), ptr(mean1), ptr(rstd1), ptr(gx), ptr(gg1),
-                                     ptr(gbt1), ptr(wsb), nbytes, B, Cc, H, W, ws, code, 1, st), "b200_swin_ln_bwd(1)")
+            call("b200_swin_ln_bwd", ptr(gn1), ptr(x), None, ptr(g1f), ptr(mean1), ptr(rstd1), ptr(gx), ptr(gg1),
+                                     ptr(gbt1), ptr(wsb), nbytes, B, Cc, H, W, ws, code, 1, st)
         grads = [gg1, gbt1, gwin, gbin, gwo, gbo, gg2, gbt2, gw1, gb1, gw2, gb2]
         grads = [g.to(d) for g, d in zip(grads, ctx.pdtypes)]
         return (gx, *grads, None, None)

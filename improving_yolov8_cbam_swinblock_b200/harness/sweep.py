@@ -1,0 +1,120 @@
+"""Per-module roofline sweep (BASELINE.json config 5 / SURVEY section 8(d)): each hand-written kernel alone, CUDA
+events on the launching stream, L2 flushed (256 MB write) between launches, algorithmic work / measured time."""
+from __future__ import annotations
+
+import torch
+
+CHANNELS = {"n": (64, 128, 256), "s": (128, 256, 512), "m": (192, 384, 576)}
+
+
+def _shapes(scale, B):
+    c3, c4, c5 = CHANNELS[scale]
+    return {"P3": (B, c3, 80, 80), "P4": (B, c4, 40, 40), "P5": (B, c5, 20, 20)}
+
+
+def algorithmic_work(scale: str, B: int, s: int = 2, ws: int = 7):
+    """ABI entry point -> algorithmic bytes / FLOPs per launch at the MODEL's shapes (SURVEY section 8(d) figures)."""
+    _, c4, c5 = CHANNELS[scale]
+    n5 = B * c5 * 400
+    n0 = B * (c5 // 2) * 400
+    tok_real = B * 1600
+    nw = -(-40 // ws)
+    T = B * nw * nw * ws * ws
+    hbm = lambda amount, note: {"bound": "hbm", "amount": float(amount), "note": note}  # noqa: E731
+    return {
+        "b200_cbam_fwd": hbm(2 * n5 * s, "2*N*s: read x once, write out once (N=B*C5*H*W)"),
+        "b200_cbam_bwd": hbm(3 * n5 * s, "3*N*s: read x, read g_out, write g_x"),
+        "b200_sppf_pool_fwd": hbm(5 * n0 * s, "5*N0*s: read y0, write the 4*c_ concat (N0=B*c_*H*W)"),
+        "b200_sppf_pool_bwd": hbm(6 * n0 * s, "6*N0*s: read 4*c_ grad + y0, write g_y0"),
+        "b200_swin_ln1_partition": hbm((tok_real + T) * c4 * s, "read x (real tokens) + write n1 (padded tokens)"),
+        "b200_swin_attn_fwd": hbm(4 * T * c4 * s, "standalone attention is HBM-bound: read qkv (3*T*C*s) + write o (T*C*s); "
+                                  f"FLOPs {tok_real * 4 * ws * ws * c4 / 1e9:.2f} G on un-padded tokens"),
+        "b200_swin_attn_bwd": hbm(8 * T * c4 * s, "read qkv, o, g_o (5*T*C*s) + write g_qkv (3*T*C*s)"),
+        "b200_swin_res_ln2": hbm(4 * T * c4 * s, "read n1, a; write y1, u"),
+        "b200_swin_gelu": hbm(2 * T * 4 * c4 * s, "read a, write h (backward: +1 read)"),
+        "b200_swin_res_reverse": hbm((2 * T + tok_real) * c4 * s, "read y1, m; write out (real tokens)"),
+        "b200_swin_partition": hbm((tok_real + T) * c4 * s, "read g (real), write token-major g"),
+        "b200_swin_ln_bwd": hbm(4 * T * c4 * s, "read g_out, x, g_res; write g_in"),
+        "b200_colsum": hbm(T * c4 * s, "read the activation-gradient matrix once (C..4C columns)"),
+    }
+
+
+def _time(fn, iters, flush):
+    ms = []
+    for _ in range(iters + 3):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        e.synchronize()
+        ms.append(s.elapsed_time(e))
+    ms = sorted(ms[3:])
+    return ms[len(ms) // 2]
+
+
+def run(scale: str, B: int, peaks: dict, iters: int = 10):
+    """-> list of {kernel, shape, dtype, ms, achieved, peak, frac, bound} for CBAM / SPPF pool / SwinBlock."""
+    from .. import functional as Fb
+    from .. import modules as M
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sh = _shapes(scale, B)
+    out = []
+    dt = torch.bfloat16
+    hbm, tf = peaks["hbm_gbs"], peaks["bf16_tflops"]
+
+    def rec(kernel, shape, ms, amount, bound, note=""):
+        ach = amount / (ms * 1e-3) / (1e9 if bound == "hbm" else 1e12)
+        peak = hbm if bound == "hbm" else tf
+        out.append({"kernel": kernel, "shape": list(shape), "dtype": "bf16", "ms": round(ms, 5), "bound": bound,
+                    "achieved": round(ach, 2), "peak": peak, "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+                    "frac": round(ach / peak, 4), "note": note})
+
+    torch.manual_seed(0)
+    # ---- CBAM at P5 (the model's use) and P4
+    for lvl in ("P5", "P4"):
+        shape = sh[lvl]
+        x = torch.randn(shape, device=dev).to(dt).contiguous(memory_format=torch.channels_last)
+        mod = M.CBAM()
+        mod(torch.zeros(1, shape[1], 2, 2))
+        mod = mod.to(dev)
+        n = x.numel()
+        with torch.no_grad():
+            rec("cbam_fwd", shape, _time(lambda: mod(x), iters, flush), 2 * n * 2, "hbm", lvl)
+        xg = x.clone().requires_grad_(True)
+        y = mod(xg)
+        g = torch.randn_like(y)
+        rec("cbam_bwd", shape, _time(lambda: torch.autograd.grad(y, xg, g, retain_graph=True), iters, flush), 3 * n * 2, "hbm", lvl)
+        del y, xg
+    # ---- SPPF pool at P5, k = 5 and 7
+    Bc, c5, H, W = sh["P5"]
+    y0 = torch.randn((Bc, c5 // 2, H, W), device=dev).to(dt).contiguous(memory_format=torch.channels_last)
+    n0 = y0.numel()
+    for k in (5, 7):
+        with torch.no_grad():
+            rec(f"sppf_pool_fwd_k{k}", y0.shape, _time(lambda: Fb.sppf_pool(y0, k), iters, flush), 5 * n0 * 2, "hbm", "P5")
+        yg = y0.clone().requires_grad_(True)
+        cat = Fb.sppf_pool(yg, k)
+        g = torch.randn_like(cat)
+        rec(f"sppf_pool_bwd_k{k}", y0.shape, _time(lambda: torch.autograd.grad(cat, yg, g, retain_graph=True), iters, flush),
+            6 * n0 * 2, "hbm", "P5")
+        del cat, yg
+    # ---- SwinBlock at P4 (whole block vs tensor peak; FLOPs counted on un-padded tokens)
+    Bs, c4, H, W = sh["P4"]
+    for ws in (7, 8):
+        blk = M.SwinBlock(c4, 2, ws).to(dev)
+        x = torch.randn((Bs, c4, H, W), device=dev).to(dt).contiguous(memory_format=torch.channels_last)
+        flops = Bs * H * W * (24 * c4 * c4 + 4 * ws * ws * c4)
+        with torch.no_grad(), torch.autocast("cuda", dtype=dt):
+            rec(f"swin_block_fwd_ws{ws}", x.shape, _time(lambda: blk(x), iters, flush), flops, "tensor", "P4, whole block")
+        xg = x.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=dt):
+            y = blk(xg)
+        g = torch.randn_like(y)
+        params = [xg] + list(blk.parameters())
+        rec(f"swin_block_bwd_ws{ws}", x.shape, _time(lambda: torch.autograd.grad(y, params, g, retain_graph=True), iters, flush),
+            2 * flops, "tensor", "P4, whole block backward (2x fwd FLOPs)")
+        del y, xg
+    return out

@@ -23,6 +23,8 @@ def test_whole_model_fp32_vs_oracle_blocks(scale):
     from improving_yolov8_cbam_swinblock_b200.harness import graph, loss as hl, synthetic
     from oracle import modules as om
 
+    torch.backends.cudnn.allow_tf32 = False  # stock convs would otherwise run TF32 and drown the comparison
+    torch.backends.cuda.matmul.allow_tf32 = False
     ob = {"CBAM": om.CBAM, "SwinBlock": om.SwinBlock, "SPPF": om.make_sppf(graph.Conv)}
     ref = _build(ob, scale, 80, 1)
     mine = _build(P.BLOCKS, scale, 80, 2)

@@ -18,7 +18,7 @@ def state_dict_of(g):
 
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     """||a-b|| / ||b|| in float64 (the 'relative error' of the bf16 tolerance in BASELINE.json)."""
-    a, b = a.double().flatten(), b.double().flatten()
+    a, b = a.detach().double().flatten().cpu(), b.detach().double().flatten().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
