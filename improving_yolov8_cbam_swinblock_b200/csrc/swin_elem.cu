@@ -50,8 +50,188 @@ __device__ __forceinline__ void row_stats(const float (&v)[MAXPL], int npl, int 
   *rstd = rsqrtf(q / (float)C + 1e-5f);
 }
 
-constexpr int kMaxPL = 32;  // C <= 1024
+constexpr int kMaxPL = 32;  // C <= 1024 (generic kernels)
 
+// ---- vectorised row access: lane owns VEC contiguous channels at c = (lane + 32*i)*VEC, i < ITERS ---------------
+template <typename T, int VEC> struct alignas(sizeof(T) * VEC) PackT { T e[VEC]; };
+
+template <typename T, int VEC, int ITERS>
+__device__ __forceinline__ void load_row(const T* __restrict__ row, int lane, float (&v)[VEC * ITERS]) {
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const PackT<T, VEC> p = *reinterpret_cast<const PackT<T, VEC>*>(row + (lane + 32 * i) * VEC);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) v[i * VEC + e] = DT<T>::to_f(p.e[e]);
+  }
+}
+template <typename T, int VEC, int ITERS>
+__device__ __forceinline__ void store_row(T* __restrict__ row, int lane, const float (&v)[VEC * ITERS]) {
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    PackT<T, VEC> p;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) p.e[e] = DT<T>::from_f(v[i * VEC + e]);
+    *reinterpret_cast<PackT<T, VEC>*>(row + (lane + 32 * i) * VEC) = p;
+  }
+}
+template <int VEC, int ITERS>
+__device__ __forceinline__ void load_vecf(const float* __restrict__ p, int lane, float (&v)[VEC * ITERS]) {
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) v[i * VEC + e] = p[(lane + 32 * i) * VEC + e];
+}
+template <int N>
+__device__ __forceinline__ void stats_full(const float (&v)[N], int C, float* mean, float* rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) s += v[i];
+  const float mu = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) { const float d = v[i] - mu; q += d * d; }
+  *mean = mu;
+  *rstd = rsqrtf(warp_sum(q) / (float)C + 1e-5f);
+}
+
+// n1[t,:] = LN1(token t of x) (padded tokens: LN(0) = beta).  Saves mean / rstd per token for the backward.
+template <typename T, int VEC, int ITERS>
+__global__ void __launch_bounds__(256) swin_ln1_partition_vec_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta, T* __restrict__ n1,
+                                                                    float* __restrict__ mean, float* __restrict__ rstd,
+                                                                    WinGeom g) {
+  constexpr int N = VEC * ITERS;
+  const int lane = threadIdx.x & 31;
+  float gm[N], bt[N];
+  load_vecf<VEC, ITERS>(gamma, lane, gm);
+  load_vecf<VEC, ITERS>(beta, lane, bt);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < g.T; t += nwarps) {
+    bool real;
+    const long long pix = token_pixel(g, t, &real);
+    float v[N];
+    if (real) load_row<T, VEC, ITERS>(x + pix * g.C, lane, v);
+    else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = 0.f;
+    }
+    float mu, rs;
+    stats_full<N>(v, g.C, &mu, &rs);
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = (v[i] - mu) * rs * gm[i] + bt[i];
+    store_row<T, VEC, ITERS>(n1 + t * g.C, lane, v);
+    if (lane == 0) { mean[t] = mu; rstd[t] = rs; }
+  }
+}
+
+template <typename T, int VEC, int ITERS>
+__global__ void __launch_bounds__(256) swin_res_ln2_vec_kernel(const T* __restrict__ n1, const T* __restrict__ a,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              T* __restrict__ y1, T* __restrict__ u, float* __restrict__ mean,
+                                                              float* __restrict__ rstd, long long Ttok, int C) {
+  constexpr int N = VEC * ITERS;
+  const int lane = threadIdx.x & 31;
+  float gm[N], bt[N];
+  load_vecf<VEC, ITERS>(gamma, lane, gm);
+  load_vecf<VEC, ITERS>(beta, lane, bt);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < Ttok; t += nwarps) {
+    float v[N], w[N];
+    load_row<T, VEC, ITERS>(n1 + t * C, lane, v);
+    load_row<T, VEC, ITERS>(a + t * C, lane, w);
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = DT<T>::to_f(DT<T>::from_f(v[i] + w[i]));  // LN2 sees exactly the stored y1
+    store_row<T, VEC, ITERS>(y1 + t * C, lane, v);
+    float mu, rs;
+    stats_full<N>(v, C, &mu, &rs);
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = (v[i] - mu) * rs * gm[i] + bt[i];
+    store_row<T, VEC, ITERS>(u + t * C, lane, v);
+    if (lane == 0) { mean[t] = mu; rstd[t] = rs; }
+  }
+}
+
+// LayerNorm backward, vectorised (see swin_ln_bwd_kernel below for the maths / modes)
+template <typename T, int VEC, int ITERS, int MODE>
+__global__ void __launch_bounds__(256) swin_ln_bwd_vec_kernel(const T* __restrict__ gout, const T* __restrict__ xin,
+                                                             const T* __restrict__ gres, const float* __restrict__ gamma,
+                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                             T* __restrict__ gin, float* __restrict__ part, WinGeom g) {
+  constexpr int N = VEC * ITERS;
+  extern __shared__ float sm[];  // [warps][2][C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int C = g.C;
+  float gm[N], accg[N], accb[N];
+  load_vecf<VEC, ITERS>(gamma, lane, gm);
+#pragma unroll
+  for (int i = 0; i < N; ++i) { accg[i] = 0.f; accb[i] = 0.f; }
+  const long long nwarps = (long long)gridDim.x * nwarp;
+  for (long long t = (long long)blockIdx.x * nwarp + warp; t < g.T; t += nwarps) {
+    bool real = true;
+    long long src = t;
+    if (MODE == 1) src = token_pixel(g, t, &real);
+    const float mu = mean[t], rs = rstd[t];
+    float go[N], xh[N];
+    load_row<T, VEC, ITERS>(gout + t * C, lane, go);
+    if (MODE == 1 && !real) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) xh[i] = 0.f;
+    } else load_row<T, VEC, ITERS>(xin + src * C, lane, xh);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      xh[i] = (xh[i] - mu) * rs;
+      accg[i] += go[i] * xh[i];
+      accb[i] += go[i];
+      go[i] *= gm[i];
+      s1 += go[i];
+      s2 += go[i] * xh[i];
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+    if (MODE == 0 || real) {
+      float r[N];
+      if (MODE == 0) load_row<T, VEC, ITERS>(gres + t * C, lane, r);
+#pragma unroll
+      for (int i = 0; i < N; ++i) r[i] = (go[i] - s1 - xh[i] * s2) * rs + (MODE == 0 ? r[i] : 0.f);
+      store_row<T, VEC, ITERS>(gin + src * C, lane, r);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const int c = (lane + 32 * i) * VEC + e;
+      sm[(warp * 2 + 0) * C + c] = accg[i * VEC + e];
+      sm[(warp * 2 + 1) * C + c] = accb[i * VEC + e];
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nwarp; ++w) s += sm[w * 2 * C + i];
+    part[(size_t)blockIdx.x * 2 * C + i] = s;
+  }
+}
+
+// pick (VEC, ITERS) with C == 32*VEC*ITERS; returns false when C has no vectorised instantiation
+template <typename T>
+inline bool pick_vec(int C, int* vec, int* iters) {
+  const int maxv = 16 / (int)sizeof(T) > 8 ? 8 : 16 / (int)sizeof(T);
+  for (int v = maxv; v >= (sizeof(T) == 2 ? 2 : 1); v >>= 1)
+    for (int it = 1; it <= 3; ++it)
+      if (C == 32 * v * it) { *vec = v; *iters = it; return true; }
+  return false;
+}
+#define B200_VEC_CASE(V, I, ...) if (vec == V && iters == I) { constexpr int VEC = V; constexpr int ITERS = I; __VA_ARGS__; }
+#define B200_DISPATCH_VEC(...)                                                                      \
+  do {                                                                                              \
+    if constexpr (sizeof(T) == 2) { B200_VEC_CASE(8, 1, __VA_ARGS__) B200_VEC_CASE(8, 2, __VA_ARGS__) B200_VEC_CASE(8, 3, __VA_ARGS__) } \
+    B200_VEC_CASE(4, 1, __VA_ARGS__) B200_VEC_CASE(4, 2, __VA_ARGS__) B200_VEC_CASE(4, 3, __VA_ARGS__)  \
+    B200_VEC_CASE(2, 1, __VA_ARGS__) B200_VEC_CASE(2, 2, __VA_ARGS__) B200_VEC_CASE(2, 3, __VA_ARGS__)  \
+    if constexpr (sizeof(T) == 4) { B200_VEC_CASE(1, 1, __VA_ARGS__) B200_VEC_CASE(1, 2, __VA_ARGS__) B200_VEC_CASE(1, 3, __VA_ARGS__) } \
+  } while (0)
+
+// ---- generic (any C <= 1024) kernels ------------------------------------------------------------------------
 // n1[t,:] = LN1(token t of x) (padded tokens: LN(0) = beta).  Saves mean / rstd per token for the backward.
 template <typename T>
 __global__ void __launch_bounds__(256) swin_ln1_partition_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
@@ -240,33 +420,69 @@ __global__ void __launch_bounds__(256) swin_ln_bwd_kernel(const T* __restrict__ 
 
 // [rows][2][C] partials -> ggamma[C], gbeta[C]   (fixed order)
 __global__ void fold_ln_kernel(const float* __restrict__ part, float* __restrict__ gg, float* __restrict__ gb, int rows, int C) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * C) return;
+  // 32 columns per warp-row: lane = column, the block's warps split the rows, fixed-order smem fold
+  __shared__ float sm[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int r = 0; r < rows; ++r) s += part[(size_t)r * 2 * C + i];
-  if (i < C) gg[i] = s; else gb[i - C] = s;
+  if (i < 2 * C)
+    for (int r = warp; r < rows; r += 8) s += part[(size_t)r * 2 * C + i];
+  sm[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && i < 2 * C) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += sm[w][lane];
+    if (i < C) gg[i] = t; else gb[i - C] = t;
+  }
 }
 
 // out[i] = sum_r part[r][i]   (fixed order)
 __global__ void fold_rows_kernel(const float* __restrict__ part, float* __restrict__ out, int rows, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  __shared__ float sm[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int r = 0; r < rows; ++r) s += part[(size_t)r * n + i];
-  out[i] = s;
+  if (i < n)
+    for (int r = warp; r < rows; r += 8) s += part[(size_t)r * n + i];
+  sm[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && i < n) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += sm[w][lane];
+    out[i] = t;
+  }
 }
 
 // column sums of a [rows, n] activation matrix -> f32 [n] (bias gradients); two-stage, deterministic
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ a, float* __restrict__ part, long long rows,
                                                             int n, int rows_per_cta) {
+  // blockIdx.x: 128-column strip (lane owns 4 columns), blockIdx.y: row slab; the 8 warps interleave the slab's rows
+  __shared__ float sm[8][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + lane * 4;
   const long long r0 = (long long)blockIdx.y * rows_per_cta;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
-  float s = 0.f;
   const long long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
-  for (long long r = r0; r < r1; ++r) s += ldf(a + r * n + c);
-  part[(size_t)blockIdx.y * n + c] = s;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c + 3 < n) {
+    for (long long r = r0 + warp; r < r1; r += 8) {
+      const PackT<T, 4> p = *reinterpret_cast<const PackT<T, 4>*>(a + r * n + c);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[e] += DT<T>::to_f(p.e[e]);
+    }
+  } else {
+    for (long long r = r0 + warp; r < r1; r += 8)
+      for (int e = 0; e < 4; ++e)
+        if (c + e < n) s[e] += ldf(a + r * n + c + e);
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) sm[warp][lane * 4 + e] = s[e];
+  __syncthreads();
+  if (threadIdx.x < 128 && blockIdx.x * 128 + threadIdx.x < n) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += sm[w][threadIdx.x];
+    part[(size_t)blockIdx.y * n + blockIdx.x * 128 + threadIdx.x] = t;
+  }
 }
 
 int make_geom(WinGeom* g, int B, int C, int H, int W, int ws) {
@@ -279,6 +495,17 @@ int make_geom(WinGeom* g, int B, int C, int H, int W, int ws) {
 }
 
 inline unsigned warps_grid(long long tokens) { return (unsigned)((tokens + 7) / 8); }
+// grid-stride kernels: enough CTAs to fill the chip a few times over, never more than the work
+inline unsigned capped_grid(long long tokens) {
+  const long long need = (tokens + 7) / 8, cap = (long long)sm_count() * 8;
+  return (unsigned)(need < cap ? need : cap);
+}
+constexpr int kLnMaxCtas = 1024;
+inline unsigned ln_bwd_ctas(long long tokens) {
+  long long need = (tokens + 63) / 64, cap = (long long)sm_count() * 4;
+  if (cap > kLnMaxCtas) cap = kLnMaxCtas;
+  return (unsigned)(need < cap ? need : cap);
+}
 
 }  // namespace
 }  // namespace b200
@@ -297,6 +524,14 @@ extern "C" B200_API int b200_swin_ln1_partition(const void* x, const float* gamm
   if (int rc = make_geom(&g, B, C, H, W, ws)) return rc;
   B200_REQUIRE(x && gamma && beta && n1 && mean && rstd, B200_ERR_SHAPE, "swin_ln1_partition: null pointer");
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
+    int vec, iters;
+    if (pick_vec<T>(C, &vec, &iters) && (((uintptr_t)x | (uintptr_t)n1) & 15) == 0) {
+      const unsigned grid = capped_grid(g.T);
+      B200_DISPATCH_VEC({
+        swin_ln1_partition_vec_kernel<T, VEC, ITERS><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, gamma, beta, (T*)n1, mean, rstd, g);
+        return check_launch("swin_ln1_partition");
+      });
+    }
     swin_ln1_partition_kernel<T><<<warps_grid(g.T), 256, 0, (cudaStream_t)stream>>>((const T*)x, gamma, beta, (T*)n1, mean, rstd, g);
     return check_launch("swin_ln1_partition");
   });
@@ -308,6 +543,15 @@ extern "C" B200_API int b200_swin_res_ln2(const void* n1, const void* a, const f
   B200_REQUIRE(n1 && a && gamma && beta && y1 && u && mean && rstd, B200_ERR_SHAPE, "swin_res_ln2: null pointer");
   B200_REQUIRE(tokens > 0 && C > 0 && C <= 32 * kMaxPL, B200_ERR_SHAPE, "swin_res_ln2: bad shape");
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
+    int vec, iters;
+    if (pick_vec<T>(C, &vec, &iters) && (((uintptr_t)n1 | (uintptr_t)a | (uintptr_t)y1 | (uintptr_t)u) & 15) == 0) {
+      const unsigned grid = capped_grid(tokens);
+      B200_DISPATCH_VEC({
+        swin_res_ln2_vec_kernel<T, VEC, ITERS><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)n1, (const T*)a, gamma, beta, (T*)y1,
+                                                                                       (T*)u, mean, rstd, tokens, C);
+        return check_launch("swin_res_ln2");
+      });
+    }
     swin_res_ln2_kernel<T><<<warps_grid(tokens), 256, 0, (cudaStream_t)stream>>>((const T*)n1, (const T*)a, gamma, beta, (T*)y1,
                                                                                  (T*)u, mean, rstd, tokens, C);
     return check_launch("swin_res_ln2");
@@ -352,11 +596,9 @@ extern "C" B200_API int b200_swin_partition(const void* src, void* tok, int32_t 
   });
 }
 
-static const int kLnTokensPerCta = 64;
-
 extern "C" B200_API size_t b200_swin_ln_bwd_workspace_bytes(int64_t tokens, int32_t C) {
-  const long long ctas = (tokens + kLnTokensPerCta - 1) / kLnTokensPerCta;
-  return (size_t)ctas * 2 * C * sizeof(float);
+  (void)tokens;
+  return (size_t)kLnMaxCtas * 2 * C * sizeof(float);
 }
 
 // mode 0: LN2 backward (token-major in/out, + residual);  mode 1: LN1 backward (gathers x / scatters gx in NHWC)
@@ -370,10 +612,26 @@ extern "C" B200_API int b200_swin_ln_bwd(const void* gout, const void* xin, cons
   B200_REQUIRE(mode == 1 || gres, B200_ERR_SHAPE, "swin_ln_bwd: LN2 mode needs the residual gradient");
   const size_t need = b200_swin_ln_bwd_workspace_bytes(g.T, C);
   B200_REQUIRE(workspace && workspace_bytes >= need, B200_ERR_WORKSPACE, "swin_ln_bwd: workspace %zu < %zu", workspace_bytes, need);
-  const unsigned ctas = (unsigned)((g.T + kLnTokensPerCta - 1) / kLnTokensPerCta);
+  const unsigned ctas = ln_bwd_ctas(g.T);
+  const int kLnTokensPerCta = (int)((g.T + ctas - 1) / ctas);
   const size_t smem = (size_t)8 * 2 * C * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   int rc = B200_DISPATCH_DTYPE(dtype, [&]() -> int {
+    int vec, iters;
+    if (pick_vec<T>(C, &vec, &iters) && (((uintptr_t)gout | (uintptr_t)xin | (uintptr_t)gres | (uintptr_t)gin) & 15) == 0) {
+      B200_DISPATCH_VEC({
+        if (mode == 0) {
+          auto k = swin_ln_bwd_vec_kernel<T, VEC, ITERS, 0>;
+          cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          k<<<ctas, 256, smem, st>>>((const T*)gout, (const T*)xin, (const T*)gres, gamma, mean, rstd, (T*)gin, (float*)workspace, g);
+        } else {
+          auto k = swin_ln_bwd_vec_kernel<T, VEC, ITERS, 1>;
+          cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          k<<<ctas, 256, smem, st>>>((const T*)gout, (const T*)xin, nullptr, gamma, mean, rstd, (T*)gin, (float*)workspace, g);
+        }
+        return check_launch("swin_ln_bwd");
+      });
+    }
     if (mode == 0) {
       auto k = swin_ln_bwd_kernel<T, 0>;
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -386,14 +644,24 @@ extern "C" B200_API int b200_swin_ln_bwd(const void* gout, const void* xin, cons
     return check_launch("swin_ln_bwd");
   });
   if (rc) return rc;
-  fold_ln_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>((const float*)workspace, ggamma, gbeta, (int)ctas, C);
+  fold_ln_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>((const float*)workspace, ggamma, gbeta, (int)ctas, C);
   return check_launch("swin_ln_bwd_fold");
 }
 
-static const int kColsumRows = 512;
+static const int kColsumMaxSlabs = 512;
+static inline int colsum_slabs(int64_t rows, int n) {
+  // ~4 CTAs per SM in total across the column strips
+  const int strips = (n + 127) / 128;
+  long long want = ((long long)b200::sm_count() * 4 + strips - 1) / strips;
+  const long long maxs = (rows + 63) / 64;
+  if (want > maxs) want = maxs;
+  if (want > kColsumMaxSlabs) want = kColsumMaxSlabs;
+  return want < 1 ? 1 : (int)want;
+}
 
 extern "C" B200_API size_t b200_colsum_workspace_bytes(int64_t rows, int32_t n) {
-  return (size_t)((rows + kColsumRows - 1) / kColsumRows) * n * sizeof(float);
+  (void)rows;
+  return (size_t)kColsumMaxSlabs * n * sizeof(float);
 }
 
 // out[n] (f32) = column sums of a [rows, n] (bias gradients: attn.in_proj_bias, out_proj.bias, mlp.{0,2}.bias)
@@ -402,13 +670,19 @@ extern "C" B200_API int b200_colsum(const void* a, float* out, void* workspace, 
   B200_REQUIRE(a && out && rows > 0 && n > 0, B200_ERR_SHAPE, "colsum: bad arguments");
   const size_t need = b200_colsum_workspace_bytes(rows, n);
   B200_REQUIRE(workspace && workspace_bytes >= need, B200_ERR_WORKSPACE, "colsum: workspace %zu < %zu", workspace_bytes, need);
-  const unsigned rblocks = (unsigned)((rows + kColsumRows - 1) / kColsumRows);
+  const unsigned rblocks = (unsigned)colsum_slabs(rows, n);
+  const int rows_per = (int)((rows + rblocks - 1) / rblocks);
+  B200_REQUIRE(((uintptr_t)a & 7) == 0 && (n % 4 == 0 || true), B200_ERR_ALIGN, "colsum: input must be 8-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   int rc = B200_DISPATCH_DTYPE(dtype, [&]() -> int {
-    colsum_partial_kernel<T><<<dim3((n + 255) / 256, rblocks), 256, 0, st>>>((const T*)a, (float*)workspace, rows, n, kColsumRows);
+    if (n % 4 != 0 || (((uintptr_t)a) & (4 * sizeof(T) - 1)) != 0) {
+      b200::set_error("colsum: n must be a multiple of 4 and the input %zu-byte aligned", 4 * sizeof(T));
+      return B200_ERR_ALIGN;
+    }
+    colsum_partial_kernel<T><<<dim3((n + 127) / 128, rblocks), 256, 0, st>>>((const T*)a, (float*)workspace, rows, n, rows_per);
     return check_launch("colsum_partial");
   });
   if (rc) return rc;
-  fold_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>((const float*)workspace, out, (int)rblocks, n);
+  fold_rows_kernel<<<(n + 31) / 32, 256, 0, st>>>((const float*)workspace, out, (int)rblocks, n);
   return check_launch("colsum_fold");
 }
