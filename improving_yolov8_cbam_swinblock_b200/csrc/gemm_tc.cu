@@ -1,0 +1,339 @@
+// tcgen05 GEMM for the SwinBlock's dense contractions:  D[M,N] = epi(A[M,K] * B[N,K]^T + bias[N]).
+// Replaces F.linear at swin_block.py:51 (in_proj / out_proj inside nn.MultiheadAttention) and :53 (mlp.0, mlp.2).
+//
+// Persistent, warp-specialised kernel (one CTA per SM, 192 threads):
+//   warp 0   : TMA producer  -- A and B tiles [128|BLOCK_N rows][64 K-elements] with 128-byte swizzle into a
+//              STAGES-deep shared-memory ring (mbarrier full/empty pairs)
+//   warp 1   : TMEM allocator + MMA issuer -- one elected lane issues tcgen05.mma (cta_group::1, kind::f16,
+//              UMMA 128 x BLOCK_N x 16), accumulators in TMEM, double-buffered (2 x BLOCK_N columns) so the
+//              epilogue of tile i overlaps the MMAs of tile i+1; tcgen05.commit releases smem slots / signals tiles
+//   warps 2-5: epilogue -- tcgen05.ld (lane = row) -> bias / GELU(erf) / residual in registers -> bf16 -> swizzled
+//              staging tile in shared memory -> TMA store (rows beyond M are clipped by the tensor map)
+// Both operands are K-major (activations [tokens, K]; nn.Linear weights [N, K]) so no transposes are needed.
+#include <mutex>
+#include <unordered_map>
+
+#include "tc.cuh"
+
+namespace b200 {
+namespace tc {
+
+// ---- tensor-map cache ---------------------------------------------------------------------------------------
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    return q == cudaDriverEntryPointSuccess ? (EncodeTiledFn)p : nullptr;
+  }();
+  return fn;
+}
+struct Key {
+  const void* base;
+  uint64_t rows, cols, stride;
+  uint32_t br, bc;
+  int dtype;
+  bool operator==(const Key& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && stride == o.stride && br == o.br && bc == o.bc && dtype == o.dtype;
+  }
+};
+struct KeyHash {
+  size_t operator()(const Key& k) const {
+    size_t h = (size_t)k.base;
+    for (uint64_t v : {k.rows, k.cols, k.stride, (uint64_t)k.br, (uint64_t)k.bc, (uint64_t)k.dtype}) h = h * 1000003u ^ (size_t)v;
+    return h;
+  }
+};
+std::mutex g_mu;
+std::unordered_map<Key, CUtensorMap*, KeyHash> g_maps;
+}  // namespace
+
+const CUtensorMap* tensor_map_2d(const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows,
+                                 uint32_t box_cols, int dtype) {
+  Key key{base, rows, cols, row_stride_elems, box_rows, box_cols, dtype};
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) return it->second;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (driver too old?)"); return nullptr; }
+  if (g_maps.size() > 4096) {  // pointers churn (caching allocator): keep the table bounded
+    for (auto& kv : g_maps) delete kv.second;
+    g_maps.clear();
+  }
+  CUtensorMap* m = new CUtensorMap;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, dtype == B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu stride=%llu box=%ux%u", (int)r, (unsigned long long)rows,
+              (unsigned long long)cols, (unsigned long long)row_stride_elems, box_rows, box_cols);
+    delete m;
+    return nullptr;
+  }
+  g_maps.emplace(key, m);
+  return m;
+}
+
+namespace {
+
+constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
+constexpr int kThreads = 192;
+enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RES = 2, EPI_MUL_GELUGRAD = 3 };
+
+struct GemmParams {
+  const float* bias;  // [N] or null
+  const void* R;      // residual [M,N] (EPI_BIAS_RES)
+  long long M;
+  int N, K, m_tiles, n_tiles, k_blocks, fmt, has_d2;
+};
+
+template <int BLOCK_N, int STAGES> struct Smem {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int D_BYTES = BLOCK_M * BLOCK_N * 2;
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
+  static constexpr int OFF_D = OFF_B + STAGES * B_BYTES;
+  static constexpr int OFF_D2 = OFF_D + D_BYTES;
+  static constexpr int OFF_BAR = OFF_D2 + D_BYTES;
+  static constexpr int TOTAL = OFF_BAR + 256 + 1024;  // + alignment slack
+};
+
+__device__ __forceinline__ float gelu_erf(float a) { return 0.5f * a * (1.f + erff(a * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_erf_grad(float a) {
+  const float cdf = 0.5f * (1.f + erff(a * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * a * a);
+  return cdf + a * pdf;
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi, int fmt) {
+  if (fmt == 1) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&p);
+  }
+  __half2 p = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ float unpack_lo(uint32_t w, int fmt) {
+  return fmt == 1 ? __uint_as_float(w << 16) : __half2float(__ushort_as_half((unsigned short)(w & 0xffff)));
+}
+__device__ __forceinline__ float unpack_hi(uint32_t w, int fmt) {
+  return fmt == 1 ? __uint_as_float(w & 0xffff0000u) : __half2float(__ushort_as_half((unsigned short)(w >> 16)));
+}
+
+template <int BLOCK_N, int STAGES, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2, GemmParams P) {
+  using S = Smem<BLOCK_N, STAGES>;
+  extern __shared__ unsigned char smem_raw_[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;   // [2] accumulator ready
+  uint64_t* tempty = tfull + 2;       // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = P.m_tiles * P.n_tiles;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmD);
+    if (P.has_d2) prefetch_tmap(&tmD2);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N); tmem_relinquish(); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / P.n_tiles) * BLOCK_M, n0 = (tile % P.n_tiles) * BLOCK_N;
+        for (int kb = 0; kb < P.k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], S::A_BYTES + S::B_BYTES);
+          tma_load_2d(smem + S::OFF_A + stage * S::A_BYTES, &tmA, &full[stage], kb * BLOCK_K, m0);
+          tma_load_2d(smem + S::OFF_B + stage * S::B_BYTES, &tmB, &full[stage], kb * BLOCK_K, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      const uint32_t idesc = idesc_f16(BLOCK_M, BLOCK_N, P.fmt);
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], aphase ^ 1);
+        fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < P.k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          fence_after_sync();
+          const uint64_t da = smem_desc_k_sw128(smem + S::OFF_A + stage * S::A_BYTES);
+          const uint64_t db = smem_desc_k_sw128(smem + S::OFF_B + stage * S::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_f16(d_tmem, da + (uint64_t)(k * UMMA_K * 2 >> 4), db + (uint64_t)(k * UMMA_K * 2 >> 4), idesc, (kb | k) != 0);
+          umma_commit(&empty[stage]);  // smem slot free once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);      // accumulator complete
+        if (++acc == 2) { acc = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;              // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;       // row within the tile
+    const int et = threadIdx.x - 64;     // 0..127
+    int acc = 0; uint32_t aphase = 0;
+    unsigned char* sD = smem + S::OFF_D;
+    unsigned char* sD2 = smem + S::OFF_D2;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / P.n_tiles) * BLOCK_M, n0 = (tile % P.n_tiles) * BLOCK_N;
+      mbar_wait(&tfull[acc], aphase);
+      fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+      const long long grow = (long long)m0 + row;
+#pragma unroll 1
+      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(taddr + ch * 32, v);
+        tmem_ld_wait();
+        uint32_t o[16], o2[16];
+        uint32_t rres[16];
+        if (EPI == EPI_BIAS_RES || EPI == EPI_MUL_GELUGRAD) {
+          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(P.R) + grow * P.N + n0 + ch * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 t = make_uint4(0, 0, 0, 0);
+            if (grow < P.M && n0 + ch * 32 + i * 8 < P.N) t = rp[i];
+            rres[4 * i] = t.x; rres[4 * i + 1] = t.y; rres[4 * i + 2] = t.z; rres[4 * i + 3] = t.w;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int c = n0 + ch * 32 + 2 * i;
+          float a0 = __uint_as_float(v[2 * i]), a1 = __uint_as_float(v[2 * i + 1]);
+          if (P.bias) {
+            if (c < P.N) a0 += __ldg(P.bias + c);
+            if (c + 1 < P.N) a1 += __ldg(P.bias + c + 1);
+          }
+          if (EPI == EPI_BIAS_GELU) {
+            o2[i] = pack2(a0, a1, P.fmt);
+            // GELU sees the stored (rounded) pre-activation so forward and backward agree bit-for-bit on `a`
+            a0 = gelu_erf(unpack_lo(o2[i], P.fmt));
+            a1 = gelu_erf(unpack_hi(o2[i], P.fmt));
+          }
+          if (EPI == EPI_BIAS_RES) { a0 += unpack_lo(rres[i], P.fmt); a1 += unpack_hi(rres[i], P.fmt); }
+          if (EPI == EPI_MUL_GELUGRAD) { a0 *= gelu_erf_grad(unpack_lo(rres[i], P.fmt)); a1 *= gelu_erf_grad(unpack_hi(rres[i], P.fmt)); }
+          o[i] = pack2(a0, a1, P.fmt);
+        }
+        // 32 columns = 4 x 16-byte chunks of the [128 rows][64 cols] swizzled box number (ch*32)/64
+        const int box = (ch * 32) / 64, c16 = ((ch * 32) % 64) / 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t off = box * (BLOCK_M * 128) + sw128_offset(row, c16 + i);
+          *reinterpret_cast<uint4*>(sD + off) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          if (EPI == EPI_BIAS_GELU)
+            *reinterpret_cast<uint4*>(sD2 + off) = make_uint4(o2[4 * i], o2[4 * i + 1], o2[4 * i + 2], o2[4 * i + 3]);
+        }
+      }
+      // accumulator drained -> MMA warp may overwrite it
+      fence_before_sync();
+      mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; aphase ^= 1; }
+      // staging complete -> one thread stores the boxes
+      fence_proxy_async();
+      named_bar_sync(1, 128);
+      if (et == 0) {
+#pragma unroll
+        for (int b = 0; b < BLOCK_N / 64; ++b) {
+          if (n0 + b * 64 < P.N) {
+            tma_store_2d(&tmD, sD + b * (BLOCK_M * 128), n0 + b * 64, m0);
+            if (EPI == EPI_BIAS_GELU && P.has_d2) tma_store_2d(&tmD2, sD2 + b * (BLOCK_M * 128), n0 + b * 64, m0);
+          }
+        }
+        bulk_commit();
+        bulk_wait_read_all();  // staging may be rewritten once the TMA engine has read it
+      }
+      named_bar_sync(1, 128);
+    }
+    if (et == 0) bulk_wait_all();
+  }
+  // teardown
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N); }
+}
+
+template <int BLOCK_N, int STAGES, int EPI>
+int launch(const void* A, const void* B, const float* bias, void* D, void* D2, const void* R, long long M, int N, int K,
+           int dtype, cudaStream_t st) {
+  using S = Smem<BLOCK_N, STAGES>;
+  const CUtensorMap* mA = tensor_map_2d(A, (uint64_t)M, (uint64_t)K, (uint64_t)K, BLOCK_M, BLOCK_K, dtype);
+  const CUtensorMap* mB = tensor_map_2d(B, (uint64_t)N, (uint64_t)K, (uint64_t)K, BLOCK_N, BLOCK_K, dtype);
+  const CUtensorMap* mD = tensor_map_2d(D, (uint64_t)M, (uint64_t)N, (uint64_t)N, BLOCK_M, 64, dtype);
+  const CUtensorMap* mD2 = D2 ? tensor_map_2d(D2, (uint64_t)M, (uint64_t)N, (uint64_t)N, BLOCK_M, 64, dtype) : mD;
+  if (!mA || !mB || !mD || !mD2) return B200_ERR_LAUNCH;
+  GemmParams P;
+  P.bias = bias; P.R = R; P.M = M; P.N = N; P.K = K;
+  P.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
+  P.n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  P.k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  P.fmt = dtype == B200_BF16 ? 1 : 0;
+  P.has_d2 = D2 != nullptr;
+  auto kern = gemm_nt_kernel<BLOCK_N, STAGES, EPI>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+  int grid = P.m_tiles * P.n_tiles;
+  if (grid > sm_count()) grid = sm_count();
+  kern<<<grid, kThreads, S::TOTAL, st>>>(*mA, *mB, *mD, *mD2, P);
+  return check_launch("gemm_nt");
+}
+
+}  // namespace
+}  // namespace tc
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" B200_API int b200_gemm_nt_supported(int64_t M, int32_t N, int32_t K, int32_t dtype) {
+  return (dtype == B200_BF16 || dtype == B200_F16) && M > 0 && N >= 16 && K >= 16 && N % 8 == 0 && K % 8 == 0;
+}
+
+extern "C" B200_API int b200_gemm_nt(const void* A, const void* B, const float* bias, void* D, void* D2, const void* R,
+                                     int64_t M, int32_t N, int32_t K, int32_t dtype, int32_t epi, void* stream) {
+  B200_REQUIRE(b200_gemm_nt_supported(M, N, K, dtype), B200_ERR_UNSUPPORTED,
+               "gemm_nt: unsupported problem M=%lld N=%d K=%d dtype=%d (16-bit dtypes, N and K multiples of 8)", (long long)M, N, K, dtype);
+  B200_REQUIRE(A && B && D, B200_ERR_SHAPE, "gemm_nt: null pointer");
+  B200_REQUIRE((((uintptr_t)A | (uintptr_t)B | (uintptr_t)D | (uintptr_t)D2 | (uintptr_t)R) & 15) == 0, B200_ERR_ALIGN,
+               "gemm_nt: pointers must be 16-byte aligned");
+  B200_REQUIRE(epi >= 0 && epi <= 3, B200_ERR_SHAPE, "gemm_nt: bad epilogue %d", epi);
+  B200_REQUIRE(epi < 2 || R, B200_ERR_SHAPE, "gemm_nt: epilogue %d needs R", epi);
+  cudaStream_t st = (cudaStream_t)stream;
+  using namespace b200::tc;
+  if (N >= 128) {
+    if (epi == 0) return launch<128, 4, EPI_BIAS>(A, B, bias, D, nullptr, nullptr, M, N, K, dtype, st);
+    if (epi == 1) return launch<128, 4, EPI_BIAS_GELU>(A, B, bias, D, D2, nullptr, M, N, K, dtype, st);
+    if (epi == 3) return launch<128, 4, EPI_MUL_GELUGRAD>(A, B, bias, D, nullptr, R, M, N, K, dtype, st);
+    return launch<128, 4, EPI_BIAS_RES>(A, B, bias, D, nullptr, R, M, N, K, dtype, st);
+  }
+  if (epi == 0) return launch<64, 4, EPI_BIAS>(A, B, bias, D, nullptr, nullptr, M, N, K, dtype, st);
+  if (epi == 1) return launch<64, 4, EPI_BIAS_GELU>(A, B, bias, D, D2, nullptr, M, N, K, dtype, st);
+  if (epi == 3) return launch<64, 4, EPI_MUL_GELUGRAD>(A, B, bias, D, nullptr, R, M, N, K, dtype, st);
+  return launch<64, 4, EPI_BIAS_RES>(A, B, bias, D, nullptr, R, M, N, K, dtype, st);
+}

@@ -136,12 +136,15 @@ __global__ void __launch_bounds__(256) swin_res_ln2_vec_kernel(const T* __restri
   load_vecf<VEC, ITERS>(beta, lane, bt);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < Ttok; t += nwarps) {
-    float v[N], w[N];
+    float v[N];
     load_row<T, VEC, ITERS>(n1 + t * C, lane, v);
-    load_row<T, VEC, ITERS>(a + t * C, lane, w);
+    if (a) {  // a == nullptr: `n1` already holds y1 (residual fused into the out_proj GEMM epilogue)
+      float w[N];
+      load_row<T, VEC, ITERS>(a + t * C, lane, w);
 #pragma unroll
-    for (int i = 0; i < N; ++i) v[i] = DT<T>::to_f(DT<T>::from_f(v[i] + w[i]));  // LN2 sees exactly the stored y1
-    store_row<T, VEC, ITERS>(y1 + t * C, lane, v);
+      for (int i = 0; i < N; ++i) v[i] = DT<T>::to_f(DT<T>::from_f(v[i] + w[i]));  // LN2 sees exactly the stored y1
+      store_row<T, VEC, ITERS>(y1 + t * C, lane, v);
+    }
     float mu, rs;
     stats_full<N>(v, C, &mu, &rs);
 #pragma unroll
@@ -276,9 +279,11 @@ __global__ void __launch_bounds__(256) swin_res_ln2_kernel(const T* __restrict__
     const int c = lane + 32 * i;
     if (i < npl && c < C) {
       // the residual sum is rounded to the activation dtype first: LN2 must see exactly the stored y1
-      const T s = DT<T>::from_f(ldf(n1 + t * C + c) + ldf(a + t * C + c));
-      y1[t * C + c] = s;
-      v[i] = DT<T>::to_f(s);
+      if (a) {
+        const T s = DT<T>::from_f(ldf(n1 + t * C + c) + ldf(a + t * C + c));
+        y1[t * C + c] = s;
+        v[i] = DT<T>::to_f(s);
+      } else v[i] = ldf(n1 + t * C + c);
     } else v[i] = 0.f;
   }
   float mu, rs;
@@ -540,7 +545,7 @@ extern "C" B200_API int b200_swin_ln1_partition(const void* x, const float* gamm
 extern "C" B200_API int b200_swin_res_ln2(const void* n1, const void* a, const float* gamma, const float* beta, void* y1,
                                           void* u, float* mean, float* rstd, int64_t tokens, int32_t C, int32_t dtype,
                                           void* stream) {
-  B200_REQUIRE(n1 && a && gamma && beta && y1 && u && mean && rstd, B200_ERR_SHAPE, "swin_res_ln2: null pointer");
+  B200_REQUIRE(n1 && gamma && beta && u && mean && rstd && (!a || y1), B200_ERR_SHAPE, "swin_res_ln2: null pointer");
   B200_REQUIRE(tokens > 0 && C > 0 && C <= 32 * kMaxPL, B200_ERR_SHAPE, "swin_res_ln2: bad shape");
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
     int vec, iters;

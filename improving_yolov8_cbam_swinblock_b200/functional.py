@@ -213,15 +213,12 @@ class SwinBlockFn(torch.autograd.Function):
             o = torch.empty((T, Cc), dtype=dt, device=dev)
             lse = torch.empty((T, num_heads), **f32)
             call("b200_swin_attn_fwd", ptr(qkv), ptr(o), ptr(lse), T, Lw, Cc, num_heads, code, st)
-            a = gemm.linear(o, wo, bo)
-            y1, u = torch.empty_like(n1), torch.empty_like(n1)
+            y1 = gemm.linear_res(o, wo, bo, n1)  # post-norm residual fused into the out_proj epilogue
+            u = torch.empty_like(n1)
             mean2, rstd2 = torch.empty(T, **f32), torch.empty(T, **f32)
-            call("b200_swin_res_ln2", ptr(n1), ptr(a), ptr(g2f), ptr(b2f), ptr(y1), ptr(u), ptr(mean2), ptr(rstd2), T, Cc,
+            call("b200_swin_res_ln2", ptr(y1), None, ptr(g2f), ptr(b2f), None, ptr(u), ptr(mean2), ptr(rstd2), T, Cc,
                                       code, st)
-            del a
-            hpre = gemm.linear(u, w1, bb1)
-            h = torch.empty_like(hpre)
-            call("b200_swin_gelu", ptr(hpre), None, ptr(h), hpre.numel(), code, 0, st)
+            h, hpre = gemm.linear_gelu(u, w1, bb1)
             m = gemm.linear(h, w2, bb2)
             out = _empty_nhwc(B, Cc, H, W, dt, dev)
             call("b200_swin_res_reverse", ptr(y1), ptr(m), ptr(out), B, Cc, H, W, ws, code, st)
@@ -248,13 +245,11 @@ class SwinBlockFn(torch.autograd.Function):
             # MLP
             gw2 = gemm.matmul_tn(gy2, h)          # [C, 4C] = gy2^T h
             gb2 = _colsum(gy2)
-            gh = gemm.matmul_nn(gy2, w2)          # [T, 4C] = gy2 W2
-            call("b200_swin_gelu", ptr(hpre), ptr(gh), ptr(gh), gh.numel(), code, 1, st)
-            ga = gh
+            ga = gemm.matmul_nn_gelu_bwd(gy2, w2, hpre)  # [T, 4C] = (gy2 W2) * gelu'(hpre)
             gw1 = gemm.matmul_tn(ga, u)           # [4C, C]
             gb1 = _colsum(ga)
             gu = gemm.matmul_nn(ga, w1)           # [T, C]
-            del ga, gh
+            del ga
             # LN2 + residual
             nbytes = L.b200_swin_ln_bwd_workspace_bytes(T, Cc)
             wsb = torch.empty(nbytes, dtype=torch.uint8, device=dev)

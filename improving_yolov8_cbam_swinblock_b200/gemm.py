@@ -1,42 +1,75 @@
-"""Dense contractions of the SwinBlock (in_proj / out_proj / mlp.0 / mlp.2 and their gradients).
+"""Dense contractions of the SwinBlock (in_proj / out_proj / mlp.0 / mlp.2 and their data gradients).
 
-16-bit activations go to the hand-written tcgen05 GEMM of ``libb200yolo.so`` (``b200_gemm_*``) when the shape
-is one it tiles; everything else (f32 activations, whose parity bar is rtol 1e-5, and odd shapes) is a plain
-library GEMM through ``torch.matmul`` (cuBLAS) -- a "plain library GEMM" in the sense of the task statement, not
-a fallback for the custom kernels.  Weights are f32 parameters and are cast to the activation dtype per call,
-mirroring what autocast does for ``F.linear`` in the reference.
+16-bit activations go to the hand-written tcgen05 GEMM of ``libb200yolo.so`` (``b200_gemm_nt``, fused bias / GELU /
+residual / GELU-backward epilogues) whenever the shape is one it tiles (N, K multiples of 64).  Everything else -- f32
+activations, whose parity bar is rtol 1e-5, odd channel counts, and the weight-gradient contractions X^T dY -- is a
+plain library GEMM through ``torch.matmul`` (cuBLAS).  Weights are f32 parameters cast to the activation dtype per
+call, which is what autocast does for ``F.linear`` in the reference (trainer.py:383).
 """
 from __future__ import annotations
 
 import torch
 
-USE_TCGEN05 = True  # flipped off only by tests that compare the two GEMM paths
+from . import gemm_tc as tc
+from ._lib import call, dtype_code, ptr, stream_ptr
+
+USE_TCGEN05 = True  # tests flip this to compare the two GEMM paths
 
 
-def _tc():
-    from . import gemm_tc
-
-    return gemm_tc
+def _use_tc(a, n, k):
+    return USE_TCGEN05 and tc.supports(a, n, k)
 
 
-def linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None) -> torch.Tensor:
-    """a[M,K] @ w[N,K]^T + bias[N] -> [M,N] (a.dtype)."""
-    if USE_TCGEN05 and _tc().supports(a, w.shape[0], w.shape[1]):
-        return _tc().linear(a, w, bias)
-    wt = w.detach().to(a.dtype)
-    if bias is None:
-        return a @ wt.t()
-    return torch.addmm(bias.detach().to(a.dtype), a, wt.t())
+def _wt(w, dtype):
+    return w.detach().to(dtype)
 
 
-def matmul_nn(a: torch.Tensor, w: torch.Tensor, add: torch.Tensor | None = None) -> torch.Tensor:
-    """a[M,K] @ w[K,N] (+ add[M,N]) -> [M,N] (a.dtype): data gradients."""
-    wt = w.detach().to(a.dtype)
-    if add is None:
-        return a @ wt
-    return torch.addmm(add, a, wt)
+def linear(a, w, bias):
+    """a[M,K] @ w[N,K]^T + bias -> [M,N]."""
+    if _use_tc(a, w.shape[0], w.shape[1]):
+        return tc.gemm_nt(a, w, bias, tc.EPI_BIAS)
+    wt = _wt(w, a.dtype)
+    return a @ wt.t() if bias is None else torch.addmm(_wt(bias, a.dtype), a, wt.t())
 
 
-def matmul_tn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """a[M,K]^T @ b[M,N] -> f32 [K,N]: weight gradients."""
+def linear_res(a, w, bias, res):
+    """res + a @ w^T + bias."""
+    if _use_tc(a, w.shape[0], w.shape[1]):
+        return tc.gemm_nt(a, w, bias, tc.EPI_BIAS_RES, residual=res)
+    out = torch.addmm(res, a, _wt(w, a.dtype).t())
+    return out if bias is None else out.add_(_wt(bias, a.dtype))
+
+
+def linear_gelu(a, w, bias):
+    """(gelu(p), p) with p = a @ w^T + bias."""
+    if _use_tc(a, w.shape[0], w.shape[1]):
+        return tc.gemm_nt(a, w, bias, tc.EPI_BIAS_GELU, want_preact=True)
+    p = linear(a, w, bias)
+    h = torch.empty_like(p)
+    call("b200_swin_gelu", ptr(p), None, ptr(h), p.numel(), dtype_code(p.dtype), 0, stream_ptr(p.device))
+    return h, p
+
+
+def matmul_nn(a, w, add=None):
+    """a[M,K] @ w[K,N] (+ add): data gradients (w is the [out,in] parameter, used un-transposed)."""
+    if _use_tc(a, w.shape[1], w.shape[0]):
+        wt = w.detach().t().contiguous()
+        if add is None:
+            return tc.gemm_nt(a, wt, None, tc.EPI_BIAS)
+        return tc.gemm_nt(a, wt, None, tc.EPI_BIAS_RES, residual=add)
+    wt = _wt(w, a.dtype)
+    return a @ wt if add is None else torch.addmm(add, a, wt)
+
+
+def matmul_nn_gelu_bwd(a, w, preact):
+    """(a @ w) * gelu'(preact): GELU backward fused into the mlp.2 data-gradient GEMM."""
+    if _use_tc(a, w.shape[1], w.shape[0]):
+        return tc.gemm_nt(a, w.detach().t().contiguous(), None, tc.EPI_MUL_GELUGRAD, residual=preact)
+    g = a @ _wt(w, a.dtype)
+    call("b200_swin_gelu", ptr(preact), ptr(g), ptr(g), g.numel(), dtype_code(g.dtype), 1, stream_ptr(g.device))
+    return g
+
+
+def matmul_tn(a, b):
+    """a[M,K]^T @ b[M,N] -> f32 [K,N]: weight gradients (library GEMM)."""
     return (a.t() @ b).to(torch.float32)

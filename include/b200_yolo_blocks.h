@@ -107,7 +107,8 @@ B200_API int b200_swin_attn_fwd(const void* qkv, void* o, float* lse, int64_t to
                                 int32_t nh, int32_t dtype, void* stream);
 B200_API int b200_swin_attn_bwd(const void* qkv, const void* o, const float* lse, const void* go, void* gqkv,
                                 int64_t tokens, int32_t L, int32_t C, int32_t nh, int32_t dtype, void* stream);
-/* y1 = n1 + a (post-norm residual, swin_block.py:52);  u = LayerNorm_2(y1) (swin_block.py:53) */
+/* y1 = n1 + a (post-norm residual, swin_block.py:52);  u = LayerNorm_2(y1) (swin_block.py:53).
+ * a == NULL: `n1` already holds y1 (residual fused into the out_proj GEMM) and y1 is not written. */
 B200_API int b200_swin_res_ln2(const void* n1, const void* a, const float* gamma, const float* beta, void* y1,
                                void* u, float* mean, float* rstd, int64_t tokens, int32_t C, int32_t dtype,
                                void* stream);
@@ -132,6 +133,17 @@ B200_API int b200_swin_ln_bwd(const void* gout, const void* xin, const void* gre
 B200_API size_t b200_colsum_workspace_bytes(int64_t rows, int32_t n);
 B200_API int b200_colsum(const void* a, float* out, void* workspace, size_t workspace_bytes, int64_t rows,
                          int32_t n, int32_t dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * tcgen05 GEMM for the SwinBlock's dense contractions (torch F.linear at swin_block.py:51,53):
+ *   D[M,N] = epi(A[M,K] * B[N,K]^T + bias[N]),  A/B/D/D2/R in the 16-bit activation dtype (bf16 | f16), f32 accumulate.
+ *   epi 0: bias;  epi 1: D = gelu_erf(a), D2 (nullable) = a = pre-activation;  epi 2: D = a + R[M,N] (residual);
+ *   epi 3: D = a * gelu_erf'(R[M,N])  (GELU backward fused into the mlp.2 data-gradient GEMM).
+ * b200_gemm_nt_supported() tells whether the problem is one the kernel tiles.
+ * ------------------------------------------------------------------------------------------------------ */
+B200_API int b200_gemm_nt_supported(int64_t M, int32_t N, int32_t K, int32_t dtype);
+B200_API int b200_gemm_nt(const void* A, const void* B, const float* bias, void* D, void* D2, const void* R,
+                          int64_t M, int32_t N, int32_t K, int32_t dtype, int32_t epi, void* stream);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,7 @@ def _header_symbols():
 def test_every_declared_symbol_is_exported_and_bound():
     from improving_yolov8_cbam_swinblock_b200 import _lib
     import improving_yolov8_cbam_swinblock_b200.functional  # noqa: F401  registers the swin entry points
+    import improving_yolov8_cbam_swinblock_b200.gemm  # noqa: F401  registers the GEMM entry points
 
     syms = _header_symbols()
     assert len(syms) >= 20

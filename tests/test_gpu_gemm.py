@@ -1,0 +1,44 @@
+"""-m gpu: the hand-written tcgen05 GEMM (b200_gemm_nt) vs torch.matmul in fp32 on the same bf16/f16 inputs."""
+import pytest
+import torch
+
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 128), (1000, 384, 128), (112896, 128, 512), (4097, 512, 128),
+                                   (77, 64, 64), (3000, 192, 192), (640, 256, 256)])
+def test_gemm_bias(dtype, M, N, K):
+    from improving_yolov8_cbam_swinblock_b200 import gemm_tc
+
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda").to(dtype)
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5)
+    b = torch.randn(N, device="cuda")
+    assert gemm_tc.supports(a, N, K)
+    got = gemm_tc.gemm_nt(a, w, b)
+    want = a.float() @ w.to(dtype).float().t() + b
+    assert got.shape == (M, N) and got.dtype == dtype
+    assert rel_err(got, want) < (4e-3 if dtype == torch.bfloat16 else 6e-4), rel_err(got, want)
+    # element-wise: every output within one rounding step of the fp32 result
+    torch.testing.assert_close(got.float(), want, rtol=2e-2 if dtype == torch.bfloat16 else 3e-3, atol=2e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 512, 128), (5000, 128, 512)])
+def test_gemm_epilogues(M, N, K):
+    from improving_yolov8_cbam_swinblock_b200 import gemm_tc
+
+    torch.manual_seed(1)
+    dt = torch.bfloat16
+    a = torch.randn(M, K, device="cuda").to(dt)
+    w = torch.randn(N, K, device="cuda") / K ** 0.5
+    b = torch.randn(N, device="cuda")
+    r = torch.randn(M, N, device="cuda").to(dt)
+    pre = a.float() @ w.to(dt).float().t() + b
+    h, hp = gemm_tc.gemm_nt(a, w, b, gemm_tc.EPI_BIAS_GELU, want_preact=True)
+    assert rel_err(hp, pre) < 4e-3
+    assert torch.equal(h, torch.nn.functional.gelu(hp.float()).to(dt)) or rel_err(h, torch.nn.functional.gelu(hp.float())) < 4e-3
+    y = gemm_tc.gemm_nt(a, w, b, gemm_tc.EPI_BIAS_RES, residual=r)
+    assert rel_err(y, pre + r.float()) < 4e-3
