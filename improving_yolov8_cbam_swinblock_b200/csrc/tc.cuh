@@ -82,9 +82,23 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw128(const void* smem_ptr) {
   d |= (uint64_t)2 << 61;                  // layout type SWIZZLE_128B
   return d;
 }
+// MN-major operand tile, 128-byte swizzle: the tile is stored as [K rows][64 MN-elements = 128 B] boxes (again what a
+// SWIZZLE_128B TMA box produces when the MN dimension is the contiguous one in global memory).  8 K-rows form a
+// 1024-byte atom (SBO); consecutive 64-element MN blocks are `lbo_bytes` apart.  Advancing K by 16 = +16 rows = +2048 B.
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(const void* smem_ptr, uint32_t lbo_bytes) {
+  const uint32_t addr = smem_u32(smem_ptr);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // instruction descriptor, kind::f16: D=f32, A/B = bf16 (fmt 1) or f16 (fmt 0), both K-major, M x N tile
-__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int fmt) {
-  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int fmt, int a_mn = 0, int b_mn = 0) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues for the CTA
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {

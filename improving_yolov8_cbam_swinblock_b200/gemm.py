@@ -71,5 +71,10 @@ def matmul_nn_gelu_bwd(a, w, preact):
 
 
 def matmul_tn(a, b):
-    """a[M,K]^T @ b[M,N] -> f32 [K,N]: weight gradients (library GEMM)."""
+    """a[T,K]^T @ b[T,N] -> f32 [K,N]: weight gradients dW = dY^T X (reduction over the T tokens).
+
+    tcgen05 split-K kernel with both operands MN-major (no transposes, f32 partials folded in a fixed order); library
+    GEMM otherwise."""
+    if USE_TCGEN05 and tc.splitk_supported(a, b):
+        return tc.gemm_splitk(a, b, True, True)
     return (a.t() @ b).to(torch.float32)

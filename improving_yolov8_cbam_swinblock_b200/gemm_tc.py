@@ -11,6 +11,9 @@ from ._lib import call, dtype_code, ptr, stream_ptr
 _lib.register("b200_gemm_nt_supported", C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32])
 _lib.register("b200_gemm_nt", C.c_int, [C.c_void_p] * 6 + [C.c_int64] + [C.c_int32] * 4 + [C.c_void_p])
 
+_lib.register("b200_gemm_splitk_workspace_bytes", C.c_size_t, [C.c_int32, C.c_int32, C.c_int64])
+_lib.register("b200_gemm_splitk", C.c_int, [C.c_void_p] * 4 + [C.c_size_t, C.c_int32, C.c_int32, C.c_int64] + [C.c_int32] * 3 + [C.c_void_p])
+
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_MUL_GELUGRAD = 0, 1, 2, 3
 
 
@@ -36,3 +39,22 @@ def gemm_nt(a, w, bias=None, epi=EPI_BIAS, residual=None, want_preact=False):
 
 def linear(a, w, bias):
     return gemm_nt(a, w, bias, EPI_BIAS)
+
+
+def splitk_supported(a: torch.Tensor, b: torch.Tensor) -> bool:
+    return (a.is_cuda and a.dtype in (torch.bfloat16, torch.float16) and a.dtype == b.dtype and a.is_contiguous()
+            and b.is_contiguous() and all(d % 8 == 0 for d in (*a.shape, *b.shape)))
+
+
+def gemm_splitk(a, b, a_mn: bool, b_mn: bool):
+    """f32 D[M,N] = sum_k A(m,k) B(n,k); a is [K,M] if a_mn else [M,K]; b is [K,N] if b_mn else [N,K]."""
+    K, M = a.shape if a_mn else a.shape[::-1]
+    Kb, N = b.shape if b_mn else b.shape[::-1]
+    assert K == Kb, (a.shape, b.shape)
+    L = _lib.lib()
+    nbytes = L.b200_gemm_splitk_workspace_bytes(M, N, K)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
+    d = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    call("b200_gemm_splitk", ptr(a), ptr(b), ptr(d), ptr(ws), nbytes, M, N, K, int(a_mn), int(b_mn), dtype_code(a.dtype),
+         stream_ptr(a.device))
+    return d

@@ -145,6 +145,15 @@ B200_API int b200_gemm_nt_supported(int64_t M, int32_t N, int32_t K, int32_t dty
 B200_API int b200_gemm_nt(const void* A, const void* B, const float* bias, void* D, void* D2, const void* R,
                           int64_t M, int32_t N, int32_t K, int32_t dtype, int32_t epi, void* stream);
 
+/* Split-K tcgen05 GEMM with selectable operand majorness, f32 output (weight gradients dW = dY^T X, autograd of
+ * F.linear at swin_block.py:51,53, are the a_mn=b_mn=1 form with K = tokens):
+ *   D[M,N] (f32) = sum_k A(m,k) * B(n,k);  a_mn=0: A is [M,K] row-major, a_mn=1: A is [K,M] row-major; same for B/N.
+ * Deterministic: per-split f32 partial tiles in `workspace` folded in a fixed order. */
+B200_API size_t b200_gemm_splitk_workspace_bytes(int32_t M, int32_t N, int64_t K);
+B200_API int b200_gemm_splitk(const void* A, const void* B, float* D, void* workspace, size_t workspace_bytes,
+                              int32_t M, int32_t N, int64_t K, int32_t a_mn, int32_t b_mn, int32_t dtype,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,3 +42,20 @@ def test_gemm_epilogues(M, N, K):
     assert torch.equal(h, torch.nn.functional.gelu(hp.float()).to(dt)) or rel_err(h, torch.nn.functional.gelu(hp.float())) < 4e-3
     y = gemm_tc.gemm_nt(a, w, b, gemm_tc.EPI_BIAS_RES, residual=r)
     assert rel_err(y, pre + r.float()) < 4e-3
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 256), (384, 128, 4096), (128, 512, 112896), (72, 200, 1000)])
+def test_gemm_splitk_all_majors(a_mn, b_mn, M, N, K):
+    """K-major and MN-major operand descriptors: D = A B^T in f32, A/B given in either storage order."""
+    from improving_yolov8_cbam_swinblock_b200 import gemm_tc
+
+    torch.manual_seed(M + N + (K % 1000))
+    dt = torch.bfloat16
+    A = torch.randn(M, K, device="cuda").to(dt)
+    Bm = torch.randn(N, K, device="cuda").to(dt)
+    a = A.t().contiguous() if a_mn else A
+    b = Bm.t().contiguous() if b_mn else Bm
+    got = gemm_tc.gemm_splitk(a, b, a_mn, b_mn)
+    want = A.double() @ Bm.double().t()
+    assert rel_err(got, want) < 1e-5, rel_err(got, want)
