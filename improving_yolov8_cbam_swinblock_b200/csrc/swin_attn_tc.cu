@@ -1,0 +1,541 @@
+// SwinBlock window attention on tcgen05 tensor cores (bf16 / f16 activations), forward.
+// Replaces the bmm / softmax / bmm core of nn.MultiheadAttention at swin_block.py:51 for 16-bit activations.
+//
+// Work unit = a PAIR of (window, head) items stacked in one M = 128 UMMA tile: rows [0,64) belong to item 0, rows
+// [64,128) to item 1 (L = ws*ws <= 64 real rows each).  Per pair:
+//   TMA   Q, K, V boxes [64 tokens][64 channels] straight out of the packed qkv[T,3C] rows (128-byte swizzle)
+//   MMA   S[128x128] = Q K^T            (A, B K-major)  -> TMEM; only the two diagonal 64x64 blocks are meaningful
+//   warps thread = row: tcgen05.ld its 64 scores, scale, mask j >= L, exp2 softmax in registers, write the
+//         un-normalised probabilities as bf16 into a K-major A tile in shared memory (off-diagonal blocks stay 0)
+//   MMA   O[128xHD] = P V               (A K-major from smem, B = the V tile as loaded, MN-major descriptor)
+//   warps tcgen05.ld O, multiply by 1/rowsum, store the L real rows to o[T,C]; lse saved for the backward
+// Persistent CTAs (one per SM), 6 warps: 0-3 softmax/epilogue (TMEM lane quadrant = warp), 4 TMA producer, 5 MMA
+// issuer.  With HD = 64 everything is double-buffered so S(k+1) is computed while softmax(k) runs.
+#include "tc.cuh"
+
+namespace b200 {
+namespace tc {
+namespace {
+
+constexpr int kThreads = 192;
+
+struct AttnParams {
+  void* o;
+  float* lse;
+  long long T;
+  int L, C, nh, n_items, n_pairs, fmt;
+  float scale_log2;
+};
+
+template <int HD> struct ACfg {
+  static constexpr int KB = HD / 64;                 // 64-wide channel blocks per head
+  static constexpr int STAGES = HD == 64 ? 2 : 1;
+  static constexpr int Q_BYTES = KB * 128 * 128;     // [KB][128 rows][128 B]
+  static constexpr int P_BYTES = 2 * 128 * 128;      // [2 key blocks][128 rows][128 B]
+  static constexpr int STAGE_BYTES = 3 * Q_BYTES + P_BYTES;
+  static constexpr int OFF_BAR = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+  static constexpr int TMEM_COLS = (STAGES * (128 + HD)) <= 256 ? 256 : 512;
+};
+
+__device__ __forceinline__ uint32_t pack2f(float lo, float hi, int fmt) {
+  if (fmt == 1) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&p);
+  }
+  __half2 p = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+template <int HD>
+__global__ void __launch_bounds__(kThreads, 1) swin_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams P) {
+  using Cfg = ACfg<HD>;
+  constexpr int KB = Cfg::KB, STAGES = Cfg::STAGES;
+  extern __shared__ unsigned char smem_raw_[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
+  uint64_t* qkv_full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* s_full = qkv_full + STAGES;
+  uint64_t* p_full = s_full + STAGES;
+  uint64_t* o_full = p_full + STAGES;
+  uint64_t* stage_free = o_full + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + STAGES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  auto sQ = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
+  auto sK = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::Q_BYTES; };
+  auto sV = [&](int s) { return smem + s * Cfg::STAGE_BYTES + 2 * Cfg::Q_BYTES; };
+  auto sP = [&](int s) { return smem + s * Cfg::STAGE_BYTES + 3 * Cfg::Q_BYTES; };
+
+  if (warp == 4 && elect_one()) {
+    prefetch_tmap(&tmQKV);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&qkv_full[s], 1); mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128);
+      mbar_init(&o_full[s], 1); mbar_init(&stage_free[s], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  if (warp < 4) {
+    // off-diagonal P blocks are never written again: zero them once (zero is swizzle-invariant)
+    const int row = warp * 32 + lane, r = row >> 6;
+    for (int s = 0; s < STAGES; ++s) {
+      uint4* z = reinterpret_cast<uint4*>(sP(s) + (1 - r) * (128 * 128) + row * 128);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  auto tS = [&](int s) { return tmem_base + s * 128; };
+  auto tO = [&](int s) { return tmem_base + STAGES * 128 + s * HD; };
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int s = 0; uint32_t ph = 0;
+      for (int pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
+        mbar_wait(&stage_free[s], ph ^ 1);
+        mbar_expect_tx(&qkv_full[s], 3 * Cfg::Q_BYTES);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          int it = 2 * pair + r;
+          if (it >= P.n_items) it = P.n_items - 1;
+          const int win = it / P.nh, h = it - win * P.nh;
+          const int t0 = win * P.L;
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {
+            const int col = h * HD + kb * 64;
+            tma_load_2d(sQ(s) + kb * 16384 + r * 8192, &tmQKV, &qkv_full[s], col, t0);
+            tma_load_2d(sK(s) + kb * 16384 + r * 8192, &tmQKV, &qkv_full[s], P.C + col, t0);
+            tma_load_2d(sV(s) + kb * 16384 + r * 8192, &tmQKV, &qkv_full[s], 2 * P.C + col, t0);
+          }
+        }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      const uint32_t idesc_s = idesc_f16(128, 128, P.fmt, 0, 0);
+      const uint32_t idesc_o = idesc_f16(128, HD, P.fmt, 0, 1);
+      auto issue_S = [&](int s) {
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tS(s), smem_desc_k_sw128(sQ(s) + kb * 16384 + k * 32), smem_desc_k_sw128(sK(s) + kb * 16384 + k * 32),
+                     idesc_s, (kb | k) != 0);
+        umma_commit(&s_full[s]);
+      };
+      int s = 0; uint32_t ph = 0;          // stage / phase of the pair whose PV is issued next
+      int sn = 0; uint32_t phn = 0;        // stage / phase of the pair whose S is issued next
+      int pair = blockIdx.x;
+      if (pair < P.n_pairs) {
+        mbar_wait(&qkv_full[sn], phn);
+        fence_after_sync();
+        issue_S(sn);
+        if (++sn == STAGES) { sn = 0; phn ^= 1; }
+      }
+      for (; pair < P.n_pairs; pair += gridDim.x) {
+        const int next = pair + gridDim.x;
+        if (STAGES > 1 && next < P.n_pairs) {  // S of the next pair overlaps the softmax of this one
+          mbar_wait(&qkv_full[sn], phn);
+          fence_after_sync();
+          issue_S(sn);
+          if (++sn == STAGES) { sn = 0; phn ^= 1; }
+        }
+        mbar_wait(&p_full[s], ph);
+        fence_after_sync();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tO(s), smem_desc_k_sw128(sP(s) + kb * 16384 + k * 32),
+                     smem_desc_mn_sw128(sV(s) + kb * 8192 + k * 2048, 16384), idesc_o, (kb | k) != 0);
+        umma_commit(&o_full[s]);
+        if (STAGES == 1 && next < P.n_pairs) {
+          mbar_wait(&qkv_full[sn], phn);
+          fence_after_sync();
+          issue_S(sn);
+          if (++sn == STAGES) { sn = 0; phn ^= 1; }
+        }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== softmax + epilogue (warps 0..3, thread = row) =====================
+    const int row = warp * 32 + lane, r = row >> 6, i = row & 63;
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    int s = 0; uint32_t ph = 0;
+    for (int pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
+      const int it = 2 * pair + r;
+      const bool valid = it < P.n_items && i < P.L;
+      const int itc = it < P.n_items ? it : P.n_items - 1;
+      const int win = itc / P.nh, h = itc - win * P.nh;
+      const long long tok = (long long)win * P.L + i;
+      mbar_wait(&s_full[s], ph);
+      fence_after_sync();
+      uint32_t v[32], w[32];
+      tmem_ld32(tS(s) + lane_sel + r * 64, v);
+      tmem_ld32(tS(s) + lane_sel + r * 64 + 32, w);
+      tmem_ld_wait();
+      float m = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float a = j < P.L ? __uint_as_float(v[j]) * P.scale_log2 : -INFINITY;
+        const float b = j + 32 < P.L ? __uint_as_float(w[j]) * P.scale_log2 : -INFINITY;
+        v[j] = __float_as_uint(a); w[j] = __float_as_uint(b);
+        m = fmaxf(m, fmaxf(a, b));
+      }
+      float sum = 0.f;
+      uint32_t pk[32];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float e0 = exp2f(__uint_as_float(v[2 * j]) - m), e1 = exp2f(__uint_as_float(v[2 * j + 1]) - m);
+        const float f0 = exp2f(__uint_as_float(w[2 * j]) - m), f1 = exp2f(__uint_as_float(w[2 * j + 1]) - m);
+        pk[j] = pack2f(e0, e1, P.fmt);
+        pk[16 + j] = pack2f(f0, f1, P.fmt);
+        // accumulate the row sum from the ROUNDED probabilities, i.e. exactly what the PV MMA will consume
+        if (P.fmt == 1) {
+          sum += __uint_as_float(pk[j] << 16) + __uint_as_float(pk[j] & 0xffff0000u) + __uint_as_float(pk[16 + j] << 16) +
+                 __uint_as_float(pk[16 + j] & 0xffff0000u);
+        } else {
+          const float2 a2 = __half22float2(*reinterpret_cast<__half2*>(&pk[j]));
+          const float2 b2 = __half22float2(*reinterpret_cast<__half2*>(&pk[16 + j]));
+          sum += a2.x + a2.y + b2.x + b2.y;
+        }
+      }
+      unsigned char* prow = sP(s) + r * (128 * 128);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(prow + sw128_offset(row, c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      fence_proxy_async();
+      fence_before_sync();
+      mbar_arrive(&p_full[s]);
+      if (valid && P.lse) P.lse[tok * P.nh + h] = (m + log2f(sum)) * 0.69314718055994530942f;
+      const float inv = 1.f / sum;
+      // ---- O ----
+      mbar_wait(&o_full[s], ph);
+      fence_after_sync();
+      uint16_t* orow = reinterpret_cast<uint16_t*>(P.o) + tok * P.C + h * HD;
+#pragma unroll
+      for (int ch = 0; ch < HD / 32; ++ch) {
+        uint32_t ov[32];
+        tmem_ld32(tO(s) + lane_sel + ch * 32, ov);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 st;
+            st.x = pack2f(__uint_as_float(ov[8 * c + 0]) * inv, __uint_as_float(ov[8 * c + 1]) * inv, P.fmt);
+            st.y = pack2f(__uint_as_float(ov[8 * c + 2]) * inv, __uint_as_float(ov[8 * c + 3]) * inv, P.fmt);
+            st.z = pack2f(__uint_as_float(ov[8 * c + 4]) * inv, __uint_as_float(ov[8 * c + 5]) * inv, P.fmt);
+            st.w = pack2f(__uint_as_float(ov[8 * c + 6]) * inv, __uint_as_float(ov[8 * c + 7]) * inv, P.fmt);
+            *reinterpret_cast<uint4*>(orow + ch * 32 + c * 8) = st;
+          }
+        }
+      }
+      fence_before_sync();
+      mbar_arrive(&stage_free[s]);
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 5) { fence_after_sync(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+template <int HD>
+int launch_fwd(const void* qkv, void* o, float* lse, long long T, int L, int C, int nh, int dtype, cudaStream_t st) {
+  using Cfg = ACfg<HD>;
+  const CUtensorMap* m = tensor_map_2d(qkv, (uint64_t)T, (uint64_t)3 * C, (uint64_t)3 * C, 64, 64, dtype);
+  if (!m) return B200_ERR_LAUNCH;
+  AttnParams P;
+  P.o = o; P.lse = lse; P.T = T; P.L = L; P.C = C; P.nh = nh;
+  P.n_items = (int)(T / L) * nh;
+  P.n_pairs = (P.n_items + 1) / 2;
+  P.fmt = dtype == B200_BF16 ? 1 : 0;
+  P.scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
+  auto k = swin_attn_fwd_tc_kernel<HD>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::TOTAL);
+  int grid = P.n_pairs < sm_count() ? P.n_pairs : sm_count();
+  k<<<grid, kThreads, Cfg::TOTAL, st>>>(*m, P);
+  return check_launch("swin_attn_fwd_tc");
+}
+
+
+// =====================================================================================================
+// backward:  gqkv[T,3C] from qkv, lse and go[T,C]   (SURVEY App. A.3 "Attention"; flash-style recompute)
+//   S  = Q K^T,  dP = dO V^T                      (K-major operands)            -> TMEM
+//   threads: P = exp2(S*c - lse), delta = sum_j P dP, dS = P (dP - delta) * hd^-0.5 -> bf16 tiles P, dS in smem
+//   dQ = dS K      (A = dS K-major,  B = K tile MN-major)
+//   dV = P^T dO    (A = P  MN-major, B = dO tile MN-major)
+//   dK = dS^T Q    (A = dS MN-major, B = Q tile MN-major)        -> TMEM (dQ/dK alias the S/dP columns) -> global
+// =====================================================================================================
+struct AttnBwdParams {
+  void* gqkv;
+  const float* lse;
+  long long T;
+  int L, C, nh, n_items, n_pairs, fmt;
+  float scale_log2, scale;
+};
+
+template <int HD> struct BCfg {
+  static constexpr int KB = HD / 64;
+  static constexpr int T_BYTES = KB * 128 * 128;   // one operand tile [KB][128 rows][128 B]
+  static constexpr int P_BYTES = 2 * 128 * 128;
+  static constexpr int OFF_Q = 0, OFF_K = T_BYTES, OFF_V = 2 * T_BYTES, OFF_DO = 3 * T_BYTES;
+  static constexpr int OFF_P = 4 * T_BYTES, OFF_DS = OFF_P + P_BYTES;
+  static constexpr int OFF_BAR = OFF_DS + P_BYTES;
+  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+  static constexpr int TMEM_COLS = 512;            // S 128 | dP 128 | dV HD   (dQ aliases S, dK aliases dP)
+};
+
+template <int HD>
+__global__ void __launch_bounds__(kThreads, 1)
+swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmGO, AttnBwdParams P) {
+  using Cfg = BCfg<HD>;
+  constexpr int KB = Cfg::KB;
+  extern __shared__ unsigned char smem_raw_[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sQ = smem + Cfg::OFF_Q;
+  unsigned char* sK = smem + Cfg::OFF_K;
+  unsigned char* sV = smem + Cfg::OFF_V;
+  unsigned char* sDO = smem + Cfg::OFF_DO;
+  unsigned char* sP = smem + Cfg::OFF_P;
+  unsigned char* sDS = smem + Cfg::OFF_DS;
+  uint64_t* in_full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* sdp_full = in_full + 1;
+  uint64_t* pds_full = in_full + 2;
+  uint64_t* out_full = in_full + 3;
+  uint64_t* smem_free = in_full + 4;
+  uint64_t* tmem_free = in_full + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + 6);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 4 && elect_one()) {
+    prefetch_tmap(&tmQKV); prefetch_tmap(&tmGO);
+    mbar_init(in_full, 1); mbar_init(sdp_full, 1); mbar_init(pds_full, 128);
+    mbar_init(out_full, 1); mbar_init(smem_free, 1); mbar_init(tmem_free, 128);
+    fence_mbar_init();
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  if (warp < 4) {
+    const int row = warp * 32 + lane, r = row >> 6;
+    uint4* z0 = reinterpret_cast<uint4*>(sP + (1 - r) * (128 * 128) + row * 128);
+    uint4* z1 = reinterpret_cast<uint4*>(sDS + (1 - r) * (128 * 128) + row * 128);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { z0[i] = make_uint4(0, 0, 0, 0); z1[i] = make_uint4(0, 0, 0, 0); }
+    fence_proxy_async();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDQ = tS, tDK = tDP;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      uint32_t ph = 0;
+      for (int pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
+        mbar_wait(smem_free, ph ^ 1);
+        mbar_expect_tx(in_full, 4 * Cfg::T_BYTES);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          int it = 2 * pair + r;
+          if (it >= P.n_items) it = P.n_items - 1;
+          const int win = it / P.nh, h = it - win * P.nh;
+          const int t0 = win * P.L;
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {
+            const int col = h * HD + kb * 64;
+            tma_load_2d(sQ + kb * 16384 + r * 8192, &tmQKV, in_full, col, t0);
+            tma_load_2d(sK + kb * 16384 + r * 8192, &tmQKV, in_full, P.C + col, t0);
+            tma_load_2d(sV + kb * 16384 + r * 8192, &tmQKV, in_full, 2 * P.C + col, t0);
+            tma_load_2d(sDO + kb * 16384 + r * 8192, &tmGO, in_full, col, t0);
+          }
+        }
+        ph ^= 1;
+      }
+    }
+  } else if (warp == 5) {
+    if (elect_one()) {
+      const uint32_t id_kk = idesc_f16(128, 128, P.fmt, 0, 0);   // S, dP
+      const uint32_t id_kmn = idesc_f16(128, HD, P.fmt, 0, 1);   // dQ
+      const uint32_t id_mnmn = idesc_f16(128, HD, P.fmt, 1, 1);  // dV, dK
+      uint32_t ph = 0;
+      for (int pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
+        mbar_wait(in_full, ph);
+        mbar_wait(tmem_free, ph ^ 1);
+        fence_after_sync();
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_f16(tS, smem_desc_k_sw128(sQ + kb * 16384 + k * 32), smem_desc_k_sw128(sK + kb * 16384 + k * 32), id_kk, (kb | k) != 0);
+            umma_f16(tDP, smem_desc_k_sw128(sDO + kb * 16384 + k * 32), smem_desc_k_sw128(sV + kb * 16384 + k * 32), id_kk, (kb | k) != 0);
+          }
+        umma_commit(sdp_full);
+        mbar_wait(pds_full, ph);
+        fence_after_sync();
+        // dQ = dS K : reduction over the 128 key slots (2 key blocks x 4 k-steps of 16)
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tDQ, smem_desc_k_sw128(sDS + kb * 16384 + k * 32), smem_desc_mn_sw128(sK + kb * 8192 + k * 2048, 16384), id_kmn,
+                     (kb | k) != 0);
+        // dV = P^T dO, dK = dS^T Q : reduction over the 128 query rows (8 k-steps of 16 rows)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          umma_f16(tDV, smem_desc_mn_sw128(sP + k * 2048, 16384), smem_desc_mn_sw128(sDO + k * 2048, 16384), id_mnmn, k != 0);
+          umma_f16(tDK, smem_desc_mn_sw128(sDS + k * 2048, 16384), smem_desc_mn_sw128(sQ + k * 2048, 16384), id_mnmn, k != 0);
+        }
+        umma_commit(smem_free);
+        umma_commit(out_full);
+        ph ^= 1;
+      }
+    }
+  } else {
+    const int row = warp * 32 + lane, r = row >> 6, i = row & 63;
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    uint32_t ph = 0;
+    for (int pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
+      const int it = 2 * pair + r;
+      const bool valid = it < P.n_items && i < P.L;
+      const int itc = it < P.n_items ? it : P.n_items - 1;
+      const int win = itc / P.nh, h = itc - win * P.nh;
+      const long long tok = (long long)win * P.L + i;
+      const float l2 = valid ? P.lse[tok * P.nh + h] * 1.4426950408889634f : 0.f;
+      mbar_wait(sdp_full, ph);
+      fence_after_sync();
+      uint32_t sv[64], dv[64];
+      {
+        uint32_t (&a0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sv[0]);
+        uint32_t (&a1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sv[32]);
+        uint32_t (&b0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&dv[0]);
+        uint32_t (&b1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&dv[32]);
+        tmem_ld32(tS + lane_sel + r * 64, a0);
+        tmem_ld32(tS + lane_sel + r * 64 + 32, a1);
+        tmem_ld32(tDP + lane_sel + r * 64, b0);
+        tmem_ld32(tDP + lane_sel + r * 64 + 32, b1);
+        tmem_ld_wait();
+      }
+      float delta = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        const float p = (j < P.L && valid) ? exp2f(__uint_as_float(sv[j]) * P.scale_log2 - l2) : 0.f;
+        sv[j] = __float_as_uint(p);
+        delta += p * __uint_as_float(dv[j]);
+      }
+      unsigned char* prow = sP + r * (128 * 128);
+      unsigned char* drow = sDS + r * (128 * 128);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t pw[4], dw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = c * 8 + 2 * e;
+          const float p0 = __uint_as_float(sv[j]), p1 = __uint_as_float(sv[j + 1]);
+          pw[e] = pack2f(p0, p1, P.fmt);
+          dw[e] = pack2f(p0 * (__uint_as_float(dv[j]) - delta) * P.scale, p1 * (__uint_as_float(dv[j + 1]) - delta) * P.scale, P.fmt);
+        }
+        *reinterpret_cast<uint4*>(prow + sw128_offset(row, c)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+        *reinterpret_cast<uint4*>(drow + sw128_offset(row, c)) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+      }
+      fence_proxy_async();
+      fence_before_sync();
+      mbar_arrive(pds_full);
+      // ---- outputs: this thread owns token `tok` as query (dQ) and as key/value (dK, dV) ----
+      mbar_wait(out_full, ph);
+      fence_after_sync();
+      uint16_t* grow = reinterpret_cast<uint16_t*>(P.gqkv) + tok * 3 * P.C + h * HD;
+#pragma unroll
+      for (int which = 0; which < 3; ++which) {
+        const uint32_t tsrc = which == 0 ? tDQ : (which == 1 ? tDK : tDV);
+#pragma unroll
+        for (int ch = 0; ch < HD / 32; ++ch) {
+          uint32_t ov[32];
+          tmem_ld32(tsrc + lane_sel + ch * 32, ov);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4 st;
+              st.x = pack2f(__uint_as_float(ov[8 * c + 0]), __uint_as_float(ov[8 * c + 1]), P.fmt);
+              st.y = pack2f(__uint_as_float(ov[8 * c + 2]), __uint_as_float(ov[8 * c + 3]), P.fmt);
+              st.z = pack2f(__uint_as_float(ov[8 * c + 4]), __uint_as_float(ov[8 * c + 5]), P.fmt);
+              st.w = pack2f(__uint_as_float(ov[8 * c + 6]), __uint_as_float(ov[8 * c + 7]), P.fmt);
+              *reinterpret_cast<uint4*>(grow + which * P.C + ch * 32 + c * 8) = st;
+            }
+          }
+        }
+      }
+      fence_before_sync();
+      mbar_arrive(tmem_free);
+      ph ^= 1;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 5) { fence_after_sync(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+template <int HD>
+int launch_bwd(const void* qkv, const float* lse, const void* go, void* gqkv, long long T, int L, int C, int nh, int dtype,
+               cudaStream_t st) {
+  using Cfg = BCfg<HD>;
+  const CUtensorMap* m = tensor_map_2d(qkv, (uint64_t)T, (uint64_t)3 * C, (uint64_t)3 * C, 64, 64, dtype);
+  const CUtensorMap* mg = tensor_map_2d(go, (uint64_t)T, (uint64_t)C, (uint64_t)C, 64, 64, dtype);
+  if (!m || !mg) return B200_ERR_LAUNCH;
+  AttnBwdParams P;
+  P.gqkv = gqkv; P.lse = lse; P.T = T; P.L = L; P.C = C; P.nh = nh;
+  P.n_items = (int)(T / L) * nh;
+  P.n_pairs = (P.n_items + 1) / 2;
+  P.fmt = dtype == B200_BF16 ? 1 : 0;
+  P.scale = 1.f / sqrtf((float)HD);
+  P.scale_log2 = 1.4426950408889634f * P.scale;
+  auto k = swin_attn_bwd_tc_kernel<HD>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::TOTAL);
+  int grid = P.n_pairs < sm_count() ? P.n_pairs : sm_count();
+  k<<<grid, kThreads, Cfg::TOTAL, st>>>(*m, *mg, P);
+  return check_launch("swin_attn_bwd_tc");
+}
+
+}  // namespace
+}  // namespace tc
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" B200_API int b200_swin_attn_tc_supported(int64_t tokens, int32_t L, int32_t C, int32_t nh, int32_t dtype) {
+  if (dtype != B200_BF16 && dtype != B200_F16) return 0;
+  if (tokens <= 0 || L <= 0 || L > 64 || tokens % L != 0 || nh <= 0 || C % nh != 0) return 0;
+  const int hd = C / nh;
+  return (hd == 64 || hd == 128) && (3 * C) % 8 == 0;
+}
+
+extern "C" B200_API int b200_swin_attn_fwd_tc(const void* qkv, void* o, float* lse, int64_t tokens, int32_t L, int32_t C,
+                                              int32_t nh, int32_t dtype, void* stream) {
+  B200_REQUIRE(b200_swin_attn_tc_supported(tokens, L, C, nh, dtype), B200_ERR_UNSUPPORTED,
+               "swin_attn_fwd_tc: unsupported problem (16-bit dtype, L<=64, head dim 64 or 128)");
+  B200_REQUIRE(qkv && o, B200_ERR_SHAPE, "swin_attn_fwd_tc: null pointer");
+  B200_REQUIRE((((uintptr_t)qkv | (uintptr_t)o) & 15) == 0, B200_ERR_ALIGN, "swin_attn_fwd_tc: 16-byte alignment required");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C / nh == 64) return tc::launch_fwd<64>(qkv, o, lse, tokens, L, C, nh, dtype, st);
+  return tc::launch_fwd<128>(qkv, o, lse, tokens, L, C, nh, dtype, st);
+}
+
+extern "C" B200_API int b200_swin_attn_bwd_tc(const void* qkv, const float* lse, const void* go, void* gqkv, int64_t tokens,
+                                              int32_t L, int32_t C, int32_t nh, int32_t dtype, void* stream) {
+  B200_REQUIRE(b200_swin_attn_tc_supported(tokens, L, C, nh, dtype), B200_ERR_UNSUPPORTED,
+               "swin_attn_bwd_tc: unsupported problem (16-bit dtype, L<=64, head dim 64 or 128)");
+  B200_REQUIRE(qkv && lse && go && gqkv, B200_ERR_SHAPE, "swin_attn_bwd_tc: null pointer");
+  B200_REQUIRE((((uintptr_t)qkv | (uintptr_t)go | (uintptr_t)gqkv) & 15) == 0, B200_ERR_ALIGN, "swin_attn_bwd_tc: 16-byte alignment required");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C / nh == 64) return tc::launch_bwd<64>(qkv, lse, go, gqkv, tokens, L, C, nh, dtype, st);
+  return tc::launch_bwd<128>(qkv, lse, go, gqkv, tokens, L, C, nh, dtype, st);
+}

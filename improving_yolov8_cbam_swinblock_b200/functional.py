@@ -19,6 +19,9 @@ _lib.register("b200_swin_num_tokens", C.c_longlong, [_I32] * 4)
 _lib.register("b200_swin_ln1_partition", C.c_int, [_VP] * 6 + [_I32] * 6 + [_VP])
 _lib.register("b200_swin_attn_fwd", C.c_int, [_VP] * 3 + [_I64] + [_I32] * 4 + [_VP])
 _lib.register("b200_swin_attn_bwd", C.c_int, [_VP] * 5 + [_I64] + [_I32] * 4 + [_VP])
+_lib.register("b200_swin_attn_tc_supported", C.c_int, [_I64] + [_I32] * 4)
+_lib.register("b200_swin_attn_fwd_tc", C.c_int, [_VP] * 3 + [_I64] + [_I32] * 4 + [_VP])
+_lib.register("b200_swin_attn_bwd_tc", C.c_int, [_VP] * 4 + [_I64] + [_I32] * 4 + [_VP])
 _lib.register("b200_swin_res_ln2", C.c_int, [_VP] * 8 + [_I64] + [_I32] * 2 + [_VP])
 _lib.register("b200_swin_gelu", C.c_int, [_VP] * 3 + [_I64] + [_I32] * 2 + [_VP])
 _lib.register("b200_swin_res_reverse", C.c_int, [_VP] * 3 + [_I32] * 6 + [_VP])
@@ -178,6 +181,32 @@ def _colsum(a: torch.Tensor) -> torch.Tensor:
     return out
 
 
+USE_TC_ATTENTION = True  # tests flip this to compare against the SIMT attention kernels
+
+
+def attn_forward(qkv, T, Lw, Cc, nh):
+    """windowed MHSA on packed qkv[T,3C] -> (o[T,C], lse[T,nh])."""
+    dev, code = qkv.device, dtype_code(qkv.dtype)
+    o = torch.empty((T, Cc), dtype=qkv.dtype, device=dev)
+    lse = torch.empty((T, nh), dtype=torch.float32, device=dev)
+    if USE_TC_ATTENTION and lib().b200_swin_attn_tc_supported(T, Lw, Cc, nh, code):
+        call("b200_swin_attn_fwd_tc", ptr(qkv), ptr(o), ptr(lse), T, Lw, Cc, nh, code, stream_ptr(dev))
+    else:
+        call("b200_swin_attn_fwd", ptr(qkv), ptr(o), ptr(lse), T, Lw, Cc, nh, code, stream_ptr(dev))
+    return o, lse
+
+
+def attn_backward(qkv, o, lse, go, T, Lw, Cc, nh):
+    """gradient of attn_forward w.r.t. the packed qkv rows."""
+    dev, code = qkv.device, dtype_code(qkv.dtype)
+    gqkv = torch.empty_like(qkv)
+    if USE_TC_ATTENTION and lib().b200_swin_attn_tc_supported(T, Lw, Cc, nh, code):
+        call("b200_swin_attn_bwd_tc", ptr(qkv), ptr(lse), ptr(go), ptr(gqkv), T, Lw, Cc, nh, code, stream_ptr(dev))
+    else:
+        call("b200_swin_attn_bwd", ptr(qkv), ptr(o), ptr(lse), ptr(go), ptr(gqkv), T, Lw, Cc, nh, code, stream_ptr(dev))
+    return gqkv
+
+
 class SwinBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, *args):
@@ -210,9 +239,7 @@ class SwinBlockFn(torch.autograd.Function):
             call("b200_swin_ln1_partition", ptr(x), ptr(g1f), ptr(b1f), ptr(n1), ptr(mean1), ptr(rstd1), B, Cc, H, W, ws,
                                             code, st)
             qkv = gemm.linear(n1, win, bin_)
-            o = torch.empty((T, Cc), dtype=dt, device=dev)
-            lse = torch.empty((T, num_heads), **f32)
-            call("b200_swin_attn_fwd", ptr(qkv), ptr(o), ptr(lse), T, Lw, Cc, num_heads, code, st)
+            o, lse = attn_forward(qkv, T, Lw, Cc, num_heads)
             y1 = gemm.linear_res(o, wo, bo, n1)  # post-norm residual fused into the out_proj epilogue
             u = torch.empty_like(n1)
             mean2, rstd2 = torch.empty(T, **f32), torch.empty(T, **f32)
@@ -263,8 +290,7 @@ class SwinBlockFn(torch.autograd.Function):
             gwo = gemm.matmul_tn(gy1, o)          # [C, C]
             gbo = _colsum(gy1)
             go = gemm.matmul_nn(gy1, wo)          # [T, C]
-            gqkv = torch.empty_like(qkv)
-            call("b200_swin_attn_bwd", ptr(qkv), ptr(o), ptr(lse), ptr(go), ptr(gqkv), T, Lw, Cc, nh, code, st)
+            gqkv = attn_backward(qkv, o, lse, go.contiguous(), T, Lw, Cc, nh)
             del go
             gwin = gemm.matmul_tn(gqkv, n1)       # [3C, C]
             gbin = _colsum(gqkv)

@@ -154,6 +154,14 @@ B200_API int b200_gemm_splitk(const void* A, const void* B, float* D, void* work
                               int32_t M, int32_t N, int64_t K, int32_t a_mn, int32_t b_mn, int32_t dtype,
                               void* stream);
 
+/* Window attention on tcgen05 tensor cores (bf16 | f16, L <= 64, head dim 64 or 128): same contract as
+ * b200_swin_attn_fwd / _bwd.  b200_swin_attn_tc_supported() says whether the problem qualifies. */
+B200_API int b200_swin_attn_tc_supported(int64_t tokens, int32_t L, int32_t C, int32_t nh, int32_t dtype);
+B200_API int b200_swin_attn_fwd_tc(const void* qkv, void* o, float* lse, int64_t tokens, int32_t L, int32_t C,
+                                   int32_t nh, int32_t dtype, void* stream);
+B200_API int b200_swin_attn_bwd_tc(const void* qkv, const float* lse, const void* go, void* gqkv, int64_t tokens,
+                                   int32_t L, int32_t C, int32_t nh, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

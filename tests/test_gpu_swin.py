@@ -77,3 +77,43 @@ def test_padded_tokens_feed_norm1_bias():
     y1 = mod(x)
     assert not torch.allclose(y0, y1)
     assert y0.shape == (1, 32, 9, 9)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("nwin,L,C,nh", [(2, 49, 128, 2), (7, 49, 128, 2), (300, 49, 128, 2), (5, 64, 128, 2), (3, 49, 256, 2),
+                                         (9, 49, 256, 4), (4, 25, 64, 1), (2304, 49, 128, 2)])
+def test_tc_attention_forward_matches_simt(dtype, nwin, L, C, nh):
+    """tcgen05 attention vs the fp32-accurate SIMT kernel (itself checked against the oracle) on the same qkv."""
+    from improving_yolov8_cbam_swinblock_b200 import functional as Fb
+
+    torch.manual_seed(nwin + L + C)
+    T = nwin * L
+    qkv = torch.randn(T, 3 * C, device="cuda").to(dtype)
+    Fb.USE_TC_ATTENTION = False
+    o_ref, lse_ref = Fb.attn_forward(qkv.float(), T, L, C, nh)  # fp32 SIMT path on the same (rounded) inputs
+    Fb.USE_TC_ATTENTION = True
+    o, lse = Fb.attn_forward(qkv, T, L, C, nh)
+    assert rel_err(o, o_ref) < (1e-2 if dtype == torch.bfloat16 else 2e-3), rel_err(o, o_ref)
+    torch.testing.assert_close(lse, lse_ref, rtol=1e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("nwin,L,C,nh", [(2, 49, 128, 2), (7, 49, 128, 2), (301, 49, 128, 2), (5, 64, 128, 2), (3, 49, 256, 2),
+                                         (9, 49, 256, 4), (5, 25, 64, 1), (2304, 49, 128, 2)])
+def test_tc_attention_backward_matches_simt(dtype, nwin, L, C, nh):
+    from improving_yolov8_cbam_swinblock_b200 import functional as Fb
+
+    torch.manual_seed(nwin + L + C + 1)
+    T = nwin * L
+    qkv = torch.randn(T, 3 * C, device="cuda").to(dtype)
+    go = torch.randn(T, C, device="cuda").to(dtype)
+    Fb.USE_TC_ATTENTION = False
+    o_ref, lse_ref = Fb.attn_forward(qkv.float(), T, L, C, nh)
+    g_ref = Fb.attn_backward(qkv.float(), o_ref, lse_ref, go.float(), T, L, C, nh)
+    Fb.USE_TC_ATTENTION = True
+    o, lse = Fb.attn_forward(qkv, T, L, C, nh)
+    g = Fb.attn_backward(qkv, o, lse, go, T, L, C, nh)
+    tol = 1.5e-2 if dtype == torch.bfloat16 else 3e-3
+    for name, sl in (("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))):
+        e = rel_err(g[:, sl], g_ref[:, sl])
+        assert e < tol, (name, e)
