@@ -208,14 +208,27 @@ def main():
         tot = {k: n * ms for k, (n, ms) in ktimes.items()}
         top = max(tot, key=tot.get)
         n, ms = ktimes[top]
-        w = work.get(top)
-        if w:
+        w = work.get(top) or sweep.gemm_work(top, peaks)
+        if not w:
+            roof = {"kernel": top, "avg_ms": ms, "calls": n, "note": "no algorithmic-work entry",
+                    "kernels_ms_per_step": {k: v / args.steps for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
+        else:
             achieved = w["amount"] / (ms * 1e-3) / (1e9 if w["bound"] == "hbm" else 1e12)
             peak = peaks["hbm_gbs"] if w["bound"] == "hbm" else peaks["bf16_tflops_sustained"]
             roof = {"kernel": top, "bound": w["bound"], "achieved": achieved, "peak": peak, "unit": "GB/s" if w["bound"] == "hbm" else "TFLOP/s",
                     "frac": achieved / peak, "traffic": None, "avg_ms": ms, "calls": n, "peak_source": peaks["source"] + " (sustained)",
                     "algorithmic": w["note"],
                     "share_of_step": tot[top] / ms_dev, "kernels_ms_per_step": {k: v / args.steps for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
+    if roof is not None:  # every hand-written kernel of the step: mean ms per launch + fraction of its roofline
+        allk = {}
+        for k, (n_, ms_) in ktimes.items():
+            w_ = work.get(k) or sweep.gemm_work(k, peaks)
+            ent = {"calls_per_step": n_ / args.steps, "avg_ms": round(ms_, 5)}
+            if w_:
+                pk = peaks["hbm_gbs"] if w_["bound"] == "hbm" else peaks["bf16_tflops_sustained"]
+                ent.update(bound=w_["bound"], frac=round(w_["amount"] / (ms_ * 1e-3) / (1e9 if w_["bound"] == "hbm" else 1e12) / pk, 4))
+            allk[k] = ent
+        roof["all_kernels"] = allk
     line = {"metric": "train_images_per_sec", "value": imgs / (ms_dev * 1e-3), "unit": "img/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),

@@ -95,8 +95,9 @@ def timing_summary():
     return out
 
 
-def call(name: str, *args):
-    """Invoke one C-ABI entry point; raise RuntimeError(b200_last_error()) on a non-zero return code."""
+def call(name: str, *args, tag: str | None = None):
+    """Invoke one C-ABI entry point; raise RuntimeError(b200_last_error()) on a non-zero return code.
+    ``tag`` refines the timing key (e.g. the GEMM shape) when kernel timing is enabled."""
     fn = getattr(lib(), name)
     if _timers is None:
         rc = fn(*args)
@@ -107,7 +108,7 @@ def call(name: str, *args):
         s.record()
         rc = fn(*args)
         e.record()
-        _timers.setdefault(name, []).append((s, e))
+        _timers.setdefault(tag or name, []).append((s, e))
     check(rc, name)
 
 

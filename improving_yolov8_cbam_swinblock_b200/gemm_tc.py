@@ -33,7 +33,7 @@ def gemm_nt(a, w, bias=None, epi=EPI_BIAS, residual=None, want_preact=False):
     if residual is not None:
         residual = residual.contiguous()
     call("b200_gemm_nt", ptr(a), ptr(wt), ptr(bf), ptr(d), ptr(d2), ptr(residual), M, N, K, dtype_code(a.dtype), epi,
-         stream_ptr(a.device))
+         stream_ptr(a.device), tag=f"b200_gemm_nt[{M}x{N}x{K},epi{epi}]")
     return (d, d2) if d2 is not None else d
 
 
@@ -56,5 +56,5 @@ def gemm_splitk(a, b, a_mn: bool, b_mn: bool):
     ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
     d = torch.empty((M, N), dtype=torch.float32, device=a.device)
     call("b200_gemm_splitk", ptr(a), ptr(b), ptr(d), ptr(ws), nbytes, M, N, K, int(a_mn), int(b_mn), dtype_code(a.dtype),
-         stream_ptr(a.device))
+         stream_ptr(a.device), tag=f"b200_gemm_splitk[{M}x{N}x{K}]")
     return d

@@ -30,6 +30,8 @@ def algorithmic_work(scale: str, B: int, s: int = 2, ws: int = 7):
         "b200_swin_attn_fwd": hbm(4 * T * c4 * s, "standalone attention is HBM-bound: read qkv (3*T*C*s) + write o (T*C*s); "
                                   f"FLOPs {tok_real * 4 * ws * ws * c4 / 1e9:.2f} G on un-padded tokens"),
         "b200_swin_attn_bwd": hbm(8 * T * c4 * s, "read qkv, o, g_o (5*T*C*s) + write g_qkv (3*T*C*s)"),
+        "b200_swin_attn_fwd_tc": hbm(4 * T * c4 * s, "stand-alone attention is HBM-bound (22 FLOP/B): read qkv + write o = 4*T*C*s"),
+        "b200_swin_attn_bwd_tc": hbm(7 * T * c4 * s, "read qkv, g_o (4*T*C*s) + write g_qkv (3*T*C*s)"),
         "b200_swin_res_ln2": hbm(4 * T * c4 * s, "read n1, a; write y1, u"),
         "b200_swin_gelu": hbm(2 * T * 4 * c4 * s, "read a, write h (backward: +1 read)"),
         "b200_swin_res_reverse": hbm((2 * T + tok_real) * c4 * s, "read y1, m; write out (real tokens)"),
@@ -37,6 +39,25 @@ def algorithmic_work(scale: str, B: int, s: int = 2, ws: int = 7):
         "b200_swin_ln_bwd": hbm(4 * T * c4 * s, "read g_out, x, g_res; write g_in"),
         "b200_colsum": hbm(T * c4 * s, "read the activation-gradient matrix once (C..4C columns)"),
     }
+
+
+def gemm_work(tag: str, peaks: dict, s: int = 2):
+    """Roofline entry for a tagged GEMM launch: b200_gemm_nt[MxNxK,epiE] / b200_gemm_splitk[MxNxK]."""
+    import re
+
+    m = re.match(r"b200_gemm_(nt|splitk)\[(\d+)x(\d+)x(\d+)(?:,epi(\d))?\]", tag)
+    if not m:
+        return None
+    kind, M, N, K, epi = m.group(1), int(m.group(2)), int(m.group(3)), int(m.group(4)), int(m.group(5) or 0)
+    flops = 2.0 * M * N * K
+    if kind == "nt":
+        byts = (M * K + N * K + M * N * (2 if epi in (1, 2, 3) else 1)) * s
+    else:
+        byts = (M * K + N * K) * s + M * N * 4
+    t_hbm, t_tc = byts / (peaks["hbm_gbs"] * 1e9), flops / (peaks["bf16_tflops_sustained"] * 1e12)
+    if t_hbm >= t_tc:
+        return {"bound": "hbm", "amount": byts, "note": f"operands + outputs once ({byts / 1e6:.1f} MB; {flops / 1e9:.1f} GFLOP)"}
+    return {"bound": "tensor", "amount": flops, "note": f"2*M*N*K ({flops / 1e9:.1f} GFLOP; {byts / 1e6:.1f} MB)"}
 
 
 def _time(fn, iters, flush):
