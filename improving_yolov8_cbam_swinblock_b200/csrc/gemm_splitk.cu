@@ -14,10 +14,13 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 64, UK = 16, STAGES = 5;
 constexpr int kThreads = 192;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
-constexpr int SMEM_TOTAL = STAGES * (A_BYTES + B_BYTES) + 256 + 1024;
+constexpr int ONES_BYTES = 16 * 128;  // [16 n-rows][64 k] K-major tile of 1.0 (swizzle-invariant)
+constexpr int SMEM_TOTAL = STAGES * (A_BYTES + B_BYTES) + ONES_BYTES + 256 + 1024;
+constexpr int TMEM_COLS = 256;        // BN accumulator columns + 16 for the fused column sums
 
 struct SplitParams {
-  float* part;  // [splits][M][N]
+  float* part;     // [splits][M][N]
+  float* part_cs;  // [splits][M] partial sums over k of A(m,k) (bias gradients), or null
   int M, N, K, m_tiles, n_tiles, kb_total, kb_per_split, fmt;
 };
 
@@ -28,7 +31,8 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = smem;
   unsigned char* sB = smem + STAGES * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
+  unsigned char* sOnes = smem + STAGES * (A_BYTES + B_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sOnes + ONES_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
@@ -44,7 +48,13 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     mbar_init(tfull, 1);
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, BN); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  const bool do_cs = P.part_cs != nullptr && n0 == 0;
+  if (do_cs && warp >= 2) {
+    const uint32_t one2 = P.fmt == 1 ? 0x3f803f80u : 0x3c003c00u;
+    for (int i = threadIdx.x - 64; i < ONES_BYTES / 4; i += 128) reinterpret_cast<uint32_t*>(sOnes)[i] = one2;
+    fence_proxy_async();
+  }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -76,6 +86,8 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 1) {
     if (elect_one()) {
       const uint32_t idesc = idesc_f16(BM, BN, P.fmt, A_MN, B_MN);
+      const uint32_t idesc_cs = idesc_f16(BM, 16, P.fmt, A_MN, 0);
+      const uint64_t d_ones = smem_desc_k_sw128(sOnes);
       int stage = 0; uint32_t phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full[stage], phase);
@@ -87,6 +99,7 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint64_t da = A_MN ? smem_desc_mn_sw128(a + k * UK * 128, BK * 128) : smem_desc_k_sw128(a + k * UK * 2);
           const uint64_t db = B_MN ? smem_desc_mn_sw128(b + k * UK * 128, BK * 128) : smem_desc_k_sw128(b + k * UK * 2);
           umma_f16(tmem_base, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          if (do_cs) umma_f16(tmem_base + BN, da, d_ones, idesc_cs, (kb > kb0 || k > 0) ? 1u : 0u);  // sum_k A(m,k) * 1
         }
         umma_commit(&empty[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -100,6 +113,16 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       fence_after_sync();
     }
     const int gm = m0 + row;
+    if (do_cs) {  // warp-uniform: tcgen05.ld is .sync.aligned and must be executed by all 32 lanes
+      float cs = 0.f;
+      if (kb1 > kb0) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + BN, v);
+        tmem_ld_wait();
+        cs = __uint_as_float(v[0]);
+      }
+      if (gm < P.M) P.part_cs[(size_t)split * P.M + gm] = cs;
+    }
     float* dst = P.part + ((size_t)split * P.M + gm) * P.N + n0;
 #pragma unroll 1
     for (int ch = 0; ch < BN / 32; ++ch) {
@@ -126,7 +149,7 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, BN); }
+  if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 __global__ void fold_splits_kernel(const float* __restrict__ part, float* __restrict__ out, int splits, size_t n) {
@@ -154,12 +177,12 @@ using namespace b200::tc;
 extern "C" B200_API size_t b200_gemm_splitk_workspace_bytes(int32_t M, int32_t N, int64_t K) {
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int kb_total = (int)((K + BK - 1) / BK);
-  return (size_t)choose_splits(tiles, kb_total) * M * N * sizeof(float);
+  return (size_t)choose_splits(tiles, kb_total) * ((size_t)M * N + M) * sizeof(float);
 }
 
-extern "C" B200_API int b200_gemm_splitk(const void* A, const void* B, float* D, void* workspace, size_t workspace_bytes,
-                                         int32_t M, int32_t N, int64_t K, int32_t a_mn, int32_t b_mn, int32_t dtype,
-                                         void* stream) {
+extern "C" B200_API int b200_gemm_splitk(const void* A, const void* B, float* D, float* colsum, void* workspace,
+                                         size_t workspace_bytes, int32_t M, int32_t N, int64_t K, int32_t a_mn, int32_t b_mn,
+                                         int32_t dtype, void* stream) {
   B200_REQUIRE(dtype == B200_BF16 || dtype == B200_F16, B200_ERR_DTYPE, "gemm_splitk: 16-bit dtypes only");
   B200_REQUIRE(A && B && D && M > 0 && N > 0 && K > 0, B200_ERR_SHAPE, "gemm_splitk: bad arguments");
   B200_REQUIRE(M % 8 == 0 && N % 8 == 0 && K % 8 == 0, B200_ERR_ALIGN, "gemm_splitk: M, N, K must be multiples of 8");
@@ -173,12 +196,14 @@ extern "C" B200_API int b200_gemm_splitk(const void* A, const void* B, float* D,
   if (!mA || !mB) return B200_ERR_LAUNCH;
   SplitParams P;
   P.part = (float*)workspace; P.M = M; P.N = N; P.K = (int)K;
+  P.part_cs = nullptr;
   P.m_tiles = (M + BM - 1) / BM; P.n_tiles = (N + BN - 1) / BN;
   P.kb_total = (int)((K + BK - 1) / BK);
   const int tiles = P.m_tiles * P.n_tiles;
   const int splits = choose_splits(tiles, P.kb_total);
   P.kb_per_split = (P.kb_total + splits - 1) / splits;
   P.fmt = dtype == B200_BF16 ? 1 : 0;
+  if (colsum) P.part_cs = (float*)workspace + (size_t)splits * M * N;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(tiles, splits);
 #define LAUNCH_SK(AM, BMN)                                                                        \
@@ -192,5 +217,10 @@ extern "C" B200_API int b200_gemm_splitk(const void* A, const void* B, float* D,
   if (int rc = check_launch("gemm_splitk")) return rc;
   const size_t n = (size_t)M * N;
   fold_splits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float*)workspace, D, splits, n);
-  return check_launch("gemm_splitk_fold");
+  if (int rc = check_launch("gemm_splitk_fold")) return rc;
+  if (colsum) {
+    fold_splits_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(P.part_cs, colsum, splits, (size_t)M);
+    return check_launch("gemm_splitk_fold_colsum");
+  }
+  return B200_OK;
 }

@@ -1,13 +1,13 @@
 // tcgen05 GEMM for the SwinBlock's dense contractions:  D[M,N] = epi(A[M,K] * B[N,K]^T + bias[N]).
 // Replaces F.linear at swin_block.py:51 (in_proj / out_proj inside nn.MultiheadAttention) and :53 (mlp.0, mlp.2).
 //
-// Persistent, warp-specialised kernel (one CTA per SM, 192 threads):
+// Persistent, warp-specialised kernel (one CTA per SM, 320 threads):
 //   warp 0   : TMA producer  -- A and B tiles [128|BLOCK_N rows][64 K-elements] with 128-byte swizzle into a
 //              STAGES-deep shared-memory ring (mbarrier full/empty pairs)
 //   warp 1   : TMEM allocator + MMA issuer -- one elected lane issues tcgen05.mma (cta_group::1, kind::f16,
 //              UMMA 128 x BLOCK_N x 16), accumulators in TMEM, double-buffered (2 x BLOCK_N columns) so the
 //              epilogue of tile i overlaps the MMAs of tile i+1; tcgen05.commit releases smem slots / signals tiles
-//   warps 2-5: epilogue -- tcgen05.ld (lane = row) -> bias / GELU(erf) / residual in registers -> bf16 -> swizzled
+//   warps 2-9: epilogue -- tcgen05.ld (lane = row) -> bias / GELU(erf) / residual in registers -> bf16 -> swizzled
 //              staging tile in shared memory -> TMA store (rows beyond M are clipped by the tensor map)
 // Both operands are K-major (activations [tokens, K]; nn.Linear weights [N, K]) so no transposes are needed.
 #include <mutex>
@@ -85,7 +85,8 @@ const CUtensorMap* tensor_map_2d(const void* base, uint64_t rows, uint64_t cols,
 namespace {
 
 constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;        // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
+constexpr int kEpiThreads = 256;
 enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RES = 2, EPI_MUL_GELUGRAD = 3 };
 
 struct GemmParams {
@@ -107,11 +108,29 @@ template <int BLOCK_N, int STAGES> struct Smem {
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;  // + alignment slack
 };
 
-__device__ __forceinline__ float gelu_erf(float a) { return 0.5f * a * (1.f + erff(a * 0.70710678118654752440f)); }
+// erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 with 5 terms) on MUFU.RCP + MUFU.EX2 (approximate forms: no
+// slow-path subroutine calls) instead of the ~35-instruction erff; far below the rounding step of the 16-bit
+// outputs this epilogue produces.
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// returns Phi(a) (standard normal cdf) and writes e = exp(-a^2/2)
+__device__ __forceinline__ float normal_cdf(float a, float* e_out) {
+  const float ax = fabsf(a) * 0.70710678118654752440f;
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = ex2_approx(-0.72134752044448170368f * a * a);  // exp(-a^2/2) = exp(-(a/sqrt2)^2)
+  *e_out = e;
+  const float erf_abs = fmaf(-p * t, e, 1.f);
+  return 0.5f * (1.f + copysignf(erf_abs, a));
+}
+__device__ __forceinline__ float gelu_erf(float a) { float e; return a * normal_cdf(a, &e); }
 __device__ __forceinline__ float gelu_erf_grad(float a) {
-  const float cdf = 0.5f * (1.f + erff(a * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * a * a);
-  return cdf + a * pdf;
+  float e;
+  const float cdf = normal_cdf(a, &e);
+  return fmaf(a * 0.39894228040143267794f, e, cdf);
 }
 __device__ __forceinline__ uint32_t pack2(float lo, float hi, int fmt) {
   if (fmt == 1) {
@@ -147,7 +166,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmD);
     if (P.has_d2) prefetch_tmap(&tmD2);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiThreads); }
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N); tmem_relinquish(); }
@@ -196,10 +215,12 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;              // TMEM lane quadrant this warp may access
-    const int row = q * 32 + lane;       // row within the tile
-    const int et = threadIdx.x - 64;     // 0..127
+    // ===================== epilogue (warps 2..9) =====================
+    const int q = warp & 3;                      // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;            // which half of the tile's columns this warp converts
+    const int row = q * 32 + lane;               // row within the tile
+    const int et = threadIdx.x - 64;             // 0..255
+    constexpr int HALF_N = BLOCK_N / 2;          // columns per thread
     int acc = 0; uint32_t aphase = 0;
     unsigned char* sD = smem + S::OFF_D;
     unsigned char* sD2 = smem + S::OFF_D2;
@@ -207,32 +228,38 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m0 = (tile / P.n_tiles) * BLOCK_M, n0 = (tile % P.n_tiles) * BLOCK_N;
       mbar_wait(&tfull[acc], aphase);
       fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + half * HALF_N;
       const long long grow = (long long)m0 + row;
-#pragma unroll 1
-      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+#pragma unroll
+      for (int ch = 0; ch < HALF_N / 32; ++ch) {
+        const int col0 = half * HALF_N + ch * 32;  // first column (within the tile) of this 32-wide chunk
         uint32_t v[32];
         tmem_ld32(taddr + ch * 32, v);
-        tmem_ld_wait();
-        uint32_t o[16], o2[16];
         uint32_t rres[16];
         if (EPI == EPI_BIAS_RES || EPI == EPI_MUL_GELUGRAD) {
-          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(P.R) + grow * P.N + n0 + ch * 32);
+          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(P.R) + grow * P.N + n0 + col0);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 t = make_uint4(0, 0, 0, 0);
-            if (grow < P.M && n0 + ch * 32 + i * 8 < P.N) t = rp[i];
+            if (grow < P.M && n0 + col0 + i * 8 < P.N) t = rp[i];
             rres[4 * i] = t.x; rres[4 * i + 1] = t.y; rres[4 * i + 2] = t.z; rres[4 * i + 3] = t.w;
           }
         }
+        float bv[32];
+        if (P.bias) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n0 + col0 + 4 * i < P.N) b4 = __ldg(reinterpret_cast<const float4*>(P.bias + n0 + col0) + i);
+            bv[4 * i] = b4.x; bv[4 * i + 1] = b4.y; bv[4 * i + 2] = b4.z; bv[4 * i + 3] = b4.w;
+          }
+        }
+        tmem_ld_wait();
+        uint32_t o[16], o2[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int c = n0 + ch * 32 + 2 * i;
           float a0 = __uint_as_float(v[2 * i]), a1 = __uint_as_float(v[2 * i + 1]);
-          if (P.bias) {
-            if (c < P.N) a0 += __ldg(P.bias + c);
-            if (c + 1 < P.N) a1 += __ldg(P.bias + c + 1);
-          }
+          if (P.bias) { a0 += bv[2 * i]; a1 += bv[2 * i + 1]; }
           if (EPI == EPI_BIAS_GELU) {
             o2[i] = pack2(a0, a1, P.fmt);
             // GELU sees the stored (rounded) pre-activation so forward and backward agree bit-for-bit on `a`
@@ -243,8 +270,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (EPI == EPI_MUL_GELUGRAD) { a0 *= gelu_erf_grad(unpack_lo(rres[i], P.fmt)); a1 *= gelu_erf_grad(unpack_hi(rres[i], P.fmt)); }
           o[i] = pack2(a0, a1, P.fmt);
         }
-        // 32 columns = 4 x 16-byte chunks of the [128 rows][64 cols] swizzled box number (ch*32)/64
-        const int box = (ch * 32) / 64, c16 = ((ch * 32) % 64) / 8;
+        // 32 columns = 4 x 16-byte chunks of the [128 rows][64 cols] swizzled box number col0/64
+        const int box = col0 / 64, c16 = (col0 % 64) / 8;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint32_t off = box * (BLOCK_M * 128) + sw128_offset(row, c16 + i);
@@ -259,7 +286,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++acc == 2) { acc = 0; aphase ^= 1; }
       // staging complete -> one thread stores the boxes
       fence_proxy_async();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kEpiThreads);
       if (et == 0) {
 #pragma unroll
         for (int b = 0; b < BLOCK_N / 64; ++b) {
@@ -271,7 +298,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         bulk_commit();
         bulk_wait_read_all();  // staging may be rewritten once the TMA engine has read it
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kEpiThreads);
     }
     if (et == 0) bulk_wait_all();
   }

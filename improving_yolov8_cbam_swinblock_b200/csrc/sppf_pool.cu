@@ -26,6 +26,11 @@ template <> struct Word<float> {
   __device__ static __forceinline__ uint32_t bits(uint32_t w, int) { return w; }
   __device__ static __forceinline__ float bits_to_f(uint32_t b) { return __uint_as_float(b); }
   __device__ static __forceinline__ uint32_t f_to_bits(float f) { return __float_as_uint(f); }
+  // exact-selection max, valid when the tile holds no NaN and no -0.0 (checked at load time)
+  __device__ static __forceinline__ uint32_t vmax(uint32_t a, uint32_t b) {
+    return __float_as_uint(fmaxf(__uint_as_float(a), __uint_as_float(b)));
+  }
+  __device__ static __forceinline__ bool special(uint32_t w) { return (w & 0x7fffffffu) > 0x7f800000u || w == 0x80000000u; }
 };
 template <> struct Word<__nv_bfloat16> {
   static constexpr int EPL = 2;
@@ -38,6 +43,14 @@ template <> struct Word<__nv_bfloat16> {
   __device__ static __forceinline__ uint32_t f_to_bits(float f) {
     return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f));
   }
+  __device__ static __forceinline__ uint32_t vmax(uint32_t a, uint32_t b) {
+    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  __device__ static __forceinline__ bool special(uint32_t w) {
+    const uint32_t lo = w & 0xffffu, hi = w >> 16;
+    return (lo & 0x7fffu) > 0x7f80u || (hi & 0x7fffu) > 0x7f80u || lo == 0x8000u || hi == 0x8000u;
+  }
 };
 template <> struct Word<__half> {
   static constexpr int EPL = 2;
@@ -49,6 +62,14 @@ template <> struct Word<__half> {
   }
   __device__ static __forceinline__ uint32_t f_to_bits(float f) {
     return (uint32_t)__half_as_ushort(__float2half_rn(f));
+  }
+  __device__ static __forceinline__ uint32_t vmax(uint32_t a, uint32_t b) {
+    const __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  __device__ static __forceinline__ bool special(uint32_t w) {
+    const uint32_t lo = w & 0xffffu, hi = w >> 16;
+    return (lo & 0x7fffu) > 0x7c00u || (hi & 0x7fffu) > 0x7c00u || lo == 0x8000u || hi == 0x8000u;
   }
 };
 
@@ -101,6 +122,239 @@ __device__ __forceinline__ void pass1d(const uint32_t* __restrict__ src, int sst
   }
 }
 
+// Values-only 1-D max pass with packed hardware max (HMNMX2 / FMNMX).  Exact selection as long as the tile has no
+// NaN and no -0.0 (the two cases where a hardware max differs from ATen's `v > best || isnan(v)` scan).
+// Optionally also stores every output word to global memory (the concat slice) with stride gstride words.
+template <typename T, int K>
+__device__ __forceinline__ void pass1d_fast(const uint32_t* __restrict__ src, int sstride, uint32_t* __restrict__ dst,
+                                            int dstride, int len, uint32_t* __restrict__ gdst, size_t gstride) {
+  using WD = Word<T>;
+  constexpr int R = K / 2;
+  uint32_t win[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const int p = j - R;
+    win[j] = (p >= 0 && p < len) ? src[p * sstride] : WD::neg_inf();
+  }
+  for (int i = 0; i < len; ++i) {
+    uint32_t o = win[0];
+#pragma unroll
+    for (int j = 1; j < K; ++j) o = WD::vmax(o, win[j]);
+    dst[i * dstride] = o;
+    if (gdst) gdst[(size_t)i * gstride] = o;
+#pragma unroll
+    for (int j = 0; j < K - 1; ++j) win[j] = win[j + 1];
+    const int p = i + 1 + R;
+    win[K - 1] = (p < len) ? src[p * sstride] : WD::neg_inf();
+  }
+}
+
+// Winner-tracking 1-D pass for 16-bit types via packed integer keys: key = sortable16(value) << 16 | (0xFFFF - pos),
+// so one unsigned max picks the larger value and, among equal values, the smaller position (first occurrence).
+// Same validity condition as pass1d_fast (no NaN / -0.0 in the tile); out-of-range slots carry key 0 (never win).
+template <typename T, int K>
+__device__ __forceinline__ void pass1d_key(const uint32_t* __restrict__ src, int sstride, uint32_t* __restrict__ dst,
+                                           int dstride, int len, uint8_t* __restrict__ win_out, int wstride) {
+  static_assert(Word<T>::EPL == 2, "key path is for 16-bit types");
+  constexpr int R = K / 2;
+  auto mk = [](uint32_t b, int pos) -> uint32_t {
+    const uint32_t sk = b ^ ((b & 0x8000u) ? 0xffffu : 0x8000u);
+    return (sk << 16) | (0xffffu - (uint32_t)pos);
+  };
+  uint32_t k0[K], k1[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const int p = j - R;
+    if (p >= 0 && p < len) {
+      const uint32_t w = src[p * sstride];
+      k0[j] = mk(w & 0xffffu, p);
+      k1[j] = mk(w >> 16, p);
+    } else { k0[j] = 0u; k1[j] = 0u; }
+  }
+  for (int i = 0; i < len; ++i) {
+    uint32_t b0 = k0[0], b1 = k1[0];
+#pragma unroll
+    for (int j = 1; j < K; ++j) { b0 = max(b0, k0[j]); b1 = max(b1, k1[j]); }
+    const uint32_t s0 = b0 >> 16, s1 = b1 >> 16;
+    const uint32_t v0 = s0 ^ ((s0 & 0x8000u) ? 0x8000u : 0xffffu), v1 = s1 ^ ((s1 & 0x8000u) ? 0x8000u : 0xffffu);
+    dst[i * dstride] = v0 | (v1 << 16);
+    const int p0 = 0xffff - (int)(b0 & 0xffffu), p1 = 0xffff - (int)(b1 & 0xffffu);
+    win_out[i * wstride] = (uint8_t)((p0 - (i - R)) | ((p1 - (i - R)) << 4));
+#pragma unroll
+    for (int j = 0; j < K - 1; ++j) { k0[j] = k0[j + 1]; k1[j] = k1[j + 1]; }
+    const int p = i + 1 + R;
+    if (p < len) {
+      const uint32_t w = src[p * sstride];
+      k0[K - 1] = mk(w & 0xffffu, p);
+      k1[K - 1] = mk(w >> 16, p);
+    } else { k0[K - 1] = 0u; k1[K - 1] = 0u; }
+  }
+}
+template <typename T, int K, bool IS16 = (Word<T>::EPL == 2)> struct KeyPass {
+  __device__ static __forceinline__ void run(const uint32_t* src, int ss, uint32_t* dst, int ds, int len, uint8_t* w, int ws) {
+    pass1d_key<T, K>(src, ss, dst, ds, len, w, ws);
+  }
+};
+template <typename T, int K> struct KeyPass<T, K, false> {
+  __device__ static __forceinline__ void run(const uint32_t* src, int ss, uint32_t* dst, int ds, int len, uint8_t* w, int ws) {
+    pass1d<T, K>(src, ss, dst, ds, len, w, ws);
+  }
+};
+
+// ---- cooperative, vectorised tile movers ------------------------------------------------------------------
+// pixel index -> (y, x) without an integer division (exact for p < 2^22)
+__device__ __forceinline__ void pix_yx(int p, int W, float invW, int* y, int* x) {
+  int yy = __float2int_rz(((float)p + 0.5f) * invW);
+  *y = yy; *x = p - yy * W;
+}
+// global words [H*W pixels][LP words] (pixel stride gstride words) -> smem [H][Wp][LP]; returns OR of Word::special
+// (and mirrors the words to gcopy when non-null: concat slice 0).  16-byte path when everything is aligned.
+template <typename T, int LP>
+__device__ __forceinline__ int tile_load_words(uint32_t* __restrict__ sm, const uint32_t* __restrict__ gsrc, size_t gstride,
+                                               uint32_t* __restrict__ gcopy, size_t cstride, int H, int W, int Wp,
+                                               int valid_words, uint32_t fill) {
+  using WD = Word<T>;
+  int special = 0;
+  const float invW = 1.f / (float)W;
+  const bool vec = (LP % 4 == 0) && valid_words == LP && (gstride % 4 == 0) && ((reinterpret_cast<uintptr_t>(gsrc) & 15) == 0) &&
+                   (!gcopy || ((cstride % 4 == 0) && (reinterpret_cast<uintptr_t>(gcopy) & 15) == 0));
+  if (vec) {
+    constexpr int VPP = LP / 4 > 0 ? LP / 4 : 1;
+    const int items = H * W * VPP;
+    for (int it0 = threadIdx.x; it0 < items; it0 += 4 * blockDim.x) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int it = it0 + u * blockDim.x;
+        if (it < items) {
+          const int p = it / VPP, q = it - p * VPP;
+          v[u] = ldg_stream16(gsrc + (size_t)p * gstride + q * 4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int it = it0 + u * blockDim.x;
+        if (it < items) {
+          const int p = it / VPP, q = it - p * VPP;
+          int y, x;
+          pix_yx(p, W, invW, &y, &x);
+          *reinterpret_cast<uint4*>(sm + (size_t)(y * Wp + x) * LP + q * 4) = v[u];
+          if (gcopy) *reinterpret_cast<uint4*>(gcopy + (size_t)p * cstride + q * 4) = v[u];
+          special |= (WD::special(v[u].x) || WD::special(v[u].y) || WD::special(v[u].z) || WD::special(v[u].w)) ? 1 : 0;
+        }
+      }
+    }
+  } else {
+    const int items = H * W * LP;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int p = it / LP, l = it - p * LP;
+      int y, x;
+      pix_yx(p, W, invW, &y, &x);
+      uint32_t w = fill;
+      if (l < valid_words) {
+        w = gsrc[(size_t)p * gstride + l];
+        if (gcopy) gcopy[(size_t)p * cstride + l] = w;
+        special |= WD::special(w) ? 1 : 0;
+      }
+      sm[(size_t)(y * Wp + x) * LP + l] = w;
+    }
+  }
+  return special;
+}
+// global words -> smem f32 [H][Wp][LP][EPL] (set or accumulate)
+template <typename T, int LP, bool ACC>
+__device__ __forceinline__ void tile_load_f32(float* __restrict__ sm, const uint32_t* __restrict__ gsrc, size_t gstride, int H,
+                                              int W, int Wp, int valid_words) {
+  using WD = Word<T>;
+  constexpr int EPL = WD::EPL;
+  const float invW = 1.f / (float)W;
+  const bool vec = (LP % 4 == 0) && valid_words == LP && (gstride % 4 == 0) && ((reinterpret_cast<uintptr_t>(gsrc) & 15) == 0);
+  if (vec) {
+    constexpr int VPP = LP / 4 > 0 ? LP / 4 : 1;
+    const int items = H * W * VPP;
+    for (int it0 = threadIdx.x; it0 < items; it0 += 4 * blockDim.x) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int it = it0 + u * blockDim.x;
+        if (it < items) {
+          const int p = it / VPP, q = it - p * VPP;
+          v[u] = ldg_stream16(gsrc + (size_t)p * gstride + q * 4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int it = it0 + u * blockDim.x;
+        if (it < items) {
+          const int p = it / VPP, q = it - p * VPP;
+          int y, x;
+          pix_yx(p, W, invW, &y, &x);
+          float* d = sm + ((size_t)(y * Wp + x) * LP + q * 4) * EPL;
+          const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) {
+              const float f = WD::bits_to_f(WD::bits(w[k], e));
+              d[k * EPL + e] = ACC ? d[k * EPL + e] + f : f;
+            }
+        }
+      }
+    }
+  } else {
+    const int items = H * W * LP;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int p = it / LP, l = it - p * LP;
+      int y, x;
+      pix_yx(p, W, invW, &y, &x);
+      const uint32_t w = l < valid_words ? gsrc[(size_t)p * gstride + l] : 0u;
+      float* d = sm + ((size_t)(y * Wp + x) * LP + l) * EPL;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const float f = l < valid_words ? WD::bits_to_f(WD::bits(w, e)) : 0.f;
+        d[e] = ACC ? d[e] + f : f;
+      }
+    }
+  }
+}
+// smem f32 [H][Wp][LP][EPL] -> global words
+template <typename T, int LP>
+__device__ __forceinline__ void tile_store_f32(const float* __restrict__ sm, uint32_t* __restrict__ gdst, size_t gstride, int H,
+                                               int W, int Wp, int valid_words) {
+  using WD = Word<T>;
+  constexpr int EPL = WD::EPL;
+  const float invW = 1.f / (float)W;
+  const bool vec = (LP % 4 == 0) && valid_words == LP && (gstride % 4 == 0) && ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0);
+  const int items = vec ? H * W * (LP / 4) : H * W * LP;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    if (vec) {
+      constexpr int VPP = LP / 4 > 0 ? LP / 4 : 1;
+      const int p = it / VPP, q = it - p * VPP;
+      int y, x;
+      pix_yx(p, W, invW, &y, &x);
+      const float* sp = sm + ((size_t)(y * Wp + x) * LP + q * 4) * EPL;
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        w[k] = 0;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) w[k] = WD::put(w[k], e, WD::f_to_bits(sp[k * EPL + e]));
+      }
+      stg_stream16(gdst + (size_t)p * gstride + q * 4, make_uint4(w[0], w[1], w[2], w[3]));
+    } else {
+      const int p = it / LP, l = it - p * LP;
+      if (l >= valid_words) continue;
+      int y, x;
+      pix_yx(p, W, invW, &y, &x);
+      const float* sp = sm + ((size_t)(y * Wp + x) * LP + l) * EPL;
+      uint32_t w = 0;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) w = WD::put(w, e, WD::f_to_bits(sp[e]));
+      gdst[(size_t)p * gstride + l] = w;
+    }
+  }
+}
+
 struct PoolGeom {
   int B, C, H, W, Wp;  // Wp: padded pitch in pixels (odd -> consecutive rows land 16 banks apart for LP=16)
 };
@@ -132,16 +386,28 @@ __global__ void __launch_bounds__(512) sppf_pool_fwd_kernel(const T* __restrict_
   const size_t out_img = (size_t)b * g.H * g.W * 4 * g.C;
 
   // stage the tile (word loads: LP*4 contiguous bytes per pixel) and emit concat slice 0
-  for (int p = sid; p < g.H * g.W; p += nstrips) {
-    const int y = p / g.W, x = p - y * g.W;
-    uint32_t w = WD::neg_inf();
-    if (cvalid) {
-      w = *reinterpret_cast<const uint32_t*>(y0 + in_img + (size_t)p * g.C + c);
-      *reinterpret_cast<uint32_t*>(cat + out_img + (size_t)p * 4 * g.C + c) = w;
+  const int valid_words = min(LP, (g.C - c0) / EPL);  // words of this chunk that exist (C bound)
+  int special = tile_load_words<T, LP>(cur, reinterpret_cast<const uint32_t*>(y0 + in_img + c0), (size_t)g.C / EPL,
+                                       reinterpret_cast<uint32_t*>(cat + out_img + c0), (size_t)4 * g.C / EPL, g.H, g.W, g.Wp,
+                                       valid_words, WD::neg_inf());
+  special = __syncthreads_or(special);
+
+  if (!WITH_IDX && !special) {
+    // fast path: packed hardware max, column pass stores straight into the concat slice
+    uint32_t* gout = reinterpret_cast<uint32_t*>(cat + out_img + c);
+    const size_t wstride = (size_t)4 * g.C * sizeof(T) / 4;   // words between vertically adjacent pixels' slices / W
+    for (int st = 0; st < 3; ++st) {
+      for (int y = sid; y < g.H; y += nstrips)
+        pass1d_fast<T, K>(cur + (y * g.Wp) * LP + lane, LP, tmp + (y * g.Wp) * LP + lane, LP, g.W, nullptr, 0);
+      __syncthreads();
+      for (int x = sid; x < g.W; x += nstrips) {
+        uint32_t* gd = cvalid ? gout + ((size_t)x * 4 * g.C + (size_t)(st + 1) * g.C) * sizeof(T) / 4 : nullptr;
+        pass1d_fast<T, K>(tmp + x * LP + lane, g.Wp * LP, cur + x * LP + lane, g.Wp * LP, g.H, gd, wstride * g.W);
+      }
+      __syncthreads();
     }
-    cur[(y * g.Wp + x) * LP + lane] = w;
+    return;
   }
-  __syncthreads();
 
   for (int st = 0; st < 3; ++st) {
     // row pass: cur -> tmp
@@ -188,18 +454,36 @@ __global__ void __launch_bounds__(512) sppf_pool_fwd_kernel(const T* __restrict_
 // backward
 // ---------------------------------------------------------------------------------------------------------
 // scatter one strip of gradients through a 1-D max pass: dst[i + off(i) - R] += src[i]; strips are thread-private.
+// Winners move monotonically along a strip, so contributions to one target are consecutive: accumulate them in a
+// register and touch shared memory once per target (summation order = strip order: deterministic).
 template <int K, int EPL>
 __device__ __forceinline__ void scatter1d(const float* __restrict__ src, int sstride, float* __restrict__ dst,
                                           int dstride, int len, const uint8_t* __restrict__ win, int wstride) {
   constexpr int R = K / 2;
+  int cur[EPL];
+  float acc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) { cur[e] = -1; acc[e] = 0.f; }
   for (int i = 0; i < len; ++i) {
     const uint32_t ws = win[i * wstride];
+    float v[EPL];
+    if (EPL == 2) {
+      const float2 t2 = *reinterpret_cast<const float2*>(src + (size_t)i * sstride);
+      v[0] = t2.x; v[EPL - 1] = t2.y;
+    } else v[0] = src[(size_t)i * sstride];
 #pragma unroll
     for (int e = 0; e < EPL; ++e) {
       const int t = i - R + (int)((ws >> (4 * e)) & 15u);
-      dst[t * dstride + e] += src[i * sstride + e];
+      if (t == cur[e]) acc[e] += v[e];
+      else {
+        if (cur[e] >= 0) dst[(size_t)cur[e] * dstride + e] += acc[e];
+        cur[e] = t; acc[e] = v[e];
+      }
     }
   }
+#pragma unroll
+  for (int e = 0; e < EPL; ++e)
+    if (cur[e] >= 0) dst[(size_t)cur[e] * dstride + e] += acc[e];
 }
 
 template <typename T, int K, int LP>
@@ -229,37 +513,34 @@ __global__ void __launch_bounds__(512) sppf_pool_bwd_kernel(const T* __restrict_
   const size_t in_img = (size_t)b * g.H * g.W * g.C;
   const size_t cat_img = (size_t)b * g.H * g.W * 4 * g.C;
 
-  for (int p = sid; p < g.H * g.W; p += nstrips) {
-    const int y = p / g.W, x = p - y * g.W;
-    uint32_t w = WD::neg_inf();
-    if (cvalid) w = *reinterpret_cast<const uint32_t*>(y0 + in_img + (size_t)p * g.C + c);
-    cur[(y * g.Wp + x) * LP + lane] = w;
-  }
-  __syncthreads();
-  // recompute winners of the three stages
+  const int valid_words = min(LP, (g.C - c0) / EPL);
+  int special = tile_load_words<T, LP>(cur, reinterpret_cast<const uint32_t*>(y0 + in_img + c0), (size_t)g.C / EPL, nullptr, 0,
+                                       g.H, g.W, g.Wp, valid_words, WD::neg_inf());
+  special = __syncthreads_or(special);
+  // recompute winners of the three stages (packed-key path unless the tile holds NaN / -0.0 or is f32)
   for (int st = 0; st < 3; ++st) {
-    for (int y = sid; y < g.H; y += nstrips)
-      pass1d<T, K>(cur + (y * g.Wp) * LP + lane, LP, tmp + (y * g.Wp) * LP + lane, LP, g.W,
-                   wrow + ((size_t)st * plane + y * g.Wp) * LP + lane, LP);
+    for (int y = sid; y < g.H; y += nstrips) {
+      const uint32_t* sp = cur + (y * g.Wp) * LP + lane;
+      uint32_t* dp = tmp + (y * g.Wp) * LP + lane;
+      uint8_t* wp = wrow + ((size_t)st * plane + y * g.Wp) * LP + lane;
+      if (special) pass1d<T, K>(sp, LP, dp, LP, g.W, wp, LP);
+      else KeyPass<T, K>::run(sp, LP, dp, LP, g.W, wp, LP);
+    }
     __syncthreads();
-    for (int x = sid; x < g.W; x += nstrips)
-      pass1d<T, K>(tmp + x * LP + lane, g.Wp * LP, cur + x * LP + lane, g.Wp * LP, g.H,
-                   wcol + ((size_t)st * plane + x) * LP + lane, g.Wp * LP);
+    for (int x = sid; x < g.W; x += nstrips) {
+      const uint32_t* sp = tmp + x * LP + lane;
+      uint32_t* dp = cur + x * LP + lane;
+      uint8_t* wp = wcol + ((size_t)st * plane + x) * LP + lane;
+      if (special) pass1d<T, K>(sp, g.Wp * LP, dp, g.Wp * LP, g.H, wp, g.Wp * LP);
+      else KeyPass<T, K>::run(sp, g.Wp * LP, dp, g.Wp * LP, g.H, wp, g.Wp * LP);
+    }
     __syncthreads();
   }
   // G3 = g3
   auto load_slice = [&](float* dstbuf, int slice, bool accumulate) {
-    for (int p = sid; p < g.H * g.W; p += nstrips) {
-      const int y = p / g.W, x = p - y * g.W;
-      uint32_t w = 0;
-      if (cvalid) w = *reinterpret_cast<const uint32_t*>(gcat + cat_img + (size_t)p * 4 * g.C + (size_t)slice * g.C + c);
-      float* d = dstbuf + ((size_t)(y * g.Wp + x) * LP + lane) * EPL;
-#pragma unroll
-      for (int e = 0; e < EPL; ++e) {
-        const float v = cvalid ? WD::bits_to_f(WD::bits(w, e)) : 0.f;
-        d[e] = accumulate ? d[e] + v : v;
-      }
-    }
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(gcat + cat_img + (size_t)slice * g.C + c0);
+    if (accumulate) tile_load_f32<T, LP, true>(dstbuf, src, (size_t)4 * g.C / EPL, g.H, g.W, g.Wp, valid_words);
+    else tile_load_f32<T, LP, false>(dstbuf, src, (size_t)4 * g.C / EPL, g.H, g.W, g.Wp, valid_words);
   };
   auto zero = [&](float* buf) {
     for (int i = threadIdx.x; i < plane * LP * EPL; i += blockDim.x) buf[i] = 0.f;
@@ -285,15 +566,7 @@ __global__ void __launch_bounds__(512) sppf_pool_bwd_kernel(const T* __restrict_
     load_slice(ga, st, true);
     __syncthreads();
   }
-  for (int p = sid; p < g.H * g.W; p += nstrips) {
-    if (!cvalid) continue;
-    const int y = p / g.W, x = p - y * g.W;
-    const float* s = ga + ((size_t)(y * g.Wp + x) * LP + lane) * EPL;
-    uint32_t w = 0;
-#pragma unroll
-    for (int e = 0; e < EPL; ++e) w = WD::put(w, e, WD::f_to_bits(s[e]));
-    *reinterpret_cast<uint32_t*>(gy0 + in_img + (size_t)p * g.C + c) = w;
-  }
+  tile_store_f32<T, LP>(ga, reinterpret_cast<uint32_t*>(gy0 + in_img + c0), (size_t)g.C / EPL, g.H, g.W, g.Wp, valid_words);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -114,7 +114,7 @@ class CBAMFn(torch.autograd.Function):
             call("b200_cbam_fwd", ptr(x), ptr(w1f), ptr(w2f), ptr(wsf), ptr(out), ptr(ca), ptr(sa), B, Cc, H, W, r,
                                       ksa, dtype_code(x.dtype), mode, stream_ptr(dev))
         ctx.mode, ctx.dims = mode, (B, Cc, H, W, r, ksa)
-        ctx.wshapes = tuple(None if w is None else (w.shape, w.dtype) for w in (w1, w2, wsa))
+        ctx.wshapes = tuple(None if w is None else (w.shape, w.dtype, w.stride()) for w in (w1, w2, wsa))
         ctx.save_for_backward(x, w1f, w2f, wsf, ca, sa)
         if mode == 0:
             return out
@@ -145,7 +145,8 @@ class CBAMFn(torch.autograd.Function):
                                   stream_ptr(dev))
         outs = []
         for gw, meta in zip((gw1, gw2, gws), ctx.wshapes):
-            outs.append(None if (gw is None or meta is None) else gw.view(meta[0]).to(meta[1]))
+            # same memory order as the parameter (size-1 dims may carry channels_last strides): DDP bucket views match
+            outs.append(None if (gw is None or meta is None) else gw.to(meta[1]).as_strided(meta[0], meta[2]))
         return gx, outs[0], outs[1], outs[2], None
 
 
@@ -270,11 +271,9 @@ class SwinBlockFn(torch.autograd.Function):
             gy2 = torch.empty((T, Cc), dtype=dt, device=dev)
             call("b200_swin_partition", ptr(gout), ptr(gy2), B, Cc, H, W, ws, code, st)
             # MLP
-            gw2 = gemm.matmul_tn(gy2, h)          # [C, 4C] = gy2^T h
-            gb2 = _colsum(gy2)
+            gw2, gb2 = gemm.matmul_tn(gy2, h)     # [C, 4C] = gy2^T h,  [C] = sum_t gy2
             ga = gemm.matmul_nn_gelu_bwd(gy2, w2, hpre)  # [T, 4C] = (gy2 W2) * gelu'(hpre)
-            gw1 = gemm.matmul_tn(ga, u)           # [4C, C]
-            gb1 = _colsum(ga)
+            gw1, gb1 = gemm.matmul_tn(ga, u)      # [4C, C], [4C]
             gu = gemm.matmul_nn(ga, w1)           # [T, C]
             del ga
             # LN2 + residual
@@ -287,13 +286,11 @@ class SwinBlockFn(torch.autograd.Function):
                                      ptr(gbt2), ptr(wsb), nbytes, B, Cc, H, W, ws, code, 0, st)
             del gu, gy2
             # attention
-            gwo = gemm.matmul_tn(gy1, o)          # [C, C]
-            gbo = _colsum(gy1)
+            gwo, gbo = gemm.matmul_tn(gy1, o)     # [C, C], [C]
             go = gemm.matmul_nn(gy1, wo)          # [T, C]
             gqkv = attn_backward(qkv, o, lse, go.contiguous(), T, Lw, Cc, nh)
             del go
-            gwin = gemm.matmul_tn(gqkv, n1)       # [3C, C]
-            gbin = _colsum(gqkv)
+            gwin, gbin = gemm.matmul_tn(gqkv, n1)  # [3C, C], [3C]
             gn1 = gemm.matmul_nn(gqkv, win, add=gy1)  # [T, C] = gy1 + gqkv Win
             del gqkv, gy1
             # LN1 + un-partition

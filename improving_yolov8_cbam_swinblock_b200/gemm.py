@@ -71,10 +71,12 @@ def matmul_nn_gelu_bwd(a, w, preact):
 
 
 def matmul_tn(a, b):
-    """a[T,K]^T @ b[T,N] -> f32 [K,N]: weight gradients dW = dY^T X (reduction over the T tokens).
+    """a[T,K]^T @ b[T,N] -> (f32 [K,N], f32 [K]): weight gradient dW = dY^T X and bias gradient sum_t dY[t,:].
 
-    tcgen05 split-K kernel with both operands MN-major (no transposes, f32 partials folded in a fixed order); library
-    GEMM otherwise."""
+    tcgen05 split-K kernel with both operands MN-major (no transposes, f32 partials folded in a fixed order; the bias
+    gradient is one extra MMA against ones in the same pass); library GEMM + column-sum kernel otherwise."""
     if USE_TCGEN05 and tc.splitk_supported(a, b):
-        return tc.gemm_splitk(a, b, True, True)
-    return (a.t() @ b).to(torch.float32)
+        return tc.gemm_splitk(a, b, True, True, want_colsum=True)
+    from .functional import _colsum
+
+    return (a.t() @ b).to(torch.float32), _colsum(a)

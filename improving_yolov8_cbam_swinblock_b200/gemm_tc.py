@@ -12,7 +12,7 @@ _lib.register("b200_gemm_nt_supported", C.c_int, [C.c_int64, C.c_int32, C.c_int3
 _lib.register("b200_gemm_nt", C.c_int, [C.c_void_p] * 6 + [C.c_int64] + [C.c_int32] * 4 + [C.c_void_p])
 
 _lib.register("b200_gemm_splitk_workspace_bytes", C.c_size_t, [C.c_int32, C.c_int32, C.c_int64])
-_lib.register("b200_gemm_splitk", C.c_int, [C.c_void_p] * 4 + [C.c_size_t, C.c_int32, C.c_int32, C.c_int64] + [C.c_int32] * 3 + [C.c_void_p])
+_lib.register("b200_gemm_splitk", C.c_int, [C.c_void_p] * 5 + [C.c_size_t, C.c_int32, C.c_int32, C.c_int64] + [C.c_int32] * 3 + [C.c_void_p])
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_MUL_GELUGRAD = 0, 1, 2, 3
 
@@ -46,8 +46,9 @@ def splitk_supported(a: torch.Tensor, b: torch.Tensor) -> bool:
             and b.is_contiguous() and all(d % 8 == 0 for d in (*a.shape, *b.shape)))
 
 
-def gemm_splitk(a, b, a_mn: bool, b_mn: bool):
-    """f32 D[M,N] = sum_k A(m,k) B(n,k); a is [K,M] if a_mn else [M,K]; b is [K,N] if b_mn else [N,K]."""
+def gemm_splitk(a, b, a_mn: bool, b_mn: bool, want_colsum: bool = False):
+    """f32 D[M,N] = sum_k A(m,k) B(n,k); a is [K,M] if a_mn else [M,K]; b is [K,N] if b_mn else [N,K].
+    want_colsum: also return f32 [M] = sum_k A(m,k) (computed by one extra MMA against ones in the same pass)."""
     K, M = a.shape if a_mn else a.shape[::-1]
     Kb, N = b.shape if b_mn else b.shape[::-1]
     assert K == Kb, (a.shape, b.shape)
@@ -55,6 +56,7 @@ def gemm_splitk(a, b, a_mn: bool, b_mn: bool):
     nbytes = L.b200_gemm_splitk_workspace_bytes(M, N, K)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
     d = torch.empty((M, N), dtype=torch.float32, device=a.device)
-    call("b200_gemm_splitk", ptr(a), ptr(b), ptr(d), ptr(ws), nbytes, M, N, K, int(a_mn), int(b_mn), dtype_code(a.dtype),
-         stream_ptr(a.device), tag=f"b200_gemm_splitk[{M}x{N}x{K}]")
-    return d
+    cs = torch.empty(M, dtype=torch.float32, device=a.device) if want_colsum else None
+    call("b200_gemm_splitk", ptr(a), ptr(b), ptr(d), ptr(cs), ptr(ws), nbytes, M, N, K, int(a_mn), int(b_mn),
+         dtype_code(a.dtype), stream_ptr(a.device), tag=f"b200_gemm_splitk[{M}x{N}x{K}]")
+    return (d, cs) if want_colsum else d

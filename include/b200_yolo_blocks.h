@@ -148,11 +148,12 @@ B200_API int b200_gemm_nt(const void* A, const void* B, const float* bias, void*
 /* Split-K tcgen05 GEMM with selectable operand majorness, f32 output (weight gradients dW = dY^T X, autograd of
  * F.linear at swin_block.py:51,53, are the a_mn=b_mn=1 form with K = tokens):
  *   D[M,N] (f32) = sum_k A(m,k) * B(n,k);  a_mn=0: A is [M,K] row-major, a_mn=1: A is [K,M] row-major; same for B/N.
- * Deterministic: per-split f32 partial tiles in `workspace` folded in a fixed order. */
+ * colsum (nullable, f32 [M]) = sum_k A(m,k): the bias gradient sum_t dY[t,:] falls out of the same pass as one extra
+ * N=16 MMA against a tile of ones.  Deterministic: per-split f32 partials in `workspace` folded in a fixed order. */
 B200_API size_t b200_gemm_splitk_workspace_bytes(int32_t M, int32_t N, int64_t K);
-B200_API int b200_gemm_splitk(const void* A, const void* B, float* D, void* workspace, size_t workspace_bytes,
-                              int32_t M, int32_t N, int64_t K, int32_t a_mn, int32_t b_mn, int32_t dtype,
-                              void* stream);
+B200_API int b200_gemm_splitk(const void* A, const void* B, float* D, float* colsum, void* workspace,
+                              size_t workspace_bytes, int32_t M, int32_t N, int64_t K, int32_t a_mn, int32_t b_mn,
+                              int32_t dtype, void* stream);
 
 /* Window attention on tcgen05 tensor cores (bf16 | f16, L <= 64, head dim 64 or 128): same contract as
  * b200_swin_attn_fwd / _bwd.  b200_swin_attn_tc_supported() says whether the problem qualifies. */

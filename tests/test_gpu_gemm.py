@@ -56,6 +56,7 @@ def test_gemm_splitk_all_majors(a_mn, b_mn, M, N, K):
     Bm = torch.randn(N, K, device="cuda").to(dt)
     a = A.t().contiguous() if a_mn else A
     b = Bm.t().contiguous() if b_mn else Bm
-    got = gemm_tc.gemm_splitk(a, b, a_mn, b_mn)
+    got, cs = gemm_tc.gemm_splitk(a, b, a_mn, b_mn, want_colsum=True)
     want = A.double() @ Bm.double().t()
     assert rel_err(got, want) < 1e-5, rel_err(got, want)
+    assert rel_err(cs, A.double().sum(1)) < 1e-5, rel_err(cs, A.double().sum(1))  # fused bias-gradient column sums
