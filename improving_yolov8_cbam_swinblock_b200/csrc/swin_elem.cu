@@ -12,19 +12,38 @@
 namespace b200 {
 namespace {
 
-struct WinGeom {
-  int B, C, H, W, ws, nWh, nWw, L;
-  long long T;  // padded token count
+// division by a run-time constant as multiply-high + shifts (Granlund-Montgomery / libdivide "branchfree" form),
+// exact for every 32-bit numerator: the token -> pixel map needs four divisions per token and the plain 64-bit
+// '/' and '%' cost more instructions than the LayerNorm itself.
+struct FastDiv {
+  uint32_t d, m, s1, s2;
+  __host__ void init(uint32_t div) {
+    d = div;
+    uint32_t l = 0;
+    while ((1ull << l) < div) ++l;
+    m = (uint32_t)((((1ull << 32) * ((1ull << l) - div)) / div) + 1);
+    s1 = l < 1 ? l : 1;
+    s2 = l > 0 ? l - 1 : 0;
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const {
+    const uint32_t t = __umulhi(m, n);
+    return (t + ((n - t) >> s1)) >> s2;
+  }
 };
 
-__device__ __forceinline__ long long token_pixel(const WinGeom& g, long long t, bool* real) {
-  const int l = (int)(t % g.L);
-  long long w = t / g.L;
-  const int ww = (int)(w % g.nWw);
-  w /= g.nWw;
-  const int wh = (int)(w % g.nWh);
-  const int b = (int)(w / g.nWh);
-  const int y = wh * g.ws + l / g.ws, x = ww * g.ws + l % g.ws;
+struct WinGeom {
+  int B, C, H, W, ws, nWh, nWw, L;
+  long long T;  // padded token count (< 2^31, checked on the host)
+  FastDiv dL, dWw, dWh, dws;
+};
+
+__device__ __forceinline__ long long token_pixel(const WinGeom& g, long long t64, bool* real) {
+  const uint32_t t = (uint32_t)t64;
+  const uint32_t win = g.dL.div(t), l = t - win * g.L;
+  const uint32_t q = g.dWw.div(win), ww = win - q * g.nWw;
+  const uint32_t b = g.dWh.div(q), wh = q - b * g.nWh;
+  const uint32_t r = g.dws.div(l), c = l - r * g.ws;
+  const int y = (int)(wh * g.ws + r), x = (int)(ww * g.ws + c);
   *real = (y < g.H) && (x < g.W);
   return ((long long)b * g.H + y) * g.W + x;
 }
@@ -52,134 +71,196 @@ __device__ __forceinline__ void row_stats(const float (&v)[MAXPL], int npl, int 
 
 constexpr int kMaxPL = 32;  // C <= 1024 (generic kernels)
 
-// ---- vectorised row access: lane owns VEC contiguous channels at c = (lane + 32*i)*VEC, i < ITERS ---------------
-template <typename T, int VEC> struct alignas(sizeof(T) * VEC) PackT { T e[VEC]; };
+// ---- sub-warp-per-token vector kernels ---------------------------------------------------------------------
+// A token's C channels are spread over LPT lanes (a power of two <= 32), each lane holding NV 16-byte vectors at
+// channel offsets (l + LPT*v)*VE, l = lane % LPT, VE = 16/sizeof(T).  A warp therefore normalises 32/LPT tokens at
+// once: the per-token costs that dominated the warp-per-token version (token->pixel index arithmetic, two chains of
+// shuffle reductions) are paid once per 32/LPT tokens and the shuffle trees are log2(LPT) deep.
+template <typename T> struct VecOf { static constexpr int VE = 16 / (int)sizeof(T); };
+template <typename T> struct alignas(16) Pack16 { T e[16 / sizeof(T)]; };
 
-template <typename T, int VEC, int ITERS>
-__device__ __forceinline__ void load_row(const T* __restrict__ row, int lane, float (&v)[VEC * ITERS]) {
+template <typename T, int LPT, int NV>
+__device__ __forceinline__ void load_row(const T* __restrict__ row, int l, float (&v)[NV * VecOf<T>::VE]) {
+  constexpr int VE = VecOf<T>::VE;
 #pragma unroll
-  for (int i = 0; i < ITERS; ++i) {
-    const PackT<T, VEC> p = *reinterpret_cast<const PackT<T, VEC>*>(row + (lane + 32 * i) * VEC);
+  for (int i = 0; i < NV; ++i) {
+    const Pack16<T> p = *reinterpret_cast<const Pack16<T>*>(row + (l + LPT * i) * VE);
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) v[i * VEC + e] = DT<T>::to_f(p.e[e]);
+    for (int e = 0; e < VE; ++e) v[i * VE + e] = DT<T>::to_f(p.e[e]);
   }
 }
-template <typename T, int VEC, int ITERS>
-__device__ __forceinline__ void store_row(T* __restrict__ row, int lane, const float (&v)[VEC * ITERS]) {
+template <typename T, int LPT, int NV>
+__device__ __forceinline__ void store_row(T* __restrict__ row, int l, const float (&v)[NV * VecOf<T>::VE]) {
+  constexpr int VE = VecOf<T>::VE;
 #pragma unroll
-  for (int i = 0; i < ITERS; ++i) {
-    PackT<T, VEC> p;
+  for (int i = 0; i < NV; ++i) {
+    Pack16<T> p;
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) p.e[e] = DT<T>::from_f(v[i * VEC + e]);
-    *reinterpret_cast<PackT<T, VEC>*>(row + (lane + 32 * i) * VEC) = p;
+    for (int e = 0; e < VE; ++e) p.e[e] = DT<T>::from_f(v[i * VE + e]);
+    *reinterpret_cast<Pack16<T>*>(row + (l + LPT * i) * VE) = p;
   }
 }
-template <int VEC, int ITERS>
-__device__ __forceinline__ void load_vecf(const float* __restrict__ p, int lane, float (&v)[VEC * ITERS]) {
+template <int VE, int LPT, int NV>
+__device__ __forceinline__ void load_vecf(const float* __restrict__ p, int l, float (&v)[NV * VE]) {
 #pragma unroll
-  for (int i = 0; i < ITERS; ++i)
+  for (int i = 0; i < NV; ++i)
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) v[i * VEC + e] = p[(lane + 32 * i) * VEC + e];
+    for (int e = 0; e < VE; ++e) v[i * VE + e] = p[(l + LPT * i) * VE + e];
 }
-template <int N>
+template <int LPT> __device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPT / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int N, int LPT>
 __device__ __forceinline__ void stats_full(const float (&v)[N], int C, float* mean, float* rstd) {
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < N; ++i) s += v[i];
-  const float mu = warp_sum(s) / (float)C;
+  const float mu = group_sum<LPT>(s) / (float)C;
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < N; ++i) { const float d = v[i] - mu; q += d * d; }
   *mean = mu;
-  *rstd = rsqrtf(warp_sum(q) / (float)C + 1e-5f);
+  *rstd = rsqrtf(group_sum<LPT>(q) / (float)C + 1e-5f);
 }
 
 // n1[t,:] = LN1(token t of x) (padded tokens: LN(0) = beta).  Saves mean / rstd per token for the backward.
-template <typename T, int VEC, int ITERS>
+template <typename T, int LPT, int NV>
 __global__ void __launch_bounds__(256) swin_ln1_partition_vec_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                                                     const float* __restrict__ beta, T* __restrict__ n1,
                                                                     float* __restrict__ mean, float* __restrict__ rstd,
                                                                     WinGeom g) {
-  constexpr int N = VEC * ITERS;
-  const int lane = threadIdx.x & 31;
+  constexpr int VE = VecOf<T>::VE, N = NV * VE, TPW = 32 / LPT;
+  const int lane = threadIdx.x & 31, l = lane % LPT, grp = lane / LPT;
   float gm[N], bt[N];
-  load_vecf<VEC, ITERS>(gamma, lane, gm);
-  load_vecf<VEC, ITERS>(beta, lane, bt);
+  load_vecf<VE, LPT, NV>(gamma, l, gm);
+  load_vecf<VE, LPT, NV>(beta, l, bt);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < g.T; t += nwarps) {
-    bool real;
-    const long long pix = token_pixel(g, t, &real);
+  for (long long t0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * TPW; t0 < g.T; t0 += nwarps * TPW) {
+    const long long t = t0 + grp;
+    const bool live = t < g.T;
+    bool real = false;
+    long long pix = 0;
+    if (live) pix = token_pixel(g, t, &real);
     float v[N];
-    if (real) load_row<T, VEC, ITERS>(x + pix * g.C, lane, v);
+    if (real) load_row<T, LPT, NV>(x + pix * g.C, l, v);
     else {
 #pragma unroll
       for (int i = 0; i < N; ++i) v[i] = 0.f;
     }
     float mu, rs;
-    stats_full<N>(v, g.C, &mu, &rs);
+    stats_full<N, LPT>(v, g.C, &mu, &rs);
+    if (live) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) v[i] = (v[i] - mu) * rs * gm[i] + bt[i];
-    store_row<T, VEC, ITERS>(n1 + t * g.C, lane, v);
-    if (lane == 0) { mean[t] = mu; rstd[t] = rs; }
+      for (int i = 0; i < N; ++i) v[i] = (v[i] - mu) * rs * gm[i] + bt[i];
+      store_row<T, LPT, NV>(n1 + t * g.C, l, v);
+      if (l == 0) { mean[t] = mu; rstd[t] = rs; }
+    }
   }
 }
 
-template <typename T, int VEC, int ITERS>
+template <typename T, int LPT, int NV>
 __global__ void __launch_bounds__(256) swin_res_ln2_vec_kernel(const T* __restrict__ n1, const T* __restrict__ a,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               T* __restrict__ y1, T* __restrict__ u, float* __restrict__ mean,
                                                               float* __restrict__ rstd, long long Ttok, int C) {
-  constexpr int N = VEC * ITERS;
-  const int lane = threadIdx.x & 31;
+  constexpr int VE = VecOf<T>::VE, N = NV * VE, TPW = 32 / LPT;
+  const int lane = threadIdx.x & 31, l = lane % LPT, grp = lane / LPT;
   float gm[N], bt[N];
-  load_vecf<VEC, ITERS>(gamma, lane, gm);
-  load_vecf<VEC, ITERS>(beta, lane, bt);
+  load_vecf<VE, LPT, NV>(gamma, l, gm);
+  load_vecf<VE, LPT, NV>(beta, l, bt);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < Ttok; t += nwarps) {
+  for (long long t0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * TPW; t0 < Ttok; t0 += nwarps * TPW) {
+    const bool live = t0 + grp < Ttok;
+    const long long t = live ? t0 + grp : Ttok - 1;
     float v[N];
-    load_row<T, VEC, ITERS>(n1 + t * C, lane, v);
+    load_row<T, LPT, NV>(n1 + t * C, l, v);
     if (a) {  // a == nullptr: `n1` already holds y1 (residual fused into the out_proj GEMM epilogue)
       float w[N];
-      load_row<T, VEC, ITERS>(a + t * C, lane, w);
+      load_row<T, LPT, NV>(a + t * C, l, w);
 #pragma unroll
       for (int i = 0; i < N; ++i) v[i] = DT<T>::to_f(DT<T>::from_f(v[i] + w[i]));  // LN2 sees exactly the stored y1
-      store_row<T, VEC, ITERS>(y1 + t * C, lane, v);
+      if (live) store_row<T, LPT, NV>(y1 + t * C, l, v);
     }
     float mu, rs;
-    stats_full<N>(v, C, &mu, &rs);
+    stats_full<N, LPT>(v, C, &mu, &rs);
+    if (live) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) v[i] = (v[i] - mu) * rs * gm[i] + bt[i];
-    store_row<T, VEC, ITERS>(u + t * C, lane, v);
-    if (lane == 0) { mean[t] = mu; rstd[t] = rs; }
+      for (int i = 0; i < N; ++i) v[i] = (v[i] - mu) * rs * gm[i] + bt[i];
+      store_row<T, LPT, NV>(u + t * C, l, v);
+      if (l == 0) { mean[t] = mu; rstd[t] = rs; }
+    }
+  }
+}
+
+// out[b,y,x,:] = y1[t,:] + m[t,:] for real tokens (MODE 0)   /   tok[t,:] = src[b,y,x,:] or 0 (MODE 1), vectorised
+template <typename T, int LPT, int NV, int MODE>
+__global__ void __launch_bounds__(256) swin_move_vec_kernel(const T* __restrict__ a, const T* __restrict__ b2, T* __restrict__ out,
+                                                           WinGeom g) {
+  constexpr int VE = VecOf<T>::VE, N = NV * VE, TPW = 32 / LPT;
+  const int lane = threadIdx.x & 31, l = lane % LPT, grp = lane / LPT;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long t0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * TPW; t0 < g.T; t0 += nwarps * TPW) {
+    const long long t = t0 + grp;
+    if (t >= g.T) continue;
+    bool real;
+    const long long pix = token_pixel(g, t, &real);
+    float v[N];
+    if (MODE == 0) {
+      if (!real) continue;
+      float w[N];
+      load_row<T, LPT, NV>(a + t * g.C, l, v);
+      load_row<T, LPT, NV>(b2 + t * g.C, l, w);
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] += w[i];
+      store_row<T, LPT, NV>(out + pix * g.C, l, v);
+    } else {
+      if (real) load_row<T, LPT, NV>(a + pix * g.C, l, v);
+      else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = 0.f;
+      }
+      store_row<T, LPT, NV>(out + t * g.C, l, v);
+    }
   }
 }
 
 // LayerNorm backward, vectorised (see swin_ln_bwd_kernel below for the maths / modes)
-template <typename T, int VEC, int ITERS, int MODE>
+template <typename T, int LPT, int NV, int MODE>
 __global__ void __launch_bounds__(256) swin_ln_bwd_vec_kernel(const T* __restrict__ gout, const T* __restrict__ xin,
                                                              const T* __restrict__ gres, const float* __restrict__ gamma,
                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
                                                              T* __restrict__ gin, float* __restrict__ part, WinGeom g) {
-  constexpr int N = VEC * ITERS;
+  constexpr int VE = VecOf<T>::VE, N = NV * VE, TPW = 32 / LPT;
   extern __shared__ float sm[];  // [warps][2][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int l = lane % LPT, grp = lane / LPT;
   const int C = g.C;
   float gm[N], accg[N], accb[N];
-  load_vecf<VEC, ITERS>(gamma, lane, gm);
+  load_vecf<VE, LPT, NV>(gamma, l, gm);
 #pragma unroll
   for (int i = 0; i < N; ++i) { accg[i] = 0.f; accb[i] = 0.f; }
   const long long nwarps = (long long)gridDim.x * nwarp;
-  for (long long t = (long long)blockIdx.x * nwarp + warp; t < g.T; t += nwarps) {
+  for (long long t0 = ((long long)blockIdx.x * nwarp + warp) * TPW; t0 < g.T; t0 += nwarps * TPW) {
+    const long long t = t0 + grp;
+    const bool live = t < g.T;
     bool real = true;
-    long long src = t;
-    if (MODE == 1) src = token_pixel(g, t, &real);
-    const float mu = mean[t], rs = rstd[t];
+    long long src = live ? t : 0;
+    if (live && MODE == 1) src = token_pixel(g, t, &real);
     float go[N], xh[N];
-    load_row<T, VEC, ITERS>(gout + t * C, lane, go);
-    if (MODE == 1 && !real) {
+    float mu = 0.f, rs = 0.f;
+    if (live) {
+      mu = mean[t]; rs = rstd[t];
+      load_row<T, LPT, NV>(gout + t * C, l, go);
+      if (MODE == 1 && !real) {
 #pragma unroll
-      for (int i = 0; i < N; ++i) xh[i] = 0.f;
-    } else load_row<T, VEC, ITERS>(xin + src * C, lane, xh);
+        for (int i = 0; i < N; ++i) xh[i] = 0.f;
+      } else load_row<T, LPT, NV>(xin + src * C, l, xh);
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) { go[i] = 0.f; xh[i] = 0.f; }
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -190,24 +271,35 @@ __global__ void __launch_bounds__(256) swin_ln_bwd_vec_kernel(const T* __restric
       s1 += go[i];
       s2 += go[i] * xh[i];
     }
-    s1 = warp_sum(s1) / (float)C;
-    s2 = warp_sum(s2) / (float)C;
-    if (MODE == 0 || real) {
+    s1 = group_sum<LPT>(s1) / (float)C;
+    s2 = group_sum<LPT>(s2) / (float)C;
+    if (live && (MODE == 0 || real)) {
       float r[N];
-      if (MODE == 0) load_row<T, VEC, ITERS>(gres + t * C, lane, r);
+      if (MODE == 0) load_row<T, LPT, NV>(gres + t * C, l, r);
 #pragma unroll
       for (int i = 0; i < N; ++i) r[i] = (go[i] - s1 - xh[i] * s2) * rs + (MODE == 0 ? r[i] : 0.f);
-      store_row<T, VEC, ITERS>(gin + src * C, lane, r);
+      store_row<T, LPT, NV>(gin + src * C, l, r);
     }
   }
+  // fold the token groups of the warp (same channels live in lanes l, l+LPT, ...), then the warps of the CTA
 #pragma unroll
-  for (int i = 0; i < ITERS; ++i)
+  for (int i = 0; i < N; ++i) {
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      const int c = (lane + 32 * i) * VEC + e;
-      sm[(warp * 2 + 0) * C + c] = accg[i * VEC + e];
-      sm[(warp * 2 + 1) * C + c] = accb[i * VEC + e];
+    for (int o = LPT; o < 32; o <<= 1) {
+      accg[i] += __shfl_xor_sync(0xffffffffu, accg[i], o);
+      accb[i] += __shfl_xor_sync(0xffffffffu, accb[i], o);
     }
+  }
+  if (grp == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int e = 0; e < VE; ++e) {
+        const int c = (l + LPT * i) * VE + e;
+        sm[(warp * 2 + 0) * C + c] = accg[i * VE + e];
+        sm[(warp * 2 + 1) * C + c] = accb[i * VE + e];
+      }
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
     float s = 0.f;
@@ -216,22 +308,21 @@ __global__ void __launch_bounds__(256) swin_ln_bwd_vec_kernel(const T* __restric
   }
 }
 
-// pick (VEC, ITERS) with C == 32*VEC*ITERS; returns false when C has no vectorised instantiation
+// pick (LPT, NV) with C == LPT*NV*VE, preferring two vectors per lane; false when C has no instantiation
 template <typename T>
-inline bool pick_vec(int C, int* vec, int* iters) {
-  const int maxv = 16 / (int)sizeof(T) > 8 ? 8 : 16 / (int)sizeof(T);
-  for (int v = maxv; v >= (sizeof(T) == 2 ? 2 : 1); v >>= 1)
-    for (int it = 1; it <= 3; ++it)
-      if (C == 32 * v * it) { *vec = v; *iters = it; return true; }
+inline bool pick_vec(int C, int* lpt, int* nv) {
+  constexpr int VE = VecOf<T>::VE;
+  for (int want : {2, 3, 1})
+    for (int L : {8, 16, 32})
+      if (C == L * want * VE) { *lpt = L; *nv = want; return true; }
   return false;
 }
-#define B200_VEC_CASE(V, I, ...) if (vec == V && iters == I) { constexpr int VEC = V; constexpr int ITERS = I; __VA_ARGS__; }
-#define B200_DISPATCH_VEC(...)                                                                      \
-  do {                                                                                              \
-    if constexpr (sizeof(T) == 2) { B200_VEC_CASE(8, 1, __VA_ARGS__) B200_VEC_CASE(8, 2, __VA_ARGS__) B200_VEC_CASE(8, 3, __VA_ARGS__) } \
-    B200_VEC_CASE(4, 1, __VA_ARGS__) B200_VEC_CASE(4, 2, __VA_ARGS__) B200_VEC_CASE(4, 3, __VA_ARGS__)  \
-    B200_VEC_CASE(2, 1, __VA_ARGS__) B200_VEC_CASE(2, 2, __VA_ARGS__) B200_VEC_CASE(2, 3, __VA_ARGS__)  \
-    if constexpr (sizeof(T) == 4) { B200_VEC_CASE(1, 1, __VA_ARGS__) B200_VEC_CASE(1, 2, __VA_ARGS__) B200_VEC_CASE(1, 3, __VA_ARGS__) } \
+#define B200_VEC_CASE(L_, N_, ...) if (vec == L_ && iters == N_) { constexpr int VEC = L_; constexpr int ITERS = N_; __VA_ARGS__; }
+#define B200_DISPATCH_VEC(...)                                                                              \
+  do {                                                                                                      \
+    B200_VEC_CASE(8, 1, __VA_ARGS__) B200_VEC_CASE(8, 2, __VA_ARGS__) B200_VEC_CASE(8, 3, __VA_ARGS__)       \
+    B200_VEC_CASE(16, 1, __VA_ARGS__) B200_VEC_CASE(16, 2, __VA_ARGS__) B200_VEC_CASE(16, 3, __VA_ARGS__)    \
+    B200_VEC_CASE(32, 1, __VA_ARGS__) B200_VEC_CASE(32, 2, __VA_ARGS__) B200_VEC_CASE(32, 3, __VA_ARGS__)    \
   } while (0)
 
 // ---- generic (any C <= 1024) kernels ------------------------------------------------------------------------
@@ -458,6 +549,8 @@ __global__ void fold_rows_kernel(const float* __restrict__ part, float* __restri
   }
 }
 
+template <typename T, int VEC> struct alignas(sizeof(T) * VEC) PackT { T e[VEC]; };
+
 // column sums of a [rows, n] activation matrix -> f32 [n] (bias gradients); two-stage, deterministic
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ a, float* __restrict__ part, long long rows,
@@ -496,13 +589,15 @@ int make_geom(WinGeom* g, int B, int C, int H, int W, int ws) {
   g->B = B; g->C = C; g->H = H; g->W = W; g->ws = ws;
   g->nWh = (H + ws - 1) / ws; g->nWw = (W + ws - 1) / ws; g->L = ws * ws;
   g->T = (long long)B * g->nWh * g->nWw * g->L;
+  B200_REQUIRE(g->T < (1ll << 31), B200_ERR_UNSUPPORTED, "swin: %lld tokens exceed the 32-bit token index", g->T);
+  g->dL.init((uint32_t)g->L); g->dWw.init((uint32_t)g->nWw); g->dWh.init((uint32_t)g->nWh); g->dws.init((uint32_t)ws);
   return B200_OK;
 }
 
 inline unsigned warps_grid(long long tokens) { return (unsigned)((tokens + 7) / 8); }
 // grid-stride kernels: enough CTAs to fill the chip a few times over, never more than the work
-inline unsigned capped_grid(long long tokens) {
-  const long long need = (tokens + 7) / 8, cap = (long long)sm_count() * 8;
+inline unsigned capped_grid(long long tokens, int tokens_per_warp = 1) {
+  const long long need = (tokens + 8 * tokens_per_warp - 1) / (8 * tokens_per_warp), cap = (long long)sm_count() * 8;
   return (unsigned)(need < cap ? need : cap);
 }
 constexpr int kLnMaxCtas = 1024;
@@ -531,7 +626,7 @@ extern "C" B200_API int b200_swin_ln1_partition(const void* x, const float* gamm
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
     int vec, iters;
     if (pick_vec<T>(C, &vec, &iters) && (((uintptr_t)x | (uintptr_t)n1) & 15) == 0) {
-      const unsigned grid = capped_grid(g.T);
+      const unsigned grid = capped_grid(g.T, 32 / vec);
       B200_DISPATCH_VEC({
         swin_ln1_partition_vec_kernel<T, VEC, ITERS><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, gamma, beta, (T*)n1, mean, rstd, g);
         return check_launch("swin_ln1_partition");
@@ -550,7 +645,7 @@ extern "C" B200_API int b200_swin_res_ln2(const void* n1, const void* a, const f
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
     int vec, iters;
     if (pick_vec<T>(C, &vec, &iters) && (((uintptr_t)n1 | (uintptr_t)a | (uintptr_t)y1 | (uintptr_t)u) & 15) == 0) {
-      const unsigned grid = capped_grid(tokens);
+      const unsigned grid = capped_grid(tokens, 32 / vec);
       B200_DISPATCH_VEC({
         swin_res_ln2_vec_kernel<T, VEC, ITERS><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)n1, (const T*)a, gamma, beta, (T*)y1,
                                                                                        (T*)u, mean, rstd, tokens, C);
@@ -585,6 +680,14 @@ extern "C" B200_API int b200_swin_res_reverse(const void* y1, const void* m, voi
   if (int rc = make_geom(&g, B, C, H, W, ws)) return rc;
   B200_REQUIRE(y1 && m && out, B200_ERR_SHAPE, "swin_res_reverse: null pointer");
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
+    int vec, iters;
+    if (pick_vec<T>(C, &vec, &iters) && (((uintptr_t)y1 | (uintptr_t)m | (uintptr_t)out) & 15) == 0) {
+      const unsigned grid = capped_grid(g.T, 32 / vec);
+      B200_DISPATCH_VEC({
+        swin_move_vec_kernel<T, VEC, ITERS, 0><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)y1, (const T*)m, (T*)out, g);
+        return check_launch("swin_res_reverse");
+      });
+    }
     swin_res_reverse_kernel<T><<<warps_grid(g.T), 256, 0, (cudaStream_t)stream>>>((const T*)y1, (const T*)m, (T*)out, g);
     return check_launch("swin_res_reverse");
   });
@@ -596,6 +699,14 @@ extern "C" B200_API int b200_swin_partition(const void* src, void* tok, int32_t 
   if (int rc = make_geom(&g, B, C, H, W, ws)) return rc;
   B200_REQUIRE(src && tok, B200_ERR_SHAPE, "swin_partition: null pointer");
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
+    int vec, iters;
+    if (pick_vec<T>(C, &vec, &iters) && (((uintptr_t)src | (uintptr_t)tok) & 15) == 0) {
+      const unsigned grid = capped_grid(g.T, 32 / vec);
+      B200_DISPATCH_VEC({
+        swin_move_vec_kernel<T, VEC, ITERS, 1><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)src, nullptr, (T*)tok, g);
+        return check_launch("swin_partition");
+      });
+    }
     swin_partition_kernel<T><<<warps_grid(g.T), 256, 0, (cudaStream_t)stream>>>((const T*)src, (T*)tok, g);
     return check_launch("swin_partition");
   });

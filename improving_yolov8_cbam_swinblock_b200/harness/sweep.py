@@ -32,7 +32,7 @@ def algorithmic_work(scale: str, B: int, s: int = 2, ws: int = 7):
         "b200_swin_attn_bwd": hbm(8 * T * c4 * s, "read qkv, o, g_o (5*T*C*s) + write g_qkv (3*T*C*s)"),
         "b200_swin_attn_fwd_tc": hbm(4 * T * c4 * s, "stand-alone attention is HBM-bound (22 FLOP/B): read qkv + write o = 4*T*C*s"),
         "b200_swin_attn_bwd_tc": hbm(7 * T * c4 * s, "read qkv, g_o (4*T*C*s) + write g_qkv (3*T*C*s)"),
-        "b200_swin_res_ln2": hbm(4 * T * c4 * s, "read n1, a; write y1, u"),
+        "b200_swin_res_ln2": hbm(2 * T * c4 * s, "read y1, write u (the residual add is fused into the out_proj GEMM epilogue)"),
         "b200_swin_gelu": hbm(2 * T * 4 * c4 * s, "read a, write h (backward: +1 read)"),
         "b200_swin_res_reverse": hbm((2 * T + tok_real) * c4 * s, "read y1, m; write out (real tokens)"),
         "b200_swin_partition": hbm((tok_real + T) * c4 * s, "read g (real), write token-major g"),
