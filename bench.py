@@ -217,8 +217,12 @@ def main():
         else:
             achieved = w["amount"] / (ms * 1e-3) / (1e9 if w["bound"] == "hbm" else 1e12)
             peak = peaks["hbm_gbs"] if w["bound"] == "hbm" else peaks["bf16_tflops_sustained"]
+            traffic = None  # dram__bytes_read+write per launch from the committed ncu --set full capture of this kernel
+            tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+            if os.path.isfile(tpath):
+                traffic = json.load(open(tpath)).get(sweep.ncu_kernel_name(top) or "")
             roof = {"kernel": top, "bound": w["bound"], "achieved": achieved, "peak": peak, "unit": "GB/s" if w["bound"] == "hbm" else "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None, "avg_ms": ms, "calls": n, "peak_source": peaks["source"] + " (sustained)",
+                    "frac": achieved / peak, "traffic": traffic, "avg_ms": ms, "calls": n, "peak_source": peaks["source"] + " (sustained)",
                     "algorithmic": w["note"],
                     "share_of_step": tot[top] / ms_dev, "kernels_ms_per_step": {k: v / args.steps for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
     if roof is not None:  # every hand-written kernel of the step: mean ms per launch + fraction of its roofline

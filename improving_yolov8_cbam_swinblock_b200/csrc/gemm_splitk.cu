@@ -19,8 +19,8 @@ constexpr int SMEM_TOTAL = STAGES * (A_BYTES + B_BYTES) + ONES_BYTES + 256 + 102
 constexpr int TMEM_COLS = 256;        // BN accumulator columns + 16 for the fused column sums
 
 struct SplitParams {
-  float* part;     // [splits][M][N]
-  float* part_cs;  // [splits][M] partial sums over k of A(m,k) (bias gradients), or null
+  float* part;     // [splits][M*N + M]: per split the f32 tile partials followed by the column-sum partials
+  int with_cs;     // 1: also produce sum_k A(m,k) (bias gradients)
   int M, N, K, m_tiles, n_tiles, kb_total, kb_per_split, fmt;
 };
 
@@ -49,7 +49,8 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
-  const bool do_cs = P.part_cs != nullptr && n0 == 0;
+  const bool do_cs = P.with_cs && n0 == 0;
+  const size_t split_stride = (size_t)P.M * P.N + P.M;
   if (do_cs && warp >= 2) {
     const uint32_t one2 = P.fmt == 1 ? 0x3f803f80u : 0x3c003c00u;
     for (int i = threadIdx.x - 64; i < ONES_BYTES / 4; i += 128) reinterpret_cast<uint32_t*>(sOnes)[i] = one2;
@@ -121,9 +122,9 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tmem_ld_wait();
         cs = __uint_as_float(v[0]);
       }
-      if (gm < P.M) P.part_cs[(size_t)split * P.M + gm] = cs;
+      if (gm < P.M) P.part[(size_t)split * split_stride + (size_t)P.M * P.N + gm] = cs;
     }
-    float* dst = P.part + ((size_t)split * P.M + gm) * P.N + n0;
+    float* dst = P.part + (size_t)split * split_stride + (size_t)gm * P.N + n0;
 #pragma unroll 1
     for (int ch = 0; ch < BN / 32; ++ch) {
       uint32_t v[32];
@@ -152,12 +153,23 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
-__global__ void fold_splits_kernel(const float* __restrict__ part, float* __restrict__ out, int splits, size_t n) {
+// out[i] = sum over splits (fixed order); the last `ncs` entries of every split go to `colsum`
+__global__ void fold_splits_kernel(const float* __restrict__ part, float* __restrict__ out, float* __restrict__ colsum, int splits,
+                                   size_t n, size_t ncs) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float s = 0.f;
-  for (int k = 0; k < splits; ++k) s += part[(size_t)k * n + i];
-  out[i] = s;
+  if (i >= n + ncs) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int k = 0;
+  for (; k + 3 < splits; k += 4) {
+    s0 += part[(size_t)k * (n + ncs) + i];
+    s1 += part[(size_t)(k + 1) * (n + ncs) + i];
+    s2 += part[(size_t)(k + 2) * (n + ncs) + i];
+    s3 += part[(size_t)(k + 3) * (n + ncs) + i];
+  }
+  for (; k < splits; ++k) s0 += part[(size_t)k * (n + ncs) + i];
+  const float s = (s0 + s1) + (s2 + s3);
+  if (i < n) out[i] = s;
+  else if (colsum) colsum[i - n] = s;
 }
 
 int choose_splits(int tiles, int kb_total) {
@@ -196,14 +208,13 @@ extern "C" B200_API int b200_gemm_splitk(const void* A, const void* B, float* D,
   if (!mA || !mB) return B200_ERR_LAUNCH;
   SplitParams P;
   P.part = (float*)workspace; P.M = M; P.N = N; P.K = (int)K;
-  P.part_cs = nullptr;
+  P.with_cs = colsum != nullptr;
   P.m_tiles = (M + BM - 1) / BM; P.n_tiles = (N + BN - 1) / BN;
   P.kb_total = (int)((K + BK - 1) / BK);
   const int tiles = P.m_tiles * P.n_tiles;
   const int splits = choose_splits(tiles, P.kb_total);
   P.kb_per_split = (P.kb_total + splits - 1) / splits;
   P.fmt = dtype == B200_BF16 ? 1 : 0;
-  if (colsum) P.part_cs = (float*)workspace + (size_t)splits * M * N;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(tiles, splits);
 #define LAUNCH_SK(AM, BMN)                                                                        \
@@ -216,11 +227,6 @@ extern "C" B200_API int b200_gemm_splitk(const void* A, const void* B, float* D,
 #undef LAUNCH_SK
   if (int rc = check_launch("gemm_splitk")) return rc;
   const size_t n = (size_t)M * N;
-  fold_splits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float*)workspace, D, splits, n);
-  if (int rc = check_launch("gemm_splitk_fold")) return rc;
-  if (colsum) {
-    fold_splits_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(P.part_cs, colsum, splits, (size_t)M);
-    return check_launch("gemm_splitk_fold_colsum");
-  }
-  return B200_OK;
+  fold_splits_kernel<<<(unsigned)((n + M + 255) / 256), 256, 0, st>>>((const float*)workspace, D, colsum, splits, n, (size_t)M);
+  return check_launch("gemm_splitk_fold");
 }

@@ -515,19 +515,21 @@ __global__ void __launch_bounds__(256) swin_ln_bwd_kernel(const T* __restrict__ 
 }
 
 // [rows][2][C] partials -> ggamma[C], gbeta[C]   (fixed order)
-__global__ void fold_ln_kernel(const float* __restrict__ part, float* __restrict__ gg, float* __restrict__ gb, int rows, int C) {
-  // 32 columns per warp-row: lane = column, the block's warps split the rows, fixed-order smem fold
-  __shared__ float sm[8][32];
+__global__ void __launch_bounds__(1024) fold_ln_kernel(const float* __restrict__ part, float* __restrict__ gg, float* __restrict__ gb,
+                                                       int rows, int C) {
+  // 32 columns per block: lane = column, the block's 32 warps split the rows, fixed-order smem fold
+  __shared__ float sm[32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;
   float s = 0.f;
   if (i < 2 * C)
-    for (int r = warp; r < rows; r += 8) s += part[(size_t)r * 2 * C + i];
+    for (int r = warp; r < rows; r += 32) s += part[(size_t)r * 2 * C + i];
   sm[warp][lane] = s;
   __syncthreads();
   if (warp == 0 && i < 2 * C) {
     float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += sm[w][lane];
+#pragma unroll
+    for (int w = 0; w < 32; ++w) t += sm[w][lane];
     if (i < C) gg[i] = t; else gb[i - C] = t;
   }
 }
@@ -760,7 +762,7 @@ extern "C" B200_API int b200_swin_ln_bwd(const void* gout, const void* xin, cons
     return check_launch("swin_ln_bwd");
   });
   if (rc) return rc;
-  fold_ln_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>((const float*)workspace, ggamma, gbeta, (int)ctas, C);
+  fold_ln_kernel<<<(2 * C + 31) / 32, 1024, 0, st>>>((const float*)workspace, ggamma, gbeta, (int)ctas, C);
   return check_launch("swin_ln_bwd_fold");
 }
 
