@@ -310,35 +310,50 @@ __global__ void __launch_bounds__(kThreads) cbam_fwd_kernel(CbamParams P) {
     shalo[ch * (P.pchunk + 2 * halo) + (i - ch * span)] = v;
   }
   __syncthreads();
-  // ---- phase C: conv + sigmoid, gate -----------------------------------------------------------------------
-  for (int p = tid; p < np; p += kThreads) {
-    const int q = p0 + p, y = q / W, x = q - y * W;
-    float z = 0.f;
-    for (int ch = 0; ch < 2; ++ch)
-      for (int u = 0; u < ks; ++u) {
-        const int yy = y + u - pad;
-        if (yy < 0 || yy >= H) continue;
-        for (int v = 0; v < ks; ++v) {
-          const int xx = x + v - pad;
-          if (xx < 0 || xx >= W) continue;
-          z += wsas[(ch * ks + u) * ks + v] * shalo[ch * (P.pchunk + 2 * halo) + (yy * W + xx) - (p0 - halo)];
-        }
+  // ---- phase C: conv + sigmoid (warp per pixel, lanes own up to 4 of the 2*ks*ks taps), gate ---------------------
+  {
+    constexpr int TPL = 4;  // taps per lane: 2*7*7 = 98 <= 128
+    int tdu[TPL], tdv[TPL], tch[TPL];
+    float tw[TPL];
+#pragma unroll
+    for (int j = 0; j < TPL; ++j) {
+      const int t = lane + 32 * j;
+      const bool ok = t < 2 * ks * ks;
+      tch[j] = ok ? t / (ks * ks) : 0;
+      tdu[j] = ok ? (t / ks) % ks - pad : 0;
+      tdv[j] = ok ? t % ks - pad : 0;
+      tw[j] = ok ? wsas[t] : 0.f;
+    }
+    const int hp_ = P.pchunk + 2 * halo;
+    for (int p = warp; p < np; p += kThreads / 32) {
+      const int q = p0 + p, y = q / W, x = q - y * W;
+      float z = 0.f;
+#pragma unroll
+      for (int j = 0; j < TPL; ++j) {
+        const int yy = y + tdu[j], xx = x + tdv[j];
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) z += tw[j] * shalo[tch[j] * hp_ + (yy * W + xx) - (p0 - halo)];
       }
-    const float a = sigmoidf_(z);
-    sas[p] = a;
-    if (P.sa) P.sa[(size_t)b * HW + q] = a;
+      z = warp_sum(z);
+      if (lane == 0) {
+        const float a = sigmoidf_(z);
+        sas[p] = a;
+        if (P.sa) P.sa[(size_t)b * HW + q] = a;
+      }
+    }
   }
   __syncthreads();
   if (P.mode == B200_CBAM_FULL) {
     T* og = reinterpret_cast<T*>(P.out) + ((size_t)b * HW + p0) * C;
     T* dst = RES ? xs : og;
-    for (int i = tid; i < np * nw; i += kThreads) {
-      const int p = i / nw, w = i - p * nw;
-      float v[EPL];
-      Vec<T>::load(xc + (size_t)p * C + w * EPL, v);
+    for (int p = warp; p < np; p += kThreads / 32) {
+      const float sp = sas[p];
+      for (int w = lane; w < nw; w += 32) {
+        float v[EPL];
+        Vec<T>::load(xc + (size_t)p * C + w * EPL, v);
 #pragma unroll
-      for (int e = 0; e < EPL; ++e) v[e] = v[e] * ca[w * EPL + e] * sas[p];
-      Vec<T>::store(dst + (size_t)p * C + w * EPL, v);
+        for (int e = 0; e < EPL; ++e) v[e] = v[e] * ca[w * EPL + e] * sp;
+        Vec<T>::store(dst + (size_t)p * C + w * EPL, v);
+      }
     }
     if (RES) {
       const size_t bytes = (size_t)np * C * sizeof(T);
@@ -488,22 +503,38 @@ __global__ void __launch_bounds__(kThreads) cbam_bwd_kernel(CbamParams P) {
       shalo[i] = v;
     }
     __syncthreads();
-    for (int p = tid; p < np; p += kThreads) {
-      const int q = p0 + p, y = q / W, x = q - y * W;
-      float g0 = 0.f, g1 = 0.f;
-      for (int u = 0; u < ks; ++u) {
-        const int yy = y - (u - pad);  // output position that used tap (u,v) on this input
-        if (yy < 0 || yy >= H) continue;
-        for (int v = 0; v < ks; ++v) {
-          const int xx = x - (v - pad);
-          if (xx < 0 || xx >= W) continue;
-          const float gz = shalo[(yy * W + xx) - (p0 - halo)];
-          g0 += wsas[(0 * ks + u) * ks + v] * gz;
-          g1 += wsas[(1 * ks + u) * ks + v] * gz;
+    {
+      constexpr int TPL = 2;  // taps per lane: ks*ks = 49 <= 64
+      int tdu[TPL], tdv[TPL];
+      float tw0[TPL], tw1[TPL];
+#pragma unroll
+      for (int j = 0; j < TPL; ++j) {
+        const int t = lane + 32 * j;
+        const bool ok = t < ks * ks;
+        tdu[j] = ok ? t / ks - pad : 0;
+        tdv[j] = ok ? t % ks - pad : 0;
+        tw0[j] = ok ? wsas[t] : 0.f;
+        tw1[j] = ok ? wsas[ks * ks + t] : 0.f;
+      }
+      for (int p = warp; p < np; p += kThreads / 32) {
+        const int q = p0 + p, y = q / W, x = q - y * W;
+        float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < TPL; ++j) {
+          const int yy = y - tdu[j], xx = x - tdv[j];  // output position that used this tap on this input
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const float gz = shalo[(yy * W + xx) - (p0 - halo)];
+            g0 += tw0[j] * gz;
+            g1 += tw1[j] * gz;
+          }
+        }
+        g0 = warp_sum(g0);
+        g1 = warp_sum(g1);
+        if (lane == 0) {
+          sas[pc + p] = g0 / (float)C;  // broadcast share of the channel mean
+          sas[2 * pc + p] = g1;         // routed to the argmax channel
         }
       }
-      sas[pc + p] = g0 / (float)C;  // broadcast share of the channel mean
-      sas[2 * pc + p] = g1;         // routed to the argmax channel
     }
     __syncthreads();
     // --- g_Wsa[j,u,v] = sum_p g_z[p] * s[j, p + (u-pad, v-pad)]: gather s halo, per-CTA partial
@@ -517,17 +548,40 @@ __global__ void __launch_bounds__(kThreads) cbam_bwd_kernel(CbamParams P) {
       shalo[ch * hp + (i - ch * span)] = v;
     }
     __syncthreads();
-    for (int t = warp; t < nwt; t += kThreads / 32) {
-      const int ch = t / (ks * ks), u = (t / ks) % ks, v = t % ks;
-      float acc = 0.f;
-      for (int p = lane; p < np; p += 32) {
-        const int q = p0 + p, y = q / W, x = q - y * W;
-        const int yy = y + u - pad, xx = x + v - pad;
-        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-        acc += smap[2 * pc + p] * shalo[ch * hp + (yy * W + xx) - (p0 - halo)];
+    if (np <= 128) {  // lanes own up to 4 pixels each; coordinates and g_z decoded once, reused for every tap
+      int py[4], px[4];
+      float pgz[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int p = lane + 32 * j;
+        const int q = p0 + (p < np ? p : 0);
+        py[j] = q / W; px[j] = q - py[j] * W;
+        pgz[j] = p < np ? smap[2 * pc + p] : 0.f;
       }
-      acc = warp_sum(acc);
-      if (lane == 0) wsas[nwt + t] = acc;
+      for (int t = warp; t < nwt; t += kThreads / 32) {
+        const int ch = t / (ks * ks), u = (t / ks) % ks - pad, v = t % ks - pad;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int yy = py[j] + u, xx = px[j] + v;
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) acc += pgz[j] * shalo[ch * hp + (yy * W + xx) - (p0 - halo)];
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) wsas[nwt + t] = acc;
+      }
+    } else {
+      for (int t = warp; t < nwt; t += kThreads / 32) {
+        const int ch = t / (ks * ks), u = (t / ks) % ks, v = t % ks;
+        float acc = 0.f;
+        for (int p = lane; p < np; p += 32) {
+          const int q = p0 + p, y = q / W, x = q - y * W;
+          const int yy = y + u - pad, xx = x + v - pad;
+          if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+          acc += smap[2 * pc + p] * shalo[ch * hp + (yy * W + xx) - (p0 - halo)];
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) wsas[nwt + t] = acc;
+      }
     }
     cluster.sync();  // (2) per-CTA g_Wsa partials visible; rank 0 folds them (fixed order -> deterministic)
     if (rank == 0)
@@ -678,19 +732,21 @@ __global__ void __launch_bounds__(kThreads) cbam_bwd_kernel(CbamParams P) {
   // (6) g_x = g_x1 * ca + g_pavg/HW + [p == argmax_hw] g_pmax
   {
     T* og = reinterpret_cast<T*>(P.out) + ((size_t)b * HW + p0) * C;
-    for (int i = tid; i < np * nw; i += kThreads) {
-      const int p = i / nw, w = i - p * nw;
-      float gv[EPL], o[EPL];
-      if (gc) Vec<T>::load(gc + (size_t)p * C + w * EPL, gv);
+    for (int p = warp; p < np; p += kThreads / 32) {
       const int am = use_sa && P.mode == B200_CBAM_FULL ? __float_as_int(smap[3 * pc + p]) : -1;
+      const float sp = sas[p], g0 = sas[pc + p], g1 = sas[2 * pc + p];
+      for (int w = lane; w < nw; w += 32) {
+        float gv[EPL], o[EPL];
+        if (gc) Vec<T>::load(gc + (size_t)p * C + w * EPL, gv);
 #pragma unroll
-      for (int e = 0; e < EPL; ++e) {
-        const int c = w * EPL + e;
-        float gx1 = 0.f;
-        if (P.mode == B200_CBAM_FULL) gx1 = gv[e] * sas[p] + sas[pc + p] + (c == am ? sas[2 * pc + p] : 0.f);
-        o[e] = gx1 * ca[c] + ca[C + c] + ((p0 + p) == __float_as_int(ca[3 * C + c]) ? ca[2 * C + c] : 0.f);
+        for (int e = 0; e < EPL; ++e) {
+          const int c = w * EPL + e;
+          float gx1 = 0.f;
+          if (P.mode == B200_CBAM_FULL) gx1 = gv[e] * sp + g0 + (c == am ? g1 : 0.f);
+          o[e] = gx1 * ca[c] + ca[C + c] + ((p0 + p) == __float_as_int(ca[3 * C + c]) ? ca[2 * C + c] : 0.f);
+        }
+        Vec<T>::store(og + (size_t)p * C + w * EPL, o);
       }
-      Vec<T>::store(og + (size_t)p * C + w * EPL, o);
     }
   }
   cluster.sync();
