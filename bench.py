@@ -101,7 +101,18 @@ def cpu_reference_leg(steps, warmup, batch=2):
     for _ in range(steps):
         tr.step_from_host(host)
     dt = time.perf_counter() - t0
-    return {"value": batch * steps / dt, "unit": "img/s", "cores": cores, "kind": "port",
+    # BASELINE config 0: inference, batch 1, 640^2, fp32, eval mode on the host cores
+    tr.raw.eval()
+    img1 = host["img"][:1].float() / 255
+    with torch.inference_mode():
+        for _ in range(2):
+            tr.raw(img1)
+        ti = time.perf_counter()
+        n_inf = 5
+        for _ in range(n_inf):
+            tr.raw(img1)
+        inf_ms = 1e3 * (time.perf_counter() - ti) / n_inf
+    return {"value": batch * steps / dt, "unit": "img/s", "cores": cores, "kind": "port", "inference_b1_fp32_ms": round(inf_ms, 2),
             "sample": f"{steps} fp32 training steps (fwd+loss+bwd+SGD+EMA) of YOLOv8{SCALE}-CBAM-Swin at {IMGSZ}^2, batch {batch}, "
                       f"oracle/modules.py blocks (CPU restatement of cbam.py/swin_block.py/block.py SPPF) in the harness graph, "
                       f"{cores} torch threads", "ms_per_step": 1e3 * dt / steps}
@@ -133,7 +144,7 @@ def main():
         line = {"impl": "reference", "metric": "train_images_per_sec", "value": cb["value"], "unit": "img/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "inference_b1_fp32_ms")},
                 "e2e": {"value": cb["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -241,10 +252,21 @@ def main():
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                     "ms_per_step": ms_e2e / args.steps, "loss_items": [float(v) for v in last["loss"]]},
             "roofline": roof}
+    # BASELINE config 1: bf16 inference, batch 64, forward only (eval mode, device-resident batch)
+    tr.raw.eval()
+    with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
+        imgf = (dev[0]["img"].float() / 255).contiguous(memory_format=torch.channels_last)
+        for _ in range(3):
+            tr.raw(imgf)
+        ms_inf = timed(lambda i: tr.raw(imgf), args.steps)
+    tr.raw.train()
+    line["inference"] = {"value": args.batch * args.steps / (ms_inf * 1e-3), "unit": "img/s", "ms_per_batch": ms_inf / args.steps,
+                         "config": "configs[1]: bf16 autocast, batch 64, forward only, eval mode, 1 GPU"}
     if not args.no_sweep:
         line["modules"] = sweep.run(SCALE, args.batch, peaks, iters=10)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = {k: v for k, v in cpu_reference_leg(6, 2).items() if k != "ms_per_step"}
+        line["cpu_baseline"]["sample"] += "; inference_b1_fp32_ms = configs[0] (batch 1, eval) on the same cores"
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -103,3 +103,24 @@ def test_half_module_and_autocast():
     h = mod.half()
     yh = h(x.half())
     assert yh.dtype == torch.float16 and rel_err(yh, ref) < 4e-3
+
+
+def test_full_size_consistency_between_modes():
+    """BASELINE size (B=64, C5=256, 20x20, bf16): the fused kernel must agree with the composition of its own
+    stand-alone map kernels, out = x * ca(x) * sa(x * ca(x)) (cbam.py:62-71) -- a size-independent identity."""
+    import improving_yolov8_cbam_swinblock_b200.modules as M
+
+    torch.manual_seed(0)
+    mod = M.CBAM()
+    mod(torch.zeros(1, 256, 2, 2))
+    mod = mod.cuda()
+    x = to_cl(torch.randn(64, 256, 20, 20, device="cuda").bfloat16())
+    with torch.no_grad():
+        out = mod(x)
+        ca = mod.ca(x)
+        x1 = (x.float() * ca.float())
+        sa = mod.sa(to_cl(x1.bfloat16()))
+        want = x1 * sa.float()
+    assert ca.shape == (64, 256, 1, 1) and sa.shape == (64, 1, 20, 20)
+    assert float(ca.min()) > 0 and float(ca.max()) < 1 and float(sa.min()) > 0 and float(sa.max()) < 1
+    assert rel_err(out, want) < 1e-2

@@ -117,3 +117,26 @@ def test_tc_attention_backward_matches_simt(dtype, nwin, L, C, nh):
     for name, sl in (("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))):
         e = rel_err(g[:, sl], g_ref[:, sl])
         assert e < tol, (name, e)
+
+
+def test_full_size_bf16_vs_own_fp32_path():
+    """BASELINE size (B=64, C4=128, 40x40): the bf16 path (tcgen05 GEMMs + tcgen05 attention) against the fp32 path of
+    the same module (SIMT attention + library GEMMs) -- two independent implementations of the block, outputs + grads."""
+    import improving_yolov8_cbam_swinblock_b200.modules as M
+
+    torch.manual_seed(0)
+    mod = M.SwinBlock(128, 2, 7).cuda()
+    x = torch.randn(64, 128, 40, 40, device="cuda")
+    g = torch.randn(64, 128, 40, 40, device="cuda")
+    res = []
+    for dt in (torch.float32, torch.bfloat16):
+        mod.zero_grad()
+        xi = to_cl(x.to(dt)).requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dt == torch.bfloat16):
+            y = mod(xi)
+        y.backward(to_cl(g.to(dt)))
+        res.append((y.detach().float(), xi.grad.float(), {k: p.grad.clone() for k, p in mod.named_parameters()}))
+    (y32, gx32, gw32), (y16, gx16, gw16) = res
+    assert rel_err(y16, y32) < 2e-2 and rel_err(gx16, gx32) < 2e-2
+    for k in gw32:
+        assert rel_err(gw16[k], gw32[k]) < 2e-2, (k, rel_err(gw16[k], gw32[k]))
