@@ -25,6 +25,7 @@ namespace b200 {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kRedBytes = 12288 + 1024;
 
 struct CbamParams {
   const void* x;
@@ -39,32 +40,23 @@ struct CbamParams {
   int B, C, H, W, r, ksa, mode, pchunk;
 };
 
-template <typename T> struct Vec;  // 32-bit word <-> EPL elements
-template <> struct Vec<float> {
-  static constexpr int EPL = 1;
-  __device__ static __forceinline__ void load(const float* p, float (&v)[1]) { v[0] = *p; }
-  __device__ static __forceinline__ void store(float* p, const float (&v)[1]) { *p = v[0]; }
-};
-template <> struct Vec<__nv_bfloat16> {
-  static constexpr int EPL = 2;
-  __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&v)[2]) {
-    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
-    v[0] = f.x; v[1] = f.y;
+// VW contiguous channels <-> floats.  VW * sizeof(T) is 16 bytes on the fast path ("vectorised NHWC loads": one
+// LDS.128 / LDG.128 feeds 8 bf16 channels) and one 32-bit word (2 x 16-bit / 1 x f32) when C is not a multiple of that.
+template <typename T, int VW> struct alignas(sizeof(T) * VW) VPack { T e[VW]; };
+template <typename T, int VW> struct Vec {
+  __device__ static __forceinline__ void load(const T* p, float (&v)[VW]) {
+    const VPack<T, VW> k = *reinterpret_cast<const VPack<T, VW>*>(p);
+#pragma unroll
+    for (int i = 0; i < VW; ++i) v[i] = DT<T>::to_f(k.e[i]);
   }
-  __device__ static __forceinline__ void store(__nv_bfloat16* p, const float (&v)[2]) {
-    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v[0], v[1]);
-  }
-};
-template <> struct Vec<__half> {
-  static constexpr int EPL = 2;
-  __device__ static __forceinline__ void load(const __half* p, float (&v)[2]) {
-    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(p));
-    v[0] = f.x; v[1] = f.y;
-  }
-  __device__ static __forceinline__ void store(__half* p, const float (&v)[2]) {
-    *reinterpret_cast<__half2*>(p) = __floats2half2_rn(v[0], v[1]);
+  __device__ static __forceinline__ void store(T* p, const float (&v)[VW]) {
+    VPack<T, VW> k;
+#pragma unroll
+    for (int i = 0; i < VW; ++i) k.e[i] = DT<T>::from_f(v[i]);
+    *reinterpret_cast<VPack<T, VW>*>(p) = k;
   }
 };
+template <typename T> struct Words { static constexpr int EPL = 4 / (int)sizeof(T), VE = 16 / (int)sizeof(T); };
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
@@ -89,7 +81,7 @@ struct SmemLayout {
     shalo = o; o += align16((size_t)2 * (pchunk + 2 * halo) * 4);     // gathered map with halo
     sa = o; o += align16((size_t)pchunk * 4 * (bwd ? 3 : 1));
     wsa = o; o += align16((size_t)2 * ksa * ksa * 4 * (bwd ? 2 : 1));
-    red = o; o += 8192;  // >= kThreads*EPL*12 B of cross-group reduction scratch
+    red = o; o += kRedBytes;  // cross-group reduction scratch
     bar = o; o += 16;
     total = o;
   }
@@ -118,12 +110,13 @@ __device__ __forceinline__ void stage_chunk(T* dst, const T* src, size_t bytes, 
 }
 
 // ---- phase A: per-channel sum / max (+ first argmax pixel) over this CTA's pixels -----------------------------
-template <typename T>
+template <typename T, int VW>
 __device__ __forceinline__ void channel_partials(const T* xc, int np, int p0, int C, float* psum, float* pmax, int* pidx,
                                                  float* red) {
-  constexpr int EPL = Vec<T>::EPL;
-  const int nw = C / EPL;                       // words per pixel
-  const int groups = nw >= kThreads ? 1 : kThreads / nw;  // pixel groups working on the same word
+  constexpr int EPL = VW;
+  const int nw = C / EPL;                       // chunks per pixel
+  int groups = nw >= kThreads ? 1 : kThreads / nw;  // pixel groups working on the same chunk
+  groups = min(groups, max(1, kRedBytes / (C * 12)));  // [groups][C] x {sum,max,idx} must fit the scratch
   const int tw = threadIdx.x % (nw < kThreads ? nw : kThreads);
   const int pg = threadIdx.x / (nw < kThreads ? nw : kThreads);
   // red layout: [groups][C] x {sum,max,idx}; groups*C*12 bytes must fit -> fall back to groups=1 otherwise
@@ -135,7 +128,7 @@ __device__ __forceinline__ void channel_partials(const T* xc, int np, int p0, in
     if (pg < groups) {
       for (int p = pg; p < np; p += groups) {
         float v[EPL];
-        Vec<T>::load(xc + (size_t)p * C + w * EPL, v);
+        Vec<T, VW>::load(xc + (size_t)p * C + w * EPL, v);
 #pragma unroll
         for (int e = 0; e < EPL; ++e) {
           s[e] += v[e];
@@ -178,9 +171,9 @@ __device__ __forceinline__ void channel_partials(const T* xc, int np, int p0, in
   }
 }
 
-template <typename T, bool RES>
+template <typename T, bool RES, int VW>
 __global__ void __launch_bounds__(kThreads) cbam_fwd_kernel(CbamParams P) {
-  constexpr int EPL = Vec<T>::EPL;
+  constexpr int EPL = VW;
   cg::cluster_group cluster = cg::this_cluster();
   const int CS = (int)cluster.num_blocks();
   const int rank = (int)cluster.block_rank();
@@ -220,7 +213,7 @@ __global__ void __launch_bounds__(kThreads) cbam_fwd_kernel(CbamParams P) {
   const int cs0 = min(rank * cper, C), cs1 = min(cs0 + cper, C);
 
   if (P.mode != B200_CBAM_SA) {
-    channel_partials<T>(xc, np, p0, C, psum, pmax, pidx, red);
+    channel_partials<T, VW>(xc, np, p0, C, psum, pmax, pidx, red);
     cluster.sync();  // (1) partials visible cluster-wide
     // reduce slice S_rank over ranks -> pooled avg/max, then partial hidden = W1[:, S] . pooled[S]
     float* pav = caslice;  // reuse: pooled avg for the slice (overwritten by ca slice later)
@@ -280,7 +273,7 @@ __global__ void __launch_bounds__(kThreads) cbam_fwd_kernel(CbamParams P) {
     float s = 0.f, m = -INFINITY;
     for (int w = lane; w < nw; w += 32) {
       float v[EPL];
-      Vec<T>::load(xc + (size_t)p * C + w * EPL, v);
+      Vec<T, VW>::load(xc + (size_t)p * C + w * EPL, v);
 #pragma unroll
       for (int e = 0; e < EPL; ++e) {
         const float t = v[e] * ca[w * EPL + e];
@@ -349,10 +342,10 @@ __global__ void __launch_bounds__(kThreads) cbam_fwd_kernel(CbamParams P) {
       const float sp = sas[p];
       for (int w = lane; w < nw; w += 32) {
         float v[EPL];
-        Vec<T>::load(xc + (size_t)p * C + w * EPL, v);
+        Vec<T, VW>::load(xc + (size_t)p * C + w * EPL, v);
 #pragma unroll
         for (int e = 0; e < EPL; ++e) v[e] = v[e] * ca[w * EPL + e] * sp;
-        Vec<T>::store(dst + (size_t)p * C + w * EPL, v);
+        Vec<T, VW>::store(dst + (size_t)p * C + w * EPL, v);
       }
     }
     if (RES) {
@@ -382,9 +375,9 @@ __global__ void __launch_bounds__(kThreads) cbam_fwd_kernel(CbamParams P) {
 // =====================================================================================================
 // backward.  Same cluster decomposition; x and g chunks both staged once.
 // =====================================================================================================
-template <typename T, bool RES>
+template <typename T, bool RES, int VW>
 __global__ void __launch_bounds__(kThreads) cbam_bwd_kernel(CbamParams P) {
-  constexpr int EPL = Vec<T>::EPL;
+  constexpr int EPL = VW;
   cg::cluster_group cluster = cg::this_cluster();
   const int CS = (int)cluster.num_blocks();
   const int rank = (int)cluster.block_rank();
@@ -458,8 +451,8 @@ __global__ void __launch_bounds__(kThreads) cbam_bwd_kernel(CbamParams P) {
       int mi = 0;
       for (int w = lane; w < nw; w += 32) {
         float v[EPL], gv[EPL];
-        Vec<T>::load(xc + (size_t)p * C + w * EPL, v);
-        if (gc) Vec<T>::load(gc + (size_t)p * C + w * EPL, gv);
+        Vec<T, VW>::load(xc + (size_t)p * C + w * EPL, v);
+        if (gc) Vec<T, VW>::load(gc + (size_t)p * C + w * EPL, gv);
 #pragma unroll
         for (int e = 0; e < EPL; ++e) {
           const float t = v[e] * ca[w * EPL + e];
@@ -601,7 +594,7 @@ __global__ void __launch_bounds__(kThreads) cbam_bwd_kernel(CbamParams P) {
       float o[EPL];
 #pragma unroll
       for (int e = 0; e < EPL; ++e) o[e] = sas[pc + p] + ((w * EPL + e) == am ? sas[2 * pc + p] : 0.f);
-      Vec<T>::store(og + (size_t)p * C + w * EPL, o);
+      Vec<T, VW>::store(og + (size_t)p * C + w * EPL, o);
     }
     cluster.sync();
     return;
@@ -609,11 +602,11 @@ __global__ void __launch_bounds__(kThreads) cbam_bwd_kernel(CbamParams P) {
 
   // (3)+(4): g_x1 = g*sa + g_s0 + [c==argmax_c] g_s1 ;  g_ca[c] = sum_p g_x1 * x  (per-CTA partial -> psum)
   // also the pooled statistics again (avg / max / argmax_hw) for the MLP backward.
-  channel_partials<T>(xc, np, p0, C, psum, pmax, pidx, red);
+  channel_partials<T, VW>(xc, np, p0, C, psum, pmax, pidx, red);
   __syncthreads();
   float* gca_part = slc;  // [C] this CTA's partial of g_ca
   if (P.mode == B200_CBAM_FULL) {
-    const int groups = nw >= kThreads ? 1 : kThreads / nw;
+    const int groups = min(nw >= kThreads ? 1 : kThreads / nw, max(1, kRedBytes / (C * 12)));
     const int tw = tid % (nw < kThreads ? nw : kThreads), pg = tid / (nw < kThreads ? nw : kThreads);
     for (int i = tid; i < C; i += kThreads) gca_part[i] = 0.f;
     __syncthreads();
@@ -624,8 +617,8 @@ __global__ void __launch_bounds__(kThreads) cbam_bwd_kernel(CbamParams P) {
       if (pg < groups)
         for (int p = pg; p < np; p += groups) {
           float v[EPL], gv[EPL];
-          Vec<T>::load(xc + (size_t)p * C + w * EPL, v);
-          Vec<T>::load(gc + (size_t)p * C + w * EPL, gv);
+          Vec<T, VW>::load(xc + (size_t)p * C + w * EPL, v);
+          Vec<T, VW>::load(gc + (size_t)p * C + w * EPL, gv);
           const int am = __float_as_int(smap[3 * pc + p]);
 #pragma unroll
           for (int e = 0; e < EPL; ++e) {
@@ -640,7 +633,7 @@ __global__ void __launch_bounds__(kThreads) cbam_bwd_kernel(CbamParams P) {
     }
     __syncthreads();
     {
-      const int groups2 = nw >= kThreads ? 1 : kThreads / nw;
+      const int groups2 = min(nw >= kThreads ? 1 : kThreads / nw, max(1, kRedBytes / (C * 12)));
       for (int c = tid; c < C; c += kThreads) {
         float s = 0.f;
         for (int gi = 0; gi < groups2; ++gi) s += red[(size_t)gi * C + c];
@@ -737,7 +730,7 @@ __global__ void __launch_bounds__(kThreads) cbam_bwd_kernel(CbamParams P) {
       const float sp = sas[p], g0 = sas[pc + p], g1 = sas[2 * pc + p];
       for (int w = lane; w < nw; w += 32) {
         float gv[EPL], o[EPL];
-        if (gc) Vec<T>::load(gc + (size_t)p * C + w * EPL, gv);
+        if (gc) Vec<T, VW>::load(gc + (size_t)p * C + w * EPL, gv);
 #pragma unroll
         for (int e = 0; e < EPL; ++e) {
           const int c = w * EPL + e;
@@ -745,7 +738,7 @@ __global__ void __launch_bounds__(kThreads) cbam_bwd_kernel(CbamParams P) {
           if (P.mode == B200_CBAM_FULL) gx1 = gv[e] * sp + g0 + (c == am ? g1 : 0.f);
           o[e] = gx1 * ca[c] + ca[C + c] + ((p0 + p) == __float_as_int(ca[3 * C + c]) ? ca[2 * C + c] : 0.f);
         }
-        Vec<T>::store(og + (size_t)p * C + w * EPL, o);
+        Vec<T, VW>::store(og + (size_t)p * C + w * EPL, o);
       }
     }
   }
@@ -838,8 +831,12 @@ extern "C" B200_API int b200_cbam_fwd(const void* x, const float* w1, const floa
   CbamParams P{x, nullptr, out, w1, w2, wsa, ca_out, sa_out, nullptr, B, C, H, W, r, ksa, mode, pc};
   cudaStream_t st = (cudaStream_t)stream;
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
-    return res ? launch_cluster(cbam_fwd_kernel<T, true>, B * cs, cs, smem, st, P)
-               : launch_cluster(cbam_fwd_kernel<T, false>, B * cs, cs, smem, st, P);
+    constexpr int VE = Words<T>::VE, EW = Words<T>::EPL;
+    if (C % VE == 0 && ((uintptr_t)x & 15) == 0 && (mode != B200_CBAM_FULL || ((uintptr_t)out & 15) == 0))
+      return res ? launch_cluster(cbam_fwd_kernel<T, true, VE>, B * cs, cs, smem, st, P)
+                 : launch_cluster(cbam_fwd_kernel<T, false, VE>, B * cs, cs, smem, st, P);
+    return res ? launch_cluster(cbam_fwd_kernel<T, true, EW>, B * cs, cs, smem, st, P)
+               : launch_cluster(cbam_fwd_kernel<T, false, EW>, B * cs, cs, smem, st, P);
   });
 }
 
@@ -871,8 +868,12 @@ extern "C" B200_API int b200_cbam_bwd(const void* g, const void* x, const float*
   // partial slots that a mode never writes must read as zero
   cudaMemsetAsync(workspace, 0, need, st);
   int rc = B200_DISPATCH_DTYPE(dtype, [&]() -> int {
-    return res ? launch_cluster(cbam_bwd_kernel<T, true>, B * cs, cs, smem, st, P)
-               : launch_cluster(cbam_bwd_kernel<T, false>, B * cs, cs, smem, st, P);
+    constexpr int VE = Words<T>::VE, EW = Words<T>::EPL;
+    if (C % VE == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)gx & 15) == 0 && (mode != B200_CBAM_FULL || ((uintptr_t)g & 15) == 0))
+      return res ? launch_cluster(cbam_bwd_kernel<T, true, VE>, B * cs, cs, smem, st, P)
+                 : launch_cluster(cbam_bwd_kernel<T, false, VE>, B * cs, cs, smem, st, P);
+    return res ? launch_cluster(cbam_bwd_kernel<T, true, EW>, B * cs, cs, smem, st, P)
+               : launch_cluster(cbam_bwd_kernel<T, false, EW>, B * cs, cs, smem, st, P);
   });
   if (rc) return rc;
   const int n1 = r * C, n2 = C * r, n3 = 2 * ksa * ksa;
