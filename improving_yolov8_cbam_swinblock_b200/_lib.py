@@ -29,6 +29,7 @@ _SIGS = {
     "b200_cbam_fwd": (C.c_int, [_vp] * 7 + [_i32] * 8 + [_vp]),
     "b200_cbam_bwd_workspace_bytes": (_sz, [_i32] * 6),
     "b200_cbam_bwd": (C.c_int, [_vp] * 12 + [_sz] + [_i32] * 8 + [_vp]),
+    "b200_debug_cbam_prof": (None, [_vp]),
 }
 
 

@@ -1,20 +1,26 @@
 // CBAM (channel attention -> spatial attention -> gate), forward and backward, one launch each.
 // Replaces cbam.py:29-38 / :48-53 / :62-71 of the reference (and their autograd backward).
 //
-// One thread-block CLUSTER per image.  The image (NHWC, so a pixel range is one contiguous byte range) is split
-// into CS contiguous pixel chunks, one per CTA of the cluster, and each chunk is pulled into shared memory ONCE
-// by a 1-D bulk TMA copy (cp.async.bulk -> UBLKCP).  Everything else happens on chip:
-//   A  per-channel sum / max over the chunk               -> partials in smem
-//      [cluster.sync]  rank k reduces the partials of channel slice S_k over all ranks (DSMEM), multiplies with
-//                      W1[:, S_k]                          -> partial hidden activations
-//      [cluster.sync]  all ranks sum the partial hiddens, rank k computes ca for S_k with W2[S_k, :]
-//      [cluster.sync]  all ranks gather the full ca vector (DSMEM)
-//   B  per-pixel mean_c / max_c of x*ca over the chunk     -> 2-channel map chunk in smem
-//      [cluster.sync]  gather the +-(pad*W+pad) halo of the map from neighbouring ranks (DSMEM)
-//   C  k x k conv + sigmoid -> sa; out = x*ca*sa written in place into the staged chunk and pushed out with one
-//      bulk shared->global store.
+// One thread-block CLUSTER per image (grid = CS x B, cluster = CS x 1).  The image (NHWC, so a pixel range is one
+// contiguous byte range) is split into CS contiguous pixel chunks, one per CTA of the cluster, and each chunk is
+// pulled into shared memory ONCE by a 1-D bulk TMA copy (cp.async.bulk -> UBLKCP).  Everything else happens on chip:
+//   A  per-channel sum / max over the chunk (thread = one 16-byte channel vector, looping over pixels)
+//      [cluster.sync]  every rank reduces the partials of all ranks over DSMEM and runs the tiny shared MLP + sigmoid
+//                      redundantly (32 KB of weights from L2 per CTA is cheaper than two more cluster barriers)
+//   B  per-pixel mean_c / max_c of x*ca (sub-warp per pixel, 16-byte vectors)  -> 2-channel map chunk in smem
+//      [cluster.sync]  gather a zero-padded 2-D tile (rows of the chunk +-3, columns -3..W+3) of the map from the
+//                      neighbouring ranks (DSMEM): the 7x7 taps then need no bounds checks
+//   C  7x7 conv + sigmoid -> sa (4 lanes per pixel); out = x*ca*sa with packed 16-bit multiplies, 16-byte stores.
 // HBM traffic = the algorithmic 1 read + 1 write of the feature map.  If a chunk does not fit in shared memory the
 // same kernel runs "non-resident": phases A/B/C re-read the chunk from global memory (L2 at these sizes).
+// A 3x3 spatial-attention kernel (cbam.py:43) runs as a 7x7 kernel embedded in zeros.  All shape-dependent
+// constants (chunking, lane mapping, shared-memory offsets) are computed once on the host (`Plan`): at the model's
+// shapes a CTA owns ~50 pixels, so scalar set-up code is what the kernel's latency is made of.
+//
+// NaN note: the channel/pixel maxima use the hardware max (which drops NaN) because every output they can reach is
+// already NaN through the sum/mean computed over the same elements (a NaN in x makes the pooled average, hence the
+// whole ca vector, NaN; a NaN in x*ca makes the channel mean at that pixel NaN, and the mean and max maps feed the
+// same conv window) -- the result is NaN in exactly the positions where the reference's is.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -25,7 +31,21 @@ namespace b200 {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int KS = 7, PADK = 3, KROW = 8;   // conv taps are stored [2][7][8] (rows padded to 8 floats)
+constexpr int NTAPS = 2 * KS * KROW;        // 112 slots, 98 used
+constexpr int NT7 = 2 * KS * KS;            // 98
+constexpr int kMaxCS = 16;
 constexpr int kRedBytes = 12288 + 1024;
+
+// Host-computed launch plan (passed by value in the kernel parameters).
+struct Plan {
+  int B, C, H, W, HW, r, ksa, mode;
+  int cs, pchunk, nch, lpp, groups, th, tw, resident;
+  float invC, invHW;
+  // shared-memory byte offsets
+  int xs, gs, psum, pmax, pidx, gca, pav, pmx, hid, ca, vec, smap, tile, pix, poff, wsa, red, bar, total;
+};
 
 struct CbamParams {
   const void* x;
@@ -36,8 +56,10 @@ struct CbamParams {
   const float* wsa;
   float* ca;  // fwd: out (nullable); bwd: in
   float* sa;
-  float* part;  // bwd: per-image weight-grad partials
-  int B, C, H, W, r, ksa, mode, pchunk;
+  float* part;   // bwd: per-image MLP weight-grad partials [B][2rC]
+  float* cpart;  // bwd: per-CTA conv weight-grad partials [B][kMaxCS][98]
+  long long* prof;  // debug: per-CTA phase timestamps (b200_debug_cbam_prof), normally null
+  Plan pl;
 };
 
 // VW contiguous channels <-> floats.  VW * sizeof(T) is 16 bytes on the fast path ("vectorised NHWC loads": one
@@ -57,98 +79,104 @@ template <typename T, int VW> struct Vec {
   }
 };
 template <typename T> struct Words { static constexpr int EPL = 4 / (int)sizeof(T), VE = 16 / (int)sizeof(T); };
+template <typename T> struct Pair2 { using type = float2; };
+template <> struct Pair2<__nv_bfloat16> { using type = __nv_bfloat162; };
+template <> struct Pair2<__half> { using type = __half2; };
+__device__ __forceinline__ __nv_bfloat162 make_pair(__nv_bfloat16, float a, float b) { return __floats2bfloat162_rn(a, b); }
+__device__ __forceinline__ __half2 make_pair(__half, float a, float b) { return __floats2half2_rn(a, b); }
 
-__host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
-
-// Shared-memory carve-up shared by host (sizing) and device.
-struct SmemLayout {
-  size_t xs, gs, psum, pmax, pidx, hpart, hid, caslice, ca, smap, shalo, sa, wsa, red, bar, total;
-  int halo;
-  __host__ __device__ SmemLayout(int C, int r, int W, int ksa, int pchunk, size_t esize, bool resident, bool bwd) {
-    const int pad = ksa / 2;
-    halo = pad * W + pad;
-    size_t o = 0;
-    xs = o; o += resident ? align16((size_t)pchunk * C * esize) : 0;
-    gs = o; o += (resident && bwd) ? align16((size_t)pchunk * C * esize) : 0;
-    psum = o; o += align16((size_t)C * 4);
-    pmax = o; o += align16((size_t)C * 4);
-    pidx = o; o += align16((size_t)C * 4);
-    hpart = o; o += align16((size_t)2 * r * 4);       // this rank's partial hidden pre-activations [2][r]
-    hid = o; o += align16((size_t)4 * r * 4);         // summed hidden [2][r] (+ bwd: grads [2][r])
-    caslice = o; o += align16((size_t)C * 4 * (bwd ? 3 : 1));  // slice-owner results (peers gather from here)
-    ca = o; o += align16((size_t)C * 4 * (bwd ? 4 : 1));       // gathered full-C vectors
-    smap = o; o += align16((size_t)2 * pchunk * 4 * (bwd ? 2 : 1));  // own map chunk [2][pchunk] (+ bwd: gz / argmax)
-    shalo = o; o += align16((size_t)2 * (pchunk + 2 * halo) * 4);     // gathered map with halo
-    sa = o; o += align16((size_t)pchunk * 4 * (bwd ? 3 : 1));
-    wsa = o; o += align16((size_t)2 * ksa * ksa * 4 * (bwd ? 2 : 1));
-    red = o; o += kRedBytes;  // cross-group reduction scratch
-    bar = o; o += 16;
-    total = o;
+__device__ __forceinline__ void prof_mark(const CbamParams& P, int slot) {
+  if (P.prof && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    P.prof[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + slot] = t;
   }
-};
+}
+long long* g_cbam_prof = nullptr;
 
-// Cooperative chunk load: bulk TMA when 16-byte aligned, plain loads otherwise.
-template <typename T>
-__device__ __forceinline__ void stage_chunk(T* dst, const T* src, size_t bytes, uint64_t* bar, uint32_t parity) {
-  const bool aligned = ((bytes & 15) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-  if (aligned) {
-    if (threadIdx.x == 0 && bytes) {
-      mbar_expect_tx(bar, (uint32_t)bytes);
-      size_t off = 0;
-      while (off < bytes) {
-        const uint32_t n = (uint32_t)((bytes - off) > 32768 ? 32768 : (bytes - off));
-        bulk_g2s(reinterpret_cast<char*>(dst) + off, reinterpret_cast<const char*>(src) + off, n, bar);
-        off += n;
-      }
+inline int align16i(size_t v) { return (int)((v + 15) & ~(size_t)15); }
+
+// conv weights -> smem [2][7][8], a 3x3 kernel centred in zeros
+__device__ __forceinline__ void load_taps(float* wsas, const float* wsa, int ks) {
+  for (int i = threadIdx.x; i < NTAPS; i += kThreads) {
+    const int ch = i / (KS * KROW), u = (i / KROW) % KS, v = i % KROW;
+    float w = 0.f;
+    if (wsa && v < KS) {
+      const int o = (KS - ks) / 2, uu = u - o, vv = v - o;
+      if (uu >= 0 && uu < ks && vv >= 0 && vv < ks) w = wsa[(ch * ks + uu) * ks + vv];
     }
-    if (bytes) mbar_wait(bar, parity);
-  } else {
-    const size_t n = bytes / sizeof(T);
-    for (size_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-    __syncthreads();
+    wsas[i] = w;
   }
 }
 
-// ---- phase A: per-channel sum / max (+ first argmax pixel) over this CTA's pixels -----------------------------
-template <typename T, int VW>
-__device__ __forceinline__ void channel_partials(const T* xc, int np, int p0, int C, float* psum, float* pmax, int* pidx,
-                                                 float* red) {
-  constexpr int EPL = VW;
-  const int nw = C / EPL;                       // chunks per pixel
-  int groups = nw >= kThreads ? 1 : kThreads / nw;  // pixel groups working on the same chunk
-  groups = min(groups, max(1, kRedBytes / (C * 12)));  // [groups][C] x {sum,max,idx} must fit the scratch
-  const int tw = threadIdx.x % (nw < kThreads ? nw : kThreads);
-  const int pg = threadIdx.x / (nw < kThreads ? nw : kThreads);
-  // red layout: [groups][C] x {sum,max,idx}; groups*C*12 bytes must fit -> fall back to groups=1 otherwise
+// bulk-TMA staging of one or two contiguous chunks; returns whether the caller has to wait on the mbarrier
+template <typename T>
+__device__ __forceinline__ bool stage_chunks(T* xs, const T* xg, T* gs, const T* gg, int n, uint64_t* bar) {
+  const size_t bytes = (size_t)n * sizeof(T);
+  const bool aligned = ((bytes & 15) == 0) && ((reinterpret_cast<uintptr_t>(xg) & 15) == 0) &&
+                       (!gg || (reinterpret_cast<uintptr_t>(gg) & 15) == 0);
+  if (aligned) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+      if (bytes) {
+        mbar_expect_tx(bar, (uint32_t)(bytes * (gg ? 2 : 1)));
+        for (size_t off = 0; off < bytes; off += 32768) {
+          const uint32_t k = (uint32_t)((bytes - off) > 32768 ? 32768 : (bytes - off));
+          bulk_g2s(reinterpret_cast<char*>(xs) + off, reinterpret_cast<const char*>(xg) + off, k, bar);
+          if (gg) bulk_g2s(reinterpret_cast<char*>(gs) + off, reinterpret_cast<const char*>(gg) + off, k, bar);
+        }
+      }
+    }
+    return bytes != 0;
+  }
+  for (int i = threadIdx.x; i < n; i += kThreads) { xs[i] = xg[i]; if (gg) gs[i] = gg[i]; }
+  return false;
+}
+
+// ---- phase A: per-channel sum / max (+ first argmax pixel when IDX) over this CTA's pixels ---------------------
+template <typename T, int VW, bool IDX>
+__device__ __forceinline__ void channel_partials(const T* xc, int np, int p0, int C, int nw, int groups, float* psum,
+                                                 float* pmax, int* pidx, float* red) {
+  const int tpg = nw < kThreads ? nw : kThreads;   // threads per pixel group
+  const int pg = threadIdx.x / tpg, tw = threadIdx.x - pg * tpg;
   for (int w = tw; w < nw; w += kThreads) {
-    float s[EPL], m[EPL];
-    int mi[EPL];
+    float s[VW], m[VW];
+    int mi[VW];
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) { s[e] = 0.f; m[e] = -INFINITY; mi[e] = p0; }
+    for (int e = 0; e < VW; ++e) { s[e] = 0.f; m[e] = -INFINITY; mi[e] = p0; }
     if (pg < groups) {
+      const T* src = xc + w * VW;
+#pragma unroll 2
       for (int p = pg; p < np; p += groups) {
-        float v[EPL];
-        Vec<T, VW>::load(xc + (size_t)p * C + w * EPL, v);
+        float v[VW];
+        Vec<T, VW>::load(src + (size_t)p * C, v);
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) {
+        for (int e = 0; e < VW; ++e) {
           s[e] += v[e];
-          const bool take = (v[e] > m[e]) || (v[e] != v[e]);
-          if (take) { m[e] = v[e]; mi[e] = p0 + p; }
+          if (IDX) {
+            if (v[e] > m[e]) { m[e] = v[e]; mi[e] = p0 + p; }
+          } else {
+            m[e] = fmaxf(m[e], v[e]);
+          }
         }
       }
     }
     if (groups == 1) {
       if (pg == 0) {
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) { psum[w * EPL + e] = s[e]; pmax[w * EPL + e] = m[e]; pidx[w * EPL + e] = mi[e]; }
+        for (int e = 0; e < VW; ++e) {
+          psum[w * VW + e] = s[e]; pmax[w * VW + e] = m[e];
+          if (IDX) pidx[w * VW + e] = mi[e];
+        }
       }
     } else if (pg < groups) {
       float* rs = red + (size_t)pg * C * 3;
 #pragma unroll
-      for (int e = 0; e < EPL; ++e) {
-        rs[w * EPL + e] = s[e];
-        rs[C + w * EPL + e] = m[e];
-        reinterpret_cast<int*>(rs)[2 * C + w * EPL + e] = mi[e];
+      for (int e = 0; e < VW; ++e) {
+        rs[w * VW + e] = s[e];
+        rs[C + w * VW + e] = m[e];
+        if (IDX) reinterpret_cast<int*>(rs)[2 * C + w * VW + e] = mi[e];
       }
     }
   }
@@ -157,626 +185,600 @@ __device__ __forceinline__ void channel_partials(const T* xc, int np, int p0, in
     for (int c = threadIdx.x; c < C; c += kThreads) {
       float s = 0.f, m = -INFINITY;
       int mi = p0;
-      bool nan = false;
       for (int gi = 0; gi < groups; ++gi) {  // groups interleave pixels: combine by (value, then smaller index)
         const float* rs = red + (size_t)gi * C * 3;
         s += rs[c];
         const float v = rs[C + c];
-        const int vi = reinterpret_cast<const int*>(rs)[2 * C + c];
-        if (v != v) { if (!nan || vi > mi) { m = v; mi = vi; nan = true; } }
-        else if (!nan && (v > m || (v == m && vi < mi && v != -INFINITY))) { m = v; mi = vi; }
+        if (IDX) {
+          const int vi = reinterpret_cast<const int*>(rs)[2 * C + c];
+          if (v > m || (v == m && vi < mi && v != -INFINITY)) { m = v; mi = vi; }
+        } else {
+          m = fmaxf(m, v);
+        }
       }
-      psum[c] = s; pmax[c] = m; pidx[c] = mi;
+      psum[c] = s; pmax[c] = m;
+      if (IDX) pidx[c] = mi;
     }
   }
 }
 
+// gather NM zero-padded [nrow][tw] tiles (rows ya-3 .., columns -3 .. W+3; tile stride th*tw) of per-pixel maps
+// that live, chunked by pchunk, in the `smap` buffers of the cluster's ranks.  Map j comes from smap + moff[j].
+template <int NM>
+__device__ __forceinline__ void gather_tiles(cg::cluster_group& cluster, float* tile, float* smap, int m0, int m1, int m2,
+                                             int ya, int nrow, const Plan& L) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int row = warp; row < NM * nrow; row += kWarps) {
+    const int j = row / nrow, ty = row - j * nrow, y = ya - PADK + ty;
+    const int mo = j == 0 ? m0 : (j == 1 ? m1 : m2);
+    float* dst = tile + (size_t)(j * L.th + ty) * L.tw;
+    for (int tx = lane; tx < L.tw; tx += 32) {
+      const int x = tx - PADK;
+      float v = 0.f;
+      if (y >= 0 && y < L.H && x >= 0 && x < L.W) {
+        const int q = y * L.W + x;
+        const int owner = min(q / L.pchunk, L.cs - 1);
+        v = cluster.map_shared_rank(smap, owner)[mo + (q - owner * L.pchunk)];
+      }
+      dst[tx] = v;
+    }
+  }
+}
+
+__device__ __forceinline__ float relu_nan(float a) { return (a != a) ? a : fmaxf(a, 0.f); }  // torch.relu keeps NaN
+
 template <typename T, bool RES, int VW>
-__global__ void __launch_bounds__(kThreads) cbam_fwd_kernel(CbamParams P) {
-  constexpr int EPL = VW;
+__global__ void __launch_bounds__(kThreads) cbam_fwd_kernel(const __grid_constant__ CbamParams P) {
   cg::cluster_group cluster = cg::this_cluster();
-  const int CS = (int)cluster.num_blocks();
-  const int rank = (int)cluster.block_rank();
-  const int b = blockIdx.x / CS;
-  const int C = P.C, HW = P.H * P.W, W = P.W, H = P.H, r = P.r, ks = P.ksa, pad = ks / 2;
-  const int p0 = min(rank * P.pchunk, HW), p1 = min(p0 + P.pchunk, HW), np = p1 - p0;
+  const Plan& L = P.pl;
+  const int CS = L.cs, rank = blockIdx.x, b = blockIdx.y;
+  const int C = L.C, HW = L.HW, W = L.W, r = L.r, nch = L.nch;
+  const int p0 = min(rank * L.pchunk, HW), p1 = min(p0 + L.pchunk, HW), np = p1 - p0;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const SmemLayout L(C, r, W, ks, P.pchunk, sizeof(T), RES, false);
   T* xs = reinterpret_cast<T*>(smem_raw + L.xs);
   float* psum = reinterpret_cast<float*>(smem_raw + L.psum);
   float* pmax = reinterpret_cast<float*>(smem_raw + L.pmax);
-  int* pidx = reinterpret_cast<int*>(smem_raw + L.pidx);
-  float* hpart = reinterpret_cast<float*>(smem_raw + L.hpart);
+  float* pav = reinterpret_cast<float*>(smem_raw + L.pav);
+  float* pmx = reinterpret_cast<float*>(smem_raw + L.pmx);
   float* hid = reinterpret_cast<float*>(smem_raw + L.hid);
-  float* caslice = reinterpret_cast<float*>(smem_raw + L.caslice);
   float* ca = reinterpret_cast<float*>(smem_raw + L.ca);
   float* smap = reinterpret_cast<float*>(smem_raw + L.smap);
-  float* shalo = reinterpret_cast<float*>(smem_raw + L.shalo);
-  float* sas = reinterpret_cast<float*>(smem_raw + L.sa);
+  float* tile = reinterpret_cast<float*>(smem_raw + L.tile);
+  float* sas = reinterpret_cast<float*>(smem_raw + L.pix);
   float* wsas = reinterpret_cast<float*>(smem_raw + L.wsa);
   float* red = reinterpret_cast<float*>(smem_raw + L.red);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  prof_mark(P, 0);
 
   const T* xg = reinterpret_cast<const T*>(P.x) + ((size_t)b * HW + p0) * C;
   const T* xc = xg;
+  bool wait_tma = false;
   if (RES) {
-    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
-    __syncthreads();
-    stage_chunk<T>(xs, xg, (size_t)np * C * sizeof(T), bar, 0);
+    wait_tma = stage_chunks<T>(xs, xg, nullptr, nullptr, np * C, bar);
     xc = xs;
   }
-  for (int i = tid; i < 2 * ks * ks; i += kThreads) wsas[i] = P.wsa ? P.wsa[i] : 0.f;
+  load_taps(wsas, P.wsa, L.ksa);   // overlaps the bulk copy
+  __syncthreads();                 // mbarrier init + taps visible
+  if (wait_tma) mbar_wait(bar, 0);
+  prof_mark(P, 1);
 
-  // channel slice owned by this rank for the cross-rank reductions
-  const int cper = (C + CS - 1) / CS;
-  const int cs0 = min(rank * cper, C), cs1 = min(cs0 + cper, C);
-
-  if (P.mode != B200_CBAM_SA) {
-    channel_partials<T, VW>(xc, np, p0, C, psum, pmax, pidx, red);
+  if (L.mode != B200_CBAM_SA) {
+    channel_partials<T, VW, false>(xc, np, p0, C, nch, L.groups, psum, pmax, nullptr, red);
+    prof_mark(P, 2);
     cluster.sync();  // (1) partials visible cluster-wide
-    // reduce slice S_rank over ranks -> pooled avg/max, then partial hidden = W1[:, S] . pooled[S]
-    float* pav = caslice;  // reuse: pooled avg for the slice (overwritten by ca slice later)
-    float* pmx = red;      // pooled max for the slice
-    for (int c = cs0 + tid; c < cs1; c += kThreads) {
+    prof_mark(P, 3);
+    for (int c = tid; c < C; c += kThreads) {   // pooled avg / max of every channel (cbam.py:8-9)
       float s = 0.f, m = -INFINITY;
-      bool nan = false;
       for (int k2 = 0; k2 < CS; ++k2) {
-        const float* rs = cluster.map_shared_rank(psum, k2);
-        const float* rm = cluster.map_shared_rank(pmax, k2);
-        s += rs[c];
-        const float v = rm[c];
-        if (v != v) nan = true;
-        else if (v > m) m = v;
+        s += cluster.map_shared_rank(psum, k2)[c];
+        m = fmaxf(m, cluster.map_shared_rank(pmax, k2)[c]);
       }
-      pav[c - cs0] = s / (float)HW;
-      pmx[c - cs0] = nan ? __int_as_float(0x7fc00000) : m;
+      pav[c] = s * L.invHW;
+      pmx[c] = (s != s) ? s : m;   // a NaN anywhere in the channel makes the pooled max NaN too
     }
     __syncthreads();
-    for (int j = warp; j < 2 * r; j += kThreads / 32) {  // j < r: avg branch, j >= r: max branch
-      const int jj = j < r ? j : j - r;
+    for (int j = warp; j < 2 * r; j += kWarps) {  // hidden = relu(W1 pooled); j < r: avg branch, j >= r: max branch
+      const float* wrow = P.w1 + (size_t)(j < r ? j : j - r) * C;
       const float* src = j < r ? pav : pmx;
       float acc = 0.f;
-      for (int c = cs0 + lane; c < cs1; c += 32) acc += P.w1[(size_t)jj * C + c] * src[c - cs0];
+#pragma unroll 4
+      for (int c = lane; c < C; c += 32) acc += wrow[c] * src[c];
       acc = warp_sum(acc);
-      if (lane == 0) hpart[j] = acc;
-    }
-    cluster.sync();  // (2) partial hiddens visible
-    for (int j = tid; j < 2 * r; j += kThreads) {
-      float acc = 0.f;
-      for (int k2 = 0; k2 < CS; ++k2) acc += cluster.map_shared_rank(hpart, k2)[j];
-      hid[j] = fmaxf(acc, 0.f);  // ReLU (cbam.py:25)
+      if (lane == 0) hid[j] = relu_nan(acc);
     }
     __syncthreads();
-    for (int c = cs0 + tid; c < cs1; c += kThreads) {
-      float z = 0.f;
-      for (int j = 0; j < r; ++j) z += P.w2[(size_t)c * r + j] * (hid[j] + hid[r + j]);
-      const float a = sigmoidf_(z);
-      ca[c] = a;  // own slice goes straight to its final place; peers read it from `ca` of this rank
-      if (P.ca) P.ca[(size_t)b * C + c] = a;
-    }
-    cluster.sync();  // (3) every rank's ca slice visible
     for (int c = tid; c < C; c += kThreads) {
-      const int owner = min(c / cper, CS - 1);
-      if (owner != rank) ca[c] = cluster.map_shared_rank(ca, owner)[c];
+      const float* wrow = P.w2 + (size_t)c * r;
+      float z = 0.f;
+#pragma unroll 4
+      for (int j = 0; j < r; ++j) z += wrow[j] * (hid[j] + hid[r + j]);
+      const float a = sigmoidf_(z);
+      ca[c] = a;
+      if (P.ca && rank == 0) P.ca[(size_t)b * C + c] = a;
     }
     __syncthreads();
-    if (P.mode == B200_CBAM_CA) { cluster.sync(); return; }
+    prof_mark(P, 4);
+    if (L.mode == B200_CBAM_CA) { cluster.sync(); return; }
   } else {
     for (int c = tid; c < C; c += kThreads) ca[c] = 1.f;
     __syncthreads();
   }
 
-  // ---- phase B: per-pixel channel mean / max of x*ca -----------------------------------------------------
-  const int nw = C / EPL;
-  for (int p = warp; p < np; p += kThreads / 32) {
+  // ---- phase B: per-pixel channel mean / max of x*ca (sub-warp of LPP lanes per pixel) ---------------------------
+  const int LPP = L.lpp, PPW = 32 / LPP, sub = lane / LPP, sl = lane & (LPP - 1);
+  const bool one = nch <= LPP;   // one chunk per lane: its ca values stay in registers
+  float car[VW];
+#pragma unroll
+  for (int e = 0; e < VW; ++e) car[e] = (one && sl < nch) ? ca[sl * VW + e] : 0.f;
+  for (int pb = warp * PPW; pb < np; pb += kWarps * PPW) {
+    const int p = pb + sub;
     float s = 0.f, m = -INFINITY;
-    for (int w = lane; w < nw; w += 32) {
-      float v[EPL];
-      Vec<T, VW>::load(xc + (size_t)p * C + w * EPL, v);
+    if (p < np) {
+      for (int w = sl; w < nch; w += LPP) {
+        float v[VW];
+        Vec<T, VW>::load(xc + (size_t)p * C + w * VW, v);
+        if (!one) {
 #pragma unroll
-      for (int e = 0; e < EPL; ++e) {
-        const float t = v[e] * ca[w * EPL + e];
-        s += t;
-        m = (t > m || t != t) ? t : m;
-      }
-    }
-    s = warp_sum(s);
-    // NaN-propagating max across lanes
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float t = __shfl_xor_sync(0xffffffffu, m, o);
-      m = (t > m || t != t) ? t : m;
-    }
-    if (lane == 0) { smap[p] = s / (float)C; smap[P.pchunk + p] = m; }
-  }
-  cluster.sync();  // (4) map chunks visible
-  // gather map with halo: flat positions [p0 - halo, p1 + halo)
-  const int halo = L.halo, span = np + 2 * halo;
-  for (int i = tid; i < 2 * span; i += kThreads) {
-    const int ch = i / span, q = p0 - halo + (i - ch * span);
-    float v = 0.f;
-    if (q >= 0 && q < HW) {
-      const int owner = min(q / P.pchunk, CS - 1);
-      v = cluster.map_shared_rank(smap, owner)[ch * P.pchunk + (q - owner * P.pchunk)];
-    }
-    shalo[ch * (P.pchunk + 2 * halo) + (i - ch * span)] = v;
-  }
-  __syncthreads();
-  // ---- phase C: conv + sigmoid (warp per pixel, lanes own up to 4 of the 2*ks*ks taps), gate ---------------------
-  {
-    constexpr int TPL = 4;  // taps per lane: 2*7*7 = 98 <= 128
-    int tdu[TPL], tdv[TPL], tch[TPL];
-    float tw[TPL];
-#pragma unroll
-    for (int j = 0; j < TPL; ++j) {
-      const int t = lane + 32 * j;
-      const bool ok = t < 2 * ks * ks;
-      tch[j] = ok ? t / (ks * ks) : 0;
-      tdu[j] = ok ? (t / ks) % ks - pad : 0;
-      tdv[j] = ok ? t % ks - pad : 0;
-      tw[j] = ok ? wsas[t] : 0.f;
-    }
-    const int hp_ = P.pchunk + 2 * halo;
-    for (int p = warp; p < np; p += kThreads / 32) {
-      const int q = p0 + p, y = q / W, x = q - y * W;
-      float z = 0.f;
-#pragma unroll
-      for (int j = 0; j < TPL; ++j) {
-        const int yy = y + tdu[j], xx = x + tdv[j];
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) z += tw[j] * shalo[tch[j] * hp_ + (yy * W + xx) - (p0 - halo)];
-      }
-      z = warp_sum(z);
-      if (lane == 0) {
-        const float a = sigmoidf_(z);
-        sas[p] = a;
-        if (P.sa) P.sa[(size_t)b * HW + q] = a;
-      }
-    }
-  }
-  __syncthreads();
-  if (P.mode == B200_CBAM_FULL) {
-    T* og = reinterpret_cast<T*>(P.out) + ((size_t)b * HW + p0) * C;
-    T* dst = RES ? xs : og;
-    for (int p = warp; p < np; p += kThreads / 32) {
-      const float sp = sas[p];
-      for (int w = lane; w < nw; w += 32) {
-        float v[EPL];
-        Vec<T, VW>::load(xc + (size_t)p * C + w * EPL, v);
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) v[e] = v[e] * ca[w * EPL + e] * sp;
-        Vec<T, VW>::store(dst + (size_t)p * C + w * EPL, v);
-      }
-    }
-    if (RES) {
-      const size_t bytes = (size_t)np * C * sizeof(T);
-      if (((bytes & 15) == 0) && ((reinterpret_cast<uintptr_t>(og) & 15) == 0)) {
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0 && bytes) {
-          size_t off = 0;
-          while (off < bytes) {
-            const uint32_t n = (uint32_t)((bytes - off) > 32768 ? 32768 : (bytes - off));
-            bulk_s2g(reinterpret_cast<char*>(og) + off, reinterpret_cast<char*>(xs) + off, n);
-            off += n;
-          }
-          bulk_commit();
-          bulk_wait_read_all();
+          for (int e = 0; e < VW; ++e) car[e] = ca[w * VW + e];
         }
-      } else {
-        __syncthreads();
-        for (size_t i = tid; i < (size_t)np * C; i += kThreads) og[i] = xs[i];
+#pragma unroll
+        for (int e = 0; e < VW; ++e) {
+          const float t = v[e] * car[e];
+          s += t;
+          m = fmaxf(m, t);
+        }
+      }
+    }
+    for (int o = LPP >> 1; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    if (sl == 0 && p < np) { smap[p] = s * L.invC; smap[L.pchunk + p] = m; }
+  }
+  prof_mark(P, 5);
+  cluster.sync();  // (2) map chunks visible
+  prof_mark(P, 6);
+  const int ya = p0 / W, tw = L.tw;
+  const int nrow = (np > 0 ? (p1 - 1) / W - ya + 1 : 0) + 2 * PADK;
+  gather_tiles<2>(cluster, tile, smap, 0, L.pchunk, 0, ya, nrow, L);
+  __syncthreads();
+  prof_mark(P, 7);
+  // ---- phase C: 7x7 conv + sigmoid; 4 lanes per pixel split the 14 tap rows, taps broadcast as float4 ------------
+  for (int base = warp * 32; base < np * 4; base += kThreads) {
+    const int i = base + lane, p = i >> 2, part = i & 3;
+    float z = 0.f;
+    if (p < np) {
+      const int q = p0 + p, y = q / W, x = q - y * W;
+      const float* t0 = tile + (size_t)(y - ya) * tw + x;
+      for (int rr = part; rr < 2 * KS; rr += 4) {       // rr = ch*7 + u
+        const int ch = rr >= KS ? 1 : 0, u = rr - ch * KS;
+        const float4 wa = *reinterpret_cast<const float4*>(wsas + rr * KROW);
+        const float4 wb = *reinterpret_cast<const float4*>(wsas + rr * KROW + 4);
+        const float* tr = t0 + (size_t)(ch * L.th + u) * tw;
+        z += wa.x * tr[0] + wa.y * tr[1] + wa.z * tr[2] + wa.w * tr[3] + wb.x * tr[4] + wb.y * tr[5] + wb.z * tr[6];
+      }
+    }
+    z += __shfl_xor_sync(0xffffffffu, z, 1);
+    z += __shfl_xor_sync(0xffffffffu, z, 2);
+    if (part == 0 && p < np) {
+      const float a = sigmoidf_(z);
+      sas[p] = a;
+      if (P.sa) P.sa[(size_t)b * HW + p0 + p] = a;
+    }
+  }
+  __syncthreads();
+  prof_mark(P, 8);
+  if (L.mode == B200_CBAM_FULL) {
+    T* og = reinterpret_cast<T*>(P.out) + ((size_t)b * HW + p0) * C;
+    if constexpr (sizeof(T) == 2 && VW == 8) {
+      // packed 16-bit gate: out = (x*ca)*sa, rounded after each product exactly like the 16-bit reference ops
+      using P2 = typename Pair2<T>::type;
+      P2 ca2[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ca2[i] = make_pair(T(), car[2 * i], car[2 * i + 1]);
+      for (int pb = warp * PPW; pb < np; pb += kWarps * PPW) {
+        const int p = pb + sub;
+        if (p >= np) continue;
+        const float sp = sas[p];
+        const P2 sp2 = make_pair(T(), sp, sp);
+        for (int w = sl; w < nch; w += LPP) {
+          uint4 raw = *reinterpret_cast<const uint4*>(xc + (size_t)p * C + w * VW);
+          P2* rp = reinterpret_cast<P2*>(&raw);
+          if (!one) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ca2[i] = make_pair(T(), ca[w * VW + 2 * i], ca[w * VW + 2 * i + 1]);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rp[i] = __hmul2(__hmul2(rp[i], ca2[i]), sp2);
+          stg_stream16(og + (size_t)p * C + w * VW, raw);
+        }
+      }
+    } else {
+      for (int pb = warp * PPW; pb < np; pb += kWarps * PPW) {
+        const int p = pb + sub;
+        if (p >= np) continue;
+        const float sp = sas[p];
+        for (int w = sl; w < nch; w += LPP) {
+          float v[VW];
+          Vec<T, VW>::load(xc + (size_t)p * C + w * VW, v);
+#pragma unroll
+          for (int e = 0; e < VW; ++e) v[e] = v[e] * (one ? car[e] : ca[w * VW + e]) * sp;
+          Vec<T, VW>::store(og + (size_t)p * C + w * VW, v);
+        }
       }
     }
   }
+  prof_mark(P, 9);
   cluster.sync();  // keep smem alive until every peer finished its DSMEM reads
+  prof_mark(P, 10);
 }
 
 // =====================================================================================================
 // backward.  Same cluster decomposition; x and g chunks both staged once.
 // =====================================================================================================
 template <typename T, bool RES, int VW>
-__global__ void __launch_bounds__(kThreads) cbam_bwd_kernel(CbamParams P) {
-  constexpr int EPL = VW;
+__global__ void __launch_bounds__(kThreads) cbam_bwd_kernel(const __grid_constant__ CbamParams P) {
   cg::cluster_group cluster = cg::this_cluster();
-  const int CS = (int)cluster.num_blocks();
-  const int rank = (int)cluster.block_rank();
-  const int b = blockIdx.x / CS;
-  const int C = P.C, HW = P.H * P.W, W = P.W, H = P.H, r = P.r, ks = P.ksa, pad = ks / 2;
-  const int p0 = min(rank * P.pchunk, HW), p1 = min(p0 + P.pchunk, HW), np = p1 - p0;
+  const Plan& L = P.pl;
+  const int CS = L.cs, rank = blockIdx.x, b = blockIdx.y;
+  const int C = L.C, HW = L.HW, W = L.W, r = L.r, nch = L.nch, pc = L.pchunk;
+  const int p0 = min(rank * pc, HW), p1 = min(p0 + pc, HW), np = p1 - p0;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const SmemLayout L(C, r, W, ks, P.pchunk, sizeof(T), RES, true);
   T* xs = reinterpret_cast<T*>(smem_raw + L.xs);
   T* gs = reinterpret_cast<T*>(smem_raw + L.gs);
   float* psum = reinterpret_cast<float*>(smem_raw + L.psum);
   float* pmax = reinterpret_cast<float*>(smem_raw + L.pmax);
   int* pidx = reinterpret_cast<int*>(smem_raw + L.pidx);
-  float* hpart = reinterpret_cast<float*>(smem_raw + L.hpart);
-  float* hid = reinterpret_cast<float*>(smem_raw + L.hid);       // [0,2r): pre-activations, [2r,4r): their grads
-  float* slc = reinterpret_cast<float*>(smem_raw + L.caslice);   // [3][C]: slice-owner scratch
-  float* ca = reinterpret_cast<float*>(smem_raw + L.ca);         // [0]=ca, [1]=g_pavg/HW, [2]=g_pmax, [3]=argmax_hw
-  float* smap = reinterpret_cast<float*>(smem_raw + L.smap);     // [0..1]: s map chunk, [2]: g_z chunk, [3]: argmax_c
-  float* shalo = reinterpret_cast<float*>(smem_raw + L.shalo);
-  float* sas = reinterpret_cast<float*>(smem_raw + L.sa);        // [0]=sa, [1]=g_s0, [2]=g_s1
+  float* gca_part = reinterpret_cast<float*>(smem_raw + L.gca);  // [C] this CTA's partial of g_ca (peers read it)
+  float* pav = reinterpret_cast<float*>(smem_raw + L.pav);
+  float* pmx = reinterpret_cast<float*>(smem_raw + L.pmx);
+  float* hid = reinterpret_cast<float*>(smem_raw + L.hid);       // [0,2r): pre-activations, [2r,3r): u = W2^T g_a
+  float* ca = reinterpret_cast<float*>(smem_raw + L.ca);
+  float* vec = reinterpret_cast<float*>(smem_raw + L.vec);       // [0]=g_pavg/HW, [1]=g_pmax, [2]=argmax_hw (int bits)
+  float* smap = reinterpret_cast<float*>(smem_raw + L.smap);     // [0..1]: s map chunk, [2]: g_z chunk
+  float* tile = reinterpret_cast<float*>(smem_raw + L.tile);     // [0]: g_z tile, [1..2]: s tiles
+  float4* pix = reinterpret_cast<float4*>(smem_raw + L.pix);     // {sa, g_s0/C, g_s1, argmax_c (int bits)}
+  int* poff = reinterpret_cast<int*>(smem_raw + L.poff);
   float* wsas = reinterpret_cast<float*>(smem_raw + L.wsa);
   float* red = reinterpret_cast<float*>(smem_raw + L.red);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nw = C / EPL;
-  const int pc = P.pchunk;
-  const int nwt = 2 * ks * ks;
+  const int mode = L.mode;
 
   const T* xg = reinterpret_cast<const T*>(P.x) + ((size_t)b * HW + p0) * C;
-  const T* gg = P.mode == B200_CBAM_FULL ? reinterpret_cast<const T*>(P.g) + ((size_t)b * HW + p0) * C : nullptr;
+  const T* gg = mode == B200_CBAM_FULL ? reinterpret_cast<const T*>(P.g) + ((size_t)b * HW + p0) * C : nullptr;
   const T* xc = xg;
   const T* gc = gg;
+  bool wait_tma = false;
   if (RES) {
-    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
-    __syncthreads();
-    const size_t bytes = (size_t)np * C * sizeof(T);
-    const bool aligned = ((bytes & 15) == 0) && ((reinterpret_cast<uintptr_t>(xg) & 15) == 0) &&
-                         (!gg || (reinterpret_cast<uintptr_t>(gg) & 15) == 0);
-    if (aligned) {
-      if (tid == 0 && bytes) {
-        mbar_expect_tx(bar, (uint32_t)(bytes * (gg ? 2 : 1)));
-        for (size_t off = 0; off < bytes; off += 32768) {
-          const uint32_t n = (uint32_t)((bytes - off) > 32768 ? 32768 : (bytes - off));
-          bulk_g2s(reinterpret_cast<char*>(xs) + off, reinterpret_cast<const char*>(xg) + off, n, bar);
-          if (gg) bulk_g2s(reinterpret_cast<char*>(gs) + off, reinterpret_cast<const char*>(gg) + off, n, bar);
-        }
-      }
-      if (bytes) mbar_wait(bar, 0);
-    } else {
-      for (size_t i = tid; i < (size_t)np * C; i += kThreads) { xs[i] = xg[i]; if (gg) gs[i] = gg[i]; }
-      __syncthreads();
-    }
+    wait_tma = stage_chunks<T>(xs, xg, gs, gg, np * C, bar);
     xc = xs;
     gc = gg ? gs : nullptr;
   }
-  for (int i = tid; i < nwt; i += kThreads) wsas[i] = P.wsa ? P.wsa[i] : 0.f;
-  const int cper = (C + CS - 1) / CS;
-  const int cs0 = min(rank * cper, C), cs1 = min(cs0 + cper, C);
-  const bool use_ca = P.mode != B200_CBAM_SA;
-  const bool use_sa = P.mode != B200_CBAM_CA;
+  load_taps(wsas, P.wsa, L.ksa);
+  const bool use_ca = mode != B200_CBAM_SA;
+  const bool use_sa = mode != B200_CBAM_CA;
   for (int c = tid; c < C; c += kThreads) ca[c] = use_ca ? P.ca[(size_t)b * C + c] : 1.f;
-  for (int p = tid; p < np; p += kThreads) sas[p] = use_sa ? P.sa[(size_t)b * HW + p0 + p] : 1.f;
+  const int ya = p0 / W, tw = L.tw;
+  const int nrow = (np > 0 ? (p1 - 1) / W - ya + 1 : 0) + 2 * PADK;
+  for (int p = tid; p < np; p += kThreads) {
+    const int q = p0 + p, y = q / W;
+    pix[p] = make_float4(use_sa ? P.sa[(size_t)b * HW + q] : 1.f, 0.f, 0.f, __int_as_float(-1));
+    poff[p] = (y - ya) * tw + (q - y * W);
+  }
   __syncthreads();
+  if (wait_tma) mbar_wait(bar, 0);
 
-  float* gw_part = P.part + (size_t)b * (2 * (size_t)r * C + nwt);  // per-image partials [r*C | C*r | nwt]
+  const int LPP = L.lpp, PPW = 32 / LPP, sub = lane / LPP, sl = lane & (LPP - 1);
+  const bool one = nch <= LPP;
 
   if (use_sa) {
     // (1) recompute s map + channel argmax; g_sa[p] = sum_c g * x * ca   (SA mode: g_sa is the input itself)
-    for (int p = warp; p < np; p += kThreads / 32) {
-      float s = 0.f, m = -INFINITY, gsa = 0.f;
-      int mi = 0;
-      for (int w = lane; w < nw; w += 32) {
-        float v[EPL], gv[EPL];
-        Vec<T, VW>::load(xc + (size_t)p * C + w * EPL, v);
-        if (gc) Vec<T, VW>::load(gc + (size_t)p * C + w * EPL, gv);
+    float car[VW];
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) {
-          const float t = v[e] * ca[w * EPL + e];
-          s += t;
-          if (t > m || t != t) { m = t; mi = w * EPL + e; }
-          if (gc) gsa += gv[e] * t;
+    for (int e = 0; e < VW; ++e) car[e] = (one && sl < nch) ? ca[sl * VW + e] : 0.f;
+    for (int pb = warp * PPW; pb < np; pb += kWarps * PPW) {
+      const int p = pb + sub;
+      float s = 0.f, m = -INFINITY, gsa = 0.f;
+      int mi = 0x7fffffff;
+      if (p < np) {
+        for (int w = sl; w < nch; w += LPP) {
+          float v[VW], gv[VW];
+          Vec<T, VW>::load(xc + (size_t)p * C + w * VW, v);
+          if (gc) Vec<T, VW>::load(gc + (size_t)p * C + w * VW, gv);
+          if (!one) {
+#pragma unroll
+            for (int e = 0; e < VW; ++e) car[e] = ca[w * VW + e];
+          }
+#pragma unroll
+          for (int e = 0; e < VW; ++e) {
+            const float t = v[e] * car[e];
+            s += t;
+            if (t > m) { m = t; mi = w * VW + e; }
+            if (gc) gsa += gv[e] * t;
+          }
         }
       }
-      s = warp_sum(s);
-      gsa = warp_sum(gsa);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {  // (value, first index) with NaN propagation: later NaN wins like ATen
+      for (int o = LPP >> 1; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        gsa += __shfl_xor_sync(0xffffffffu, gsa, o);
         const float tm = __shfl_xor_sync(0xffffffffu, m, o);
         const int ti = __shfl_xor_sync(0xffffffffu, mi, o);
-        const bool tnan = tm != tm, mnan = m != m;
-        bool take;
-        if (tnan || mnan) take = tnan && (!mnan || ti > mi);
-        else take = (tm > m) || (tm == m && ti < mi);
-        if (take) { m = tm; mi = ti; }
+        if (tm > m || (tm == m && ti < mi)) { m = tm; mi = ti; }   // larger value, then first channel (max.dim rule)
       }
-      if (lane == 0) {
-        smap[p] = s / (float)C;
+      if (sl == 0 && p < np) {
+        smap[p] = s * L.invC;
         smap[pc + p] = m;
-        smap[3 * pc + p] = __int_as_float(mi);
-        const float a = sas[p];
-        const float gsa_in = P.mode == B200_CBAM_SA ? reinterpret_cast<const float*>(P.g)[(size_t)b * HW + p0 + p] : gsa;
+        const float a = pix[p].x;
+        const float gsa_in = mode == B200_CBAM_SA ? reinterpret_cast<const float*>(P.g)[(size_t)b * HW + p0 + p] : gsa;
         smap[2 * pc + p] = gsa_in * a * (1.f - a);  // g_z
+        pix[p].w = __int_as_float(mi == 0x7fffffff ? 0 : mi);
       }
     }
     cluster.sync();  // (1) s map + g_z chunks visible
-    // gather g_z with halo (for the transposed conv) and s with halo (for the weight gradient)
-    const int halo = L.halo, span = np + 2 * halo, hp = pc + 2 * halo;
-    // --- g_s = conv^T(g_z): needs g_z halo
-    for (int i = tid; i < span; i += kThreads) {
-      const int q = p0 - halo + i;
-      float v = 0.f;
-      if (q >= 0 && q < HW) {
-        const int owner = min(q / pc, CS - 1);
-        v = cluster.map_shared_rank(smap, owner)[2 * pc + (q - owner * pc)];
-      }
-      shalo[i] = v;
-    }
+    gather_tiles<3>(cluster, tile, smap, 2 * pc, 0, pc, ya, nrow, L);
     __syncthreads();
-    {
-      constexpr int TPL = 2;  // taps per lane: ks*ks = 49 <= 64
-      int tdu[TPL], tdv[TPL];
-      float tw0[TPL], tw1[TPL];
+    // g_s = conv^T(g_z): g_s[j][y][x] = sum_{u,v} w[j][u][v] * g_z[y-(u-3)][x-(v-3)]; 4 lanes per pixel split the rows u
+    for (int base = warp * 32; base < np * 4; base += kThreads) {
+      const int i = base + lane, p = i >> 2, part = i & 3;
+      float g0 = 0.f, g1 = 0.f;
+      if (p < np) {
+        const float* t0 = tile + poff[p];
+        for (int u = part; u < KS; u += 4) {
+          const float* tr = t0 + (KS - 1 - u) * tw;
+          const float* w0 = wsas + u * KROW;
+          const float* w1 = wsas + (KS + u) * KROW;
 #pragma unroll
-      for (int j = 0; j < TPL; ++j) {
-        const int t = lane + 32 * j;
-        const bool ok = t < ks * ks;
-        tdu[j] = ok ? t / ks - pad : 0;
-        tdv[j] = ok ? t % ks - pad : 0;
-        tw0[j] = ok ? wsas[t] : 0.f;
-        tw1[j] = ok ? wsas[ks * ks + t] : 0.f;
-      }
-      for (int p = warp; p < np; p += kThreads / 32) {
-        const int q = p0 + p, y = q / W, x = q - y * W;
-        float g0 = 0.f, g1 = 0.f;
-#pragma unroll
-        for (int j = 0; j < TPL; ++j) {
-          const int yy = y - tdu[j], xx = x - tdv[j];  // output position that used this tap on this input
-          if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-            const float gz = shalo[(yy * W + xx) - (p0 - halo)];
-            g0 += tw0[j] * gz;
-            g1 += tw1[j] * gz;
+          for (int v = 0; v < KS; ++v) {
+            const float gz = tr[KS - 1 - v];
+            g0 += w0[v] * gz;
+            g1 += w1[v] * gz;
           }
         }
-        g0 = warp_sum(g0);
-        g1 = warp_sum(g1);
-        if (lane == 0) {
-          sas[pc + p] = g0 / (float)C;  // broadcast share of the channel mean
-          sas[2 * pc + p] = g1;         // routed to the argmax channel
-        }
+      }
+      g0 += __shfl_xor_sync(0xffffffffu, g0, 1);
+      g1 += __shfl_xor_sync(0xffffffffu, g1, 1);
+      g0 += __shfl_xor_sync(0xffffffffu, g0, 2);
+      g1 += __shfl_xor_sync(0xffffffffu, g1, 2);
+      if (part == 0 && p < np) {
+        pix[p].y = g0 * L.invC;  // broadcast share of the channel mean
+        pix[p].z = g1;           // routed to the argmax channel
       }
     }
-    __syncthreads();
-    // --- g_Wsa[j,u,v] = sum_p g_z[p] * s[j, p + (u-pad, v-pad)]: gather s halo, per-CTA partial
-    for (int i = tid; i < 2 * span; i += kThreads) {
-      const int ch = i / span, q = p0 - halo + (i - ch * span);
-      float v = 0.f;
-      if (q >= 0 && q < HW) {
-        const int owner = min(q / pc, CS - 1);
-        v = cluster.map_shared_rank(smap, owner)[ch * pc + (q - owner * pc)];
-      }
-      shalo[ch * hp + (i - ch * span)] = v;
+    // g_Wsa[j,u,v] = sum_p g_z[p] * s[j, p + (u-3, v-3)]: warp per tap over this CTA's pixels -> per-CTA partial in the
+    // workspace (folded over images and ranks in a fixed order by fold_partials_kernel: deterministic, no atomics)
+    float* cp = P.cpart + ((size_t)b * kMaxCS + rank) * NT7;
+    for (int t = warp; t < NT7; t += kWarps) {
+      const int j = t / (KS * KS), u = (t / KS) % KS, v = t % KS;
+      const float* tj = tile + (size_t)((1 + j) * L.th + u) * tw + v;
+      float acc = 0.f;
+      for (int p = lane; p < np; p += 32) acc += smap[2 * pc + p] * tj[poff[p]];
+      acc = warp_sum(acc);
+      if (lane == 0) cp[t] = acc;
     }
-    __syncthreads();
-    if (np <= 128) {  // lanes own up to 4 pixels each; coordinates and g_z decoded once, reused for every tap
-      int py[4], px[4];
-      float pgz[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int p = lane + 32 * j;
-        const int q = p0 + (p < np ? p : 0);
-        py[j] = q / W; px[j] = q - py[j] * W;
-        pgz[j] = p < np ? smap[2 * pc + p] : 0.f;
-      }
-      for (int t = warp; t < nwt; t += kThreads / 32) {
-        const int ch = t / (ks * ks), u = (t / ks) % ks - pad, v = t % ks - pad;
-        float acc = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int yy = py[j] + u, xx = px[j] + v;
-          if (yy >= 0 && yy < H && xx >= 0 && xx < W) acc += pgz[j] * shalo[ch * hp + (yy * W + xx) - (p0 - halo)];
-        }
-        acc = warp_sum(acc);
-        if (lane == 0) wsas[nwt + t] = acc;
-      }
-    } else {
-      for (int t = warp; t < nwt; t += kThreads / 32) {
-        const int ch = t / (ks * ks), u = (t / ks) % ks, v = t % ks;
-        float acc = 0.f;
-        for (int p = lane; p < np; p += 32) {
-          const int q = p0 + p, y = q / W, x = q - y * W;
-          const int yy = y + u - pad, xx = x + v - pad;
-          if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-          acc += smap[2 * pc + p] * shalo[ch * hp + (yy * W + xx) - (p0 - halo)];
-        }
-        acc = warp_sum(acc);
-        if (lane == 0) wsas[nwt + t] = acc;
-      }
-    }
-    cluster.sync();  // (2) per-CTA g_Wsa partials visible; rank 0 folds them (fixed order -> deterministic)
-    if (rank == 0)
-      for (int t = tid; t < nwt; t += kThreads) {
-        float acc = 0.f;
-        for (int k2 = 0; k2 < CS; ++k2) acc += cluster.map_shared_rank(wsas, k2)[nwt + t];
-        gw_part[2 * (size_t)r * C + t] = acc;
-      }
+    __syncthreads();  // pix complete
   }
 
-  if (P.mode == B200_CBAM_SA) {
+  T* og = reinterpret_cast<T*>(P.out) + ((size_t)b * HW + p0) * C;
+  if (mode == B200_CBAM_SA) {
     // gx = (g_s0 + [c == argmax] g_s1), no channel attention involved
-    T* og = reinterpret_cast<T*>(P.out) + ((size_t)b * HW + p0) * C;
-    for (int i = tid; i < np * nw; i += kThreads) {
-      const int p = i / nw, w = i - p * nw;
-      const int am = __float_as_int(smap[3 * pc + p]);
-      float o[EPL];
+    for (int i = tid; i < np * nch; i += kThreads) {
+      const int p = i / nch, w = i - p * nch;
+      const float4 pp = pix[p];
+      const int am = __float_as_int(pp.w);
+      float o[VW];
 #pragma unroll
-      for (int e = 0; e < EPL; ++e) o[e] = sas[pc + p] + ((w * EPL + e) == am ? sas[2 * pc + p] : 0.f);
-      Vec<T, VW>::store(og + (size_t)p * C + w * EPL, o);
+      for (int e = 0; e < VW; ++e) o[e] = pp.y + ((w * VW + e) == am ? pp.z : 0.f);
+      Vec<T, VW>::store(og + (size_t)p * C + w * VW, o);
     }
     cluster.sync();
     return;
   }
 
-  // (3)+(4): g_x1 = g*sa + g_s0 + [c==argmax_c] g_s1 ;  g_ca[c] = sum_p g_x1 * x  (per-CTA partial -> psum)
+  // (3)+(4): g_x1 = g*sa + g_s0 + [c==argmax_c] g_s1 ;  g_ca[c] = sum_p g_x1 * x  (per-CTA partial)
   // also the pooled statistics again (avg / max / argmax_hw) for the MLP backward.
-  channel_partials<T, VW>(xc, np, p0, C, psum, pmax, pidx, red);
+  channel_partials<T, VW, true>(xc, np, p0, C, nch, L.groups, psum, pmax, pidx, red);
   __syncthreads();
-  float* gca_part = slc;  // [C] this CTA's partial of g_ca
-  if (P.mode == B200_CBAM_FULL) {
-    const int groups = min(nw >= kThreads ? 1 : kThreads / nw, max(1, kRedBytes / (C * 12)));
-    const int tw = tid % (nw < kThreads ? nw : kThreads), pg = tid / (nw < kThreads ? nw : kThreads);
-    for (int i = tid; i < C; i += kThreads) gca_part[i] = 0.f;
-    __syncthreads();
-    for (int w = tw; w < nw; w += kThreads) {
-      float acc[EPL];
+  if (mode == B200_CBAM_FULL) {
+    const int groups = L.groups;
+    const int tpg = nch < kThreads ? nch : kThreads;
+    const int pg = tid / tpg, twi = tid - pg * tpg;
+    for (int w = twi; w < nch; w += kThreads) {
+      float acc[VW];
 #pragma unroll
-      for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
-      if (pg < groups)
+      for (int e = 0; e < VW; ++e) acc[e] = 0.f;
+      if (pg < groups) {
+#pragma unroll 2
         for (int p = pg; p < np; p += groups) {
-          float v[EPL], gv[EPL];
-          Vec<T, VW>::load(xc + (size_t)p * C + w * EPL, v);
-          Vec<T, VW>::load(gc + (size_t)p * C + w * EPL, gv);
-          const int am = __float_as_int(smap[3 * pc + p]);
+          float v[VW], gv[VW];
+          Vec<T, VW>::load(xc + (size_t)p * C + w * VW, v);
+          Vec<T, VW>::load(gc + (size_t)p * C + w * VW, gv);
+          const float4 pp = pix[p];
+          const unsigned d = (unsigned)(__float_as_int(pp.w) - w * VW);
 #pragma unroll
-          for (int e = 0; e < EPL; ++e) {
-            const float gx1 = gv[e] * sas[p] + sas[pc + p] + ((w * EPL + e) == am ? sas[2 * pc + p] : 0.f);
-            acc[e] += gx1 * v[e];
+          for (int e = 0; e < VW; ++e) acc[e] += (gv[e] * pp.x + pp.y) * v[e];
+          if (d < (unsigned)VW) {   // the argmax channel of this pixel lies in this thread's vector (1 lane per pixel)
+#pragma unroll
+            for (int e = 0; e < VW; ++e) acc[e] += (d == (unsigned)e) ? pp.z * v[e] : 0.f;
           }
         }
-      if (pg < groups) {
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) red[(size_t)pg * C + w * EPL + e] = acc[e];
+        for (int e = 0; e < VW; ++e) red[(size_t)pg * C + w * VW + e] = acc[e];
       }
     }
     __syncthreads();
-    {
-      const int groups2 = min(nw >= kThreads ? 1 : kThreads / nw, max(1, kRedBytes / (C * 12)));
-      for (int c = tid; c < C; c += kThreads) {
-        float s = 0.f;
-        for (int gi = 0; gi < groups2; ++gi) s += red[(size_t)gi * C + c];
-        gca_part[c] = s;
-      }
+    for (int c = tid; c < C; c += kThreads) {
+      float s = 0.f;
+      for (int gi = 0; gi < groups; ++gi) s += red[(size_t)gi * C + c];
+      gca_part[c] = s;
     }
   }
-  cluster.sync();  // (3) g_ca partials + pooled partials visible
-  // slice owner: reduce g_ca and pooled stats over ranks; hidden partials for the forward recompute
-  float* pav = slc + C;      // [cper] pooled avg (slice)
-  float* pmx = slc + 2 * C;  // [cper] pooled max (slice)
-  float* gca_s = red;        // [cper] g_a = g_ca * ca * (1-ca) for the slice
-  int* amx = reinterpret_cast<int*>(red) + cper;  // [cper] argmax_hw for the slice
-  for (int c = cs0 + tid; c < cs1; c += kThreads) {
+  cluster.sync();  // (2) g_ca partials + pooled partials visible
+  // every rank: totals over the ranks for all channels, then the (tiny) MLP backward redundantly
+  float* ga = red;  // [C] g_a = g_ca * ca * (1-ca)
+  for (int c = tid; c < C; c += kThreads) {
     float s = 0.f, m = -INFINITY, gsum = 0.f;
     int mi = 0;
-    bool nan = false;
     for (int k2 = 0; k2 < CS; ++k2) {
       s += cluster.map_shared_rank(psum, k2)[c];
       const float v = cluster.map_shared_rank(pmax, k2)[c];
       const int vi = cluster.map_shared_rank(pidx, k2)[c];
-      if (v != v) { m = v; mi = vi; nan = true; }          // ranks ascend in pixel order: last NaN wins
-      else if (!nan && v > m) { m = v; mi = vi; }          // strict >: first occurrence
-      else if (!nan && k2 == 0) { mi = vi; }
-      if (P.mode == B200_CBAM_FULL) gsum += cluster.map_shared_rank(gca_part, k2)[c];
+      if (v > m) { m = v; mi = vi; }          // ranks ascend in pixel order, strict >: first occurrence
+      else if (k2 == 0) { mi = vi; }
+      if (mode == B200_CBAM_FULL) gsum += cluster.map_shared_rank(gca_part, k2)[c];
     }
-    if (P.mode == B200_CBAM_CA) gsum = reinterpret_cast<const float*>(P.g)[(size_t)b * C + c];
-    pav[c - cs0] = s / (float)HW;
-    pmx[c - cs0] = m;
-    amx[c - cs0] = mi;
+    if (mode == B200_CBAM_CA) gsum = reinterpret_cast<const float*>(P.g)[(size_t)b * C + c];
+    pav[c] = s * L.invHW;
+    pmx[c] = (s != s) ? s : m;
+    vec[2 * C + c] = __int_as_float(mi);
     const float a = ca[c];
-    gca_s[c - cs0] = gsum * a * (1.f - a);
+    ga[c] = gsum * a * (1.f - a);
   }
   __syncthreads();
-  // partial hidden pre-activations (forward recompute) and partial W2^T g_a, both over the slice
-  for (int j = warp; j < 3 * r; j += kThreads / 32) {
+  // hidden pre-activations h[2][r] (forward recompute) and u[r] = W2^T g_a
+  for (int j = warp; j < 3 * r; j += kWarps) {
     float acc = 0.f;
     if (j < 2 * r) {
-      const int jj = j < r ? j : j - r;
+      const float* wrow = P.w1 + (size_t)(j < r ? j : j - r) * C;
       const float* src = j < r ? pav : pmx;
-      for (int c = cs0 + lane; c < cs1; c += 32) acc += P.w1[(size_t)jj * C + c] * src[c - cs0];
+#pragma unroll 4
+      for (int c = lane; c < C; c += 32) acc += wrow[c] * src[c];
     } else {
-      const int jj = j - 2 * r;
-      for (int c = cs0 + lane; c < cs1; c += 32) acc += P.w2[(size_t)c * r + jj] * gca_s[c - cs0];
+      const float* wcol = P.w2 + (j - 2 * r);
+#pragma unroll 4
+      for (int c = lane; c < C; c += 32) acc += wcol[(size_t)c * r] * ga[c];
     }
     acc = warp_sum(acc);
-    if (lane == 0) {
-      if (j < 2 * r) hpart[j] = acc;
-      else hid[2 * r + (j - 2 * r)] = acc;
-    }
-  }
-  cluster.sync();  // (4) hidden partials visible
-  // h[2][r] pre-activations and u[r] = W2^T g_a, summed over ranks
-  float* hfull = hid;          // [2r] pre-activations (hid[2r,3r) holds this rank's partial of u, read by peers)
-  float* ufull = hid + 3 * r;  // [r]
-  for (int j = tid; j < 3 * r; j += kThreads) {
-    float acc = 0.f;
-    for (int k2 = 0; k2 < CS; ++k2)
-      acc += (j < 2 * r) ? cluster.map_shared_rank(hpart, k2)[j] : cluster.map_shared_rank(hid, k2)[2 * r + (j - 2 * r)];
-    if (j < 2 * r) hfull[j] = acc; else ufull[j - 2 * r] = acc;
+    if (lane == 0) hid[j] = acc;
   }
   __syncthreads();
-  // slice owner: weight-gradient partials for its channel slice and g_p_t = W1^T g_h_t
-  for (int c = cs0 + tid; c < cs1; c += kThreads) {
-    const float ga = gca_s[c - cs0];
-    float gpa = 0.f, gpm = 0.f;
-    for (int j = 0; j < r; ++j) {
-      const float ha = hfull[j], hm = hfull[r + j], u = ufull[j];
-      const float gha = ha > 0.f ? u : 0.f, ghm = hm > 0.f ? u : 0.f;
-      gw_part[(size_t)r * C + (size_t)c * r + j] = ga * (fmaxf(ha, 0.f) + fmaxf(hm, 0.f));           // g_W2[c,j]
-      gw_part[(size_t)j * C + c] = gha * pav[c - cs0] + ghm * pmx[c - cs0];                          // g_W1[j,c]
-      const float w = P.w1[(size_t)j * C + c];
-      gpa += w * gha;
-      gpm += w * ghm;
-    }
-    ca[C + c] = gpa / (float)HW;
-    ca[2 * C + c] = gpm;
-    ca[3 * C + c] = __int_as_float(amx[c - cs0]);
-  }
-  cluster.sync();  // (5) slice results visible
-  for (int c = tid; c < C; c += kThreads) {
-    const int owner = min(c / cper, CS - 1);
-    if (owner != rank) {
-      const float* rc = cluster.map_shared_rank(ca, owner);
-      ca[C + c] = rc[C + c]; ca[2 * C + c] = rc[2 * C + c]; ca[3 * C + c] = rc[3 * C + c];
-    }
-  }
-  __syncthreads();
-  // (6) g_x = g_x1 * ca + g_pavg/HW + [p == argmax_hw] g_pmax
+  // per channel: g_p_t = W1^T g_h_t; the rank's own channel slice also emits the weight-gradient partials
   {
-    T* og = reinterpret_cast<T*>(P.out) + ((size_t)b * HW + p0) * C;
-    for (int p = warp; p < np; p += kThreads / 32) {
-      const int am = use_sa && P.mode == B200_CBAM_FULL ? __float_as_int(smap[3 * pc + p]) : -1;
-      const float sp = sas[p], g0 = sas[pc + p], g1 = sas[2 * pc + p];
-      for (int w = lane; w < nw; w += 32) {
-        float gv[EPL], o[EPL];
-        if (gc) Vec<T, VW>::load(gc + (size_t)p * C + w * EPL, gv);
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) {
-          const int c = w * EPL + e;
-          float gx1 = 0.f;
-          if (P.mode == B200_CBAM_FULL) gx1 = gv[e] * sp + g0 + (c == am ? g1 : 0.f);
-          o[e] = gx1 * ca[c] + ca[C + c] + ((p0 + p) == __float_as_int(ca[3 * C + c]) ? ca[2 * C + c] : 0.f);
+    float* gw_part = P.part + (size_t)b * (2 * (size_t)r * C);  // per-image partials [r*C | C*r]
+    const int cper = (C + CS - 1) / CS, cs0 = rank * cper, cs1 = min(cs0 + cper, C);
+    for (int c = tid; c < C; c += kThreads) {
+      const float gac = ga[c];
+      const bool mine = c >= cs0 && c < cs1;
+      float gpa = 0.f, gpm = 0.f;
+      for (int j = 0; j < r; ++j) {
+        const float ha = hid[j], hm = hid[r + j], u = hid[2 * r + j];
+        const float gha = ha > 0.f ? u : 0.f, ghm = hm > 0.f ? u : 0.f;
+        if (mine) {
+          gw_part[(size_t)r * C + (size_t)c * r + j] = gac * (fmaxf(ha, 0.f) + fmaxf(hm, 0.f));  // g_W2[c,j]
+          gw_part[(size_t)j * C + c] = gha * pav[c] + ghm * pmx[c];                              // g_W1[j,c]
         }
-        Vec<T, VW>::store(og + (size_t)p * C + w * EPL, o);
+        const float w = P.w1[(size_t)j * C + c];
+        gpa += w * gha;
+        gpm += w * ghm;
+      }
+      vec[c] = gpa * L.invHW;
+      vec[C + c] = gpm;
+    }
+  }
+  __syncthreads();
+  // (6) g_x = g_x1 * ca + g_pavg/HW (+ g_pmax at the pooled-max pixel, patched in below)
+  {
+    float car[VW], gav[VW];
+#pragma unroll
+    for (int e = 0; e < VW; ++e) {
+      car[e] = (one && sl < nch) ? ca[sl * VW + e] : 0.f;
+      gav[e] = (one && sl < nch) ? vec[sl * VW + e] : 0.f;
+    }
+    const bool full = mode == B200_CBAM_FULL;
+    for (int pb = warp * PPW; pb < np; pb += kWarps * PPW) {
+      const int p = pb + sub;
+      if (p >= np) continue;
+      const float4 pp = pix[p];
+      const int am = __float_as_int(pp.w);
+      for (int w = sl; w < nch; w += LPP) {
+        float gv[VW], o[VW];
+        if (full) Vec<T, VW>::load(gc + (size_t)p * C + w * VW, gv);
+        if (!one) {
+#pragma unroll
+          for (int e = 0; e < VW; ++e) { car[e] = ca[w * VW + e]; gav[e] = vec[w * VW + e]; }
+        }
+        const unsigned d = (unsigned)(am - w * VW);
+#pragma unroll
+        for (int e = 0; e < VW; ++e) {
+          float gx1 = 0.f;
+          if (full) gx1 = gv[e] * pp.x + pp.y;
+          o[e] = gx1 * car[e] + gav[e];
+        }
+        if (full && d < (unsigned)VW) {
+#pragma unroll
+          for (int e = 0; e < VW; ++e) o[e] += (d == (unsigned)e) ? pp.z * car[e] : 0.f;
+        }
+        Vec<T, VW>::store(og + (size_t)p * C + w * VW, o);
       }
     }
   }
-  cluster.sync();
+  __syncthreads();
+  // the pooled-max pixel of each channel receives g_pmax on top (adaptive_max_pool2d backward, first occurrence)
+  for (int c = tid; c < C; c += kThreads) {
+    const int pm = __float_as_int(vec[2 * C + c]) - p0;
+    if (pm >= 0 && pm < np) {
+      T* dst = og + (size_t)pm * C + c;
+      *dst = DT<T>::from_f(DT<T>::to_f(*dst) + vec[C + c]);
+    }
+  }
+  cluster.sync();  // keep smem alive until every peer finished its DSMEM reads
 }
 
-// fold per-image weight-gradient partials [B][n] -> [n] in a fixed order (deterministic)
-__global__ void fold_partials_kernel(const float* __restrict__ part, float* gw1, float* gw2, float* gwsa, int B,
-                                     int n1, int n2, int n3) {
-  const int n = n1 + n2 + n3;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc += part[(size_t)b * n + i];
-    if (i < n1) { if (gw1) gw1[i] = acc; }
-    else if (i < n1 + n2) { if (gw2) gw2[i - n1] = acc; }
-    else if (gwsa) gwsa[i - n1 - n2] = acc;
+// fold the weight-gradient partials in a fixed order (deterministic): MLP weights [B][n12] -> [n12] (thread per
+// element), conv taps [B][kMaxCS][98] -> [2*ks*ks] (warp per tap; blocks past the MLP part)
+__global__ void fold_partials_kernel(const float* __restrict__ part, const float* __restrict__ cpart, float* gw1,
+                                     float* gw2, float* gwsa, int B, int CS, int n1, int n2, int ks, int mlp_blocks) {
+  if ((int)blockIdx.x < mlp_blocks) {
+    const int n = n1 + n2, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int b = 0;
+    for (; b + 4 <= B; b += 4) {
+      a0 += part[(size_t)b * n + i];
+      a1 += part[(size_t)(b + 1) * n + i];
+      a2 += part[(size_t)(b + 2) * n + i];
+      a3 += part[(size_t)(b + 3) * n + i];
+    }
+    for (; b < B; ++b) a0 += part[(size_t)b * n + i];
+    const float acc = (a0 + a1) + (a2 + a3);
+    if (i < n1) gw1[i] = acc; else gw2[i - n1] = acc;
+    return;
   }
+  const int warps = blockDim.x / 32, lane = threadIdx.x & 31;
+  const int t = ((int)blockIdx.x - mlp_blocks) * warps + (threadIdx.x >> 5);
+  if (t >= 2 * ks * ks) return;
+  const int j = t / (ks * ks), uu = (t / ks) % ks, vv = t % ks, o = (KS - ks) / 2;
+  const int slot = (j * KS + uu + o) * KS + vv + o;
+  float acc = 0.f;
+  for (int i = lane; i < B * CS; i += 32) {
+    const int b = i / CS, k2 = i - b * CS;
+    acc += cpart[((size_t)b * kMaxCS + k2) * NT7 + slot];
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) gwsa[t] = acc;
 }
 
 template <typename K>
-int launch_cluster(K kern, int grid, int cs, size_t smem, cudaStream_t st, CbamParams P) {
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (cs > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+int launch_cluster(K kern, const CbamParams& P, cudaStream_t st) {
+  const Plan& L = P.pl;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+  if (L.cs > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
+  cfg.gridDim = dim3(L.cs, L.B);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem;
+  cfg.dynamicSmemBytes = L.total;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = cs;
+  at[0].val.clusterDim.x = L.cs;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, P);
   if (e != cudaSuccess) {
-    set_error("cbam: cluster launch failed (grid=%d cs=%d smem=%zu): %s", grid, cs, smem, cudaGetErrorString(e));
+    set_error("cbam: cluster launch failed (grid=%dx%d cs=%d smem=%d): %s", L.cs, L.B, L.cs, L.total, cudaGetErrorString(e));
     cudaGetLastError();
     return B200_ERR_LAUNCH;
   }
@@ -786,6 +788,7 @@ int launch_cluster(K kern, int grid, int cs, size_t smem, cudaStream_t st, CbamP
 int check_common(const void* x, int B, int C, int H, int W, int r, int ksa, int dtype, int mode) {
   B200_REQUIRE(x, B200_ERR_SHAPE, "cbam: null input");
   B200_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, B200_ERR_SHAPE, "cbam: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
+  B200_REQUIRE(B <= 65535, B200_ERR_SHAPE, "cbam: batch %d > 65535", B);
   B200_REQUIRE(mode >= 0 && mode <= 2, B200_ERR_SHAPE, "cbam: bad mode %d", mode);
   if (mode != B200_CBAM_SA) B200_REQUIRE(r > 0, B200_ERR_SHAPE, "cbam: hidden width r must be > 0");
   if (mode != B200_CBAM_CA) B200_REQUIRE(ksa == 3 || ksa == 7, B200_ERR_SHAPE, "cbam: kernel size must be 3 or 7 (cbam.py:43), got %d", ksa);
@@ -794,19 +797,53 @@ int check_common(const void* x, int B, int C, int H, int W, int r, int ksa, int 
   return B200_OK;
 }
 
-// choose cluster size + residency.  Returns pchunk; sets cs/resident/smem.
-void plan(int C, int r, int H, int W, int ksa, size_t esize, bool bwd, int* cs, bool* resident, size_t* smem, int* pchunk) {
-  const int HW = H * W;
+// shared-memory carve-up for a given chunking
+void layout(Plan& L, size_t esize, bool bwd) {
+  const int C = L.C, r = L.r, pc = L.pchunk;
+  L.tw = L.W + 2 * PADK;
+  L.th = (pc - 1) / L.W + 2 + 2 * PADK;
+  const size_t tsz = (size_t)L.th * L.tw;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { const int at = (int)o; o += (bytes + 15) & ~(size_t)15; return at; };
+  L.xs = take(L.resident ? (size_t)pc * C * esize : 0);
+  L.gs = take((L.resident && bwd) ? (size_t)pc * C * esize : 0);
+  L.psum = take((size_t)C * 4);
+  L.pmax = take((size_t)C * 4);
+  L.pidx = take(bwd ? (size_t)C * 4 : 0);
+  L.gca = take(bwd ? (size_t)C * 4 : 0);
+  L.pav = take((size_t)C * 4);
+  L.pmx = take((size_t)C * 4);
+  L.hid = take((size_t)3 * r * 4);
+  L.ca = take((size_t)C * 4);
+  L.vec = take(bwd ? (size_t)3 * C * 4 : 0);
+  L.smap = take((size_t)pc * 4 * (bwd ? 3 : 2));
+  L.tile = take(tsz * 4 * (bwd ? 3 : 2));
+  L.pix = take((size_t)pc * (bwd ? 16 : 4));
+  L.poff = take(bwd ? (size_t)pc * 4 : 0);
+  L.wsa = take((size_t)NTAPS * 4);
+  L.red = take(L.groups > 1 ? (size_t)L.groups * C * 12 : (size_t)C * 4);
+  L.bar = take(16);
+  L.total = (int)o;
+}
+
+// choose cluster size + residency and fill the plan
+void make_plan(Plan& L, int B, int C, int H, int W, int r, int ksa, int mode, int vw, size_t esize, bool bwd) {
+  L.B = B; L.C = C; L.H = H; L.W = W; L.HW = H * W; L.r = r; L.ksa = ksa; L.mode = mode;
+  L.nch = C / vw;
+  L.lpp = 1;
+  while (L.lpp < L.nch && L.lpp < 32) L.lpp <<= 1;
+  L.groups = L.nch >= kThreads ? 1 : std::min(kThreads / L.nch, std::max(1, kRedBytes / (C * 12)));
+  L.invC = 1.f / (float)C;
+  L.invHW = 1.f / (float)L.HW;
   const size_t lim = (size_t)max_smem_optin();
   for (int c : {8, 16}) {
-    int pc = (HW + c - 1) / c;
-    SmemLayout L(C, r, W, ksa, pc, esize, true, bwd);
+    L.cs = c; L.pchunk = (L.HW + c - 1) / c; L.resident = 1;
+    layout(L, esize, bwd);
     // 16-CTA clusters are non-portable: only take them when 2 CTAs still fit per SM
-    if (L.total <= (c == 8 ? lim : (size_t)100 * 1024)) { *cs = c; *resident = true; *smem = L.total; *pchunk = pc; return; }
+    if ((size_t)L.total <= (c == 8 ? lim : (size_t)100 * 1024)) return;
   }
-  int pc = (HW + 7) / 8;
-  SmemLayout L(C, r, W, ksa, pc, esize, false, bwd);
-  *cs = 8; *resident = false; *smem = L.total; *pchunk = pc;
+  L.cs = 8; L.pchunk = (L.HW + 7) / 8; L.resident = 0;
+  layout(L, esize, bwd);
 }
 
 }  // namespace
@@ -825,24 +862,24 @@ extern "C" B200_API int b200_cbam_fwd(const void* x, const float* w1, const floa
   if (mode == B200_CBAM_CA) B200_REQUIRE(ca_out, B200_ERR_SHAPE, "cbam_fwd: null ca output");
   if (mode == B200_CBAM_SA) B200_REQUIRE(sa_out, B200_ERR_SHAPE, "cbam_fwd: null sa output");
   const size_t esize = dtype == B200_F32 ? 4 : 2;
-  int cs; bool res; size_t smem; int pc;
-  plan(C, r, H, W, ksa, esize, false, &cs, &res, &smem, &pc);
-  B200_REQUIRE(smem <= (size_t)max_smem_optin(), B200_ERR_UNSUPPORTED, "cbam_fwd: shape needs %zu B of shared memory", smem);
-  CbamParams P{x, nullptr, out, w1, w2, wsa, ca_out, sa_out, nullptr, B, C, H, W, r, ksa, mode, pc};
+  const int ve = 16 / (int)esize, ew = 4 / (int)esize;
+  const bool vec16 = C % ve == 0 && ((uintptr_t)x & 15) == 0 && (mode != B200_CBAM_FULL || ((uintptr_t)out & 15) == 0);
+  CbamParams P{x, nullptr, out, w1, w2, wsa, ca_out, sa_out, nullptr, nullptr, g_cbam_prof, {}};
+  make_plan(P.pl, B, C, H, W, r, ksa, mode, vec16 ? ve : ew, esize, false);
+  B200_REQUIRE((size_t)P.pl.total <= (size_t)max_smem_optin(), B200_ERR_UNSUPPORTED, "cbam_fwd: shape needs %d B of shared memory", P.pl.total);
   cudaStream_t st = (cudaStream_t)stream;
+  const bool res = P.pl.resident != 0;
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
     constexpr int VE = Words<T>::VE, EW = Words<T>::EPL;
-    if (C % VE == 0 && ((uintptr_t)x & 15) == 0 && (mode != B200_CBAM_FULL || ((uintptr_t)out & 15) == 0))
-      return res ? launch_cluster(cbam_fwd_kernel<T, true, VE>, B * cs, cs, smem, st, P)
-                 : launch_cluster(cbam_fwd_kernel<T, false, VE>, B * cs, cs, smem, st, P);
-    return res ? launch_cluster(cbam_fwd_kernel<T, true, EW>, B * cs, cs, smem, st, P)
-               : launch_cluster(cbam_fwd_kernel<T, false, EW>, B * cs, cs, smem, st, P);
+    if (vec16)
+      return res ? launch_cluster(cbam_fwd_kernel<T, true, VE>, P, st) : launch_cluster(cbam_fwd_kernel<T, false, VE>, P, st);
+    return res ? launch_cluster(cbam_fwd_kernel<T, true, EW>, P, st) : launch_cluster(cbam_fwd_kernel<T, false, EW>, P, st);
   });
 }
 
 extern "C" B200_API size_t b200_cbam_bwd_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W, int32_t r, int32_t ksa) {
-  (void)H; (void)W;
-  return (size_t)B * (2 * (size_t)r * C + 2 * (size_t)ksa * ksa) * sizeof(float);
+  (void)H; (void)W; (void)ksa;
+  return (size_t)B * (2 * (size_t)r * C + (size_t)b200::kMaxCS * b200::NT7) * sizeof(float);
 }
 
 extern "C" B200_API int b200_cbam_bwd(const void* g, const void* x, const float* w1, const float* w2, const float* wsa,
@@ -854,32 +891,35 @@ extern "C" B200_API int b200_cbam_bwd(const void* g, const void* x, const float*
   if (mode == B200_CBAM_SA) r = 1;
   if (int rc = check_common(x, B, C, H, W, r, ksa, dtype, mode)) return rc;
   B200_REQUIRE(g && gx, B200_ERR_SHAPE, "cbam_bwd: null gradient pointer");
-  if (mode != B200_CBAM_SA) B200_REQUIRE(w1 && w2 && ca, B200_ERR_SHAPE, "cbam_bwd: null MLP weights / ca map");
-  if (mode != B200_CBAM_CA) B200_REQUIRE(wsa && sa, B200_ERR_SHAPE, "cbam_bwd: null conv weight / sa map");
+  if (mode != B200_CBAM_SA) B200_REQUIRE(w1 && w2 && ca && gw1 && gw2, B200_ERR_SHAPE, "cbam_bwd: null MLP weights / ca map / gradients");
+  if (mode != B200_CBAM_CA) B200_REQUIRE(wsa && sa && gwsa, B200_ERR_SHAPE, "cbam_bwd: null conv weight / sa map / gradient");
   const size_t need = b200_cbam_bwd_workspace_bytes(B, C, H, W, r, ksa);
   B200_REQUIRE(workspace && workspace_bytes >= need, B200_ERR_WORKSPACE, "cbam_bwd: workspace %zu < %zu bytes", workspace_bytes, need);
   const size_t esize = dtype == B200_F32 ? 4 : 2;
-  int cs; bool res; size_t smem; int pc;
-  plan(C, r, H, W, ksa, esize, true, &cs, &res, &smem, &pc);
-  B200_REQUIRE(smem <= (size_t)max_smem_optin(), B200_ERR_UNSUPPORTED, "cbam_bwd: shape needs %zu B of shared memory", smem);
-  CbamParams P{x, g, gx, w1, w2, wsa, const_cast<float*>(ca), const_cast<float*>(sa), (float*)workspace,
-               B, C, H, W, r, ksa, mode, pc};
+  const int ve = 16 / (int)esize, ew = 4 / (int)esize;
+  const bool vec16 = C % ve == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)gx & 15) == 0 &&
+                     (mode != B200_CBAM_FULL || ((uintptr_t)g & 15) == 0);
+  float* part = (float*)workspace;
+  float* cpart = part + (size_t)B * 2 * r * C;
+  CbamParams P{x, g, gx, w1, w2, wsa, const_cast<float*>(ca), const_cast<float*>(sa), part, cpart, nullptr, {}};
+  make_plan(P.pl, B, C, H, W, r, ksa, mode, vec16 ? ve : ew, esize, true);
+  B200_REQUIRE((size_t)P.pl.total <= (size_t)max_smem_optin(), B200_ERR_UNSUPPORTED, "cbam_bwd: shape needs %d B of shared memory", P.pl.total);
   cudaStream_t st = (cudaStream_t)stream;
-  // partial slots that a mode never writes must read as zero
-  cudaMemsetAsync(workspace, 0, need, st);
+  const bool res = P.pl.resident != 0;
   int rc = B200_DISPATCH_DTYPE(dtype, [&]() -> int {
     constexpr int VE = Words<T>::VE, EW = Words<T>::EPL;
-    if (C % VE == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)gx & 15) == 0 && (mode != B200_CBAM_FULL || ((uintptr_t)g & 15) == 0))
-      return res ? launch_cluster(cbam_bwd_kernel<T, true, VE>, B * cs, cs, smem, st, P)
-                 : launch_cluster(cbam_bwd_kernel<T, false, VE>, B * cs, cs, smem, st, P);
-    return res ? launch_cluster(cbam_bwd_kernel<T, true, EW>, B * cs, cs, smem, st, P)
-               : launch_cluster(cbam_bwd_kernel<T, false, EW>, B * cs, cs, smem, st, P);
+    if (vec16)
+      return res ? launch_cluster(cbam_bwd_kernel<T, true, VE>, P, st) : launch_cluster(cbam_bwd_kernel<T, false, VE>, P, st);
+    return res ? launch_cluster(cbam_bwd_kernel<T, true, EW>, P, st) : launch_cluster(cbam_bwd_kernel<T, false, EW>, P, st);
   });
   if (rc) return rc;
-  const int n1 = r * C, n2 = C * r, n3 = 2 * ksa * ksa;
-  const int n = n1 + n2 + n3;
-  fold_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>((const float*)workspace, mode != B200_CBAM_SA ? gw1 : nullptr,
-                                                        mode != B200_CBAM_SA ? gw2 : nullptr,
-                                                        mode != B200_CBAM_CA ? gwsa : nullptr, B, n1, n2, n3);
+  const int n1 = mode != B200_CBAM_SA ? r * C : 0, n2 = n1;
+  const int mlp_blocks = (n1 + n2 + 127) / 128;
+  const int tap_blocks = mode != B200_CBAM_CA ? (2 * ksa * ksa + 3) / 4 : 0;
+  fold_partials_kernel<<<mlp_blocks + tap_blocks, 128, 0, st>>>(part, cpart, gw1, gw2, gwsa, B, P.pl.cs, n1, n2, ksa, mlp_blocks);
   return check_launch("cbam_bwd_fold");
 }
+
+/* debug hook (not part of the drop-in ABI): device buffer of [grid][16] int64 that receives %globaltimer stamps of the
+ * forward kernel's phases for CTA-level latency analysis (profiles/cbam_phases.py); NULL switches it off. */
+extern "C" B200_API void b200_debug_cbam_prof(void* dev_buffer) { b200::g_cbam_prof = (long long*)dev_buffer; }

@@ -82,7 +82,8 @@ B200_API int b200_cbam_fwd(const void* x, const float* w1, const float* w2, cons
  *   FULL: g = dL/dout [B,H,W,C];  CA: g = dL/dca [B,C] (f32);  SA: g = dL/dsa [B,H*W] (f32).
  *   ca/sa: the maps saved by the forward (f32).  gx [B,H,W,C] out (activation dtype).
  *   gw1 [r,C], gw2 [C,r], gwsa [2,ksa,ksa]: f32, OVERWRITTEN (not accumulated).
- *   workspace: b200_cbam_bwd_workspace_bytes(...) bytes of device scratch. */
+ *   workspace: b200_cbam_bwd_workspace_bytes(...) bytes of device scratch (per-image / per-CTA weight-gradient
+ *   partials, folded in a fixed order: deterministic). */
 B200_API size_t b200_cbam_bwd_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W, int32_t r, int32_t ksa);
 B200_API int b200_cbam_bwd(const void* g, const void* x, const float* w1, const float* w2, const float* wsa,
                   const float* ca, const float* sa, void* gx, float* gw1, float* gw2, float* gwsa,
@@ -162,6 +163,10 @@ B200_API int b200_swin_attn_fwd_tc(const void* qkv, void* o, float* lse, int64_t
                                    int32_t nh, int32_t dtype, void* stream);
 B200_API int b200_swin_attn_bwd_tc(const void* qkv, const float* lse, const void* go, void* gqkv, int64_t tokens,
                                    int32_t L, int32_t C, int32_t nh, int32_t dtype, void* stream);
+
+/* Debug hook, not part of the drop-in surface: device buffer of [grid][16] int64 that receives %globaltimer stamps
+ * of the CBAM forward kernel's phases (profiles/cbam_phases.py); NULL switches it off. */
+B200_API void b200_debug_cbam_prof(void* dev_buffer);
 
 #ifdef __cplusplus
 }

@@ -44,7 +44,7 @@ def test_error_convention_without_gpu():
     rc = L.b200_swin_attn_fwd(one, one, None, 81 * 2, 81, 32, 2, 0, None)  # window too large
     assert rc == 6
     assert L.b200_swin_num_tokens(64, 40, 40, 7) == 64 * 36 * 49
-    assert L.b200_cbam_bwd_workspace_bytes(2, 32, 4, 4, 2, 7) == 2 * (2 * 2 * 32 + 98) * 4
+    assert L.b200_cbam_bwd_workspace_bytes(2, 32, 4, 4, 2, 7) == 2 * (2 * 2 * 32 + 16 * 98) * 4
 
 
 def test_missing_library_fails_loudly(tmp_path, monkeypatch):
