@@ -26,10 +26,11 @@ _SIGS = {
     "b200_launch_count": (C.c_uint64, []),
     "b200_sppf_pool_fwd": (C.c_int, [_vp, _vp, _vp] + [_i32] * 6 + [_vp]),
     "b200_sppf_pool_bwd": (C.c_int, [_vp, _vp, _vp] + [_i32] * 6 + [_vp]),
-    "b200_cbam_fwd": (C.c_int, [_vp] * 7 + [_i32] * 8 + [_vp]),
+    "b200_cbam_stash_bytes": (_sz, [_i32] * 4),
+    "b200_cbam_fwd_workspace_bytes": (_sz, [_i32] * 5),
+    "b200_cbam_fwd": (C.c_int, [_vp] * 9 + [_sz] + [_i32] * 8 + [_vp]),
     "b200_cbam_bwd_workspace_bytes": (_sz, [_i32] * 6),
-    "b200_cbam_bwd": (C.c_int, [_vp] * 12 + [_sz] + [_i32] * 8 + [_vp]),
-    "b200_debug_cbam_prof": (None, [_vp]),
+    "b200_cbam_bwd": (C.c_int, [_vp] * 13 + [_sz] + [_i32] * 8 + [_vp]),
 }
 
 

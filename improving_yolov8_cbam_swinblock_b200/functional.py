@@ -101,21 +101,27 @@ class CBAMFn(torch.autograd.Function):
         x = _nhwc(x)
         B, Cc, H, W = x.shape
         dev = x.device
+        code = dtype_code(x.dtype)
         r = w1.shape[0] if w1 is not None else 1
         ksa = wsa.shape[-1] if wsa is not None else 3
         w1f = _f32(w1).view(r, Cc) if w1 is not None else None
         w2f = _f32(w2).view(Cc, r) if w2 is not None else None
         wsf = _f32(wsa).view(2, ksa, ksa) if wsa is not None else None
         need_grad = any(ctx.needs_input_grad)
-        ca = torch.empty((B, Cc), dtype=torch.float32, device=dev) if (mode == 1 or (need_grad and mode == 0)) else None
+        L = lib()
+        ca = torch.empty((B, Cc), dtype=torch.float32, device=dev) if mode != 2 else None
         sa = torch.empty((B, H * W), dtype=torch.float32, device=dev) if (mode == 2 or (need_grad and mode == 0)) else None
         out = _empty_nhwc(B, Cc, H, W, x.dtype, dev) if mode == 0 else None
+        # small by-products (pooled avg/max, argmax maps, the 2-channel map) kept for the backward
+        stash = torch.empty(L.b200_cbam_stash_bytes(B, Cc, H, W), dtype=torch.uint8, device=dev) if need_grad else None
+        nbytes = L.b200_cbam_fwd_workspace_bytes(B, Cc, H, W, code)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            call("b200_cbam_fwd", ptr(x), ptr(w1f), ptr(w2f), ptr(wsf), ptr(out), ptr(ca), ptr(sa), B, Cc, H, W, r,
-                                      ksa, dtype_code(x.dtype), mode, stream_ptr(dev))
+            call("b200_cbam_fwd", ptr(x), ptr(w1f), ptr(w2f), ptr(wsf), ptr(out), ptr(ca), ptr(sa), ptr(stash), ptr(ws),
+                                  nbytes, B, Cc, H, W, r, ksa, code, mode, stream_ptr(dev))
         ctx.mode, ctx.dims = mode, (B, Cc, H, W, r, ksa)
         ctx.wshapes = tuple(None if w is None else (w.shape, w.dtype, w.stride()) for w in (w1, w2, wsa))
-        ctx.save_for_backward(x, w1f, w2f, wsf, ca, sa)
+        ctx.save_for_backward(x, w1f, w2f, wsf, ca, sa, stash)
         if mode == 0:
             return out
         if mode == 1:
@@ -125,9 +131,10 @@ class CBAMFn(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g):
-        x, w1f, w2f, wsf, ca, sa = ctx.saved_tensors
+        x, w1f, w2f, wsf, ca, sa, stash = ctx.saved_tensors
         B, Cc, H, W, r, ksa = ctx.dims
         dev, mode = x.device, ctx.mode
+        code = dtype_code(x.dtype)
         if mode == 0:
             g = _nhwc(g.to(x.dtype))
         else:
@@ -137,11 +144,11 @@ class CBAMFn(torch.autograd.Function):
         gw2 = torch.empty((Cc, r), dtype=torch.float32, device=dev) if mode != 2 else None
         gws = torch.empty((2, ksa, ksa), dtype=torch.float32, device=dev) if mode != 1 else None
         L = lib()
-        nbytes = L.b200_cbam_bwd_workspace_bytes(B, Cc, H, W, r, ksa)
+        nbytes = L.b200_cbam_bwd_workspace_bytes(B, Cc, H, W, r, code)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            call("b200_cbam_bwd", ptr(g), ptr(x), ptr(w1f), ptr(w2f), ptr(wsf), ptr(ca), ptr(sa), ptr(gx), ptr(gw1),
-                                  ptr(gw2), ptr(gws), ptr(ws), nbytes, B, Cc, H, W, r, ksa, dtype_code(x.dtype), mode,
+            call("b200_cbam_bwd", ptr(g), ptr(x), ptr(w1f), ptr(w2f), ptr(wsf), ptr(ca), ptr(sa), ptr(stash), ptr(gx),
+                                  ptr(gw1), ptr(gw2), ptr(gws), ptr(ws), nbytes, B, Cc, H, W, r, ksa, code, mode,
                                   stream_ptr(dev))
         outs = []
         for gw, meta in zip((gw1, gw2, gws), ctx.wshapes):

@@ -73,21 +73,26 @@ B200_API int b200_sppf_pool_bwd(const void* gcat, const void* y0, void* gy0, int
  *   mode B200_CBAM_SA   : sa_out[B,H*W] = sigmoid(conv(cat[mean_c x, max_c x])) only (cbam.py:48-53)
  *   w1 [r,C], w2 [C,r]  shared_MLP.{0,2}.weight (no bias, cbam.py:24-26); wsa [2,ksa,ksa] sa.conv.weight,
  *   ksa in {3,7} (cbam.py:43).  ca_out / sa_out (f32) may be NULL in FULL mode when no backward is needed.
+ *   stash (nullable): b200_cbam_stash_bytes(...) bytes that receive the forward's small by-products for the
+ *   backward (pooled avg/max [B,2,C], first-argmax pixel per channel [B,C], mean_c / max_c / argmax_c maps [B,3,HW]).
+ *   workspace: b200_cbam_fwd_workspace_bytes(...) bytes of device scratch.
  * ------------------------------------------------------------------------------------------------------ */
 enum { B200_CBAM_FULL = 0, B200_CBAM_CA = 1, B200_CBAM_SA = 2 };
+B200_API size_t b200_cbam_stash_bytes(int32_t B, int32_t C, int32_t H, int32_t W);
+B200_API size_t b200_cbam_fwd_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W, int32_t dtype);
 B200_API int b200_cbam_fwd(const void* x, const float* w1, const float* w2, const float* wsa, void* out, float* ca_out,
-                  float* sa_out, int32_t B, int32_t C, int32_t H, int32_t W, int32_t r, int32_t ksa,
-                  int32_t dtype, int32_t mode, void* stream);
+                  float* sa_out, void* stash, void* workspace, size_t workspace_bytes, int32_t B, int32_t C,
+                  int32_t H, int32_t W, int32_t r, int32_t ksa, int32_t dtype, int32_t mode, void* stream);
 /* backward (autograd of the same forwards).
  *   FULL: g = dL/dout [B,H,W,C];  CA: g = dL/dca [B,C] (f32);  SA: g = dL/dsa [B,H*W] (f32).
- *   ca/sa: the maps saved by the forward (f32).  gx [B,H,W,C] out (activation dtype).
+ *   ca/sa: the maps written by the forward (f32); stash: the forward's stash.  gx [B,H,W,C] out (activation dtype).
  *   gw1 [r,C], gw2 [C,r], gwsa [2,ksa,ksa]: f32, OVERWRITTEN (not accumulated).
- *   workspace: b200_cbam_bwd_workspace_bytes(...) bytes of device scratch (per-image / per-CTA weight-gradient
- *   partials, folded in a fixed order: deterministic). */
-B200_API size_t b200_cbam_bwd_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W, int32_t r, int32_t ksa);
+ *   workspace: b200_cbam_bwd_workspace_bytes(...) bytes of device scratch (per-pixel maps and per-image / per-slice
+ *   weight-gradient partials, folded in a fixed order: deterministic, no atomics). */
+B200_API size_t b200_cbam_bwd_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W, int32_t r, int32_t dtype);
 B200_API int b200_cbam_bwd(const void* g, const void* x, const float* w1, const float* w2, const float* wsa,
-                  const float* ca, const float* sa, void* gx, float* gw1, float* gw2, float* gwsa,
-                  void* workspace, size_t workspace_bytes, int32_t B, int32_t C, int32_t H, int32_t W,
+                  const float* ca, const float* sa, const void* stash, void* gx, float* gw1, float* gw2,
+                  float* gwsa, void* workspace, size_t workspace_bytes, int32_t B, int32_t C, int32_t H, int32_t W,
                   int32_t r, int32_t ksa, int32_t dtype, int32_t mode, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
@@ -163,10 +168,6 @@ B200_API int b200_swin_attn_fwd_tc(const void* qkv, void* o, float* lse, int64_t
                                    int32_t nh, int32_t dtype, void* stream);
 B200_API int b200_swin_attn_bwd_tc(const void* qkv, const float* lse, const void* go, void* gqkv, int64_t tokens,
                                    int32_t L, int32_t C, int32_t nh, int32_t dtype, void* stream);
-
-/* Debug hook, not part of the drop-in surface: device buffer of [grid][16] int64 that receives %globaltimer stamps
- * of the CBAM forward kernel's phases (profiles/cbam_phases.py); NULL switches it off. */
-B200_API void b200_debug_cbam_prof(void* dev_buffer);
 
 #ifdef __cplusplus
 }

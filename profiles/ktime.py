@@ -1,6 +1,6 @@
 """Kernel-only timings of the HBM-bound blocks through the public autograd wrappers, host launch latency hidden.
 
-Each timed launch is preceded (on the same stream) by an L2 flush (256 MB write) and a ~150 us spin kernel, so the
+Each timed launch is preceded (on the same stream) by an L2 flush (256 MB write) and a ~1 ms spin kernel, so the
 start event is recorded while the GPU is still busy and the Python/ctypes overhead of the call is NOT inside the
 event pair.  Prints algorithmic GB/s next to a plain 1R+1W copy of the same tensor.
 
@@ -31,7 +31,7 @@ def ktime(fn, iters=12, do_flush=True):
     for _ in range(iters + 3):
         if do_flush:
             flush.zero_()
-        torch.cuda._sleep(300_000)
+        torch.cuda._sleep(2_000_000)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         fn()

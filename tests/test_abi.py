@@ -37,14 +37,15 @@ def test_error_convention_without_gpu():
     assert rc == 3
     rc = L.b200_sppf_pool_fwd(one, one, None, 1, 8, 4, 4, 5, 9, None)  # unknown dtype
     assert rc == 2
-    rc = L.b200_cbam_fwd(one, one, one, one, one, None, None, 1, 8, 4, 4, 1, 5, 0, 0, None)  # ksa not in {3,7}
+    rc = L.b200_cbam_fwd(one, one, one, one, one, None, None, None, one, 1 << 20, 1, 8, 4, 4, 1, 5, 0, 0, None)  # ksa not in {3,7}
     assert rc == 1 and b"3 or 7" in L.b200_last_error()
     rc = L.b200_swin_attn_fwd(one, one, None, 100, 49, 32, 2, 0, None)  # tokens not a multiple of L
     assert rc == 1
     rc = L.b200_swin_attn_fwd(one, one, None, 81 * 2, 81, 32, 2, 0, None)  # window too large
     assert rc == 6
     assert L.b200_swin_num_tokens(64, 40, 40, 7) == 64 * 36 * 49
-    assert L.b200_cbam_bwd_workspace_bytes(2, 32, 4, 4, 2, 7) == 2 * (2 * 2 * 32 + 16 * 98) * 4
+    assert L.b200_cbam_bwd_workspace_bytes(2, 32, 4, 4, 2, 0) >= 2 * (2 * 2 * 32 + 98) * 4
+    assert L.b200_cbam_stash_bytes(2, 32, 4, 4) >= 2 * (3 * 32 + 3 * 16) * 4
 
 
 def test_missing_library_fails_loudly(tmp_path, monkeypatch):
