@@ -45,7 +45,7 @@ def ncu_kernel_name(tag: str):
     """ABI entry point (or shape-tagged GEMM) -> kernel instantiation name used in profiles/traffic_rNN.json."""
     import re
 
-    fixed = {"b200_cbam_fwd": "b200::cbam_fwd_kernel<__nv_bfloat16, 1>", "b200_cbam_bwd": "b200::cbam_bwd_kernel<__nv_bfloat16, 1>",
+    fixed = {"b200_cbam_fwd": "b200::cbam::cbam_cluster_fwd_kernel<__nv_bfloat16, 8, 1>",
              "b200_swin_attn_fwd_tc": "b200::swin_attn_fwd_tc_kernel<64>", "b200_swin_attn_bwd_tc": "b200::swin_attn_bwd_tc_kernel<64>",
              "b200_swin_ln1_partition": "b200::swin_ln1_partition_vec_kernel<__nv_bfloat16, 8, 2>",
              "b200_swin_res_ln2": "b200::swin_res_ln2_vec_kernel<__nv_bfloat16, 8, 2>"}
@@ -77,9 +77,12 @@ def gemm_work(tag: str, peaks: dict, s: int = 2):
 
 
 def _time(fn, iters, flush):
+    """median ms of fn's GPU work: L2 flushed, and a ~1 ms spin kernel queued first so that the host-side launch
+    latency of fn (Python + ctypes) is not inside the event pair."""
     ms = []
     for _ in range(iters + 3):
         flush.zero_()
+        torch.cuda._sleep(2_000_000)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         fn()
