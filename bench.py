@@ -221,7 +221,7 @@ def main():
         tot = {k: n * ms for k, (n, ms) in ktimes.items()}
         top = max(tot, key=tot.get)
         n, ms = ktimes[top]
-        w = work.get(top) or sweep.gemm_work(top, peaks)
+        w = work.get(top) or sweep.gemm_work(top, peaks) or sweep.bn_work(top)
         if not w:
             roof = {"kernel": top, "avg_ms": ms, "calls": n, "note": "no algorithmic-work entry",
                     "kernels_ms_per_step": {k: v / args.steps for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
@@ -239,7 +239,7 @@ def main():
     if roof is not None:  # every hand-written kernel of the step: mean ms per launch + fraction of its roofline
         allk = {}
         for k, (n_, ms_) in ktimes.items():
-            w_ = work.get(k) or sweep.gemm_work(k, peaks)
+            w_ = work.get(k) or sweep.gemm_work(k, peaks) or sweep.bn_work(k)
             ent = {"calls_per_step": n_ / args.steps, "avg_ms": round(ms_, 5)}
             if w_:
                 pk = peaks["hbm_gbs"] if w_["bound"] == "hbm" else peaks["bf16_tflops_sustained"]

@@ -30,6 +30,10 @@ _lib.register("b200_swin_ln_bwd_workspace_bytes", _SZ, [_I64, _I32])
 _lib.register("b200_swin_ln_bwd", C.c_int, [_VP] * 10 + [_SZ] + [_I32] * 7 + [_VP])
 _lib.register("b200_colsum_workspace_bytes", _SZ, [_I64, _I32])
 _lib.register("b200_colsum", C.c_int, [_VP] * 3 + [_SZ] + [_I64] + [_I32] * 2 + [_VP])
+_lib.register("b200_bn_silu_supported", C.c_int, [_I64, _I32, _I32])
+_lib.register("b200_bn_silu_workspace_bytes", _SZ, [_I64, _I32, _I32])
+_lib.register("b200_bn_silu_fwd", C.c_int, [_VP] * 9 + [_SZ, _I64, _I32, C.c_float, C.c_float, _I32, _I32, _I32, _VP])
+_lib.register("b200_bn_silu_bwd", C.c_int, [_VP] * 10 + [_SZ, _I64, _I32, _I32, _I32, _I32, _VP])
 
 
 def _nhwc(x: torch.Tensor) -> torch.Tensor:
@@ -88,6 +92,67 @@ class SPPFPoolFn(torch.autograd.Function):
 def sppf_pool(y0: torch.Tensor, k: int) -> torch.Tensor:
     """[B,c,H,W] -> [B,4c,H,W] = cat[y0, m(y0), m(m(y0)), m(m(m(y0)))], m = MaxPool2d(k,1,k//2)."""
     return SPPFPoolFn.apply(y0, k)
+
+
+# --------------------------------------------------------------------------------------------------
+# Conv epilogue: BatchNorm2d (+ SiLU) fused   (conv.py:65-79; SPPF cv1/cv2, block.py:218-219)
+# --------------------------------------------------------------------------------------------------
+class BnActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, act):
+        x = _nhwc(x)
+        B, Cc, H, W = x.shape
+        rows, dev, code = B * H * W, x.device, dtype_code(x.dtype)
+        z = torch.empty_like(x)
+        need_grad = any(ctx.needs_input_grad)
+        mean = torch.empty(Cc, dtype=torch.float32, device=dev) if need_grad else None
+        rstd = torch.empty(Cc, dtype=torch.float32, device=dev) if need_grad else None
+        nbytes = lib().b200_bn_silu_workspace_bytes(rows, Cc, code)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        wf, bf = _f32(weight), _f32(bias)
+        with torch.cuda.device(dev):
+            call("b200_bn_silu_fwd", ptr(x), ptr(wf), ptr(bf), ptr(running_mean), ptr(running_var), ptr(z), ptr(mean),
+                                     ptr(rstd), ptr(ws), nbytes, rows, Cc, float(eps), float(momentum), int(training), int(act),
+                                     code, stream_ptr(dev), tag=f"b200_bn_silu_fwd[{rows}x{Cc}]")
+        ctx.save_for_backward(x, wf, bf, mean, rstd)
+        ctx.cfg = (rows, Cc, int(training), int(act), weight.dtype, bias.dtype)
+        return z
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gz):
+        x, wf, bf, mean, rstd = ctx.saved_tensors
+        rows, Cc, training, act, wdt, bdt = ctx.cfg
+        dev, code = x.device, dtype_code(x.dtype)
+        gz = _nhwc(gz.to(x.dtype))
+        gx = torch.empty_like(x)
+        gg = torch.empty(Cc, dtype=torch.float32, device=dev)
+        gb = torch.empty(Cc, dtype=torch.float32, device=dev)
+        nbytes = lib().b200_bn_silu_workspace_bytes(rows, Cc, code)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            call("b200_bn_silu_bwd", ptr(gz), ptr(x), ptr(wf), ptr(bf), ptr(mean), ptr(rstd), ptr(gx), ptr(gg), ptr(gb),
+                                     ptr(ws), nbytes, rows, Cc, training, act, code, stream_ptr(dev),
+                                     tag=f"b200_bn_silu_bwd[{rows}x{Cc}]")
+        return gx, gg.to(wdt), gb.to(bdt), None, None, None, None, None, None
+
+
+def bn_act_supported(x: torch.Tensor, bn) -> bool:
+    """True when the fused epilogue kernel tiles this BatchNorm2d input (16-byte channel vectors, affine, tracked)."""
+    if not (x.is_cuda and x.dim() == 4 and type(bn) is torch.nn.BatchNorm2d and bn.affine and bn.track_running_stats):
+        return False
+    if bn.momentum is None or x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+        return False
+    B, Cc, H, W = x.shape
+    return bool(lib().b200_bn_silu_supported(B * H * W, Cc, dtype_code(x.dtype)))
+
+
+def bn_act(x: torch.Tensor, bn, silu: bool) -> torch.Tensor:
+    """act(bn(x)) for the conv output x [B,C,H,W] with `bn` an nn.BatchNorm2d (conv.py:65-79); batch statistics and
+    the running-stat update in training mode, running statistics in eval mode."""
+    if bn.training:
+        bn.num_batches_tracked.add_(1)   # nn.BatchNorm2d.forward bookkeeping (state_dict parity)
+    return BnActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.training, bn.momentum, bn.eps, silu)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -83,8 +83,11 @@ class Conv(nn.Module):
         self.bn = nn.BatchNorm2d(c2)
         self.act = nn.SiLU() if act is True else act if isinstance(act, nn.Module) else nn.Identity()
 
+    epilogue = None  # DetectionGraph sets blocks["conv_epilogue"] here: callable (conv_module, y) -> act(bn(y))
+
     def forward(self, x):
-        return self.act(self.bn(self.conv(x)))
+        y = self.conv(x)
+        return self.act(self.bn(y)) if self.epilogue is None else self.epilogue(self, y)
 
 
 class Bottleneck(nn.Module):
@@ -225,6 +228,11 @@ class DetectionGraph(nn.Module):
                 chans = []
             chans.append(c2)
         self.model = nn.Sequential(*layers)
+        epi = blocks.get("conv_epilogue")  # fused BN+SiLU epilogue for the Conv callers (None = stock ops)
+        if epi is not None:
+            for m_ in self.modules():
+                if isinstance(m_, Conv):
+                    m_.epilogue = epi
         self.save = sorted(save)
         self.nc, self.scale = nc, scale
         det = self.model[-1]

@@ -41,6 +41,19 @@ def algorithmic_work(scale: str, B: int, s: int = 2, ws: int = 7):
     }
 
 
+def bn_work(tag: str, s: int = 2):
+    """Roofline entry for a shape-tagged Conv-epilogue launch: b200_bn_silu_{fwd,bwd}[rows x C]."""
+    import re
+
+    m = re.match(r"b200_bn_silu_(fwd|bwd)\[(\d+)x(\d+)\]", tag)
+    if not m:
+        return None
+    n = int(m.group(2)) * int(m.group(3))
+    if m.group(1) == "fwd":
+        return {"bound": "hbm", "amount": 2.0 * n * s, "note": "2*N*s: read the conv output once, write act(bn(.)) once (the kernel reads it twice: statistics, apply)"}
+    return {"bound": "hbm", "amount": 3.0 * n * s, "note": "3*N*s: read x and g once, write g_x once (the kernel reads both twice: reduce, apply)"}
+
+
 def ncu_kernel_name(tag: str):
     """ABI entry point (or shape-tagged GEMM) -> kernel instantiation name used in profiles/traffic_rNN.json."""
     import re

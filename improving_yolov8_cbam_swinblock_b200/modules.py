@@ -137,6 +137,34 @@ class SwinBlock(nn.Module):
         return Fb.swin_block(x, p, self.num_heads, self.window_size)
 
 
+FUSE_CONV_EPILOGUE = [True]  # process-wide switch (tests / A-B timing); False = the caller's stock BatchNorm2d + SiLU
+
+
+def conv_epilogue(conv_module, y):
+    """``act(bn(y))`` of the reference ``Conv.forward`` (conv.py:65-79) on the conv output ``y``: one fused B200
+    epilogue (batch statistics + affine + SiLU; csrc/conv_epilogue.cu) when the layer is BatchNorm2d + SiLU/Identity on
+    a CUDA tensor the kernel tiles, else the module's own stock ops."""
+    bn, act = conv_module.bn, conv_module.act
+    if FUSE_CONV_EPILOGUE[0] and y.is_cuda and type(act) in (nn.SiLU, nn.Identity) and Fb.bn_act_supported(y, bn):
+        return Fb.bn_act(y, bn, type(act) is nn.SiLU)
+    return act(bn(y))
+
+
+def make_conv(conv_cls, name="Conv", module=None):
+    """Subclass of the caller's ``Conv`` (conv.py:37-91) whose un-fused forward runs the B200 BN+SiLU epilogue.
+    Still a ``Conv`` instance with the same sub-modules / state_dict, so ``BaseModel.fuse`` (tasks.py:219-225) keeps
+    folding its BN and swapping in ``forward_fuse``."""
+
+    class Conv(conv_cls):
+        def forward(self, x):
+            return conv_epilogue(self, self.conv(x))
+
+    Conv.__name__ = Conv.__qualname__ = name
+    if module is not None:
+        Conv.__module__ = module
+    return Conv
+
+
 def make_sppf(conv_cls, name="SPPF", module=None):
     """SPPF bound to the caller's stock ``Conv`` (cv1/cv2 stay Conv instances so ``BaseModel.fuse`` keeps folding
     their BN, tasks.py:219-225); only the pooling cascade + concat (block.py:224-226) runs in our kernel."""
@@ -170,4 +198,4 @@ def _harness_sppf():
 
 
 SPPF = _harness_sppf()
-BLOCKS = {"CBAM": CBAM, "SwinBlock": SwinBlock, "SPPF": SPPF}
+BLOCKS = {"CBAM": CBAM, "SwinBlock": SwinBlock, "SPPF": SPPF, "conv_epilogue": conv_epilogue}

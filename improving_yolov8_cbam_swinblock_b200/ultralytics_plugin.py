@@ -27,15 +27,29 @@ ChannelAttentionMap = _m.ChannelAttention
 SpatialAttentionMap = _m.SpatialAttention
 SwinBlock = _m.SwinBlock
 SPPF = None  # created by install() against ultralytics' Conv
+Conv = None  # ultralytics' Conv with the fused BN+SiLU epilogue, created by install()
+_CONV_TARGETS = ("ultralytics.nn.tasks", "ultralytics.nn.modules", "ultralytics.nn.modules.conv",
+                 "ultralytics.nn.modules.block", "ultralytics.nn.modules.head")
 
 
-def install():
-    """Rebind CBAM / SwinBlock / SPPF in the reference's namespaces.  Returns the {name: class} table."""
-    global SPPF
+def install(conv_epilogue: bool = False):
+    """Rebind CBAM / SwinBlock / SPPF in the reference's namespaces.  Returns the {name: class} table.
+
+    SPPF's own cv1/cv2 always use the fused BN+SiLU epilogue; ``conv_epilogue=True`` additionally rebinds ``Conv``
+    itself (a subclass of the reference's, same state_dict / ``fuse()`` behaviour) so every Conv caller gets it."""
+    global SPPF, Conv
     conv_mod = importlib.import_module("ultralytics.nn.modules.conv")
+    if Conv is None:
+        Conv = _m.make_conv(_saved.get(("ultralytics.nn.modules.conv", "Conv"), conv_mod.Conv), module=__name__)
     if SPPF is None:
-        SPPF = _m.make_sppf(conv_mod.Conv, module=__name__)
+        SPPF = _m.make_sppf(Conv, module=__name__)
     table = {"CBAM": CBAM, "SwinBlock": SwinBlock, "SPPF": SPPF}
+    if conv_epilogue:
+        for modname in _CONV_TARGETS:
+            mod = importlib.import_module(modname)
+            if hasattr(mod, "Conv"):
+                _saved.setdefault((modname, "Conv"), getattr(mod, "Conv"))
+                setattr(mod, "Conv", Conv)
     for modname in _TARGETS:
         mod = importlib.import_module(modname)
         for name, cls in table.items():

@@ -169,6 +169,29 @@ B200_API int b200_swin_attn_fwd_tc(const void* qkv, void* o, float* lse, int64_t
 B200_API int b200_swin_attn_bwd_tc(const void* qkv, const float* lse, const void* go, void* gqkv, int64_t tokens,
                                    int32_t L, int32_t C, int32_t nh, int32_t dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Conv epilogue -- replaces `self.act(self.bn(y))` of Conv.forward (ultralytics/nn/modules/conv.py:65-79:
+ * BatchNorm2d then SiLU) on the conv output y, for SPPF's cv1/cv2 (block.py:218-219) and the
+ * other Conv callers either side of the path.  x/z/gz/gx: NHWC viewed as [rows = B*H*W, C] in the activation dtype;
+ * gamma, beta, running_mean, running_var, mean, rstd, ggamma, gbeta: f32 [C].
+ *   training != 0: batch statistics of THIS GPU (no SyncBN, like the reference), running_mean/var updated in place
+ *                  as torch does (momentum; unbiased variance); mean_out/rstd_out (nullable) saved for the backward.
+ *   training == 0: running statistics.   act: 1 = SiLU, 0 = identity.
+ * b200_bn_silu_supported(): C a multiple of 16 bytes of elements, C <= 256 vectors.
+ * ------------------------------------------------------------------------------------------------------ */
+B200_API int b200_bn_silu_supported(int64_t rows, int32_t C, int32_t dtype);
+B200_API size_t b200_bn_silu_workspace_bytes(int64_t rows, int32_t C, int32_t dtype);
+B200_API int b200_bn_silu_fwd(const void* x, const float* gamma, const float* beta, float* running_mean,
+                              float* running_var, void* z, float* mean_out, float* rstd_out, void* workspace,
+                              size_t workspace_bytes, int64_t rows, int32_t C, float eps, float momentum,
+                              int32_t training, int32_t act, int32_t dtype, void* stream);
+/* backward: gx = dL/dx, ggamma / gbeta OVERWRITTEN; mean/rstd = the statistics the forward normalised with
+ * (training == 0: pass running_mean and 1/sqrt(running_var + eps)).  Deterministic (no atomics). */
+B200_API int b200_bn_silu_bwd(const void* gz, const void* x, const float* gamma, const float* beta, const float* mean,
+                              const float* rstd, void* gx, float* ggamma, float* gbeta, void* workspace,
+                              size_t workspace_bytes, int64_t rows, int32_t C, int32_t training, int32_t act,
+                              int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,28 @@ def cbam_forward(x, w1, w2, wsa):
 
 
 # --------------------------------------------------------------------------------------------------
+# Conv epilogue: BatchNorm2d (+ SiLU) on a conv output (conv.py:65-79; used by SPPF cv1/cv2, block.py:218-219)
+# --------------------------------------------------------------------------------------------------
+def bn_act_forward(x, gamma, beta, running_mean, running_var, training=True, momentum=0.03, eps=1e-3, silu=True):
+    """act(BatchNorm2d(x)) from primitives.  Training: per-channel batch statistics over (B,H,W), biased variance for
+    the normalisation, running stats updated with the UNBIASED variance (torch.nn.BatchNorm2d semantics).
+    Returns (z, new_running_mean, new_running_var)."""
+    B, C, H, W = x.shape
+    if training:
+        n = B * H * W
+        mean = x.mean(dim=(0, 2, 3))
+        var = ((x - mean[None, :, None, None]) ** 2).mean(dim=(0, 2, 3))
+        rm = (1 - momentum) * running_mean + momentum * mean.detach()
+        rv = (1 - momentum) * running_var + momentum * var.detach() * (n / max(n - 1, 1))
+    else:
+        mean, var, rm, rv = running_mean, running_var, running_mean, running_var
+    y = (x - mean[None, :, None, None]) / torch.sqrt(var[None, :, None, None] + eps)
+    y = y * gamma[None, :, None, None] + beta[None, :, None, None]
+    z = y * torch.sigmoid(y) if silu else y
+    return z, rm, rv
+
+
+# --------------------------------------------------------------------------------------------------
 # SwinBlock (swin_block.py:37-58)
 # --------------------------------------------------------------------------------------------------
 def layer_norm(t, gamma, beta, eps=1e-5):

@@ -119,6 +119,24 @@ def main():
     m = SPPF(16, 16, 5).train()
     d = _run(m, torch.randn(2, 16, 6, 6), 151)
     np.savez_compressed(os.path.join(OUT, "sppf_module_k5.npz"), **d)
+    # ---- the reference Conv block (conv -> BatchNorm2d -> SiLU, conv.py:37-79), train mode: pins the fused epilogue
+    from ultralytics.nn.modules.conv import Conv
+
+    for name, args, shape, seed in [("conv_k1_c16", (8, 16, 1, 1), (3, 8, 6, 5), 61), ("conv_k3_c32", (16, 32, 3, 2), (2, 16, 9, 9), 62)]:
+        torch.manual_seed(seed)
+        m = Conv(*args).train()
+        with torch.no_grad():
+            m.bn.weight.add_(0.3 * torch.randn_like(m.bn.weight))
+            m.bn.bias.add_(0.3 * torch.randn_like(m.bn.bias))
+        before = {k: v.clone() for k, v in m.state_dict().items()}
+        x = torch.randn(shape)
+        d = _run(m, x, seed + 100)
+        for k, v in before.items():
+            d["w0." + k] = v.numpy()       # state BEFORE the forward (running stats are updated by it)
+        with torch.no_grad():
+            d["conv_out"] = m.conv(x).numpy()
+        d["bn_eps"], d["bn_momentum"] = np.array(m.bn.eps), np.array(m.bn.momentum)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("wrote", len(os.listdir(OUT)), "fixtures,", tot // 1024, "KiB")
 

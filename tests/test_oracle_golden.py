@@ -17,7 +17,7 @@ def _t(a, grad=False):
 
 def test_fixture_inventory():
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
-    assert len(names) == 16 and all(n.split("_")[0] in ("cbam", "swin", "sppf") for n in names)
+    assert len(names) == 18 and all(n.split("_")[0] in ("cbam", "swin", "sppf", "conv") for n in names)
 
 
 @pytest.mark.parametrize("name", ["cbam_lazy_c32", "cbam_c64_r8", "cbam_lazy_c256_p5"])
@@ -86,3 +86,20 @@ def test_sppf_module_matches_reference():
     y.backward(torch.from_numpy(g["gy"]))
     np.testing.assert_allclose(y.detach().numpy(), g["y"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(x.grad.numpy(), g["gx"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["conv_k1_c16", "conv_k3_c32"])
+def test_conv_epilogue_bn_silu(name):
+    """oracle BN(train)+SiLU restatement vs the reference Conv block (conv.py:65-79): output, input/affine gradients
+    and the running-statistics update."""
+    g = load_golden(name)
+    x = _t(g["conv_out"], True)
+    gamma, beta = _t(g["w0.bn.weight"], True), _t(g["w0.bn.bias"], True)
+    z, rm, rv = ob.bn_act_forward(x, gamma, beta, _t(g["w0.bn.running_mean"]), _t(g["w0.bn.running_var"]), True,
+                                  float(g["bn_momentum"]), float(g["bn_eps"]), True)
+    z.backward(_t(g["gy"]))
+    np.testing.assert_allclose(z.detach().numpy(), g["y"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(gamma.grad.numpy(), g["gw.bn.weight"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(beta.grad.numpy(), g["gw.bn.bias"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(rm.numpy(), g["w.bn.running_mean"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(rv.numpy(), g["w.bn.running_var"], rtol=1e-5, atol=1e-7)
