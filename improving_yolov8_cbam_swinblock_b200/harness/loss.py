@@ -87,7 +87,7 @@ class DetectionLoss:
         out = torch.zeros(batch_size, max_boxes, 5, device=device)
         if n == 0:
             return out
-        counts = torch.bincount(bi, minlength=batch_size)
+        counts = torch.zeros(batch_size, dtype=torch.long, device=device).scatter_add_(0, bi, torch.ones_like(bi))  # no host sync
         start = torch.cumsum(counts, 0) - counts
         order = torch.argsort(bi, stable=True)
         rank = torch.empty_like(bi)
@@ -107,7 +107,8 @@ class DetectionLoss:
         pred_distri = pred_distri.permute(0, 2, 1).contiguous()
         dtype = pred_scores.dtype
         h, w = feats[0].shape[2:]
-        wh = torch.tensor([w, h], device=device, dtype=torch.float32) * self.strides[0]
+        wh = torch.stack((torch.full((), w * self.strides[0], device=device),      # fill kernels, no host->device copy:
+                          torch.full((), h * self.strides[0], device=device)))     # the step stays CUDA-graph capturable
         anchor_points, stride_tensor = make_anchors(feats, self.strides, 0.5)
         if max_boxes is None:
             bi = batch["batch_idx"].long().view(-1)

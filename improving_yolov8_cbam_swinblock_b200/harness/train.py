@@ -76,12 +76,50 @@ class Trainer:
         self.opt = torch.optim.SGD(param_groups(model), lr=lr, momentum=momentum, nesterov=True, fused=fused)
         self.ema = EMA(model) if ema else None
         self.max_boxes = None
+        self._graph, self._graph_error, self._static, self._static_items = None, None, None, None
 
     def to_device(self, host_batch):
         return {k: v.to(self.device, non_blocking=True) for k, v in host_batch.items()}
 
+    # ---- CUDA-graph replay of the step (host-side step overhead) ------------------------------
+    def enable_graph(self, dev_batch, warmup: int = 3) -> bool:
+        """Capture forward + loss + backward (+ DDP all-reduce) + clip + SGD of one step into a CUDA graph; shapes are
+        static for the synthetic batches.  Falls back to eager launches (returns False) if capture is not possible."""
+        if self.device.type != "cuda" or self._graph is not None:
+            return self._graph is not None
+        try:
+            self._static = {k: v.clone() for k, v in dev_batch.items()}
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(max(warmup, 11 if self.world_size > 1 else 3)):
+                    self._core(self._static)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._static_items = self._core(self._static)
+            self._graph = g
+        except Exception as e:  # noqa: BLE001  capture is an optimisation; eager launches remain correct
+            self._graph, self._graph_error = None, f"{type(e).__name__}: {e}"
+            torch.cuda.synchronize(self.device)
+        return self._graph is not None
+
     def step(self, dev_batch):
         """One optimizer step on a device-resident batch; returns the detached loss items [box, cls, dfl]."""
+        if self._graph is not None:
+            for k, v in dev_batch.items():
+                self._static[k].copy_(v, non_blocking=True)
+            self._graph.replay()
+            items = self._static_items.clone()
+        else:
+            items = self._core(dev_batch)
+        if self.ema is not None:
+            self.ema.update(self.raw)
+        return items
+
+    def _core(self, dev_batch):
         img = dev_batch["img"].float() / 255  # detect/train.py:100
         if self.channels_last:
             img = img.contiguous(memory_format=torch.channels_last)
@@ -96,8 +134,6 @@ class Trainer:
         torch.nn.utils.clip_grad_norm_(self.raw.parameters(), max_norm=10.0, foreach=True)
         self.opt.step()
         self.opt.zero_grad(set_to_none=True)
-        if self.ema is not None:
-            self.ema.update(self.raw)
         return items
 
     def step_from_host(self, host_batch):
