@@ -17,6 +17,8 @@
 //        apply : gx = gamma*rstd*(gy - sum(gy)/M - xhat*sum(gy*xhat)/M)     (4R + 1W; torch: 6R + 2W)
 // Nothing but x, mean and rstd is kept for the backward (torch keeps x, the BN output and mean/rstd).
 // Deterministic: no atomics, fixed summation order.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -32,25 +34,56 @@ struct BnGeo {
 
 template <typename T, int VW> struct alignas(sizeof(T) * VW) VP { T e[VW]; };
 template <typename T, int VW>
-__device__ __forceinline__ void ldv(const T* p, float (&v)[VW]) {
-  const uint4 raw = ldg_stream16(p);
-  const VP<T, VW> k = *reinterpret_cast<const VP<T, VW>*>(&raw);
+__device__ __forceinline__ void unpack(const uint4& raw, float (&v)[VW]) {
+  if constexpr (sizeof(T) == 4) {
+    v[0] = __uint_as_float(raw.x); v[1] = __uint_as_float(raw.y); v[2] = __uint_as_float(raw.z); v[3] = __uint_as_float(raw.w);
+  } else if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-  for (int i = 0; i < VW; ++i) v[i] = DT<T>::to_f(k.e[i]);
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  } else {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
 }
 template <typename T, int VW>
-__device__ __forceinline__ void stv(T* p, const float (&v)[VW]) {
-  VP<T, VW> k;
+__device__ __forceinline__ uint4 pack(const float (&v)[VW]) {
+  uint4 r;
+  if constexpr (sizeof(T) == 4) {
+    r = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+  } else {
+    uint32_t w[4];
 #pragma unroll
-  for (int i = 0; i < VW; ++i) k.e[i] = DT<T>::from_f(v[i]);
-  stg_stream16(p, *reinterpret_cast<const uint4*>(&k));
+    for (int i = 0; i < 4; ++i) {
+      if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        const __nv_bfloat162 p = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&p);
+      } else {
+        const __half2 p = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&p);
+      }
+    }
+    r = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  return r;
 }
 
-__device__ __forceinline__ float silu_f(float y) { return y * __frcp_rn(1.f + __expf(-y)); }
-__device__ __forceinline__ float dsilu_f(float y) {
-  const float s = __frcp_rn(1.f + __expf(-y));
-  return s * (1.f + y * (1.f - s));
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
+// sigmoid: exact-ish (ex2 + rcp) for f32 activations, one MUFU.TANH for 16-bit activations (error 2^-11 << 2^-8 of bf16)
+template <bool FAST> __device__ __forceinline__ float sigmoid_t(float y) {
+  if (FAST) return fmaf(0.5f, tanh_fast(0.5f * y), 0.5f);
+  return __frcp_rn(1.f + __expf(-y));
+}
+
+constexpr int RB = 4;   // rows in flight per thread: RB independent 16-byte loads before any use
 
 // per-CTA additive reduction of NV values per channel held by the row groups: red[ngrp][NV][C] -> out via f(c, v[NV])
 template <int NV, typename F>
@@ -68,7 +101,8 @@ __device__ __forceinline__ void cta_fold(float* red, int C, int ngrp, F emit) {
   }
 }
 
-// ---- forward statistics: per-CTA (mean, M2) of every channel over the CTA's rows ------------------------------
+// ---- forward statistics: per-CTA sums of (x-k), (x-k)^2 with ONE shift k[c] = x[0][c] for the whole tensor, so the
+// partials of different CTAs simply add up and E[d^2] - E[d]^2 does not cancel (|mean - k| ~ one standard deviation)
 template <typename T, int VW>
 __global__ void __launch_bounds__(kT) bn_stats_kernel(const T* __restrict__ x, float* __restrict__ part, const BnGeo G) {
   extern __shared__ __align__(16) float red[];   // [ngrp][2][C]
@@ -76,68 +110,57 @@ __global__ void __launch_bounds__(kT) bn_stats_kernel(const T* __restrict__ x, f
   const int rg = threadIdx.x / tpr, ch = threadIdx.x - rg * tpr;
   const long long r0 = (long long)blockIdx.x * G.rpb;
   const int nrows = (int)min((long long)G.rpb, G.M - r0);
-  float s[VW], q[VW], k[VW];
-#pragma unroll
-  for (int e = 0; e < VW; ++e) { s[e] = 0.f; q[e] = 0.f; }
   if (rg < G.ngrp) {
-    const T* base = x + (size_t)r0 * C + ch * VW;
-    ldv<T, VW>(base, k);   // the block's first row: common shift of this CTA
-#pragma unroll 4
-    for (int r = rg; r < nrows; r += G.ngrp) {
-      float v[VW];
-      ldv<T, VW>(base + (size_t)r * C, v);
+    float s[VW], q[VW], k[VW];
 #pragma unroll
-      for (int e = 0; e < VW; ++e) { const float d = v[e] - k[e]; s[e] += d; q[e] += d * d; }
+    for (int e = 0; e < VW; ++e) { s[e] = 0.f; q[e] = 0.f; }
+    unpack<T, VW>(ldg_stream16(x + ch * VW), k);
+    const T* base = x + (size_t)r0 * C + ch * VW;
+    for (int r = rg; r < nrows; r += RB * G.ngrp) {
+      uint4 raw[RB];
+#pragma unroll
+      for (int u = 0; u < RB; ++u)
+        if (r + u * G.ngrp < nrows) raw[u] = ldg_stream16(base + (size_t)(r + u * G.ngrp) * C);
+#pragma unroll
+      for (int u = 0; u < RB; ++u)
+        if (r + u * G.ngrp < nrows) {
+          float v[VW];
+          unpack<T, VW>(raw[u], v);
+#pragma unroll
+          for (int e = 0; e < VW; ++e) { const float d = v[e] - k[e]; s[e] += d; q[e] = fmaf(d, d, q[e]); }
+        }
     }
     float* rs = red + (size_t)rg * 2 * C + ch * VW;
 #pragma unroll
     for (int e = 0; e < VW; ++e) { rs[e] = s[e]; rs[C + e] = q[e]; }
   }
-  const float n = (float)nrows;
   float* dst = part + (size_t)blockIdx.x * 2 * C;
-  const T* krow = x + (size_t)r0 * C;
-  cta_fold<2>(red, C, G.ngrp, [&](int c, const float (&a)[2]) {
-    const float kk = DT<T>::to_f(krow[c]);
-    const float m = a[0] / n;
-    dst[c] = kk + m;
-    dst[C + c] = fmaxf(a[1] - a[0] * m, 0.f);
-  });
+  cta_fold<2>(red, C, G.ngrp, [&](int c, const float (&a)[2]) { dst[c] = a[0]; dst[C + c] = a[1]; });
 }
 
-// ---- forward finalize: warp per channel, Chan merge of the G partials (fixed order) -----------------------------
-__global__ void __launch_bounds__(kT) bn_final_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
-                                                      const float* __restrict__ beta, float* __restrict__ running_mean,
-                                                      float* __restrict__ running_var, float* __restrict__ mean_out,
-                                                      float* __restrict__ rstd_out, float* __restrict__ scsh, float eps,
-                                                      float momentum, int training, const BnGeo G) {
+// ---- forward finalize: warp per channel sums the G partials (fixed order) -> mean, rstd, running stats, scale/shift
+template <typename T>
+__global__ void __launch_bounds__(kT) bn_final_kernel(const T* __restrict__ x, const float* __restrict__ part,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                      float* __restrict__ scsh, float eps, float momentum, int training,
+                                                      const BnGeo G) {
   const int lane = threadIdx.x & 31, c = blockIdx.x * (kT / 32) + (threadIdx.x >> 5), C = G.C;
   if (c >= C) return;
   float mean, rstd;
   if (training) {
-    float n = 0.f, mu = 0.f, m2 = 0.f;
-    for (int g = lane; g < G.G; g += 32) {
-      const float nb = (float)min((long long)G.rpb, G.M - (long long)g * G.rpb);
-      const float mb = part[(size_t)g * 2 * C + c], qb = part[(size_t)g * 2 * C + C + c];
-      const float nt = n + nb, d = mb - mu;
-      mu += d * (nb / nt);
-      m2 += qb + d * d * (n * nb / nt);
-      n = nt;
+    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+    int g = lane;
+    for (; g + 32 < G.G; g += 64) {
+      s0 += part[(size_t)g * 2 * C + c]; q0 += part[(size_t)g * 2 * C + C + c];
+      s1 += part[(size_t)(g + 32) * 2 * C + c]; q1 += part[(size_t)(g + 32) * 2 * C + C + c];
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mu, o),
-                  qb = __shfl_xor_sync(0xffffffffu, m2, o);
-      const float nt = n + nb;
-      if (nt > 0.f) {
-        // symmetric form: both partners compute the same merged triple
-        const float d = mb - mu;
-        const float mu_new = (n * mu + nb * mb) / nt;
-        m2 = m2 + qb + d * d * (n * nb / nt);
-        mu = mu_new;
-        n = nt;
-      }
-    }
-    mean = mu;
+    if (g < G.G) { s0 += part[(size_t)g * 2 * C + c]; q0 += part[(size_t)g * 2 * C + C + c]; }
+    const float S = warp_sum(s0 + s1), Q = warp_sum(q0 + q1);
+    const float dm = S * G.invM;
+    mean = DT<T>::to_f(x[c]) + dm;
+    const float m2 = fmaxf(Q - S * dm, 0.f);
     const float var = m2 * G.invM;   // biased variance normalises (torch BatchNorm)
     rstd = rsqrtf(var + eps);
     if (lane == 0 && running_mean) {
@@ -161,6 +184,7 @@ __global__ void __launch_bounds__(kT) bn_final_kernel(const float* __restrict__ 
 template <typename T, int VW, int ACT>
 __global__ void __launch_bounds__(kT) bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ scsh,
                                                       T* __restrict__ z, const BnGeo G) {
+  constexpr bool FAST = sizeof(T) == 2;
   const int C = G.C, tpr = G.tpr;
   const int rg = threadIdx.x / tpr, ch = threadIdx.x - rg * tpr;
   if (rg >= G.ngrp) return;
@@ -171,107 +195,177 @@ __global__ void __launch_bounds__(kT) bn_apply_kernel(const T* __restrict__ x, c
   for (int e = 0; e < VW; ++e) { sc[e] = scsh[ch * VW + e]; sh[e] = scsh[C + ch * VW + e]; }
   const T* xb = x + (size_t)r0 * C + ch * VW;
   T* zb = z + (size_t)r0 * C + ch * VW;
-#pragma unroll 4
-  for (int r = rg; r < nrows; r += G.ngrp) {
-    float v[VW];
-    ldv<T, VW>(xb + (size_t)r * C, v);
+  for (int r = rg; r < nrows; r += RB * G.ngrp) {
+    uint4 raw[RB];
 #pragma unroll
-    for (int e = 0; e < VW; ++e) {
-      const float y = v[e] * sc[e] + sh[e];
-      v[e] = ACT ? silu_f(y) : y;
-    }
-    stv<T, VW>(zb + (size_t)r * C, v);
+    for (int u = 0; u < RB; ++u)
+      if (r + u * G.ngrp < nrows) raw[u] = ldg_stream16(xb + (size_t)(r + u * G.ngrp) * C);
+#pragma unroll
+    for (int u = 0; u < RB; ++u)
+      if (r + u * G.ngrp < nrows) {
+        float v[VW];
+        unpack<T, VW>(raw[u], v);
+#pragma unroll
+        for (int e = 0; e < VW; ++e) {
+          const float y = fmaf(v[e], sc[e], sh[e]);
+          v[e] = ACT ? y * sigmoid_t<FAST>(y) : y;
+        }
+        stg_stream16(zb + (size_t)(r + u * G.ngrp) * C, pack<T, VW>(v));
+      }
   }
 }
 
-// ---- backward reduce: per-CTA sum(gy), sum(gy*xhat) with gy = gz*act'(y) recomputed from x -----------------------
+// gy = gz * act'(y), y = x*a + b
+template <bool FAST, int ACT> __device__ __forceinline__ float grad_y(float g, float y) {
+  if (!ACT) return g;
+  const float sg = sigmoid_t<FAST>(y);
+  return g * (sg * fmaf(y, 1.f - sg, 1.f));
+}
+
+// ---- backward reduce: per-CTA sum(gy), sum(gy*x) with gy recomputed from x (sum(gy*xhat) follows in the finalize) --
 template <typename T, int VW, int ACT>
 __global__ void __launch_bounds__(kT) bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ gz,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            float* __restrict__ part, const BnGeo G) {
+  constexpr bool FAST = sizeof(T) == 2;
   extern __shared__ __align__(16) float red[];   // [ngrp][2][C]
   const int C = G.C, tpr = G.tpr;
   const int rg = threadIdx.x / tpr, ch = threadIdx.x - rg * tpr;
   const long long r0 = (long long)blockIdx.x * G.rpb;
   const int nrows = (int)min((long long)G.rpb, G.M - r0);
   if (rg < G.ngrp) {
-    float mu[VW], rs[VW], ga[VW], be[VW], a1[VW], a2[VW];
+    float a[VW], b[VW], a1[VW], a2[VW];
 #pragma unroll
     for (int e = 0; e < VW; ++e) {
       const int c = ch * VW + e;
-      mu[e] = mean[c]; rs[e] = rstd[c]; ga[e] = gamma[c]; be[e] = beta[c]; a1[e] = 0.f; a2[e] = 0.f;
+      a[e] = gamma[c] * rstd[c];
+      b[e] = beta[c] - mean[c] * a[e];
+      a1[e] = 0.f; a2[e] = 0.f;
     }
     const T* xb = x + (size_t)r0 * C + ch * VW;
     const T* gb = gz + (size_t)r0 * C + ch * VW;
-#pragma unroll 2
-    for (int r = rg; r < nrows; r += G.ngrp) {
-      float v[VW], g[VW];
-      ldv<T, VW>(xb + (size_t)r * C, v);
-      ldv<T, VW>(gb + (size_t)r * C, g);
+    constexpr int RB2 = RB / 2;
+    for (int r = rg; r < nrows; r += RB2 * G.ngrp) {
+      uint4 rx[RB2], rgz[RB2];
 #pragma unroll
-      for (int e = 0; e < VW; ++e) {
-        const float xh = (v[e] - mu[e]) * rs[e];
-        const float gy = ACT ? g[e] * dsilu_f(xh * ga[e] + be[e]) : g[e];
-        a1[e] += gy;
-        a2[e] += gy * xh;
-      }
+      for (int u = 0; u < RB2; ++u)
+        if (r + u * G.ngrp < nrows) {
+          rx[u] = ldg_stream16(xb + (size_t)(r + u * G.ngrp) * C);
+          rgz[u] = ldg_stream16(gb + (size_t)(r + u * G.ngrp) * C);
+        }
+#pragma unroll
+      for (int u = 0; u < RB2; ++u)
+        if (r + u * G.ngrp < nrows) {
+          float v[VW], g[VW];
+          unpack<T, VW>(rx[u], v);
+          unpack<T, VW>(rgz[u], g);
+#pragma unroll
+          for (int e = 0; e < VW; ++e) {
+            const float gy = grad_y<FAST, ACT>(g[e], fmaf(v[e], a[e], b[e]));
+            a1[e] += gy;
+            a2[e] = fmaf(gy, v[e], a2[e]);
+          }
+        }
     }
     float* rr = red + (size_t)rg * 2 * C + ch * VW;
 #pragma unroll
     for (int e = 0; e < VW; ++e) { rr[e] = a1[e]; rr[C + e] = a2[e]; }
   }
   float* dst = part + (size_t)blockIdx.x * 2 * C;
-  cta_fold<2>(red, C, G.ngrp, [&](int c, const float (&a)[2]) { dst[c] = a[0]; dst[C + c] = a[1]; });
+  cta_fold<2>(red, C, G.ngrp, [&](int c, const float (&acc)[2]) { dst[c] = acc[0]; dst[C + c] = acc[1]; });
 }
 
-// ---- backward finalize: warp per channel -> g_gamma = sum(gy*xhat), g_beta = sum(gy) --------------------------------
-__global__ void __launch_bounds__(kT) bn_bwd_final_kernel(const float* __restrict__ part, float* __restrict__ ggamma,
-                                                          float* __restrict__ gbeta, const BnGeo G) {
+// ---- backward finalize: warp per channel -> g_beta = sum(gy), g_gamma = sum(gy*xhat) = rstd*(sum(gy*x) - mean*sum(gy)),
+// and the three coefficients of g_x = A*gy + Bc*x + Cc  (coef[3][C]) --------------------------------------------------
+__global__ void __launch_bounds__(kT) bn_bwd_final_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
+                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                          float* __restrict__ ggamma, float* __restrict__ gbeta,
+                                                          float* __restrict__ coef, int training, const BnGeo G) {
   const int lane = threadIdx.x & 31, c = blockIdx.x * (kT / 32) + (threadIdx.x >> 5), C = G.C;
   if (c >= C) return;
-  float a1 = 0.f, a2 = 0.f;
-  for (int g = lane; g < G.G; g += 32) { a1 += part[(size_t)g * 2 * C + c]; a2 += part[(size_t)g * 2 * C + C + c]; }
-  a1 = warp_sum(a1);
-  a2 = warp_sum(a2);
-  if (lane == 0) { gbeta[c] = a1; ggamma[c] = a2; }
+  float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+  int g = lane;
+  for (; g + 32 < G.G; g += 64) {
+    s0 += part[(size_t)g * 2 * C + c]; q0 += part[(size_t)g * 2 * C + C + c];
+    s1 += part[(size_t)(g + 32) * 2 * C + c]; q1 += part[(size_t)(g + 32) * 2 * C + C + c];
+  }
+  if (g < G.G) { s0 += part[(size_t)g * 2 * C + c]; q0 += part[(size_t)g * 2 * C + C + c]; }
+  const float sgy = warp_sum(s0 + s1), sgyx = warp_sum(q0 + q1);
+  if (lane == 0) {
+    const float mu = mean[c], rs = rstd[c], ga = gamma[c];
+    const float gg = rs * (sgyx - mu * sgy);
+    gbeta[c] = sgy;
+    ggamma[c] = gg;
+    // gx = ga*rs*(gy - sgy/M - xhat*gg/M), xhat = (x - mu)*rs   (eval mode: statistics are constants -> gx = ga*rs*gy)
+    const float A = ga * rs, k1 = training ? sgy * G.invM : 0.f, k2 = training ? gg * G.invM : 0.f;
+    coef[c] = A;
+    coef[C + c] = -A * k2 * rs;
+    coef[2 * C + c] = -A * k1 + A * k2 * rs * mu;
+  }
 }
 
-// ---- backward apply: gx = gamma*rstd*(gy - sum(gy)/M - xhat*sum(gy*xhat)/M) -----------------------------------------
+// ---- backward apply: g_x = A*gy + Bc*x + Cc -----------------------------------------------------------------------
 template <typename T, int VW, int ACT>
 __global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ gz,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                          const float* __restrict__ ggamma, const float* __restrict__ gbeta,
-                                                          T* __restrict__ gx, int training, const BnGeo G) {
+                                                          const float* __restrict__ coef, T* __restrict__ gx, const BnGeo G) {
+  constexpr bool FAST = sizeof(T) == 2;
+  extern __shared__ __align__(16) float cs[];   // [5][C]: a, b (y = x*a + b), A, Bc, Cc
   const int C = G.C, tpr = G.tpr;
+  for (int c = threadIdx.x; c < C; c += kT) {
+    const float a = gamma[c] * rstd[c];
+    cs[c] = a;
+    cs[C + c] = beta[c] - mean[c] * a;
+    cs[2 * C + c] = coef[c];
+    cs[3 * C + c] = coef[C + c];
+    cs[4 * C + c] = coef[2 * C + c];
+  }
+  __syncthreads();
   const int rg = threadIdx.x / tpr, ch = threadIdx.x - rg * tpr;
   if (rg >= G.ngrp) return;
   const long long r0 = (long long)blockIdx.x * G.rpb;
   const int nrows = (int)min((long long)G.rpb, G.M - r0);
-  float mu[VW], rs[VW], ga[VW], be[VW], k1[VW], k2[VW];
-#pragma unroll
-  for (int e = 0; e < VW; ++e) {
-    const int c = ch * VW + e;
-    mu[e] = mean[c]; rs[e] = rstd[c]; ga[e] = gamma[c]; be[e] = beta[c];
-    k1[e] = training ? gbeta[c] * G.invM : 0.f;    // eval mode: statistics are constants, gx = gamma*rstd*gy
-    k2[e] = training ? ggamma[c] * G.invM : 0.f;
-  }
   const T* xb = x + (size_t)r0 * C + ch * VW;
   const T* gb = gz + (size_t)r0 * C + ch * VW;
   T* ob = gx + (size_t)r0 * C + ch * VW;
-#pragma unroll 2
-  for (int r = rg; r < nrows; r += G.ngrp) {
-    float v[VW], g[VW];
-    ldv<T, VW>(xb + (size_t)r * C, v);
-    ldv<T, VW>(gb + (size_t)r * C, g);
+  float a[VW], b[VW], kA[VW], kB[VW], kC[VW];   // this thread's channel vector: loaded once as float4s
 #pragma unroll
-    for (int e = 0; e < VW; ++e) {
-      const float xh = (v[e] - mu[e]) * rs[e];
-      const float gy = ACT ? g[e] * dsilu_f(xh * ga[e] + be[e]) : g[e];
-      v[e] = ga[e] * rs[e] * (gy - k1[e] - xh * k2[e]);
-    }
-    stv<T, VW>(ob + (size_t)r * C, v);
+  for (int q = 0; q < VW / 4; ++q) {
+    const float4 t0 = *reinterpret_cast<const float4*>(cs + ch * VW + 4 * q);
+    const float4 t1 = *reinterpret_cast<const float4*>(cs + C + ch * VW + 4 * q);
+    const float4 t2 = *reinterpret_cast<const float4*>(cs + 2 * C + ch * VW + 4 * q);
+    const float4 t3 = *reinterpret_cast<const float4*>(cs + 3 * C + ch * VW + 4 * q);
+    const float4 t4 = *reinterpret_cast<const float4*>(cs + 4 * C + ch * VW + 4 * q);
+    a[4 * q] = t0.x; a[4 * q + 1] = t0.y; a[4 * q + 2] = t0.z; a[4 * q + 3] = t0.w;
+    b[4 * q] = t1.x; b[4 * q + 1] = t1.y; b[4 * q + 2] = t1.z; b[4 * q + 3] = t1.w;
+    kA[4 * q] = t2.x; kA[4 * q + 1] = t2.y; kA[4 * q + 2] = t2.z; kA[4 * q + 3] = t2.w;
+    kB[4 * q] = t3.x; kB[4 * q + 1] = t3.y; kB[4 * q + 2] = t3.z; kB[4 * q + 3] = t3.w;
+    kC[4 * q] = t4.x; kC[4 * q + 1] = t4.y; kC[4 * q + 2] = t4.z; kC[4 * q + 3] = t4.w;
+  }
+  constexpr int RB2 = RB / 2;
+  for (int r = rg; r < nrows; r += RB2 * G.ngrp) {
+    uint4 rx[RB2], rgz[RB2];
+#pragma unroll
+    for (int u = 0; u < RB2; ++u)
+      if (r + u * G.ngrp < nrows) {
+        rx[u] = ldg_stream16(xb + (size_t)(r + u * G.ngrp) * C);
+        rgz[u] = ldg_stream16(gb + (size_t)(r + u * G.ngrp) * C);
+      }
+#pragma unroll
+    for (int u = 0; u < RB2; ++u)
+      if (r + u * G.ngrp < nrows) {
+        float v[VW], g[VW];
+        unpack<T, VW>(rx[u], v);
+        unpack<T, VW>(rgz[u], g);
+#pragma unroll
+        for (int e = 0; e < VW; ++e) {
+          const float gy = grad_y<FAST, ACT>(g[e], fmaf(v[e], a[e], b[e]));
+          v[e] = fmaf(kA[e], gy, fmaf(kB[e], v[e], kC[e]));
+        }
+        stg_stream16(ob + (size_t)(r + u * G.ngrp) * C, pack<T, VW>(v));
+      }
   }
 }
 
@@ -310,7 +404,7 @@ extern "C" B200_API size_t b200_bn_silu_workspace_bytes(int64_t rows, int32_t C,
   if (!b200_bn_silu_supported(rows, C, dtype)) return 0;
   b200::BnGeo G;
   b200::fill_geo(G, rows, C, dtype == B200_F32 ? 4 : 8);
-  return b200::up256((size_t)G.G * 2 * C * 4) + b200::up256((size_t)2 * C * 4);   // per-CTA partials + scale/shift
+  return b200::up256((size_t)G.G * 2 * C * 4) + b200::up256((size_t)3 * C * 4);   // per-CTA partials + scale/shift | bwd coefficients
 }
 
 extern "C" B200_API int b200_bn_silu_fwd(const void* x, const float* gamma, const float* beta, float* running_mean,
@@ -322,7 +416,7 @@ extern "C" B200_API int b200_bn_silu_fwd(const void* x, const float* gamma, cons
   B200_REQUIRE(training || (running_mean && running_var), B200_ERR_SHAPE, "bn_silu_fwd: eval mode needs running statistics");
   BnGeo G;
   if (int rc = make_geo(G, rows, C, dtype, x, z, nullptr)) return rc;
-  const size_t need = up256((size_t)G.G * 2 * C * 4) + up256((size_t)2 * C * 4);
+  const size_t need = up256((size_t)G.G * 2 * C * 4) + up256((size_t)3 * C * 4);
   B200_REQUIRE(workspace && workspace_bytes >= need, B200_ERR_WORKSPACE, "bn_silu_fwd: workspace %zu < %zu bytes", workspace_bytes, need);
   float* part = (float*)workspace;
   float* scsh = (float*)((char*)workspace + up256((size_t)G.G * 2 * C * 4));
@@ -331,8 +425,8 @@ extern "C" B200_API int b200_bn_silu_fwd(const void* x, const float* gamma, cons
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
     constexpr int VW = 16 / (int)sizeof(T);
     if (training) bn_stats_kernel<T, VW><<<G.G, kT, smem, st>>>((const T*)x, part, G);
-    bn_final_kernel<<<(C + 7) / 8, kT, 0, st>>>(part, gamma, beta, running_mean, running_var, mean_out, rstd_out, scsh, eps,
-                                               momentum, training, G);
+    bn_final_kernel<T><<<(C + 7) / 8, kT, 0, st>>>((const T*)x, part, gamma, beta, running_mean, running_var, mean_out, rstd_out,
+                                                  scsh, eps, momentum, training, G);
     if (act) bn_apply_kernel<T, VW, 1><<<G.G, kT, 0, st>>>((const T*)x, scsh, (T*)z, G);
     else bn_apply_kernel<T, VW, 0><<<G.G, kT, 0, st>>>((const T*)x, scsh, (T*)z, G);
     return check_launch("bn_silu_fwd");
@@ -347,18 +441,20 @@ extern "C" B200_API int b200_bn_silu_bwd(const void* gz, const void* x, const fl
   B200_REQUIRE(gz && x && gamma && beta && mean && rstd && gx && ggamma && gbeta, B200_ERR_SHAPE, "bn_silu_bwd: null tensor pointer");
   BnGeo G;
   if (int rc = make_geo(G, rows, C, dtype, x, gz, gx)) return rc;
-  const size_t need = up256((size_t)G.G * 2 * C * 4);
+  const size_t need = up256((size_t)G.G * 2 * C * 4) + up256((size_t)3 * C * 4);
   B200_REQUIRE(workspace && workspace_bytes >= need, B200_ERR_WORKSPACE, "bn_silu_bwd: workspace %zu < %zu bytes", workspace_bytes, need);
   float* part = (float*)workspace;
+  float* coef = (float*)((char*)workspace + up256((size_t)G.G * 2 * C * 4));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)G.ngrp * 2 * C * 4;
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
     constexpr int VW = 16 / (int)sizeof(T);
     if (act) bn_bwd_reduce_kernel<T, VW, 1><<<G.G, kT, smem, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, part, G);
     else bn_bwd_reduce_kernel<T, VW, 0><<<G.G, kT, smem, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, part, G);
-    bn_bwd_final_kernel<<<(C + 7) / 8, kT, 0, st>>>(part, ggamma, gbeta, G);
-    if (act) bn_bwd_apply_kernel<T, VW, 1><<<G.G, kT, 0, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, ggamma, gbeta, (T*)gx, training, G);
-    else bn_bwd_apply_kernel<T, VW, 0><<<G.G, kT, 0, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, ggamma, gbeta, (T*)gx, training, G);
+    bn_bwd_final_kernel<<<(C + 7) / 8, kT, 0, st>>>(part, gamma, mean, rstd, ggamma, gbeta, coef, training, G);
+    const size_t smc = (size_t)5 * C * 4;
+    if (act) bn_bwd_apply_kernel<T, VW, 1><<<G.G, kT, smc, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, coef, (T*)gx, G);
+    else bn_bwd_apply_kernel<T, VW, 0><<<G.G, kT, smc, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, coef, (T*)gx, G);
     return check_launch("bn_silu_bwd");
   });
 }

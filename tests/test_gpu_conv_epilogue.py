@@ -138,8 +138,8 @@ def test_graph_with_and_without_fused_epilogue():
     sum(f.square().mean() for f in fa).backward()
     sum(f.square().mean() for f in fb).backward()
     worst = max(rel_err(pa.grad, pb.grad) for (_, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters())
-                if pa.grad is not None and float(pb.grad.abs().max()) > 1e-8)
-    assert worst < 5e-2, worst
+                if pa.grad is not None and float(pb.grad.norm()) > 1e-6)   # e.g. a bias in front of a BN: exact-zero gradient
+    assert worst < 5e-3, worst
     for (ka, va), (_, vb) in zip(a.state_dict().items(), b.state_dict().items()):
         if "running" in ka or "num_batches" in ka:
             assert rel_err(va.float(), vb.float()) < 5e-3, ka
