@@ -87,6 +87,10 @@ class Trainer:
         static for the synthetic batches.  Falls back to eager launches (returns False) if capture is not possible."""
         if self.device.type != "cuda" or self._graph is not None:
             return self._graph is not None
+        if self.world_size > 1:
+            # capturing DDP's bucketed NCCL all-reduce deadlocked on the 2-GPU box (round 1): data-parallel runs launch eagerly
+            self._graph_error = "graph capture is single-process only; DDP steps are launched eagerly"
+            return False
         try:
             self._static = {k: v.clone() for k, v in dev_batch.items()}
             cur = torch.cuda.current_stream(self.device)
