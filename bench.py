@@ -119,6 +119,10 @@ def cpu_reference_leg(steps, warmup, batch=2):
 
 
 def main():
+    if os.environ.get("B200_BENCH_WATCHDOG"):  # debugging aid: dump every thread's stack and exit if the run stalls
+        import faulthandler
+
+        faulthandler.dump_traceback_later(int(os.environ["B200_BENCH_WATCHDOG"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -175,16 +179,17 @@ def main():
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        barrier()
+    def timed(fn, steps, collective=True):
+        """collective=False: rank-local leg (run by rank 0 alone after the other ranks left): no barrier / all-reduce."""
+        barrier() if collective else torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for i in range(steps):
             fn(i)
         e.record()
-        barrier()
+        barrier() if collective else torch.cuda.synchronize()
         ms = torch.tensor([s.elapsed_time(e)], device=f"cuda:{local_rank}")
-        if world > 1:
+        if world > 1 and collective:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # max over ranks
         return float(ms.item())
 
@@ -216,8 +221,9 @@ def main():
     ms_e2e = timed(e2e_step, args.steps)
     imgs = args.batch * world * args.steps
     kernels_per_step = sum(n for n, _ in ktimes.values()) / max(args.steps, 1) if ktimes else 0   # C-ABI calls per step
-    config["launch_mode"] = ("CUDA-graph replay of fwd+loss+bwd+clip+SGD (captured once; gpu_launches = C-ABI kernel calls "
-                             "replayed inside the graph)") if graphed else f"eager launches ({tr._graph_error or 'graph capture disabled'})"
+    config["launch_mode"] = (("CUDA-graph replay of fwd+loss+bwd+clip+SGD" if world == 1 else
+                              "CUDA-graph replay: graph A fwd+loss+bwd into one flat gradient buffer, one eager NCCL all-reduce, graph B clip+SGD") +
+                             " (captured once; gpu_launches = C-ABI kernel calls replayed inside the graph)") if graphed else f"eager launches ({tr._graph_error or 'graph capture disabled'})"
     config["eager_ms_per_step"] = ms_eager / args.steps
     if rank != 0:
         if world > 1:
@@ -270,7 +276,7 @@ def main():
         imgf = (dev[0]["img"].float() / 255).contiguous(memory_format=torch.channels_last)
         for _ in range(3):
             tr.raw(imgf)
-        ms_inf = timed(lambda i: tr.raw(imgf), args.steps)
+        ms_inf = timed(lambda i: tr.raw(imgf), args.steps, collective=False)
     tr.raw.train()
     line["inference"] = {"value": args.batch * args.steps / (ms_inf * 1e-3), "unit": "img/s", "ms_per_batch": ms_inf / args.steps,
                          "config": "configs[1]: bf16 autocast, batch 64, forward only, eval mode, 1 GPU"}

@@ -2,13 +2,15 @@
 
 Mirrors the reference's hot loop (engine/trainer.py:367-399,614-622): H2D copy + ``img.float()/255`` (detect/train.py:
 90-115), autocast forward, v8 detection loss, ``loss.sum() * world_size`` (trainer.py:386-388; DDP averages grads),
-backward (DDP bucketed NCCL all-reduce of gradients only -- the path's ONE exchange step), ``clip_grad_norm_(10)``,
+backward, ONE all-reduce of the flat gradient buffer (NCCL over NVLink; gradients only -- the path's one exchange step),
+``clip_grad_norm_(10)``,
 SGD(momentum 0.937, nesterov) with the trainer's three parameter groups (trainer.py:788-830) and the EMA update
 (torch_utils.py:657-672).  One process per GPU; nothing but gradients crosses GPUs.
 """
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -52,6 +54,12 @@ class EMA:
 
 
 class Trainer:
+    """One process per GPU.  world_size > 1: every rank holds a replica; the local backward accumulates into ONE flat
+    fp32 gradient buffer (each ``p.grad`` is a view of it, laid out like the parameter) and the path's single exchange
+    step is one NCCL/gloo all-reduce(SUM) of that buffer -- gradients only.  Summing per-rank gradients of the local
+    ``loss.sum()`` equals the reference's ``loss * world_size`` followed by DDP's mean (trainer.py:278,386-388).  Doing
+    the all-reduce explicitly (instead of through DDP's autograd hooks) keeps forward+backward CUDA-graph capturable."""
+
     def __init__(self, blocks: dict, scale="n", nc=80, device="cuda", amp_dtype=torch.bfloat16, world_size=1,
                  local_rank=0, channels_last=True, lr=0.01, momentum=0.937, seed=0, ema=True):
         self.device = torch.device(device)
@@ -66,47 +74,90 @@ class Trainer:
         model = model.to(self.device).train()
         if self.channels_last:
             model = model.to(memory_format=torch.channels_last)
-        self.raw = model
-        self.model = model
-        if world_size > 1:
-            kw = dict(device_ids=[local_rank]) if self.device.type == "cuda" else {}
-            self.model = nn.parallel.DistributedDataParallel(model, gradient_as_bucket_view=True, static_graph=True, **kw)
+        self.raw = self.model = model
         self.criterion = hloss.DetectionLoss(nc, model.stride)
         fused = self.device.type == "cuda"
         self.opt = torch.optim.SGD(param_groups(model), lr=lr, momentum=momentum, nesterov=True, fused=fused)
         self.ema = EMA(model) if ema else None
         self.max_boxes = None
-        self._graph, self._graph_error, self._static, self._static_items = None, None, None, None
+        self._params = [p for p in model.parameters() if p.requires_grad]
+        self._flat = None
+        if world_size > 1:
+            self._flat = torch.zeros(sum(p.numel() for p in self._params), dtype=torch.float32, device=self.device)
+            off = 0
+            for p in self._params:
+                p.grad = self._flat[off:off + p.numel()].as_strided(p.shape, p.stride())  # same memory order as the parameter
+                off += p.numel()
+        self._graph, self._graph_b, self._graph_error, self._static, self._static_items = None, None, None, None, None
 
     def to_device(self, host_batch):
         return {k: v.to(self.device, non_blocking=True) for k, v in host_batch.items()}
 
+    # ---- the step, in two halves so that the gradient exchange sits between them ---------------------------------
+    def _forward_loss(self, dev_batch):
+        img = dev_batch["img"].float() / 255  # detect/train.py:100
+        if self.channels_last:
+            img = img.contiguous(memory_format=torch.channels_last)
+        use_amp = self.amp_dtype is not None and self.amp_dtype != torch.float32
+        with torch.autocast(self.device.type, dtype=self.amp_dtype or torch.bfloat16, enabled=use_amp):
+            feats = self.model(img)
+            return self.criterion([f.float() for f in feats], dev_batch, max_boxes=self.max_boxes)
+
+    def _fwd_bwd(self, dev_batch):
+        if self._flat is not None:
+            self._flat.zero_()              # grads are views of the flat buffer: autograd accumulates in place
+        loss, items = self._forward_loss(dev_batch)
+        loss.sum().backward()
+        return items
+
+    def _exchange(self):
+        if self._flat is not None:
+            import torch.distributed as dist
+
+            dist.all_reduce(self._flat)     # SUM over ranks; gradients only -- the one exchange step of the path
+
+    def _update(self):
+        torch.nn.utils.clip_grad_norm_(self._params, max_norm=10.0, foreach=True)
+        self.opt.step()
+        if self._flat is None:
+            self.opt.zero_grad(set_to_none=True)
+
     # ---- CUDA-graph replay of the step (host-side step overhead) ------------------------------
     def enable_graph(self, dev_batch, warmup: int = 3) -> bool:
-        """Capture forward + loss + backward (+ DDP all-reduce) + clip + SGD of one step into a CUDA graph; shapes are
-        static for the synthetic batches.  Falls back to eager launches (returns False) if capture is not possible."""
+        """Capture the step into CUDA graphs (shapes are static for the synthetic batches): one graph at world_size 1
+        (forward + loss + backward + clip + SGD); at world_size > 1 graph A = forward + loss + backward, the all-reduce
+        launched eagerly between, graph B = clip + SGD.  Falls back to eager launches (returns False) if capture fails."""
         if self.device.type != "cuda" or self._graph is not None:
             return self._graph is not None
-        if self.world_size > 1:
-            # capturing DDP's bucketed NCCL all-reduce deadlocked on the 2-GPU box (round 1): data-parallel runs launch eagerly
-            self._graph_error = "graph capture is single-process only; DDP steps are launched eagerly"
-            return False
         try:
             self._static = {k: v.clone() for k, v in dev_batch.items()}
             cur = torch.cuda.current_stream(self.device)
             side = torch.cuda.Stream(self.device)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                for _ in range(max(warmup, 11 if self.world_size > 1 else 3)):
-                    self._core(self._static)
+                for _ in range(max(warmup, 3)):
+                    self._fwd_bwd(self._static)
+                    self._exchange()
+                    self._update()
             cur.wait_stream(side)
             torch.cuda.synchronize(self.device)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._static_items = self._core(self._static)
-            self._graph = g
+            ga = torch.cuda.CUDAGraph()
+            if self._flat is None:
+                with torch.cuda.graph(ga):
+                    self._static_items = self._fwd_bwd(self._static)
+                    self._update()
+            else:
+                gb = torch.cuda.CUDAGraph()
+                # thread_local: the NCCL watchdog thread may make CUDA calls while this thread captures
+                with torch.cuda.graph(ga, capture_error_mode="thread_local"):
+                    self._static_items = self._fwd_bwd(self._static)
+                self._exchange()
+                with torch.cuda.graph(gb, pool=ga.pool(), capture_error_mode="thread_local"):
+                    self._update()
+                self._graph_b = gb
+            self._graph = ga
         except Exception as e:  # noqa: BLE001  capture is an optimisation; eager launches remain correct
-            self._graph, self._graph_error = None, f"{type(e).__name__}: {e}"
+            self._graph, self._graph_b, self._graph_error = None, None, f"{type(e).__name__}: {e}"
             torch.cuda.synchronize(self.device)
         return self._graph is not None
 
@@ -116,28 +167,16 @@ class Trainer:
             for k, v in dev_batch.items():
                 self._static[k].copy_(v, non_blocking=True)
             self._graph.replay()
+            if self._graph_b is not None:
+                self._exchange()
+                self._graph_b.replay()
             items = self._static_items.clone()
         else:
-            items = self._core(dev_batch)
+            items = self._fwd_bwd(dev_batch)
+            self._exchange()
+            self._update()
         if self.ema is not None:
             self.ema.update(self.raw)
-        return items
-
-    def _core(self, dev_batch):
-        img = dev_batch["img"].float() / 255  # detect/train.py:100
-        if self.channels_last:
-            img = img.contiguous(memory_format=torch.channels_last)
-        use_amp = self.amp_dtype is not None and self.amp_dtype != torch.float32
-        with torch.autocast(self.device.type, dtype=self.amp_dtype or torch.bfloat16, enabled=use_amp):
-            feats = self.model(img)
-            loss, items = self.criterion([f.float() for f in feats], dev_batch, max_boxes=self.max_boxes)
-        total = loss.sum()
-        if self.world_size > 1:
-            total = total * self.world_size
-        total.backward()
-        torch.nn.utils.clip_grad_norm_(self.raw.parameters(), max_norm=10.0, foreach=True)
-        self.opt.step()
-        self.opt.zero_grad(set_to_none=True)
         return items
 
     def step_from_host(self, host_batch):
