@@ -126,8 +126,8 @@ def run(scale: str, B: int, peaks: dict, iters: int = 10):
                     "frac": round(ach / peak, 4), "note": note})
 
     torch.manual_seed(0)
-    # ---- CBAM at P5 (the model's use) and P4
-    for lvl in ("P5", "P4"):
+    # ---- CBAM at P5 (the model's use), P4 and P3 (BASELINE configs[3]/[4]: CBAM at P3/P4/P5)
+    for lvl in ("P5", "P4", "P3"):
         shape = sh[lvl]
         x = torch.randn(shape, device=dev).to(dt).contiguous(memory_format=torch.channels_last)
         mod = M.CBAM()
@@ -141,6 +141,20 @@ def run(scale: str, B: int, peaks: dict, iters: int = 10):
         g = torch.randn_like(y)
         rec("cbam_bwd", shape, _time(lambda: torch.autograd.grad(y, xg, g, retain_graph=True), iters, flush), 3 * n * 2, "hbm", lvl)
         del y, xg
+    # ---- Conv epilogue (BatchNorm2d + SiLU) at the SPPF cv1 shape and at a P3 Conv shape
+    import torch.nn as nn
+
+    for lvl, shape in (("P5 SPPF.cv1", (sh["P5"][0], sh["P5"][1] // 2, 20, 20)), ("P3 Conv", sh["P3"])):
+        bn = nn.BatchNorm2d(shape[1], eps=1e-3, momentum=0.03).to(dev).train()
+        x = torch.randn(shape, device=dev).to(dt).contiguous(memory_format=torch.channels_last)
+        n = x.numel()
+        with torch.no_grad():
+            rec("bn_silu_fwd", shape, _time(lambda: Fb.bn_act(x, bn, True), iters, flush), 2 * n * 2, "hbm", lvl)
+        xg = x.clone().requires_grad_(True)
+        z = Fb.bn_act(xg, bn, True)
+        g = torch.randn_like(z)
+        rec("bn_silu_bwd", shape, _time(lambda: torch.autograd.grad(z, xg, g, retain_graph=True), iters, flush), 3 * n * 2, "hbm", lvl)
+        del z, xg
     # ---- SPPF pool at P5, k = 5 and 7
     Bc, c5, H, W = sh["P5"]
     y0 = torch.randn((Bc, c5 // 2, H, W), device=dev).to(dt).contiguous(memory_format=torch.channels_last)

@@ -71,3 +71,20 @@ def test_module_protocols_on_gpu():
     assert torch.equal(m2(x)[0], y) and torch.equal(m3(x)[0], y)
     yh = m2.half()(x.half())[0]
     assert yh.dtype == torch.float16 and rel_err(yh, y) < 5e-2
+
+
+@pytest.mark.parametrize("scale", ["s", "m"])
+def test_scaled_variants_train_step_bf16(scale):
+    """BASELINE configs[3]: the s / m width-depth variants (SwinBlock [256] / [384]; m has head dim 192, served by the
+    SIMT attention kernels) take a finite bf16 training step with the B200 blocks and the fused Conv epilogue."""
+    import improving_yolov8_cbam_swinblock_b200 as P
+    from improving_yolov8_cbam_swinblock_b200.harness import synthetic, train
+
+    tr = train.Trainer(P.BLOCKS, scale, 80, device="cuda:0", amp_dtype=torch.bfloat16)
+    tr.max_boxes = synthetic.BOXES_PER_IMAGE
+    batch = tr.to_device(synthetic.make_batch(2, 320, 80, seed=5))
+    before = [p.detach().clone() for p in tr.raw.parameters()]
+    items = tr.step(batch)
+    assert torch.isfinite(items).all()
+    moved = sum(int(not torch.equal(a, b)) for a, b in zip(before, tr.raw.parameters()))
+    assert moved > 0.9 * len(before)
