@@ -216,11 +216,12 @@ def main():
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     for i in range(2):
-        tr.step_from_host(host[i % 2])
+        tr.step_from_host(host[i % 2], host[(i + 1) % 2])
     last = {}
 
     def e2e_step(i):
-        last["loss"] = tr.step_from_host(host[i % 2])
+        # the next pinned batch is handed over like a data loader would: its H2D copy overlaps this step's compute
+        last["loss"] = tr.step_from_host(host[i % 2], host[(i + 1) % 2])
 
     ms_e2e = timed(e2e_step, args.steps)
     imgs = args.batch * world * args.steps

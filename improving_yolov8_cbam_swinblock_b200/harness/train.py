@@ -89,6 +89,7 @@ class Trainer:
                 p.grad = self._flat[off:off + p.numel()].as_strided(p.shape, p.stride())  # same memory order as the parameter
                 off += p.numel()
         self._graph, self._graph_b, self._graph_error, self._static, self._static_items = None, None, None, None, None
+        self._prefetched, self._copy_stream = None, None
 
     def to_device(self, host_batch):
         return {k: v.to(self.device, non_blocking=True) for k, v in host_batch.items()}
@@ -179,7 +180,28 @@ class Trainer:
             self.ema.update(self.raw)
         return items
 
-    def step_from_host(self, host_batch):
-        """The user-facing call: pinned host batch in, host loss items out (H2D + D2H inside)."""
-        items = self.step(self.to_device(host_batch))
+    def step_from_host(self, host_batch, next_host_batch=None):
+        """The user-facing call: pinned host batch in, host loss items out (H2D + D2H inside).  ``next_host_batch``
+        (optional) is what a data loader would hand over next: its H2D copy is issued on a copy stream before this call
+        blocks on the loss, so it overlaps this step's compute (every step still copies its own inputs exactly once)."""
+        if self.device.type != "cuda":
+            return self.step(self.to_device(host_batch)).cpu()
+        cur = torch.cuda.current_stream(self.device)
+        if self._prefetched is not None and self._prefetched[0] is host_batch:
+            dev_batch, ev = self._prefetched[1], self._prefetched[2]
+            cur.wait_event(ev)
+        else:
+            dev_batch = self.to_device(host_batch)
+        self._prefetched = None
+        items = self.step(dev_batch)
+        if next_host_batch is not None:
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(self.device)
+            with torch.cuda.stream(self._copy_stream):
+                nxt = self.to_device(next_host_batch)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            for v in dev_batch.values():
+                v.record_stream(cur)
+            self._prefetched = (next_host_batch, nxt, ev)
         return items.cpu()

@@ -20,6 +20,8 @@ cb = P.CBAM()
 cb(torch.zeros(1, 256, 2, 2))
 cb = cb.to(dev)
 sw = P.SwinBlock(128, 2, 7).to(dev)
+bn = torch.nn.BatchNorm2d(64, eps=1e-3, momentum=0.03).to(dev).train()
+x3 = cl(torch.randn(B, 64, 80, 80, device=dev).to(dt)).requires_grad_(True)
 
 
 def once():
@@ -31,6 +33,8 @@ def once():
     with torch.autocast("cuda", dtype=dt):
         z = sw(x4)
     z.backward(torch.ones_like(z))
+    e = Fb.bn_act(x3, bn, True)   # Conv epilogue at a P3 Conv shape
+    e.backward(torch.ones_like(e))
 
 
 for _ in range(2):

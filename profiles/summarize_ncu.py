@@ -17,7 +17,7 @@ def _num(v):
         return float("nan")
 
 
-MINE = re.compile(r"\b(cbam_(?:fwd|bwd)_kernel|fold_partials_kernel|sppf_pool_(?:fwd|bwd)_kernel|swin_\w+_kernel|gemm_nt_kernel|"
+MINE = re.compile(r"\b(cbam_\w+_kernel|fold_partials_kernel|bn_\w+_kernel|sppf_pool_(?:fwd|bwd)_kernel|swin_\w+_kernel|gemm_nt_kernel|"
                   r"gemm_splitk_kernel|fold_splits_kernel|fold_ln_kernel|fold_rows_kernel|colsum_partial_kernel)\b")
 
 
