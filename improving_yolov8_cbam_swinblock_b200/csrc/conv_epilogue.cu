@@ -104,7 +104,7 @@ __device__ __forceinline__ void cta_fold(float* red, int C, int ngrp, F emit) {
 // ---- forward statistics: per-CTA sums of (x-k), (x-k)^2 with ONE shift k[c] = x[0][c] for the whole tensor, so the
 // partials of different CTAs simply add up and E[d^2] - E[d]^2 does not cancel (|mean - k| ~ one standard deviation)
 template <typename T, int VW>
-__global__ void __launch_bounds__(kT) bn_stats_kernel(const T* __restrict__ x, float* __restrict__ part, const BnGeo G) {
+__global__ void __launch_bounds__(kT, 4) bn_stats_kernel(const T* __restrict__ x, float* __restrict__ part, const BnGeo G) {
   extern __shared__ __align__(16) float red[];   // [ngrp][2][C]
   const int C = G.C, tpr = G.tpr;
   const int rg = threadIdx.x / tpr, ch = threadIdx.x - rg * tpr;
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kT) bn_final_kernel(const T* __restrict__ x, c
 
 // ---- forward apply: z = act(x*scale + shift) ---------------------------------------------------------------
 template <typename T, int VW, int ACT>
-__global__ void __launch_bounds__(kT) bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ scsh,
+__global__ void __launch_bounds__(kT, 4) bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ scsh,
                                                       T* __restrict__ z, const BnGeo G) {
   constexpr bool FAST = sizeof(T) == 2;
   const int C = G.C, tpr = G.tpr;
@@ -224,7 +224,7 @@ template <bool FAST, int ACT> __device__ __forceinline__ float grad_y(float g, f
 
 // ---- backward reduce: per-CTA sum(gy), sum(gy*x) with gy recomputed from x (sum(gy*xhat) follows in the finalize) --
 template <typename T, int VW, int ACT>
-__global__ void __launch_bounds__(kT) bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ gz,
+__global__ void __launch_bounds__(kT, 4) bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ gz,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            float* __restrict__ part, const BnGeo G) {

@@ -117,6 +117,19 @@ class C2f(nn.Module):
         return self.cv2(torch.cat(y, 1))
 
 
+class Upsample(nn.Upsample):
+    """``nn.Upsample`` (yolov8.yaml head rows) that keeps the activation dtype under autocast.  torch's autocast runs
+    ``upsample_nearest2d`` in fp32, which turns the following ``Concat`` and its consumers' input casts into fp32 passes;
+    nearest-neighbour upsampling only copies values, so staying in bf16/f16 is bit-identical (dtype/layout at
+    the seams of the path).  Same constructor, no parameters, so state_dicts are unaffected."""
+
+    def forward(self, x):
+        if x.is_cuda and self.mode == "nearest" and torch.is_autocast_enabled("cuda"):
+            with torch.autocast("cuda", enabled=False):
+                return super().forward(x)
+        return super().forward(x)
+
+
 class Concat(nn.Module):
     def __init__(self, dimension=1):
         super().__init__()
@@ -219,7 +232,7 @@ class DetectionGraph(nn.Module):
                 c2 = None
             else:  # CBAM / SwinBlock / nn.Upsample: args verbatim, c2 = ch[f]  (tasks.py:1503-1504)
                 c2 = chans[f]
-            cls = getattr(nn, m[3:]) if m.startswith("nn.") else table[m]
+            cls = Upsample if m == "nn.Upsample" else getattr(nn, m[3:]) if m.startswith("nn.") else table[m]
             mod = nn.Sequential(*(cls(*args) for _ in range(n))) if n > 1 else cls(*args)
             mod.i, mod.f, mod.type = i, f, m
             save.extend(x % i for x in ([f] if isinstance(f, int) else f) if x != -1)
