@@ -50,6 +50,14 @@ int max_smem_optin() {
   }
   return cached > 0 ? cached : 232448;  // 227 KB on sm_100
 }
+int check_shift(int64_t tokens, int L, int nWh, int nWw, int ws, int shift) {
+  if (shift == 0) return B200_OK;
+  B200_REQUIRE(ws > 0 && shift > 0 && shift < ws, B200_ERR_SHAPE, "swin: shift %d must lie in [0, window size %d)", shift, ws);
+  B200_REQUIRE(L == ws * ws && L <= 64, B200_ERR_UNSUPPORTED, "swin: shifted windows need L = ws*ws <= 64 (L=%d ws=%d)", L, ws);
+  B200_REQUIRE(nWh > 0 && nWw > 0 && (tokens / L) % ((int64_t)nWh * nWw) == 0, B200_ERR_SHAPE,
+               "swin: %lld windows are not a multiple of the %dx%d window grid", (long long)(tokens / L), nWh, nWw);
+  return B200_OK;
+}
 }  // namespace b200
 
 extern "C" B200_API int b200_abi_version(void) { return B200_ABI_VERSION; }

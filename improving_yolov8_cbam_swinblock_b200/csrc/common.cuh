@@ -83,6 +83,34 @@ __device__ __forceinline__ void stg_stream16(void* p, uint4 v) {
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// ---- shifted-window mask (SwinBlock extension; the reference block is unshifted: shift == 0 disables it) ----------
+// After the cyclic shift by `shift` only the windows of the last window row / column mix image regions; inside them a
+// query attends to the keys on its own side of the seam (row/col index >= ws-shift or not).  ra / ca: bit j = key j
+// lies past the seam in the row / column direction (window length L <= 64).
+struct ShiftMask {
+  int nWh, nWw, shift;
+  unsigned long long ra, ca;
+};
+inline ShiftMask make_shift_mask(int nWh, int nWw, int ws, int shift) {
+  ShiftMask m{nWh, nWw, shift, 0ull, 0ull};
+  if (shift > 0)
+    for (int j = 0; j < ws * ws && j < 64; ++j) {
+      if (j / ws >= ws - shift) m.ra |= 1ull << j;
+      if (j % ws >= ws - shift) m.ca |= 1ull << j;
+    }
+  return m;
+}
+__device__ __forceinline__ unsigned long long allowed_keys(const ShiftMask& M, int win, int i) {
+  unsigned long long a = ~0ull;
+  if (M.shift) {
+    const int ww = win % M.nWw, wh = (win / M.nWw) % M.nWh;
+    if (wh == M.nWh - 1) a &= ~(M.ra ^ (((M.ra >> (i & 63)) & 1ull) ? ~0ull : 0ull));
+    if (ww == M.nWw - 1) a &= ~(M.ca ^ (((M.ca >> (i & 63)) & 1ull) ? ~0ull : 0ull));
+  }
+  return a;
+}
+int check_shift(int64_t tokens, int L, int nWh, int nWw, int ws, int shift);
+
 // ---- mbarrier + 1-D bulk TMA (cp.async.bulk: SASS UBLKCP) -------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));

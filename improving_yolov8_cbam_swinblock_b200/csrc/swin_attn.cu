@@ -22,7 +22,7 @@ template <typename T> __device__ __forceinline__ float ldf(const T* p) { return 
 
 template <typename T>
 __global__ void __launch_bounds__(LMAX) swin_attn_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ o, float* __restrict__ lse,
-                                                             int L, int C, int nh) {
+                                                             int L, int C, int nh, const ShiftMask M) {
   extern __shared__ __align__(16) float sm[];
   const int hd = C / nh, hp = hd + 4;
   float* ks = sm;             // [L][hp]
@@ -53,10 +53,14 @@ __global__ void __launch_bounds__(LMAX) swin_attn_fwd_kernel(const T* __restrict
         s[j] += q0 * kv.x + q1 * kv.y + q2 * kv.z + q3 * kv.w;
       }
   }
+  const unsigned long long allowed = allowed_keys(M, win, i);   // shifted-window mask (all ones when shift == 0)
   float m = -INFINITY;
 #pragma unroll
   for (int j = 0; j < LMAX; ++j)
-    if (j < L) m = fmaxf(m, s[j]);
+    if (j < L) {
+      if (!((allowed >> j) & 1ull)) s[j] = -INFINITY;
+      m = fmaxf(m, s[j]);
+    }
   float sum = 0.f;
 #pragma unroll
   for (int j = 0; j < LMAX; ++j)
@@ -81,7 +85,7 @@ __global__ void __launch_bounds__(LMAX) swin_attn_fwd_kernel(const T* __restrict
 template <typename T>
 __global__ void __launch_bounds__(LMAX) swin_attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ o,
                                                              const float* __restrict__ lse, const T* __restrict__ go,
-                                                             T* __restrict__ gqkv, int L, int C, int nh) {
+                                                             T* __restrict__ gqkv, int L, int C, int nh, const ShiftMask M) {
   extern __shared__ __align__(16) float sm[];
   const int hd = C / nh, hp = hd + 4, lp = L + 1;
   float* b0 = sm;               // phase 1: K rows     phase 2: dO rows
@@ -124,10 +128,11 @@ __global__ void __launch_bounds__(LMAX) swin_attn_bwd_kernel(const T* __restrict
         }
     }
     const float l = lse[(t0 + i) * nh + h];
+    const unsigned long long allowed = allowed_keys(M, win, i);
 #pragma unroll
     for (int j = 0; j < LMAX; ++j)
       if (j < L) {
-        const float p = expf(s[j] - l);
+        const float p = ((allowed >> j) & 1ull) ? expf(s[j] - l) : 0.f;
         const float dsj = p * (dp[j] - delta) * scale;
         ps[i * lp + j] = p;
         ds[i * lp + j] = dsj;
@@ -191,8 +196,11 @@ int check_attn(int64_t tokens, int L, int C, int nh) {
 using namespace b200;
 
 extern "C" B200_API int b200_swin_attn_fwd(const void* qkv, void* o, float* lse, int64_t tokens, int32_t L, int32_t C,
-                                           int32_t nh, int32_t dtype, void* stream) {
+                                           int32_t nh, int32_t nWh, int32_t nWw, int32_t ws, int32_t shift, int32_t dtype,
+                                           void* stream) {
   if (int rc = check_attn(tokens, L, C, nh)) return rc;
+  if (int rc = check_shift(tokens, L, nWh, nWw, ws, shift)) return rc;
+  const ShiftMask M = make_shift_mask(nWh, nWw, ws, shift);
   B200_REQUIRE(qkv && o, B200_ERR_SHAPE, "swin_attn_fwd: null pointer");
   const int hd = C / nh;
   const size_t smem = (size_t)2 * L * (hd + 4) * sizeof(float);
@@ -201,14 +209,17 @@ extern "C" B200_API int b200_swin_attn_fwd(const void* qkv, void* o, float* lse,
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
     auto k = swin_attn_fwd_kernel<T>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, LMAX, smem, (cudaStream_t)stream>>>((const T*)qkv, (T*)o, lse, L, C, nh);
+    k<<<grid, LMAX, smem, (cudaStream_t)stream>>>((const T*)qkv, (T*)o, lse, L, C, nh, M);
     return check_launch("swin_attn_fwd");
   });
 }
 
 extern "C" B200_API int b200_swin_attn_bwd(const void* qkv, const void* o, const float* lse, const void* go, void* gqkv,
-                                           int64_t tokens, int32_t L, int32_t C, int32_t nh, int32_t dtype, void* stream) {
+                                           int64_t tokens, int32_t L, int32_t C, int32_t nh, int32_t nWh, int32_t nWw, int32_t ws,
+                                           int32_t shift, int32_t dtype, void* stream) {
   if (int rc = check_attn(tokens, L, C, nh)) return rc;
+  if (int rc = check_shift(tokens, L, nWh, nWw, ws, shift)) return rc;
+  const ShiftMask M = make_shift_mask(nWh, nWw, ws, shift);
   B200_REQUIRE(qkv && o && lse && go && gqkv, B200_ERR_SHAPE, "swin_attn_bwd: null pointer");
   const int hd = C / nh;
   const size_t smem = ((size_t)2 * L * (hd + 4) + (size_t)2 * L * (L + 1)) * sizeof(float);
@@ -217,7 +228,7 @@ extern "C" B200_API int b200_swin_attn_bwd(const void* qkv, const void* o, const
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
     auto k = swin_attn_bwd_kernel<T>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, LMAX, smem, (cudaStream_t)stream>>>((const T*)qkv, (const T*)o, lse, (const T*)go, (T*)gqkv, L, C, nh);
+    k<<<grid, LMAX, smem, (cudaStream_t)stream>>>((const T*)qkv, (const T*)o, lse, (const T*)go, (T*)gqkv, L, C, nh, M);
     return check_launch("swin_attn_bwd");
   });
 }

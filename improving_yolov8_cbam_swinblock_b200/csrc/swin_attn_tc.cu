@@ -25,6 +25,7 @@ struct AttnParams {
   long long T;
   int L, C, nh, n_items, n_pairs, fmt;
   float scale_log2;
+  ShiftMask mask;
 };
 
 template <int HD> struct ACfg {
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_fwd_tc_kernel(const __g
       const int itc = it < P.n_items ? it : P.n_items - 1;
       const int win = itc / P.nh, h = itc - win * P.nh;
       const long long tok = (long long)win * P.L + i;
+      const unsigned long long allowed = allowed_keys(P.mask, win, i);   // shifted-window mask (all ones when shift == 0)
       mbar_wait(&s_full[s], ph);
       fence_after_sync();
       uint32_t v[32], w[32];
@@ -185,8 +187,8 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_fwd_tc_kernel(const __g
       float m = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float a = j < P.L ? __uint_as_float(v[j]) * P.scale_log2 : -INFINITY;
-        const float b = j + 32 < P.L ? __uint_as_float(w[j]) * P.scale_log2 : -INFINITY;
+        const float a = (j < P.L && ((allowed >> j) & 1ull)) ? __uint_as_float(v[j]) * P.scale_log2 : -INFINITY;
+        const float b = (j + 32 < P.L && ((allowed >> (j + 32)) & 1ull)) ? __uint_as_float(w[j]) * P.scale_log2 : -INFINITY;
         v[j] = __float_as_uint(a); w[j] = __float_as_uint(b);
         m = fmaxf(m, fmaxf(a, b));
       }
@@ -249,12 +251,12 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_fwd_tc_kernel(const __g
 }
 
 template <int HD>
-int launch_fwd(const void* qkv, void* o, float* lse, long long T, int L, int C, int nh, int dtype, cudaStream_t st) {
+int launch_fwd(const void* qkv, void* o, float* lse, long long T, int L, int C, int nh, const ShiftMask& M, int dtype, cudaStream_t st) {
   using Cfg = ACfg<HD>;
   const CUtensorMap* m = tensor_map_2d(qkv, (uint64_t)T, (uint64_t)3 * C, (uint64_t)3 * C, 64, 64, dtype);
   if (!m) return B200_ERR_LAUNCH;
   AttnParams P;
-  P.o = o; P.lse = lse; P.T = T; P.L = L; P.C = C; P.nh = nh;
+  P.o = o; P.lse = lse; P.T = T; P.L = L; P.C = C; P.nh = nh; P.mask = M;
   P.n_items = (int)(T / L) * nh;
   P.n_pairs = (P.n_items + 1) / 2;
   P.fmt = dtype == B200_BF16 ? 1 : 0;
@@ -281,6 +283,7 @@ struct AttnBwdParams {
   long long T;
   int L, C, nh, n_items, n_pairs, fmt;
   float scale_log2, scale;
+  ShiftMask mask;
 };
 
 template <int HD> struct BCfg {
@@ -409,6 +412,7 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       const int itc = it < P.n_items ? it : P.n_items - 1;
       const int win = itc / P.nh, h = itc - win * P.nh;
       const long long tok = (long long)win * P.L + i;
+      const unsigned long long allowed = allowed_keys(P.mask, win, i);   // shifted-window mask (all ones when shift == 0)
       const float l2 = valid ? P.lse[tok * P.nh + h] * 1.4426950408889634f : 0.f;
       mbar_wait(sdp_full, ph);
       fence_after_sync();
@@ -427,7 +431,7 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       float delta = 0.f;
 #pragma unroll
       for (int j = 0; j < 64; ++j) {
-        const float p = (j < P.L && valid) ? exp2f(__uint_as_float(sv[j]) * P.scale_log2 - l2) : 0.f;
+        const float p = (j < P.L && valid && ((allowed >> j) & 1ull)) ? exp2f(__uint_as_float(sv[j]) * P.scale_log2 - l2) : 0.f;
         sv[j] = __float_as_uint(p);
         delta += p * __uint_as_float(dv[j]);
       }
@@ -485,14 +489,14 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 }
 
 template <int HD>
-int launch_bwd(const void* qkv, const float* lse, const void* go, void* gqkv, long long T, int L, int C, int nh, int dtype,
+int launch_bwd(const void* qkv, const float* lse, const void* go, void* gqkv, long long T, int L, int C, int nh, const ShiftMask& M, int dtype,
                cudaStream_t st) {
   using Cfg = BCfg<HD>;
   const CUtensorMap* m = tensor_map_2d(qkv, (uint64_t)T, (uint64_t)3 * C, (uint64_t)3 * C, 64, 64, dtype);
   const CUtensorMap* mg = tensor_map_2d(go, (uint64_t)T, (uint64_t)C, (uint64_t)C, 64, 64, dtype);
   if (!m || !mg) return B200_ERR_LAUNCH;
   AttnBwdParams P;
-  P.gqkv = gqkv; P.lse = lse; P.T = T; P.L = L; P.C = C; P.nh = nh;
+  P.gqkv = gqkv; P.lse = lse; P.T = T; P.L = L; P.C = C; P.nh = nh; P.mask = M;
   P.n_items = (int)(T / L) * nh;
   P.n_pairs = (P.n_items + 1) / 2;
   P.fmt = dtype == B200_BF16 ? 1 : 0;
@@ -519,23 +523,29 @@ extern "C" B200_API int b200_swin_attn_tc_supported(int64_t tokens, int32_t L, i
 }
 
 extern "C" B200_API int b200_swin_attn_fwd_tc(const void* qkv, void* o, float* lse, int64_t tokens, int32_t L, int32_t C,
-                                              int32_t nh, int32_t dtype, void* stream) {
+                                              int32_t nh, int32_t nWh, int32_t nWw, int32_t ws, int32_t shift, int32_t dtype,
+                                              void* stream) {
+  if (int rc = check_shift(tokens, L, nWh, nWw, ws, shift)) return rc;
+  const ShiftMask M = make_shift_mask(nWh, nWw, ws, shift);
   B200_REQUIRE(b200_swin_attn_tc_supported(tokens, L, C, nh, dtype), B200_ERR_UNSUPPORTED,
                "swin_attn_fwd_tc: unsupported problem (16-bit dtype, L<=64, head dim 64 or 128)");
   B200_REQUIRE(qkv && o, B200_ERR_SHAPE, "swin_attn_fwd_tc: null pointer");
   B200_REQUIRE((((uintptr_t)qkv | (uintptr_t)o) & 15) == 0, B200_ERR_ALIGN, "swin_attn_fwd_tc: 16-byte alignment required");
   cudaStream_t st = (cudaStream_t)stream;
-  if (C / nh == 64) return tc::launch_fwd<64>(qkv, o, lse, tokens, L, C, nh, dtype, st);
-  return tc::launch_fwd<128>(qkv, o, lse, tokens, L, C, nh, dtype, st);
+  if (C / nh == 64) return tc::launch_fwd<64>(qkv, o, lse, tokens, L, C, nh, M, dtype, st);
+  return tc::launch_fwd<128>(qkv, o, lse, tokens, L, C, nh, M, dtype, st);
 }
 
 extern "C" B200_API int b200_swin_attn_bwd_tc(const void* qkv, const float* lse, const void* go, void* gqkv, int64_t tokens,
-                                              int32_t L, int32_t C, int32_t nh, int32_t dtype, void* stream) {
+                                              int32_t L, int32_t C, int32_t nh, int32_t nWh, int32_t nWw, int32_t ws,
+                                              int32_t shift, int32_t dtype, void* stream) {
+  if (int rc = check_shift(tokens, L, nWh, nWw, ws, shift)) return rc;
+  const ShiftMask M = make_shift_mask(nWh, nWw, ws, shift);
   B200_REQUIRE(b200_swin_attn_tc_supported(tokens, L, C, nh, dtype), B200_ERR_UNSUPPORTED,
                "swin_attn_bwd_tc: unsupported problem (16-bit dtype, L<=64, head dim 64 or 128)");
   B200_REQUIRE(qkv && lse && go && gqkv, B200_ERR_SHAPE, "swin_attn_bwd_tc: null pointer");
   B200_REQUIRE((((uintptr_t)qkv | (uintptr_t)go | (uintptr_t)gqkv) & 15) == 0, B200_ERR_ALIGN, "swin_attn_bwd_tc: 16-byte alignment required");
   cudaStream_t st = (cudaStream_t)stream;
-  if (C / nh == 64) return tc::launch_bwd<64>(qkv, lse, go, gqkv, tokens, L, C, nh, dtype, st);
-  return tc::launch_bwd<128>(qkv, lse, go, gqkv, tokens, L, C, nh, dtype, st);
+  if (C / nh == 64) return tc::launch_bwd<64>(qkv, lse, go, gqkv, tokens, L, C, nh, M, dtype, st);
+  return tc::launch_bwd<128>(qkv, lse, go, gqkv, tokens, L, C, nh, M, dtype, st);
 }

@@ -32,7 +32,7 @@ struct FastDiv {
 };
 
 struct WinGeom {
-  int B, C, H, W, ws, nWh, nWw, L;
+  int B, C, H, W, ws, nWh, nWw, L, shift;
   long long T;  // padded token count (< 2^31, checked on the host)
   FastDiv dL, dWw, dWh, dws;
 };
@@ -43,7 +43,10 @@ __device__ __forceinline__ long long token_pixel(const WinGeom& g, long long t64
   const uint32_t q = g.dWw.div(win), ww = win - q * g.nWw;
   const uint32_t b = g.dWh.div(q), wh = q - b * g.nWh;
   const uint32_t r = g.dws.div(l), c = l - r * g.ws;
-  const int y = (int)(wh * g.ws + r), x = (int)(ww * g.ws + c);
+  // window coordinates index the padded map AFTER the cyclic shift by (-shift, -shift): source pixel = (+shift) mod size
+  int y = (int)(wh * g.ws + r) + g.shift, x = (int)(ww * g.ws + c) + g.shift;
+  if (y >= g.nWh * g.ws) y -= g.nWh * g.ws;
+  if (x >= g.nWw * g.ws) x -= g.nWw * g.ws;
   *real = (y < g.H) && (x < g.W);
   return ((long long)b * g.H + y) * g.W + x;
 }
@@ -585,8 +588,10 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
   }
 }
 
-int make_geom(WinGeom* g, int B, int C, int H, int W, int ws) {
+int make_geom(WinGeom* g, int B, int C, int H, int W, int ws, int shift = 0) {
   B200_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && ws > 0, B200_ERR_SHAPE, "swin: bad shape B=%d C=%d H=%d W=%d ws=%d", B, C, H, W, ws);
+  B200_REQUIRE(shift >= 0 && shift < ws, B200_ERR_SHAPE, "swin: shift %d must lie in [0, window size %d)", shift, ws);
+  g->shift = shift;
   B200_REQUIRE(C <= 32 * kMaxPL, B200_ERR_UNSUPPORTED, "swin: C=%d > %d unsupported", C, 32 * kMaxPL);
   g->B = B; g->C = C; g->H = H; g->W = W; g->ws = ws;
   g->nWh = (H + ws - 1) / ws; g->nWw = (W + ws - 1) / ws; g->L = ws * ws;
@@ -621,9 +626,9 @@ extern "C" B200_API long long b200_swin_num_tokens(int32_t B, int32_t H, int32_t
 
 extern "C" B200_API int b200_swin_ln1_partition(const void* x, const float* gamma, const float* beta, void* n1, float* mean,
                                                 float* rstd, int32_t B, int32_t C, int32_t H, int32_t W, int32_t ws,
-                                                int32_t dtype, void* stream) {
+                                                int32_t shift, int32_t dtype, void* stream) {
   WinGeom g;
-  if (int rc = make_geom(&g, B, C, H, W, ws)) return rc;
+  if (int rc = make_geom(&g, B, C, H, W, ws, shift)) return rc;
   B200_REQUIRE(x && gamma && beta && n1 && mean && rstd, B200_ERR_SHAPE, "swin_ln1_partition: null pointer");
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
     int vec, iters;
@@ -677,9 +682,9 @@ extern "C" B200_API int b200_swin_gelu(const void* a, const void* gh, void* out,
 }
 
 extern "C" B200_API int b200_swin_res_reverse(const void* y1, const void* m, void* out, int32_t B, int32_t C, int32_t H,
-                                              int32_t W, int32_t ws, int32_t dtype, void* stream) {
+                                              int32_t W, int32_t ws, int32_t shift, int32_t dtype, void* stream) {
   WinGeom g;
-  if (int rc = make_geom(&g, B, C, H, W, ws)) return rc;
+  if (int rc = make_geom(&g, B, C, H, W, ws, shift)) return rc;
   B200_REQUIRE(y1 && m && out, B200_ERR_SHAPE, "swin_res_reverse: null pointer");
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
     int vec, iters;
@@ -696,9 +701,9 @@ extern "C" B200_API int b200_swin_res_reverse(const void* y1, const void* m, voi
 }
 
 extern "C" B200_API int b200_swin_partition(const void* src, void* tok, int32_t B, int32_t C, int32_t H, int32_t W,
-                                            int32_t ws, int32_t dtype, void* stream) {
+                                            int32_t ws, int32_t shift, int32_t dtype, void* stream) {
   WinGeom g;
-  if (int rc = make_geom(&g, B, C, H, W, ws)) return rc;
+  if (int rc = make_geom(&g, B, C, H, W, ws, shift)) return rc;
   B200_REQUIRE(src && tok, B200_ERR_SHAPE, "swin_partition: null pointer");
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
     int vec, iters;
@@ -723,9 +728,9 @@ extern "C" B200_API size_t b200_swin_ln_bwd_workspace_bytes(int64_t tokens, int3
 extern "C" B200_API int b200_swin_ln_bwd(const void* gout, const void* xin, const void* gres, const float* gamma,
                                          const float* mean, const float* rstd, void* gin, float* ggamma, float* gbeta,
                                          void* workspace, size_t workspace_bytes, int32_t B, int32_t C, int32_t H,
-                                         int32_t W, int32_t ws, int32_t dtype, int32_t mode, void* stream) {
+                                         int32_t W, int32_t ws, int32_t shift, int32_t dtype, int32_t mode, void* stream) {
   WinGeom g;
-  if (int rc = make_geom(&g, B, C, H, W, ws)) return rc;
+  if (int rc = make_geom(&g, B, C, H, W, ws, shift)) return rc;
   B200_REQUIRE(gout && xin && gamma && mean && rstd && gin && ggamma && gbeta, B200_ERR_SHAPE, "swin_ln_bwd: null pointer");
   B200_REQUIRE(mode == 1 || gres, B200_ERR_SHAPE, "swin_ln_bwd: LN2 mode needs the residual gradient");
   const size_t need = b200_swin_ln_bwd_workspace_bytes(g.T, C);

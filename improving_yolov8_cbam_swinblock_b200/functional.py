@@ -16,18 +16,18 @@ from ._lib import call, dtype_code, lib, ptr, stream_ptr
 
 _I64, _I32, _VP, _SZ = C.c_int64, C.c_int32, C.c_void_p, C.c_size_t
 _lib.register("b200_swin_num_tokens", C.c_longlong, [_I32] * 4)
-_lib.register("b200_swin_ln1_partition", C.c_int, [_VP] * 6 + [_I32] * 6 + [_VP])
-_lib.register("b200_swin_attn_fwd", C.c_int, [_VP] * 3 + [_I64] + [_I32] * 4 + [_VP])
-_lib.register("b200_swin_attn_bwd", C.c_int, [_VP] * 5 + [_I64] + [_I32] * 4 + [_VP])
+_lib.register("b200_swin_ln1_partition", C.c_int, [_VP] * 6 + [_I32] * 7 + [_VP])
+_lib.register("b200_swin_attn_fwd", C.c_int, [_VP] * 3 + [_I64] + [_I32] * 8 + [_VP])
+_lib.register("b200_swin_attn_bwd", C.c_int, [_VP] * 5 + [_I64] + [_I32] * 8 + [_VP])
 _lib.register("b200_swin_attn_tc_supported", C.c_int, [_I64] + [_I32] * 4)
-_lib.register("b200_swin_attn_fwd_tc", C.c_int, [_VP] * 3 + [_I64] + [_I32] * 4 + [_VP])
-_lib.register("b200_swin_attn_bwd_tc", C.c_int, [_VP] * 4 + [_I64] + [_I32] * 4 + [_VP])
+_lib.register("b200_swin_attn_fwd_tc", C.c_int, [_VP] * 3 + [_I64] + [_I32] * 8 + [_VP])
+_lib.register("b200_swin_attn_bwd_tc", C.c_int, [_VP] * 4 + [_I64] + [_I32] * 8 + [_VP])
 _lib.register("b200_swin_res_ln2", C.c_int, [_VP] * 8 + [_I64] + [_I32] * 2 + [_VP])
 _lib.register("b200_swin_gelu", C.c_int, [_VP] * 3 + [_I64] + [_I32] * 2 + [_VP])
-_lib.register("b200_swin_res_reverse", C.c_int, [_VP] * 3 + [_I32] * 6 + [_VP])
-_lib.register("b200_swin_partition", C.c_int, [_VP] * 2 + [_I32] * 6 + [_VP])
+_lib.register("b200_swin_res_reverse", C.c_int, [_VP] * 3 + [_I32] * 7 + [_VP])
+_lib.register("b200_swin_partition", C.c_int, [_VP] * 2 + [_I32] * 7 + [_VP])
 _lib.register("b200_swin_ln_bwd_workspace_bytes", _SZ, [_I64, _I32])
-_lib.register("b200_swin_ln_bwd", C.c_int, [_VP] * 10 + [_SZ] + [_I32] * 7 + [_VP])
+_lib.register("b200_swin_ln_bwd", C.c_int, [_VP] * 10 + [_SZ] + [_I32] * 8 + [_VP])
 _lib.register("b200_colsum_workspace_bytes", _SZ, [_I64, _I32])
 _lib.register("b200_colsum", C.c_int, [_VP] * 3 + [_SZ] + [_I64] + [_I32] * 2 + [_VP])
 _lib.register("b200_bn_silu_supported", C.c_int, [_I64, _I32, _I32])
@@ -143,6 +143,8 @@ def bn_act_supported(x: torch.Tensor, bn) -> bool:
         return False
     if bn.momentum is None or x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
         return False
+    if bn.training and bn.running_mean.dtype != torch.float32:
+        return False   # a .half()-ed module in training mode: the in-place running-stat update needs f32 buffers
     B, Cc, H, W = x.shape
     return bool(lib().b200_bn_silu_supported(B * H * W, Cc, dtype_code(x.dtype)))
 
@@ -152,7 +154,10 @@ def bn_act(x: torch.Tensor, bn, silu: bool) -> torch.Tensor:
     the running-stat update in training mode, running statistics in eval mode."""
     if bn.training:
         bn.num_batches_tracked.add_(1)   # nn.BatchNorm2d.forward bookkeeping (state_dict parity)
-    return BnActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.training, bn.momentum, bn.eps, silu)
+    rm, rv = bn.running_mean, bn.running_var
+    if rm.dtype != torch.float32:   # eval mode of a .half()-ed module (validator.py:147-149): read-only f32 copies
+        rm, rv = rm.float(), rv.float()
+    return BnActFn.apply(x, bn.weight, bn.bias, rm, rv, bn.training, bn.momentum, bn.eps, silu)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -257,26 +262,27 @@ def _colsum(a: torch.Tensor) -> torch.Tensor:
 USE_TC_ATTENTION = True  # tests flip this to compare against the SIMT attention kernels
 
 
-def attn_forward(qkv, T, Lw, Cc, nh):
-    """windowed MHSA on packed qkv[T,3C] -> (o[T,C], lse[T,nh])."""
+def attn_forward(qkv, T, Lw, Cc, nh, grid=(0, 0, 0, 0)):
+    """windowed MHSA on packed qkv[T,3C] -> (o[T,C], lse[T,nh]).  grid = (nWh, nWw, ws, shift): shifted-window mask
+    (extension; shift 0 = the reference's unmasked attention)."""
     dev, code = qkv.device, dtype_code(qkv.dtype)
     o = torch.empty((T, Cc), dtype=qkv.dtype, device=dev)
     lse = torch.empty((T, nh), dtype=torch.float32, device=dev)
     if USE_TC_ATTENTION and lib().b200_swin_attn_tc_supported(T, Lw, Cc, nh, code):
-        call("b200_swin_attn_fwd_tc", ptr(qkv), ptr(o), ptr(lse), T, Lw, Cc, nh, code, stream_ptr(dev))
+        call("b200_swin_attn_fwd_tc", ptr(qkv), ptr(o), ptr(lse), T, Lw, Cc, nh, *grid, code, stream_ptr(dev))
     else:
-        call("b200_swin_attn_fwd", ptr(qkv), ptr(o), ptr(lse), T, Lw, Cc, nh, code, stream_ptr(dev))
+        call("b200_swin_attn_fwd", ptr(qkv), ptr(o), ptr(lse), T, Lw, Cc, nh, *grid, code, stream_ptr(dev))
     return o, lse
 
 
-def attn_backward(qkv, o, lse, go, T, Lw, Cc, nh):
+def attn_backward(qkv, o, lse, go, T, Lw, Cc, nh, grid=(0, 0, 0, 0)):
     """gradient of attn_forward w.r.t. the packed qkv rows."""
     dev, code = qkv.device, dtype_code(qkv.dtype)
     gqkv = torch.empty_like(qkv)
     if USE_TC_ATTENTION and lib().b200_swin_attn_tc_supported(T, Lw, Cc, nh, code):
-        call("b200_swin_attn_bwd_tc", ptr(qkv), ptr(lse), ptr(go), ptr(gqkv), T, Lw, Cc, nh, code, stream_ptr(dev))
+        call("b200_swin_attn_bwd_tc", ptr(qkv), ptr(lse), ptr(go), ptr(gqkv), T, Lw, Cc, nh, *grid, code, stream_ptr(dev))
     else:
-        call("b200_swin_attn_bwd", ptr(qkv), ptr(o), ptr(lse), ptr(go), ptr(gqkv), T, Lw, Cc, nh, code, stream_ptr(dev))
+        call("b200_swin_attn_bwd", ptr(qkv), ptr(o), ptr(lse), ptr(go), ptr(gqkv), T, Lw, Cc, nh, *grid, code, stream_ptr(dev))
     return gqkv
 
 
@@ -293,7 +299,7 @@ class SwinBlockFn(torch.autograd.Function):
             return SwinBlockFn._backward(ctx, gout)
 
     @staticmethod
-    def _forward(ctx, x, g1, b1, win, bin_, wo, bo, g2, b2, w1, bb1, w2, bb2, num_heads, ws):
+    def _forward(ctx, x, g1, b1, win, bin_, wo, bo, g2, b2, w1, bb1, w2, bb2, num_heads, ws, shift):
         from . import gemm
 
         x = _nhwc(x)
@@ -309,10 +315,11 @@ class SwinBlockFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             n1 = torch.empty((T, Cc), dtype=dt, device=dev)
             mean1, rstd1 = torch.empty(T, **f32), torch.empty(T, **f32)
+            grid = (-(-H // ws), -(-W // ws), ws, shift)
             call("b200_swin_ln1_partition", ptr(x), ptr(g1f), ptr(b1f), ptr(n1), ptr(mean1), ptr(rstd1), B, Cc, H, W, ws,
-                                            code, st)
+                                            shift, code, st)
             qkv = gemm.linear(n1, win, bin_)
-            o, lse = attn_forward(qkv, T, Lw, Cc, num_heads)
+            o, lse = attn_forward(qkv, T, Lw, Cc, num_heads, grid)
             y1 = gemm.linear_res(o, wo, bo, n1)  # post-norm residual fused into the out_proj epilogue
             u = torch.empty_like(n1)
             mean2, rstd2 = torch.empty(T, **f32), torch.empty(T, **f32)
@@ -321,9 +328,9 @@ class SwinBlockFn(torch.autograd.Function):
             h, hpre = gemm.linear_gelu(u, w1, bb1)
             m = gemm.linear(h, w2, bb2)
             out = _empty_nhwc(B, Cc, H, W, dt, dev)
-            call("b200_swin_res_reverse", ptr(y1), ptr(m), ptr(out), B, Cc, H, W, ws, code, st)
+            call("b200_swin_res_reverse", ptr(y1), ptr(m), ptr(out), B, Cc, H, W, ws, shift, code, st)
         ctx.save_for_backward(x, g1f, g2f, win, wo, w1, w2, n1, mean1, rstd1, qkv, o, lse, y1, u, mean2, rstd2, hpre, h)
-        ctx.cfg = (B, Cc, H, W, ws, num_heads, T)
+        ctx.cfg = (B, Cc, H, W, ws, num_heads, T, shift)
         ctx.pdtypes = tuple(p.dtype for p in (g1, b1, win, bin_, wo, bo, g2, b2, w1, bb1, w2, bb2))
         return out
 
@@ -332,7 +339,8 @@ class SwinBlockFn(torch.autograd.Function):
         from . import gemm
 
         (x, g1f, g2f, win, wo, w1, w2, n1, mean1, rstd1, qkv, o, lse, y1, u, mean2, rstd2, hpre, h) = ctx.saved_tensors
-        B, Cc, H, W, ws, nh, T = ctx.cfg
+        B, Cc, H, W, ws, nh, T, shift = ctx.cfg
+        grid = (-(-H // ws), -(-W // ws), ws, shift)
         dev, dt = x.device, x.dtype
         code = dtype_code(dt)
         L = lib()
@@ -341,7 +349,7 @@ class SwinBlockFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             gout = _nhwc(gout.to(dt))
             gy2 = torch.empty((T, Cc), dtype=dt, device=dev)
-            call("b200_swin_partition", ptr(gout), ptr(gy2), B, Cc, H, W, ws, code, st)
+            call("b200_swin_partition", ptr(gout), ptr(gy2), B, Cc, H, W, ws, shift, code, st)
             # MLP
             gw2, gb2 = gemm.matmul_tn(gy2, h)     # [C, 4C] = gy2^T h,  [C] = sum_t gy2
             ga = gemm.matmul_nn_gelu_bwd(gy2, w2, hpre)  # [T, 4C] = (gy2 W2) * gelu'(hpre)
@@ -355,12 +363,12 @@ class SwinBlockFn(torch.autograd.Function):
             gg2 = torch.empty(Cc, dtype=torch.float32, device=dev)
             gbt2 = torch.empty(Cc, dtype=torch.float32, device=dev)
             call("b200_swin_ln_bwd", ptr(gu), ptr(y1), ptr(gy2), ptr(g2f), ptr(mean2), ptr(rstd2), ptr(gy1), ptr(gg2),
-                                     ptr(gbt2), ptr(wsb), nbytes, B, Cc, H, W, ws, code, 0, st)
+                                     ptr(gbt2), ptr(wsb), nbytes, B, Cc, H, W, ws, shift, code, 0, st)
             del gu, gy2
             # attention
             gwo, gbo = gemm.matmul_tn(gy1, o)     # [C, C], [C]
             go = gemm.matmul_nn(gy1, wo)          # [T, C]
-            gqkv = attn_backward(qkv, o, lse, go.contiguous(), T, Lw, Cc, nh)
+            gqkv = attn_backward(qkv, o, lse, go.contiguous(), T, Lw, Cc, nh, grid)
             del go
             gwin, gbin = gemm.matmul_tn(gqkv, n1)  # [3C, C], [3C]
             gn1 = gemm.matmul_nn(gqkv, win, add=gy1)  # [T, C] = gy1 + gqkv Win
@@ -370,14 +378,16 @@ class SwinBlockFn(torch.autograd.Function):
             gg1 = torch.empty(Cc, dtype=torch.float32, device=dev)
             gbt1 = torch.empty(Cc, dtype=torch.float32, device=dev)
             call("b200_swin_ln_bwd", ptr(gn1), ptr(x), None, ptr(g1f), ptr(mean1), ptr(rstd1), ptr(gx), ptr(gg1),
-                                     ptr(gbt1), ptr(wsb), nbytes, B, Cc, H, W, ws, code, 1, st)
+                                     ptr(gbt1), ptr(wsb), nbytes, B, Cc, H, W, ws, shift, code, 1, st)
         grads = [gg1, gbt1, gwin, gbin, gwo, gbo, gg2, gbt2, gw1, gb1, gw2, gb2]
         grads = [g.to(d) for g, d in zip(grads, ctx.pdtypes)]
-        return (gx, *grads, None, None)
+        return (gx, *grads, None, None, None)
 
 
-def swin_block(x, p: dict, num_heads: int, ws: int):
+def swin_block(x, p: dict, num_heads: int, ws: int, shift: int = 0):
     """p: parameters keyed like the reference state_dict (norm1.weight, attn.in_proj_weight, ...).
+    shift > 0: shifted-window extension (cyclic shift folded into the token addressing, seam mask applied in registers
+    before the softmax); 0 = the reference block (swin_block.py has no shift).
 
     Compute dtype = the autocast dtype when autocast is on (the reference runs its GEMMs there; trainer.py:383),
     else x.dtype."""
@@ -386,4 +396,4 @@ def swin_block(x, p: dict, num_heads: int, ws: int):
     return SwinBlockFn.apply(
         x, p["norm1.weight"], p["norm1.bias"], p["attn.in_proj_weight"], p["attn.in_proj_bias"],
         p["attn.out_proj.weight"], p["attn.out_proj.bias"], p["norm2.weight"], p["norm2.bias"],
-        p["mlp.0.weight"], p["mlp.0.bias"], p["mlp.2.weight"], p["mlp.2.bias"], num_heads, ws)
+        p["mlp.0.weight"], p["mlp.0.bias"], p["mlp.2.weight"], p["mlp.2.bias"], num_heads, ws, int(shift))

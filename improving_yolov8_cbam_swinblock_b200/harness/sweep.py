@@ -170,18 +170,19 @@ def run(scale: str, B: int, peaks: dict, iters: int = 10):
         del cat, yg
     # ---- SwinBlock at P4 (whole block vs tensor peak; FLOPs counted on un-padded tokens)
     Bs, c4, H, W = sh["P4"]
-    for ws in (7, 8):
-        blk = M.SwinBlock(c4, 2, ws).to(dev)
+    for ws, shift in ((7, 0), (7, 3), (8, 0), (8, 4)):   # configs[4]: window 7 and 8, shift off / on (shift = extension)
+        blk = M.SwinBlock(c4, 2, ws, shift).to(dev)
         x = torch.randn((Bs, c4, H, W), device=dev).to(dt).contiguous(memory_format=torch.channels_last)
         flops = Bs * H * W * (24 * c4 * c4 + 4 * ws * ws * c4)
         with torch.no_grad(), torch.autocast("cuda", dtype=dt):
-            rec(f"swin_block_fwd_ws{ws}", x.shape, _time(lambda: blk(x), iters, flush), flops, "tensor", "P4, whole block")
+            tag = f"ws{ws}" + (f"_shift{shift}" if shift else "")
+            rec(f"swin_block_fwd_{tag}", x.shape, _time(lambda: blk(x), iters, flush), flops, "tensor", "P4, whole block")
         xg = x.clone().requires_grad_(True)
         with torch.autocast("cuda", dtype=dt):
             y = blk(xg)
         g = torch.randn_like(y)
         params = [xg] + list(blk.parameters())
-        rec(f"swin_block_bwd_ws{ws}", x.shape, _time(lambda: torch.autograd.grad(y, params, g, retain_graph=True), iters, flush),
+        rec(f"swin_block_bwd_{tag}", x.shape, _time(lambda: torch.autograd.grad(y, params, g, retain_graph=True), iters, flush),
             2 * flops, "tensor", "P4, whole block backward (2x fwd FLOPs)")
         del y, xg
     return out

@@ -108,13 +108,19 @@ class CBAM(nn.Module):
 
 class SwinBlock(nn.Module):
     """swin_block.py:23-58.  ``attn`` is a real nn.MultiheadAttention used purely as the parameter container, so
-    initialisation (xavier in_proj, zero biases), state_dict keys and optimizer grouping match the reference."""
+    initialisation (xavier in_proj, zero biases), state_dict keys and optimizer grouping match the reference.
 
-    def __init__(self, dim, num_heads=2, window_size=7):
+    ``shift_size`` (trailing optional yaml arg, default 0 = the reference block) is an EXTENSION: shifted windows with
+    the seam mask, as in Swin; it adds no parameters, so state_dicts stay interchangeable."""
+
+    def __init__(self, dim, num_heads=2, window_size=7, shift_size=0):
         super().__init__()
+        if not 0 <= shift_size < window_size:
+            raise ValueError(f"shift_size {shift_size} must lie in [0, window_size {window_size})")
         self.dim = dim
         self.num_heads = num_heads
         self.window_size = window_size
+        self.shift_size = shift_size
         self.norm1 = nn.LayerNorm(dim)
         self.attn = nn.MultiheadAttention(embed_dim=dim, num_heads=num_heads, batch_first=True)
         self.norm2 = nn.LayerNorm(dim)
@@ -134,7 +140,7 @@ class SwinBlock(nn.Module):
             "mlp.0.weight": self.mlp[0].weight, "mlp.0.bias": self.mlp[0].bias,
             "mlp.2.weight": self.mlp[2].weight, "mlp.2.bias": self.mlp[2].bias,
         }
-        return Fb.swin_block(x, p, self.num_heads, self.window_size)
+        return Fb.swin_block(x, p, self.num_heads, self.window_size, getattr(self, "shift_size", 0))
 
 
 FUSE_CONV_EPILOGUE = [True]  # process-wide switch (tests / A-B timing); False = the caller's stock BatchNorm2d + SiLU

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 1
+#define B200_ABI_VERSION 2
 #if defined(__GNUC__)
 #define B200_API __attribute__((visibility("default")))
 #else
@@ -99,20 +99,27 @@ B200_API int b200_cbam_bwd(const void* g, const void* x, const float* w1, const 
  * SwinBlock stages -- replace SwinBlock.forward (ultralytics/nn/modules/swin_block.py:37-58) and its autograd
  * backward.  x is NHWC [B,H,W,C]; "tokens" are the zero-padded, window-partitioned rows
  *   t = ((b*nWh + wh)*nWw + ww)*L + r*ws + c,   L = ws*ws,  nWh = ceil(H/ws), nWw = ceil(W/ws)
- * (swin_block.py:8-13,41-47).  T = b200_swin_num_tokens(...).  The dense contractions between the stages
+ * (swin_block.py:8-13,41-47).  T = b200_swin_num_tokens(...).
+ * EXTENSION (not in the reference, whose block is unshifted -- SURVEY D1): `shift` in [0, ws) cyclically shifts the padded
+ * map by (-shift, -shift) before partitioning (folded into the token -> pixel addressing of every stage) and the
+ * attention entry points then mask, in registers before the softmax, the keys that lie across the wrap-around seam
+ * (windows of the last window row / column; `nWh, nWw, ws` describe the window grid).  shift == 0 is the reference block
+ * and ignores nWh / nWw / ws.  The dense contractions between the stages
  * (in_proj / out_proj / mlp.0 / mlp.2, torch F.linear in the reference) are b200_gemm_* below.
  * ------------------------------------------------------------------------------------------------------ */
 B200_API long long b200_swin_num_tokens(int32_t B, int32_t H, int32_t W, int32_t ws);
 /* n1[T,C] = LayerNorm_1(partition(pad(x)))  (swin_block.py:41-50); mean/rstd [T] f32 saved for the backward */
 B200_API int b200_swin_ln1_partition(const void* x, const float* gamma, const float* beta, void* n1, float* mean,
                                      float* rstd, int32_t B, int32_t C, int32_t H, int32_t W, int32_t ws,
-                                     int32_t dtype, void* stream);
+                                     int32_t shift, int32_t dtype, void* stream);
 /* windowed multi-head attention on packed rows qkv[T,3C] (q|k|v) -> o[T,C]; lse[T,nh] f32 (swin_block.py:51,
  * torch F.multi_head_attention_forward: q*hd^-0.5, softmax over the window's L keys, heads concatenated) */
 B200_API int b200_swin_attn_fwd(const void* qkv, void* o, float* lse, int64_t tokens, int32_t L, int32_t C,
-                                int32_t nh, int32_t dtype, void* stream);
+                                int32_t nh, int32_t nWh, int32_t nWw, int32_t ws, int32_t shift, int32_t dtype,
+                                void* stream);
 B200_API int b200_swin_attn_bwd(const void* qkv, const void* o, const float* lse, const void* go, void* gqkv,
-                                int64_t tokens, int32_t L, int32_t C, int32_t nh, int32_t dtype, void* stream);
+                                int64_t tokens, int32_t L, int32_t C, int32_t nh, int32_t nWh, int32_t nWw,
+                                int32_t ws, int32_t shift, int32_t dtype, void* stream);
 /* y1 = n1 + a (post-norm residual, swin_block.py:52);  u = LayerNorm_2(y1) (swin_block.py:53).
  * a == NULL: `n1` already holds y1 (residual fused into the out_proj GEMM) and y1 is not written. */
 B200_API int b200_swin_res_ln2(const void* n1, const void* a, const float* gamma, const float* beta, void* y1,
@@ -123,10 +130,10 @@ B200_API int b200_swin_gelu(const void* a, const void* gh, void* out, int64_t n,
                             void* stream);
 /* out[B,H,W,C] = reverse(crop(y1 + m))  (swin_block.py:53-58) */
 B200_API int b200_swin_res_reverse(const void* y1, const void* m, void* out, int32_t B, int32_t C, int32_t H,
-                                   int32_t W, int32_t ws, int32_t dtype, void* stream);
+                                   int32_t W, int32_t ws, int32_t shift, int32_t dtype, void* stream);
 /* tok[T,C] = partition(pad(src)) without normalisation (used for the upstream gradient) */
 B200_API int b200_swin_partition(const void* src, void* tok, int32_t B, int32_t C, int32_t H, int32_t W,
-                                 int32_t ws, int32_t dtype, void* stream);
+                                 int32_t ws, int32_t shift, int32_t dtype, void* stream);
 /* LayerNorm backward.  mode 0 (LN2): token-major, gin = LN^T(gout) + gres.  mode 1 (LN1): xin = x (NHWC, gathered
  * through the window map), gin = gx scattered back to NHWC; ggamma/gbeta [C] f32 overwritten; norm1.bias receives
  * gradient from padded tokens too. */
@@ -134,7 +141,7 @@ B200_API size_t b200_swin_ln_bwd_workspace_bytes(int64_t tokens, int32_t C);
 B200_API int b200_swin_ln_bwd(const void* gout, const void* xin, const void* gres, const float* gamma,
                               const float* mean, const float* rstd, void* gin, float* ggamma, float* gbeta,
                               void* workspace, size_t workspace_bytes, int32_t B, int32_t C, int32_t H,
-                              int32_t W, int32_t ws, int32_t dtype, int32_t mode, void* stream);
+                              int32_t W, int32_t ws, int32_t shift, int32_t dtype, int32_t mode, void* stream);
 /* out[n] f32 = column sums of a[rows,n]  (bias gradients) */
 B200_API size_t b200_colsum_workspace_bytes(int64_t rows, int32_t n);
 B200_API int b200_colsum(const void* a, float* out, void* workspace, size_t workspace_bytes, int64_t rows,
@@ -165,9 +172,11 @@ B200_API int b200_gemm_splitk(const void* A, const void* B, float* D, float* col
  * b200_swin_attn_fwd / _bwd.  b200_swin_attn_tc_supported() says whether the problem qualifies. */
 B200_API int b200_swin_attn_tc_supported(int64_t tokens, int32_t L, int32_t C, int32_t nh, int32_t dtype);
 B200_API int b200_swin_attn_fwd_tc(const void* qkv, void* o, float* lse, int64_t tokens, int32_t L, int32_t C,
-                                   int32_t nh, int32_t dtype, void* stream);
+                                   int32_t nh, int32_t nWh, int32_t nWw, int32_t ws, int32_t shift, int32_t dtype,
+                                   void* stream);
 B200_API int b200_swin_attn_bwd_tc(const void* qkv, const float* lse, const void* go, void* gqkv, int64_t tokens,
-                                   int32_t L, int32_t C, int32_t nh, int32_t dtype, void* stream);
+                                   int32_t L, int32_t C, int32_t nh, int32_t nWh, int32_t nWw, int32_t ws,
+                                   int32_t shift, int32_t dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Conv epilogue -- replaces `self.act(self.bn(y))` of Conv.forward (ultralytics/nn/modules/conv.py:65-79:

@@ -113,8 +113,24 @@ def window_reverse(win, ws, Hp, Wp):
     return t.permute(0, 1, 3, 2, 4, 5).reshape(B, Hp, Wp, C)
 
 
-def swin_forward(x, p, num_heads=2, ws=7):
-    """SwinBlock.forward (swin_block.py:37-58) restated.
+def shift_attention_mask(Hp, Wp, ws, shift, dtype, device=None):
+    """Additive mask [nW, L, L] of shifted-window attention (the standard Swin construction): label the padded map by
+    the 3x3 regions the cyclic shift creates, partition the labels like the tokens, and put -100 between tokens of
+    different regions.  EXTENSION: the reference block has no shift; this is our own specification."""
+    img = torch.zeros(1, Hp, Wp, 1, dtype=dtype, device=device)
+    cnt = 0
+    for hs in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+        for wsl in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+            img[:, hs, wsl, :] = cnt
+            cnt += 1
+    lab = window_partition(img, ws).squeeze(-1)  # [nW, L]
+    diff = lab[:, None, :] - lab[:, :, None]
+    return torch.where(diff != 0, torch.full_like(diff, -100.0), torch.zeros_like(diff))
+
+
+def swin_forward(x, p, num_heads=2, ws=7, shift=0):
+    """SwinBlock.forward (swin_block.py:37-58) restated.  ``shift`` > 0 (EXTENSION, not in the reference): cyclic shift of
+    the padded map by (-shift, -shift) before partitioning, region mask on the scores, shift back before the crop.
 
     p: dict with the reference state_dict keys: norm1.weight/bias, attn.in_proj_weight [3C,C],
     attn.in_proj_bias [3C], attn.out_proj.weight [C,C], attn.out_proj.bias, norm2.weight/bias,
@@ -129,6 +145,8 @@ def swin_forward(x, p, num_heads=2, ws=7):
     pad_w = (ws - W % ws) % ws
     xp = F.pad(x, (0, pad_w, 0, pad_h))
     Hp, Wp = H + pad_h, W + pad_w
+    if shift:
+        xp = torch.roll(xp, shifts=(-shift, -shift), dims=(2, 3))
     t = window_partition(xp.permute(0, 2, 3, 1), ws)  # [nWB, L, C]
     n1 = layer_norm(t, p["norm1.weight"], p["norm1.bias"])
     nWB, L, _ = n1.shape
@@ -141,6 +159,9 @@ def swin_forward(x, p, num_heads=2, ws=7):
 
     q, k, v = heads(q) * (1.0 / math.sqrt(hd)), heads(k), heads(v)
     s = q @ k.transpose(-1, -2)
+    if shift:
+        m = shift_attention_mask(Hp, Wp, ws, shift, s.dtype, s.device)  # [nW, L, L], windows ordered (wh, ww)
+        s = (s.reshape(B, -1, num_heads, L, L) + m[None, :, None]).reshape(nWB, num_heads, L, L)
     s = s - s.max(dim=-1, keepdim=True).values
     e = torch.exp(s)
     pr = e / e.sum(dim=-1, keepdim=True)
@@ -151,6 +172,8 @@ def swin_forward(x, p, num_heads=2, ws=7):
     hmid = gelu_erf(u @ p["mlp.0.weight"].t() + p["mlp.0.bias"])
     y2 = y1 + hmid @ p["mlp.2.weight"].t() + p["mlp.2.bias"]
     out = window_reverse(y2, ws, Hp, Wp).permute(0, 3, 1, 2)
+    if shift:
+        out = torch.roll(out, shifts=(shift, shift), dims=(2, 3))
     return out[:, :, :H, :W]
 
 

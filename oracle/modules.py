@@ -71,9 +71,9 @@ class _InProj(nn.Module):
 
 
 class SwinBlock(nn.Module):
-    def __init__(self, dim, num_heads=2, window_size=7):
+    def __init__(self, dim, num_heads=2, window_size=7, shift_size=0):
         super().__init__()
-        self.dim, self.num_heads, self.window_size = dim, num_heads, window_size
+        self.dim, self.num_heads, self.window_size, self.shift_size = dim, num_heads, window_size, shift_size
         self.norm1 = nn.LayerNorm(dim)
         self.attn = _InProj(dim)
         self.norm2 = nn.LayerNorm(dim)
@@ -81,7 +81,7 @@ class SwinBlock(nn.Module):
 
     def forward(self, x):
         p = {k: v for k, v in self.named_parameters()}
-        return ob.swin_forward(x, p, self.num_heads, self.window_size)
+        return ob.swin_forward(x, p, self.num_heads, self.window_size, self.shift_size)
 
 
 def make_sppf(conv_cls):

