@@ -85,8 +85,9 @@ const CUtensorMap* tensor_map_2d(const void* base, uint64_t rows, uint64_t cols,
 namespace {
 
 constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
-constexpr int kThreads = 320;        // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
-constexpr int kEpiThreads = 256;
+// warp 0 TMA, warp 1 MMA, warps 2.. epilogue: EW = 8 (two per TMEM lane quadrant, 64 columns each) or 16 (four per quadrant,
+// 32 columns each -- the GELU epilogues are bound by their FP32/MUFU work, so they get twice the warps to hide its latency)
+template <int EW> struct Thr { static constexpr int kThreads = 64 + EW * 32, kEpiThreads = EW * 32; };
 enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RES = 2, EPI_MUL_GELUGRAD = 3 };
 
 struct GemmParams {
@@ -96,15 +97,17 @@ struct GemmParams {
   int N, K, m_tiles, n_tiles, k_blocks, fmt, has_d2;
 };
 
-template <int BLOCK_N, int STAGES> struct Smem {
+// NBUF = 2: the output staging tile(s) are double-buffered, so the epilogue of tile i+1 fills one buffer while the TMA
+// engine still reads tile i out of the other (the epilogue warps otherwise idle ~30 % of the time at the store hand-off)
+template <int BLOCK_N, int STAGES, int NBUF = 1, int NB2 = NBUF> struct Smem {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int D_BYTES = BLOCK_M * BLOCK_N * 2;
   static constexpr int OFF_A = 0;
   static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
   static constexpr int OFF_D = OFF_B + STAGES * B_BYTES;
-  static constexpr int OFF_D2 = OFF_D + D_BYTES;
-  static constexpr int OFF_BAR = OFF_D2 + D_BYTES;
+  static constexpr int OFF_D2 = OFF_D + NBUF * D_BYTES;
+  static constexpr int OFF_BAR = OFF_D2 + NB2 * D_BYTES;   // second area: D2 (GELU pre-activation) or the R tile; absent for EPI_BIAS
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;  // + alignment slack
 };
 
@@ -147,18 +150,26 @@ __device__ __forceinline__ float unpack_hi(uint32_t w, int fmt) {
   return fmt == 1 ? __uint_as_float(w & 0xffff0000u) : __half2float(__ushort_as_half((unsigned short)(w >> 16)));
 }
 
-template <int BLOCK_N, int STAGES, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BLOCK_N, int STAGES, int EPI, int EW, int NBUF>
+__global__ void __launch_bounds__(Thr<EW>::kThreads, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2, GemmParams P) {
-  using S = Smem<BLOCK_N, STAGES>;
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
+               const __grid_constant__ CUtensorMap tmR, GemmParams P) {
+  using S = Smem<BLOCK_N, STAGES, NBUF, (EPI == EPI_BIAS ? 0 : NBUF)>;
+  constexpr int kEpiThreads = Thr<EW>::kEpiThreads;
   extern __shared__ unsigned char smem_raw_[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;   // [2] accumulator ready
   uint64_t* tempty = tfull + 2;       // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* rfull = tempty + 2;       // [2] R tile landed (TMA_R)
+  uint64_t* rempty = rfull + 2;       // [2] R tile consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + 2);
+  // the GELU-backward epilogue reads a whole [128 x BLOCK_N] tile of R: fetched by TMA into the (otherwise unused) second
+  // staging area instead of 32 scattered 64-byte row segments per warp load
+  constexpr bool TMA_R = ((EPI == EPI_MUL_GELUGRAD || EPI == EPI_BIAS_RES) && NBUF == 2);
+  constexpr int R_TILE_BYTES = BLOCK_M * BLOCK_N * 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = P.m_tiles * P.n_tiles;
 
@@ -167,6 +178,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (P.has_d2) prefetch_tmap(&tmD2);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiThreads); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&rfull[i], 1); mbar_init(&rempty[i], kEpiThreads); }
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N); tmem_relinquish(); }
@@ -178,9 +190,17 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      int stage = 0; uint32_t phase = 0;
+      int stage = 0; uint32_t phase = 0; int rb = 0; uint32_t rphase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m0 = (tile / P.n_tiles) * BLOCK_M, n0 = (tile % P.n_tiles) * BLOCK_N;
+        if (TMA_R) {
+          mbar_wait(&rempty[rb], rphase ^ 1);
+          mbar_expect_tx(&rfull[rb], R_TILE_BYTES);
+#pragma unroll
+          for (int b = 0; b < BLOCK_N / 64; ++b)
+            tma_load_2d(smem + S::OFF_D2 + rb * S::D_BYTES + b * (BLOCK_M * 128), &tmR, &rfull[rb], n0 + b * 64, m0);
+          if (++rb == 2) { rb = 0; rphase ^= 1; }
+        }
         for (int kb = 0; kb < P.k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], S::A_BYTES + S::B_BYTES);
@@ -215,17 +235,40 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
+    // ===================== epilogue (warps 2..) =====================
     const int q = warp & 3;                      // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;            // which half of the tile's columns this warp converts
+    const int half = (warp - 2) >> 2;            // which slice of the tile's columns this warp converts
     const int row = q * 32 + lane;               // row within the tile
-    const int et = threadIdx.x - 64;             // 0..255
-    constexpr int HALF_N = BLOCK_N / 2;          // columns per thread
+    const int et = threadIdx.x - 64;             // 0..kEpiThreads-1
+    constexpr int HALF_N = BLOCK_N / (EW / 4);   // columns per thread
     int acc = 0; uint32_t aphase = 0;
-    unsigned char* sD = smem + S::OFF_D;
-    unsigned char* sD2 = smem + S::OFF_D2;
+    // R operand (residual / GELU pre-activation) of this thread's 32-column chunk, software-prefetched one chunk ahead so
+    // its L2/HBM latency hides behind the previous chunk's epilogue arithmetic
+    constexpr bool kHasR = (EPI == EPI_BIAS_RES || EPI == EPI_MUL_GELUGRAD);
+    auto load_R = [&](int tile_, int ch_, uint32_t (&dst)[16]) {
+      const int m0_ = (tile_ / P.n_tiles) * BLOCK_M, n0_ = (tile_ % P.n_tiles) * BLOCK_N;
+      const long long grow_ = (long long)m0_ + row;
+      const int col0_ = half * HALF_N + ch_ * 32;
+      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(P.R) + grow_ * P.N + n0_ + col0_);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 t = make_uint4(0, 0, 0, 0);
+        if (tile_ < total_tiles && grow_ < P.M && n0_ + col0_ + i * 8 < P.N) t = rp[i];
+        dst[4 * i] = t.x; dst[4 * i + 1] = t.y; dst[4 * i + 2] = t.z; dst[4 * i + 3] = t.w;
+      }
+    };
+    uint32_t rres[16], rnext[16];
+    if (kHasR && !TMA_R) load_R(blockIdx.x, 0, rnext);
+    int rb = 0; uint32_t rphase = 0;
+    int dbuf = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile / P.n_tiles) * BLOCK_M, n0 = (tile % P.n_tiles) * BLOCK_N;
+      unsigned char* sD = smem + S::OFF_D + dbuf * S::D_BYTES;
+      unsigned char* sD2 = smem + S::OFF_D2 + dbuf * S::D_BYTES;
+      if (NBUF == 2) {   // this buffer was last used two tiles ago: at most the previous tile's stores may still be reading
+        if (et == 0) bulk_wait_read_1();
+        named_bar_sync(2, kEpiThreads);
+      }
       mbar_wait(&tfull[acc], aphase);
       fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + half * HALF_N;
@@ -235,15 +278,19 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int col0 = half * HALF_N + ch * 32;  // first column (within the tile) of this 32-wide chunk
         uint32_t v[32];
         tmem_ld32(taddr + ch * 32, v);
-        uint32_t rres[16];
-        if (EPI == EPI_BIAS_RES || EPI == EPI_MUL_GELUGRAD) {
-          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(P.R) + grow * P.N + n0 + col0);
+        if (TMA_R) {
+          if (ch == 0) mbar_wait(&rfull[rb], rphase);
+          const unsigned char* sR = smem + S::OFF_D2 + rb * S::D_BYTES + (col0 / 64) * (BLOCK_M * 128);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            uint4 t = make_uint4(0, 0, 0, 0);
-            if (grow < P.M && n0 + col0 + i * 8 < P.N) t = rp[i];
+            const uint4 t = *reinterpret_cast<const uint4*>(sR + sw128_offset(row, (col0 % 64) / 8 + i));
             rres[4 * i] = t.x; rres[4 * i + 1] = t.y; rres[4 * i + 2] = t.z; rres[4 * i + 3] = t.w;
           }
+        } else if (kHasR) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) rres[i] = rnext[i];
+          if (ch + 1 < HALF_N / 32) load_R(tile, ch + 1, rnext);
+          else load_R(tile + (int)gridDim.x, 0, rnext);
         }
         float bv[32];
         if (P.bias) {
@@ -280,6 +327,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             *reinterpret_cast<uint4*>(sD2 + off) = make_uint4(o2[4 * i], o2[4 * i + 1], o2[4 * i + 2], o2[4 * i + 3]);
         }
       }
+      if (TMA_R) { mbar_arrive(&rempty[rb]); if (++rb == 2) { rb = 0; rphase ^= 1; } }   // R tile consumed
       // accumulator drained -> MMA warp may overwrite it
       fence_before_sync();
       mbar_arrive(&tempty[acc]);
@@ -296,9 +344,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         bulk_commit();
-        bulk_wait_read_all();  // staging may be rewritten once the TMA engine has read it
+        if (NBUF == 1) bulk_wait_read_all();  // staging may be rewritten once the TMA engine has read it
       }
-      named_bar_sync(1, kEpiThreads);
+      if (NBUF == 1) named_bar_sync(1, kEpiThreads);
+      dbuf ^= (NBUF - 1);
     }
     if (et == 0) bulk_wait_all();
   }
@@ -308,15 +357,16 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N); }
 }
 
-template <int BLOCK_N, int STAGES, int EPI>
+template <int BLOCK_N, int STAGES, int EPI, int EW = 8, int NBUF = 1>
 int launch(const void* A, const void* B, const float* bias, void* D, void* D2, const void* R, long long M, int N, int K,
            int dtype, cudaStream_t st) {
-  using S = Smem<BLOCK_N, STAGES>;
+  using S = Smem<BLOCK_N, STAGES, NBUF, (EPI == EPI_BIAS ? 0 : NBUF)>;
   const CUtensorMap* mA = tensor_map_2d(A, (uint64_t)M, (uint64_t)K, (uint64_t)K, BLOCK_M, BLOCK_K, dtype);
   const CUtensorMap* mB = tensor_map_2d(B, (uint64_t)N, (uint64_t)K, (uint64_t)K, BLOCK_N, BLOCK_K, dtype);
   const CUtensorMap* mD = tensor_map_2d(D, (uint64_t)M, (uint64_t)N, (uint64_t)N, BLOCK_M, 64, dtype);
   const CUtensorMap* mD2 = D2 ? tensor_map_2d(D2, (uint64_t)M, (uint64_t)N, (uint64_t)N, BLOCK_M, 64, dtype) : mD;
-  if (!mA || !mB || !mD || !mD2) return B200_ERR_LAUNCH;
+  const CUtensorMap* mR = R ? tensor_map_2d(R, (uint64_t)M, (uint64_t)N, (uint64_t)N, BLOCK_M, 64, dtype) : mD;
+  if (!mA || !mB || !mD || !mD2 || !mR) return B200_ERR_LAUNCH;
   GemmParams P;
   P.bias = bias; P.R = R; P.M = M; P.N = N; P.K = K;
   P.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
@@ -324,11 +374,11 @@ int launch(const void* A, const void* B, const float* bias, void* D, void* D2, c
   P.k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
   P.fmt = dtype == B200_BF16 ? 1 : 0;
   P.has_d2 = D2 != nullptr;
-  auto kern = gemm_nt_kernel<BLOCK_N, STAGES, EPI>;
+  auto kern = gemm_nt_kernel<BLOCK_N, STAGES, EPI, EW, NBUF>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
   int grid = P.m_tiles * P.n_tiles;
   if (grid > sm_count()) grid = sm_count();
-  kern<<<grid, kThreads, S::TOTAL, st>>>(*mA, *mB, *mD, *mD2, P);
+  kern<<<grid, Thr<EW>::kThreads, S::TOTAL, st>>>(*mA, *mB, *mD, *mD2, *mR, P);
   return check_launch("gemm_nt");
 }
 
@@ -354,10 +404,10 @@ extern "C" B200_API int b200_gemm_nt(const void* A, const void* B, const float* 
   cudaStream_t st = (cudaStream_t)stream;
   using namespace b200::tc;
   if (N >= 128) {
-    if (epi == 0) return launch<128, 4, EPI_BIAS>(A, B, bias, D, nullptr, nullptr, M, N, K, dtype, st);
-    if (epi == 1) return launch<128, 4, EPI_BIAS_GELU>(A, B, bias, D, D2, nullptr, M, N, K, dtype, st);
-    if (epi == 3) return launch<128, 4, EPI_MUL_GELUGRAD>(A, B, bias, D, nullptr, R, M, N, K, dtype, st);
-    return launch<128, 4, EPI_BIAS_RES>(A, B, bias, D, nullptr, R, M, N, K, dtype, st);
+    if (epi == 0) return launch<128, 4, EPI_BIAS, 8, 2>(A, B, bias, D, nullptr, nullptr, M, N, K, dtype, st);
+    if (epi == 1) return launch<128, 3, EPI_BIAS_GELU, 8, 2>(A, B, bias, D, D2, nullptr, M, N, K, dtype, st);
+    if (epi == 3) return launch<128, 3, EPI_MUL_GELUGRAD, 8, 2>(A, B, bias, D, nullptr, R, M, N, K, dtype, st);
+    return launch<128, 3, EPI_BIAS_RES, 8, 2>(A, B, bias, D, nullptr, R, M, N, K, dtype, st);
   }
   if (epi == 0) return launch<64, 4, EPI_BIAS>(A, B, bias, D, nullptr, nullptr, M, N, K, dtype, st);
   if (epi == 1) return launch<64, 4, EPI_BIAS_GELU>(A, B, bias, D, D2, nullptr, M, N, K, dtype, st);
