@@ -12,6 +12,8 @@
 // Backward: the per-stage winners (row offset, col offset: 4+4 bits) are recomputed from y0 with the same rule,
 // then gradients are routed stage 3 -> 1 by two 1-D scatters per stage.  Every strip (row / column, channel)
 // is owned by exactly one thread, so the scatter is race-free and summation order is fixed: deterministic.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -80,17 +82,19 @@ template <> struct Word<__half> {
 // Returns nothing; writes dst[i*dstride] for i in [0,len).
 template <typename T, int K>
 __device__ __forceinline__ void pass1d(const uint32_t* __restrict__ src, int sstride, uint32_t* __restrict__ dst,
-                                       int dstride, int len, uint8_t* __restrict__ win_out, int wstride) {
+                                       int dstride, int len, uint8_t* __restrict__ win_out, int wstride, int i0 = 0,
+                                       int i1 = -1) {
+  if (i1 < 0) i1 = len;   // [i0, i1): the outputs this thread produces (a strip may be split over several threads)
   using WD = Word<T>;
   constexpr int R = K / 2;
   constexpr int EPL = WD::EPL;
   uint32_t win[K];  // sliding window of words, win[j] = src[i - R + j] (or -inf outside)
 #pragma unroll
   for (int j = 0; j < K; ++j) {
-    int s = j - R - 1 + 1;  // position for i = 0 is j - R; we pre-load then shift at loop top
+    int s = i0 + j - R;  // position for the first output i0 is i0 + j - R
     win[j] = (s >= 0 && s < len) ? src[s * sstride] : WD::neg_inf();
   }
-  for (int i = 0; i < len; ++i) {
+  for (int i = i0; i < i1; ++i) {
     uint32_t outw = 0;
     uint32_t wsel = 0;
 #pragma unroll
@@ -154,7 +158,7 @@ __device__ __forceinline__ void pass1d_fast(const uint32_t* __restrict__ src, in
 // Same validity condition as pass1d_fast (no NaN / -0.0 in the tile); out-of-range slots carry key 0 (never win).
 template <typename T, int K>
 __device__ __forceinline__ void pass1d_key(const uint32_t* __restrict__ src, int sstride, uint32_t* __restrict__ dst,
-                                           int dstride, int len, uint8_t* __restrict__ win_out, int wstride) {
+                                           int dstride, int len, uint8_t* __restrict__ win_out, int wstride, int i0, int i1) {
   static_assert(Word<T>::EPL == 2, "key path is for 16-bit types");
   constexpr int R = K / 2;
   auto mk = [](uint32_t b, int pos) -> uint32_t {
@@ -164,14 +168,14 @@ __device__ __forceinline__ void pass1d_key(const uint32_t* __restrict__ src, int
   uint32_t k0[K], k1[K];
 #pragma unroll
   for (int j = 0; j < K; ++j) {
-    const int p = j - R;
+    const int p = i0 + j - R;
     if (p >= 0 && p < len) {
       const uint32_t w = src[p * sstride];
       k0[j] = mk(w & 0xffffu, p);
       k1[j] = mk(w >> 16, p);
     } else { k0[j] = 0u; k1[j] = 0u; }
   }
-  for (int i = 0; i < len; ++i) {
+  for (int i = i0; i < i1; ++i) {
     uint32_t b0 = k0[0], b1 = k1[0];
 #pragma unroll
     for (int j = 1; j < K; ++j) { b0 = max(b0, k0[j]); b1 = max(b1, k1[j]); }
@@ -191,13 +195,15 @@ __device__ __forceinline__ void pass1d_key(const uint32_t* __restrict__ src, int
   }
 }
 template <typename T, int K, bool IS16 = (Word<T>::EPL == 2)> struct KeyPass {
-  __device__ static __forceinline__ void run(const uint32_t* src, int ss, uint32_t* dst, int ds, int len, uint8_t* w, int ws) {
-    pass1d_key<T, K>(src, ss, dst, ds, len, w, ws);
+  __device__ static __forceinline__ void run(const uint32_t* src, int ss, uint32_t* dst, int ds, int len, uint8_t* w, int ws,
+                                             int i0, int i1) {
+    pass1d_key<T, K>(src, ss, dst, ds, len, w, ws, i0, i1);
   }
 };
 template <typename T, int K> struct KeyPass<T, K, false> {
-  __device__ static __forceinline__ void run(const uint32_t* src, int ss, uint32_t* dst, int ds, int len, uint8_t* w, int ws) {
-    pass1d<T, K>(src, ss, dst, ds, len, w, ws);
+  __device__ static __forceinline__ void run(const uint32_t* src, int ss, uint32_t* dst, int ds, int len, uint8_t* w, int ws,
+                                             int i0, int i1) {
+    pass1d<T, K>(src, ss, dst, ds, len, w, ws, i0, i1);
   }
 };
 
@@ -357,6 +363,7 @@ __device__ __forceinline__ void tile_store_f32(const float* __restrict__ sm, uin
 
 struct PoolGeom {
   int B, C, H, W, Wp;  // Wp: padded pitch in pixels (odd -> consecutive rows land 16 banks apart for LP=16)
+  int nseg;            // backward: segments per strip (threads = strips * nseg * lanes)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -456,15 +463,18 @@ __global__ void __launch_bounds__(512) sppf_pool_fwd_kernel(const T* __restrict_
 // scatter one strip of gradients through a 1-D max pass: dst[i + off(i) - R] += src[i]; strips are thread-private.
 // Winners move monotonically along a strip, so contributions to one target are consecutive: accumulate them in a
 // register and touch shared memory once per target (summation order = strip order: deterministic).
+// A strip may be split over several threads by TARGET range [t0, t1): each scans the sources that can reach its range
+// ([t0-R, t1+R)) and keeps those landing inside, so every target still has exactly one owner and one summation order.
 template <int K, int EPL>
 __device__ __forceinline__ void scatter1d(const float* __restrict__ src, int sstride, float* __restrict__ dst,
-                                          int dstride, int len, const uint8_t* __restrict__ win, int wstride) {
+                                          int dstride, int len, const uint8_t* __restrict__ win, int wstride, int t0, int t1) {
   constexpr int R = K / 2;
-  int cur[EPL];
-  float acc[EPL];
-#pragma unroll
-  for (int e = 0; e < EPL; ++e) { cur[e] = -1; acc[e] = 0.f; }
-  for (int i = 0; i < len; ++i) {
+  // Branch-free: every source adds straight into its (thread-private, pre-zeroed) target.  Sources are visited in strip
+  // order, so each target still sums its contributions in the same fixed order; data-dependent run tracking in registers
+  // made the lanes of a warp diverge on every element and cost 5x the instructions.
+  const int ia = max(t0 - R, 0), ib = min(t1 + R, len);
+#pragma unroll 2
+  for (int i = ia; i < ib; ++i) {
     const uint32_t ws = win[i * wstride];
     float v[EPL];
     if (EPL == 2) {
@@ -474,16 +484,9 @@ __device__ __forceinline__ void scatter1d(const float* __restrict__ src, int sst
 #pragma unroll
     for (int e = 0; e < EPL; ++e) {
       const int t = i - R + (int)((ws >> (4 * e)) & 15u);
-      if (t == cur[e]) acc[e] += v[e];
-      else {
-        if (cur[e] >= 0) dst[(size_t)cur[e] * dstride + e] += acc[e];
-        cur[e] = t; acc[e] = v[e];
-      }
+      if (t >= t0 && t < t1) dst[(size_t)t * dstride + e] += v[e];
     }
   }
-#pragma unroll
-  for (int e = 0; e < EPL; ++e)
-    if (cur[e] >= 0) dst[(size_t)cur[e] * dstride + e] += acc[e];
 }
 
 template <typename T, int K, int LP>
@@ -517,22 +520,28 @@ __global__ void __launch_bounds__(512) sppf_pool_bwd_kernel(const T* __restrict_
   int special = tile_load_words<T, LP>(cur, reinterpret_cast<const uint32_t*>(y0 + in_img + c0), (size_t)g.C / EPL, nullptr, 0,
                                        g.H, g.W, g.Wp, valid_words, WD::neg_inf());
   special = __syncthreads_or(special);
+  // Every strip (row or column of one lane word) is split into `nseg` segments walked by different threads: the smem
+  // state (74 KB per CTA) bounds the strips in flight, so segmenting is what raises the number of resident warps.
+  const int nseg = g.nseg;
+  auto seg_lo = [&](int len, int sg) { return (len * sg) / nseg; };
   // recompute winners of the three stages (packed-key path unless the tile holds NaN / -0.0 or is f32)
   for (int st = 0; st < 3; ++st) {
-    for (int y = sid; y < g.H; y += nstrips) {
+    for (int u = sid; u < g.H * nseg; u += nstrips) {
+      const int y = u / nseg, sg = u - y * nseg, i0 = seg_lo(g.W, sg), i1 = seg_lo(g.W, sg + 1);
       const uint32_t* sp = cur + (y * g.Wp) * LP + lane;
       uint32_t* dp = tmp + (y * g.Wp) * LP + lane;
       uint8_t* wp = wrow + ((size_t)st * plane + y * g.Wp) * LP + lane;
-      if (special) pass1d<T, K>(sp, LP, dp, LP, g.W, wp, LP);
-      else KeyPass<T, K>::run(sp, LP, dp, LP, g.W, wp, LP);
+      if (special) pass1d<T, K>(sp, LP, dp, LP, g.W, wp, LP, i0, i1);
+      else KeyPass<T, K>::run(sp, LP, dp, LP, g.W, wp, LP, i0, i1);
     }
     __syncthreads();
-    for (int x = sid; x < g.W; x += nstrips) {
+    for (int u = sid; u < g.W * nseg; u += nstrips) {
+      const int x = u / nseg, sg = u - x * nseg, i0 = seg_lo(g.H, sg), i1 = seg_lo(g.H, sg + 1);
       const uint32_t* sp = tmp + x * LP + lane;
       uint32_t* dp = cur + x * LP + lane;
       uint8_t* wp = wcol + ((size_t)st * plane + x) * LP + lane;
-      if (special) pass1d<T, K>(sp, g.Wp * LP, dp, g.Wp * LP, g.H, wp, g.Wp * LP);
-      else KeyPass<T, K>::run(sp, g.Wp * LP, dp, g.Wp * LP, g.H, wp, g.Wp * LP);
+      if (special) pass1d<T, K>(sp, g.Wp * LP, dp, g.Wp * LP, g.H, wp, g.Wp * LP, i0, i1);
+      else KeyPass<T, K>::run(sp, g.Wp * LP, dp, g.Wp * LP, g.H, wp, g.Wp * LP, i0, i1);
     }
     __syncthreads();
   }
@@ -551,17 +560,22 @@ __global__ void __launch_bounds__(512) sppf_pool_bwd_kernel(const T* __restrict_
     // column-pass backward: ga (grad of stage output) -> gb (grad of row-pass output)
     zero(gb);
     __syncthreads();
-    for (int x = sid; x < g.W; x += nstrips)
+    for (int u = sid; u < g.W * nseg; u += nstrips) {
+      const int x = u / nseg, sg = u - x * nseg;
       scatter1d<K, EPL>(ga + ((size_t)x * LP + lane) * EPL, g.Wp * LP * EPL, gb + ((size_t)x * LP + lane) * EPL,
-                        g.Wp * LP * EPL, g.H, wcol + ((size_t)st * plane + x) * LP + lane, g.Wp * LP);
+                        g.Wp * LP * EPL, g.H, wcol + ((size_t)st * plane + x) * LP + lane, g.Wp * LP, seg_lo(g.H, sg),
+                        seg_lo(g.H, sg + 1));
+    }
     __syncthreads();
     // row-pass backward: gb -> ga (grad of stage input), then add the concat slice gradient g_st
     zero(ga);
     __syncthreads();
-    for (int y = sid; y < g.H; y += nstrips)
+    for (int u = sid; u < g.H * nseg; u += nstrips) {
+      const int y = u / nseg, sg = u - y * nseg;
       scatter1d<K, EPL>(gb + ((size_t)(y * g.Wp) * LP + lane) * EPL, LP * EPL,
                         ga + ((size_t)(y * g.Wp) * LP + lane) * EPL, LP * EPL, g.W,
-                        wrow + ((size_t)st * plane + y * g.Wp) * LP + lane, LP);
+                        wrow + ((size_t)st * plane + y * g.Wp) * LP + lane, LP, seg_lo(g.W, sg), seg_lo(g.W, sg + 1));
+    }
     __syncthreads();
     load_slice(ga, st, true);
     __syncthreads();
@@ -606,7 +620,12 @@ int launch_bwd(const void* gcat, const void* y0, void* gy0, PoolGeom g, cudaStre
   *done = true;
   const int chunks = (g.C + LP * EPL - 1) / (LP * EPL);
   int strips = g.H > g.W ? g.H : g.W;
-  int threads = ((strips * LP + 31) / 32) * 32;
+  g.nseg = 1;
+  // two segments per strip measured best (89 us vs 107 with one, 97 with three at 64x128x20x20): the kernel is bound by
+  // instruction issue, and every extra segment re-scans K-1 sources
+  while (g.nseg < 2 && strips * (g.nseg + 1) * LP <= 512 && (g.H < g.W ? g.H : g.W) / (g.nseg + 1) >= K) ++g.nseg;
+  if (const char* ov = getenv("B200_SPPF_NSEG")) g.nseg = atoi(ov) > 0 ? atoi(ov) : g.nseg;   // tuning aid
+  int threads = ((strips * g.nseg * LP + 31) / 32) * 32;
   if (threads > 512) threads = 512;
   if (threads < 64) threads = 64;
   auto kern = sppf_pool_bwd_kernel<T, K, LP>;
