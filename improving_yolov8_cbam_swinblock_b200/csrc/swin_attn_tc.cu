@@ -290,8 +290,10 @@ template <int HD> struct BCfg {
   static constexpr int KB = HD / 64;
   static constexpr int T_BYTES = KB * 128 * 128;   // one operand tile [KB][128 rows][128 B]
   static constexpr int P_BYTES = 2 * 128 * 128;
+  static constexpr int STAGES = HD == 64 ? 2 : 1;  // operand tiles double-buffered: TMA of pair i+1 overlaps the MMAs / softmax of pair i
+  static constexpr int STAGE_BYTES = 4 * T_BYTES;
   static constexpr int OFF_Q = 0, OFF_K = T_BYTES, OFF_V = 2 * T_BYTES, OFF_DO = 3 * T_BYTES;
-  static constexpr int OFF_P = 4 * T_BYTES, OFF_DS = OFF_P + P_BYTES;
+  static constexpr int OFF_P = STAGES * STAGE_BYTES, OFF_DS = OFF_P + P_BYTES;
   static constexpr int OFF_BAR = OFF_DS + P_BYTES;
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;
   static constexpr int TMEM_COLS = 512;            // S 128 | dP 128 | dV HD   (dQ aliases S, dK aliases dP)
@@ -301,28 +303,25 @@ template <int HD>
 __global__ void __launch_bounds__(kThreads, 1)
 swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmGO, AttnBwdParams P) {
   using Cfg = BCfg<HD>;
-  constexpr int KB = Cfg::KB;
+  constexpr int KB = Cfg::KB, STAGES = Cfg::STAGES;
   extern __shared__ unsigned char smem_raw_[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
-  unsigned char* sQ = smem + Cfg::OFF_Q;
-  unsigned char* sK = smem + Cfg::OFF_K;
-  unsigned char* sV = smem + Cfg::OFF_V;
-  unsigned char* sDO = smem + Cfg::OFF_DO;
   unsigned char* sP = smem + Cfg::OFF_P;
   unsigned char* sDS = smem + Cfg::OFF_DS;
-  uint64_t* in_full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-  uint64_t* sdp_full = in_full + 1;
-  uint64_t* pds_full = in_full + 2;
-  uint64_t* out_full = in_full + 3;
-  uint64_t* smem_free = in_full + 4;
-  uint64_t* tmem_free = in_full + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + 6);
+  uint64_t* in_full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);   // [2]
+  uint64_t* smem_free = in_full + 2;                                       // [2]
+  uint64_t* sdp_full = in_full + 4;
+  uint64_t* pds_full = in_full + 5;
+  uint64_t* out_full = in_full + 6;
+  uint64_t* tmem_free = in_full + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 4 && elect_one()) {
     prefetch_tmap(&tmQKV); prefetch_tmap(&tmGO);
-    mbar_init(in_full, 1); mbar_init(sdp_full, 1); mbar_init(pds_full, 128);
-    mbar_init(out_full, 1); mbar_init(smem_free, 1); mbar_init(tmem_free, 128);
+    for (int i = 0; i < 2; ++i) { mbar_init(&in_full[i], 1); mbar_init(&smem_free[i], 1); }
+    mbar_init(sdp_full, 1); mbar_init(pds_full, 128);
+    mbar_init(out_full, 1); mbar_init(tmem_free, 128);
     fence_mbar_init();
   }
   if (warp == 5) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
@@ -342,10 +341,15 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 
   if (warp == 4) {
     if (elect_one()) {
-      uint32_t ph = 0;
+      uint32_t ph = 0; int st = 0;
       for (int pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
-        mbar_wait(smem_free, ph ^ 1);
-        mbar_expect_tx(in_full, 4 * Cfg::T_BYTES);
+        unsigned char* sQ = smem + st * Cfg::STAGE_BYTES + Cfg::OFF_Q;
+        unsigned char* sK = smem + st * Cfg::STAGE_BYTES + Cfg::OFF_K;
+        unsigned char* sV = smem + st * Cfg::STAGE_BYTES + Cfg::OFF_V;
+        unsigned char* sDO = smem + st * Cfg::STAGE_BYTES + Cfg::OFF_DO;
+        uint64_t* in_full_s = &in_full[st];
+        mbar_wait(&smem_free[st], ph ^ 1);
+        mbar_expect_tx(in_full_s, 4 * Cfg::T_BYTES);
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           int it = 2 * pair + r;
@@ -355,13 +359,13 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb) {
             const int col = h * HD + kb * 64;
-            tma_load_2d(sQ + kb * 16384 + r * 8192, &tmQKV, in_full, col, t0);
-            tma_load_2d(sK + kb * 16384 + r * 8192, &tmQKV, in_full, P.C + col, t0);
-            tma_load_2d(sV + kb * 16384 + r * 8192, &tmQKV, in_full, 2 * P.C + col, t0);
-            tma_load_2d(sDO + kb * 16384 + r * 8192, &tmGO, in_full, col, t0);
+            tma_load_2d(sQ + kb * 16384 + r * 8192, &tmQKV, in_full_s, col, t0);
+            tma_load_2d(sK + kb * 16384 + r * 8192, &tmQKV, in_full_s, P.C + col, t0);
+            tma_load_2d(sV + kb * 16384 + r * 8192, &tmQKV, in_full_s, 2 * P.C + col, t0);
+            tma_load_2d(sDO + kb * 16384 + r * 8192, &tmGO, in_full_s, col, t0);
           }
         }
-        ph ^= 1;
+        if (++st == STAGES) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 5) {
@@ -369,9 +373,13 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       const uint32_t id_kk = idesc_f16(128, 128, P.fmt, 0, 0);   // S, dP
       const uint32_t id_kmn = idesc_f16(128, HD, P.fmt, 0, 1);   // dQ
       const uint32_t id_mnmn = idesc_f16(128, HD, P.fmt, 1, 1);  // dV, dK
-      uint32_t ph = 0;
+      uint32_t ph = 0, phs = 0; int st = 0;
       for (int pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
-        mbar_wait(in_full, ph);
+        unsigned char* sQ = smem + st * Cfg::STAGE_BYTES + Cfg::OFF_Q;
+        unsigned char* sK = smem + st * Cfg::STAGE_BYTES + Cfg::OFF_K;
+        unsigned char* sV = smem + st * Cfg::STAGE_BYTES + Cfg::OFF_V;
+        unsigned char* sDO = smem + st * Cfg::STAGE_BYTES + Cfg::OFF_DO;
+        mbar_wait(&in_full[st], phs);
         mbar_wait(tmem_free, ph ^ 1);
         fence_after_sync();
 #pragma unroll
@@ -397,9 +405,10 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           umma_f16(tDV, smem_desc_mn_sw128(sP + k * 2048, 16384), smem_desc_mn_sw128(sDO + k * 2048, 16384), id_mnmn, k != 0);
           umma_f16(tDK, smem_desc_mn_sw128(sDS + k * 2048, 16384), smem_desc_mn_sw128(sQ + k * 2048, 16384), id_mnmn, k != 0);
         }
-        umma_commit(smem_free);
+        umma_commit(&smem_free[st]);
         umma_commit(out_full);
         ph ^= 1;
+        if (++st == STAGES) { st = 0; phs ^= 1; }
       }
     }
   } else {
