@@ -17,7 +17,7 @@ namespace b200 {
 namespace tc {
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads10 = 320;   // 8 softmax/epilogue warps + TMA warp + MMA warp
 
 struct AttnParams {
   void* o;
@@ -49,17 +49,21 @@ __device__ __forceinline__ uint32_t pack2f(float lo, float hi, int fmt) {
 }
 
 template <int HD>
-__global__ void __launch_bounds__(kThreads, 1) swin_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams P) {
+__global__ void __launch_bounds__(kThreads10, 1) swin_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams P) {
   using Cfg = ACfg<HD>;
   constexpr int KB = Cfg::KB, STAGES = Cfg::STAGES;
   extern __shared__ unsigned char smem_raw_[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
-  uint64_t* qkv_full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-  uint64_t* s_full = qkv_full + STAGES;
-  uint64_t* p_full = s_full + STAGES;
+  // per stage: Q/K landed, V landed (TMA); S done + Q/K reusable, O done + V/P reusable (tcgen05.commit); P written (128 threads)
+  uint64_t* qk_full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* v_full = qk_full + STAGES;
+  uint64_t* s_full = v_full + STAGES;
+  uint64_t* qk_free = s_full + STAGES;
+  uint64_t* p_full = qk_free + STAGES;
   uint64_t* o_full = p_full + STAGES;
-  uint64_t* stage_free = o_full + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + STAGES);
+  uint64_t* v_free = o_full + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_free + STAGES);
+  const int n_local = blockIdx.x < P.n_pairs ? (P.n_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   auto sQ = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
@@ -67,15 +71,15 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_fwd_tc_kernel(const __g
   auto sV = [&](int s) { return smem + s * Cfg::STAGE_BYTES + 2 * Cfg::Q_BYTES; };
   auto sP = [&](int s) { return smem + s * Cfg::STAGE_BYTES + 3 * Cfg::Q_BYTES; };
 
-  if (warp == 4 && elect_one()) {
+  if (warp == 8 && elect_one()) {
     prefetch_tmap(&tmQKV);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&qkv_full[s], 1); mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128);
-      mbar_init(&o_full[s], 1); mbar_init(&stage_free[s], 128);
+      mbar_init(&qk_full[s], 1); mbar_init(&v_full[s], 1); mbar_init(&s_full[s], 1); mbar_init(&qk_free[s], 1);
+      mbar_init(&p_full[s], 128); mbar_init(&o_full[s], 1); mbar_init(&v_free[s], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 5) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  if (warp == 9) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   if (warp < 4) {
     // off-diagonal P blocks are never written again: zero them once (zero is swizzle-invariant)
     const int row = warp * 32 + lane, r = row >> 6;
@@ -93,85 +97,95 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_fwd_tc_kernel(const __g
   auto tS = [&](int s) { return tmem_base + s * 128; };
   auto tO = [&](int s) { return tmem_base + STAGES * 128 + s * HD; };
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================== TMA producer =====================
+    // Q/K of a stage are reloaded as soon as the S MMAs that read them have completed, V once the PV MMAs have: the loads of
+    // pair n+STAGES are in flight while pair n is still in its softmax / epilogue
     if (elect_one()) {
-      int s = 0; uint32_t ph = 0;
-      for (int pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
-        mbar_wait(&stage_free[s], ph ^ 1);
-        mbar_expect_tx(&qkv_full[s], 3 * Cfg::Q_BYTES);
+      for (int n = 0; n < n_local; ++n) {
+        const int pair = blockIdx.x + n * gridDim.x;
+        const int s = n % STAGES;
+        const uint32_t ph = (n / STAGES) & 1;
+        int t0[2], col[2];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           int it = 2 * pair + r;
           if (it >= P.n_items) it = P.n_items - 1;
           const int win = it / P.nh, h = it - win * P.nh;
-          const int t0 = win * P.L;
+          t0[r] = win * P.L; col[r] = h * HD;
+        }
+        mbar_wait(&qk_free[s], ph ^ 1);
+        mbar_expect_tx(&qk_full[s], 2 * Cfg::Q_BYTES);
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb) {
-            const int col = h * HD + kb * 64;
-            tma_load_2d(sQ(s) + kb * 16384 + r * 8192, &tmQKV, &qkv_full[s], col, t0);
-            tma_load_2d(sK(s) + kb * 16384 + r * 8192, &tmQKV, &qkv_full[s], P.C + col, t0);
-            tma_load_2d(sV(s) + kb * 16384 + r * 8192, &tmQKV, &qkv_full[s], 2 * P.C + col, t0);
+            tma_load_2d(sQ(s) + kb * 16384 + r * 8192, &tmQKV, &qk_full[s], col[r] + kb * 64, t0[r]);
+            tma_load_2d(sK(s) + kb * 16384 + r * 8192, &tmQKV, &qk_full[s], P.C + col[r] + kb * 64, t0[r]);
           }
-        }
-        if (++s == STAGES) { s = 0; ph ^= 1; }
+        mbar_wait(&v_free[s], ph ^ 1);
+        mbar_expect_tx(&v_full[s], Cfg::Q_BYTES);
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_2d(sV(s) + kb * 16384 + r * 8192, &tmQKV, &v_full[s], 2 * P.C + col[r] + kb * 64, t0[r]);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================== MMA issuer =====================
+    // S of pair a and PV of pair b are issued in whichever order their inputs become ready (a < b + STAGES: S(a) overwrites
+    // the TMEM columns softmax(a-STAGES) read, which p_full(a-STAGES) -- waited on before PV(a-STAGES) -- covers)
     if (elect_one()) {
       const uint32_t idesc_s = idesc_f16(128, 128, P.fmt, 0, 0);
       const uint32_t idesc_o = idesc_f16(128, HD, P.fmt, 0, 1);
-      auto issue_S = [&](int s) {
+      int a = 0, b = 0;
+      while (b < n_local) {
+        bool did = false;
+        if (a < n_local && a < b + STAGES) {
+          const int s = a % STAGES;
+          if (mbar_test(&qk_full[s], (a / STAGES) & 1)) {
+            fence_after_sync();
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb)
+            for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(tS(s), smem_desc_k_sw128(sQ(s) + kb * 16384 + k * 32), smem_desc_k_sw128(sK(s) + kb * 16384 + k * 32),
-                     idesc_s, (kb | k) != 0);
-        umma_commit(&s_full[s]);
-      };
-      int s = 0; uint32_t ph = 0;          // stage / phase of the pair whose PV is issued next
-      int sn = 0; uint32_t phn = 0;        // stage / phase of the pair whose S is issued next
-      int pair = blockIdx.x;
-      if (pair < P.n_pairs) {
-        mbar_wait(&qkv_full[sn], phn);
-        fence_after_sync();
-        issue_S(sn);
-        if (++sn == STAGES) { sn = 0; phn ^= 1; }
-      }
-      for (; pair < P.n_pairs; pair += gridDim.x) {
-        const int next = pair + gridDim.x;
-        if (STAGES > 1 && next < P.n_pairs) {  // S of the next pair overlaps the softmax of this one
-          mbar_wait(&qkv_full[sn], phn);
-          fence_after_sync();
-          issue_S(sn);
-          if (++sn == STAGES) { sn = 0; phn ^= 1; }
+              for (int k = 0; k < 4; ++k)
+                umma_f16(tS(s), smem_desc_k_sw128(sQ(s) + kb * 16384 + k * 32), smem_desc_k_sw128(sK(s) + kb * 16384 + k * 32),
+                         idesc_s, (kb | k) != 0);
+            umma_commit(&s_full[s]);
+            umma_commit(&qk_free[s]);
+            ++a; did = true;
+          }
         }
-        mbar_wait(&p_full[s], ph);
-        fence_after_sync();
+        if (!did) {
+          const int s = b % STAGES;
+          const uint32_t ph = (b / STAGES) & 1;
+          if (mbar_test(&p_full[s], ph)) {
+            mbar_wait(&v_full[s], ph);
+            fence_after_sync();
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb)
+            for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(tO(s), smem_desc_k_sw128(sP(s) + kb * 16384 + k * 32),
-                     smem_desc_mn_sw128(sV(s) + kb * 8192 + k * 2048, 16384), idesc_o, (kb | k) != 0);
-        umma_commit(&o_full[s]);
-        if (STAGES == 1 && next < P.n_pairs) {
-          mbar_wait(&qkv_full[sn], phn);
-          fence_after_sync();
-          issue_S(sn);
-          if (++sn == STAGES) { sn = 0; phn ^= 1; }
+              for (int k = 0; k < 4; ++k)
+                umma_f16(tO(s), smem_desc_k_sw128(sP(s) + kb * 16384 + k * 32),
+                         smem_desc_mn_sw128(sV(s) + kb * 8192 + k * 2048, 16384), idesc_o, (kb | k) != 0);
+            umma_commit(&o_full[s]);
+            umma_commit(&v_free[s]);
+            ++b;
+          }
         }
-        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
-  } else {
-    // ===================== softmax + epilogue (warps 0..3, thread = row) =====================
-    const int row = warp * 32 + lane, r = row >> 6, i = row & 63;
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-    int s = 0; uint32_t ph = 0;
-    for (int pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
+  } else if ((warp >> 2) < STAGES) {
+    // ===================== softmax + epilogue: warp group g = warp >> 2 owns stage g (thread = row) =====================
+    // the two groups work on alternate pairs, so one group's softmax overlaps the other's PV MMA + epilogue
+    const int g = warp >> 2, q = warp & 3;
+    const int row = q * 32 + lane, r = row >> 6, i = row & 63;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const int s = g;
+    for (int n = g; n < n_local; n += STAGES) {
+      const int pair = blockIdx.x + n * gridDim.x;
+      const uint32_t ph = (n / STAGES) & 1;
       const int it = 2 * pair + r;
       const bool valid = it < P.n_items && i < P.L;
       const int itc = it < P.n_items ? it : P.n_items - 1;
@@ -240,14 +254,11 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_fwd_tc_kernel(const __g
           }
         }
       }
-      fence_before_sync();
-      mbar_arrive(&stage_free[s]);
-      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 5) { fence_after_sync(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+  if (warp == 9) { fence_after_sync(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
 template <int HD>
@@ -264,7 +275,7 @@ int launch_fwd(const void* qkv, void* o, float* lse, long long T, int L, int C, 
   auto k = swin_attn_fwd_tc_kernel<HD>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::TOTAL);
   int grid = P.n_pairs < sm_count() ? P.n_pairs : sm_count();
-  k<<<grid, kThreads, Cfg::TOTAL, st>>>(*m, P);
+  k<<<grid, kThreads10, Cfg::TOTAL, st>>>(*m, P);
   return check_launch("swin_attn_fwd_tc");
 }
 
@@ -294,13 +305,13 @@ template <int HD> struct BCfg {
   static constexpr int STAGE_BYTES = 4 * T_BYTES;
   static constexpr int OFF_Q = 0, OFF_K = T_BYTES, OFF_V = 2 * T_BYTES, OFF_DO = 3 * T_BYTES;
   static constexpr int OFF_P = STAGES * STAGE_BYTES, OFF_DS = OFF_P + P_BYTES;
-  static constexpr int OFF_BAR = OFF_DS + P_BYTES;
-  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+  static constexpr int OFF_BAR = OFF_DS + P_BYTES;          // 128 B of mbarriers + TMEM slot, then 1 KB of partial row sums
+  static constexpr int TOTAL = OFF_BAR + 128 + 1024 + 1024;
   static constexpr int TMEM_COLS = 512;            // S 128 | dP 128 | dV HD   (dQ aliases S, dK aliases dP)
 };
 
 template <int HD>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads10, 1)
 swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmGO, AttnBwdParams P) {
   using Cfg = BCfg<HD>;
   constexpr int KB = Cfg::KB, STAGES = Cfg::STAGES;
@@ -315,16 +326,17 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   uint64_t* out_full = in_full + 6;
   uint64_t* tmem_free = in_full + 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + 8);
+  float* dsh = reinterpret_cast<float*>(smem + Cfg::OFF_BAR + 128);   // [2][128] partial row sums of the two column halves
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 4 && elect_one()) {
+  if (warp == 8 && elect_one()) {
     prefetch_tmap(&tmQKV); prefetch_tmap(&tmGO);
     for (int i = 0; i < 2; ++i) { mbar_init(&in_full[i], 1); mbar_init(&smem_free[i], 1); }
-    mbar_init(sdp_full, 1); mbar_init(pds_full, 128);
-    mbar_init(out_full, 1); mbar_init(tmem_free, 128);
+    mbar_init(sdp_full, 1); mbar_init(pds_full, 256);
+    mbar_init(out_full, 1); mbar_init(tmem_free, 256);
     fence_mbar_init();
   }
-  if (warp == 5) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  if (warp == 9) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   if (warp < 4) {
     const int row = warp * 32 + lane, r = row >> 6;
     uint4* z0 = reinterpret_cast<uint4*>(sP + (1 - r) * (128 * 128) + row * 128);
@@ -339,7 +351,7 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDQ = tS, tDK = tDP;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (elect_one()) {
       uint32_t ph = 0; int st = 0;
       for (int pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
@@ -368,7 +380,7 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         if (++st == STAGES) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (elect_one()) {
       const uint32_t id_kk = idesc_f16(128, 128, P.fmt, 0, 0);   // S, dP
       const uint32_t id_kmn = idesc_f16(128, HD, P.fmt, 0, 1);   // dQ
@@ -412,8 +424,11 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       }
     }
   } else {
-    const int row = warp * 32 + lane, r = row >> 6, i = row & 63;
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    // 8 warps: warp & 3 = TMEM lane quadrant (thread = row), warp >> 2 = which half of the 64 key columns (softmax part) /
+    // of the HD output columns (epilogue) this thread converts; the row sum `delta` is completed through shared memory
+    const int q = warp & 3, hf = warp >> 2;
+    const int row = q * 32 + lane, r = row >> 6, i = row & 63;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     uint32_t ph = 0;
     for (int pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
       const int it = 2 * pair + r;
@@ -425,33 +440,30 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       const float l2 = valid ? P.lse[tok * P.nh + h] * 1.4426950408889634f : 0.f;
       mbar_wait(sdp_full, ph);
       fence_after_sync();
-      uint32_t sv[64], dv[64];
-      {
-        uint32_t (&a0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sv[0]);
-        uint32_t (&a1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sv[32]);
-        uint32_t (&b0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&dv[0]);
-        uint32_t (&b1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&dv[32]);
-        tmem_ld32(tS + lane_sel + r * 64, a0);
-        tmem_ld32(tS + lane_sel + r * 64 + 32, a1);
-        tmem_ld32(tDP + lane_sel + r * 64, b0);
-        tmem_ld32(tDP + lane_sel + r * 64 + 32, b1);
-        tmem_ld_wait();
-      }
-      float delta = 0.f;
+      uint32_t sv[32], dv[32];
+      tmem_ld32(tS + lane_sel + r * 64 + hf * 32, sv);
+      tmem_ld32(tDP + lane_sel + r * 64 + hf * 32, dv);
+      tmem_ld_wait();
+      float dpart = 0.f;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        const float p = (j < P.L && valid && ((allowed >> j) & 1ull)) ? exp2f(__uint_as_float(sv[j]) * P.scale_log2 - l2) : 0.f;
-        sv[j] = __float_as_uint(p);
-        delta += p * __uint_as_float(dv[j]);
+      for (int jj = 0; jj < 32; ++jj) {
+        const int j = hf * 32 + jj;
+        const float p = (j < P.L && valid && ((allowed >> j) & 1ull)) ? exp2f(__uint_as_float(sv[jj]) * P.scale_log2 - l2) : 0.f;
+        sv[jj] = __float_as_uint(p);
+        dpart += p * __uint_as_float(dv[jj]);
       }
+      dsh[hf * 128 + row] = dpart;
+      named_bar_sync(1, 256);
+      const float delta = dsh[row] + dsh[128 + row];   // same order in both halves: identical value
       unsigned char* prow = sP + r * (128 * 128);
       unsigned char* drow = sDS + r * (128 * 128);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c = hf * 4 + cc;
         uint32_t pw[4], dw[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int j = c * 8 + 2 * e;
+          const int j = cc * 8 + 2 * e;
           const float p0 = __uint_as_float(sv[j]), p1 = __uint_as_float(sv[j + 1]);
           pw[e] = pack2f(p0, p1, P.fmt);
           dw[e] = pack2f(p0 * (__uint_as_float(dv[j]) - delta) * P.scale, p1 * (__uint_as_float(dv[j + 1]) - delta) * P.scale, P.fmt);
@@ -470,7 +482,8 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       for (int which = 0; which < 3; ++which) {
         const uint32_t tsrc = which == 0 ? tDQ : (which == 1 ? tDK : tDV);
 #pragma unroll
-        for (int ch = 0; ch < HD / 32; ++ch) {
+        for (int cq = 0; cq < HD / 64; ++cq) {
+          const int ch = hf * (HD / 64) + cq;
           uint32_t ov[32];
           tmem_ld32(tsrc + lane_sel + ch * 32, ov);
           tmem_ld_wait();
@@ -494,7 +507,7 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 5) { fence_after_sync(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+  if (warp == 9) { fence_after_sync(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
 template <int HD>
@@ -514,7 +527,7 @@ int launch_bwd(const void* qkv, const float* lse, const void* go, void* gqkv, lo
   auto k = swin_attn_bwd_tc_kernel<HD>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::TOTAL);
   int grid = P.n_pairs < sm_count() ? P.n_pairs : sm_count();
-  k<<<grid, kThreads, Cfg::TOTAL, st>>>(*m, *mg, P);
+  k<<<grid, kThreads10, Cfg::TOTAL, st>>>(*m, *mg, P);
   return check_launch("swin_attn_bwd_tc");
 }
 

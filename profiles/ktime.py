@@ -74,6 +74,20 @@ def run_cbam(shapes):
         del y, xg
 
 
+def run_attn(ws_list=(7, 8)):
+    """window attention alone (packed qkv rows in, o / gqkv out) at the model's P4 SwinBlock: [64,128,40,40], 2 heads."""
+    for ws in ws_list:
+        Hp = -(-40 // ws) * ws
+        L, C, nh = ws * ws, 128, 2
+        T = 64 * (Hp // ws) ** 2 * L
+        qkv = torch.randn(T, 3 * C, device=dev).to(dt)
+        go = torch.randn(T, C, device=dev).to(dt)
+        o, lse = Fb.attn_forward(qkv, T, L, C, nh)
+        rec(f"attn_fwd ws={ws}", (T, 3 * C), ktime(lambda: Fb.attn_forward(qkv, T, L, C, nh)), T * C * 2 * 4 + T * nh * 4)
+        rec(f"attn_bwd ws={ws}", (T, 3 * C), ktime(lambda: Fb.attn_backward(qkv, o, lse, go, T, L, C, nh)),
+            T * C * 2 * 7 + T * nh * 4)
+
+
 def run_sppf(shapes):
     for shape in shapes:
         torch.manual_seed(0)
@@ -96,5 +110,7 @@ if __name__ == "__main__":
         run_cbam([(B, 256, 20, 20), (B, 128, 40, 40), (B, 64, 80, 80), (B, 512, 20, 20), (B, 576, 20, 20), (B, 256, 40, 40)])
     if what in ("sppf", "all"):
         run_sppf([(B, 128, 20, 20), (B, 256, 20, 20), (B, 288, 20, 20), (B, 64, 40, 40)])
+    if what in ("attn", "all"):
+        run_attn()
     if "--json" in sys.argv:
         json.dump(rows, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
