@@ -300,68 +300,85 @@ struct AttnBwdParams {
 template <int HD> struct BCfg {
   static constexpr int KB = HD / 64;
   static constexpr int T_BYTES = KB * 128 * 128;   // one operand tile [KB][128 rows][128 B]
-  static constexpr int P_BYTES = 2 * 128 * 128;
-  static constexpr int STAGES = HD == 64 ? 2 : 1;  // operand tiles double-buffered: TMA of pair i+1 overlaps the MMAs / softmax of pair i
-  static constexpr int STAGE_BYTES = 4 * T_BYTES;
+  // P / dS of a window pair are block diagonal ([item 0 | 0 ; 0 | item 1]).  Stored as [item 0 rows: 8 KB][64 zero rows: 8 KB]
+  // [item 1 rows: 8 KB]: key block 0 = bytes 0..16K, key block 1 = bytes 8K..24K -- the zero rows are shared by both.
+  static constexpr int P_BYTES = 3 * 64 * 128;
+  static constexpr int KB_STRIDE = 64 * 128;       // byte distance between the two key blocks of P / dS
+  static constexpr int STAGES = HD == 64 ? 2 : 1;  // a stage = operand tiles + P/dS + TMEM columns of one pair in flight
   static constexpr int OFF_Q = 0, OFF_K = T_BYTES, OFF_V = 2 * T_BYTES, OFF_DO = 3 * T_BYTES;
-  static constexpr int OFF_P = STAGES * STAGE_BYTES, OFF_DS = OFF_P + P_BYTES;
-  static constexpr int OFF_BAR = OFF_DS + P_BYTES;          // 128 B of mbarriers + TMEM slot, then 1 KB of partial row sums
-  static constexpr int TOTAL = OFF_BAR + 128 + 1024 + 1024;
-  static constexpr int TMEM_COLS = 512;            // S 128 | dP 128 | dV HD   (dQ aliases S, dK aliases dP)
+  static constexpr int OFF_P = 4 * T_BYTES, OFF_DS = OFF_P + P_BYTES;
+  static constexpr int STAGE_BYTES = OFF_DS + P_BYTES;
+  static constexpr int OFF_BAR = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = OFF_BAR + 128 + 1024;
+  // HD 64: per stage S 128 (dQ aliases columns 0..63, dV columns 64..127) | dP 128 (dK aliases 0..63)  -> 2 x 256
+  // HD 128: S 128 (= dQ) | dP 128 (= dK) | dV 128
+  static constexpr int TMEM_STAGE = 256;
+  static constexpr int TMEM_COLS = 512;
 };
 
 template <int HD>
 __global__ void __launch_bounds__(kThreads10, 1)
-swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmGO, AttnBwdParams P) {
+swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmGO,
+                        const __grid_constant__ CUtensorMap tmOut, AttnBwdParams P) {
   using Cfg = BCfg<HD>;
-  constexpr int KB = Cfg::KB, STAGES = Cfg::STAGES;
+  constexpr int KB = Cfg::KB, STAGES = Cfg::STAGES, KBS = Cfg::KB_STRIDE;
   extern __shared__ unsigned char smem_raw_[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
-  unsigned char* sP = smem + Cfg::OFF_P;
-  unsigned char* sDS = smem + Cfg::OFF_DS;
-  uint64_t* in_full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);   // [2]
-  uint64_t* smem_free = in_full + 2;                                       // [2]
+  // per stage: operands landed (TMA) | operands reusable (commit) | S, dP done (commit) | P, dS written (128 threads) |
+  // dQ, dK, dV done (commit) | TMEM columns read back (128 threads)
+  uint64_t* in_full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* smem_free = in_full + 2;
   uint64_t* sdp_full = in_full + 4;
-  uint64_t* pds_full = in_full + 5;
-  uint64_t* out_full = in_full + 6;
-  uint64_t* tmem_free = in_full + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + 8);
-  float* dsh = reinterpret_cast<float*>(smem + Cfg::OFF_BAR + 128);   // [2][128] partial row sums of the two column halves
+  uint64_t* pds_full = in_full + 6;
+  uint64_t* out_full = in_full + 8;
+  uint64_t* tmem_free = in_full + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + 12);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_local = blockIdx.x < P.n_pairs ? (P.n_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto stage = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
 
   if (warp == 8 && elect_one()) {
-    prefetch_tmap(&tmQKV); prefetch_tmap(&tmGO);
-    for (int i = 0; i < 2; ++i) { mbar_init(&in_full[i], 1); mbar_init(&smem_free[i], 1); }
-    mbar_init(sdp_full, 1); mbar_init(pds_full, 256);
-    mbar_init(out_full, 1); mbar_init(tmem_free, 256);
+    prefetch_tmap(&tmQKV); prefetch_tmap(&tmGO); prefetch_tmap(&tmOut);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&in_full[s], 1); mbar_init(&smem_free[s], 1); mbar_init(&sdp_full[s], 1); mbar_init(&pds_full[s], 128);
+      mbar_init(&out_full[s], 1); mbar_init(&tmem_free[s], 128);
+    }
     fence_mbar_init();
   }
   if (warp == 9) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   if (warp < 4) {
-    const int row = warp * 32 + lane, r = row >> 6;
-    uint4* z0 = reinterpret_cast<uint4*>(sP + (1 - r) * (128 * 128) + row * 128);
-    uint4* z1 = reinterpret_cast<uint4*>(sDS + (1 - r) * (128 * 128) + row * 128);
+    // the shared zero rows of P / dS are never written again (zero is swizzle-invariant)
+    const int t = warp * 32 + lane;            // 128 threads x 64 B = 8 KB per matrix
+    for (int s = 0; s < STAGES; ++s) {
+      uint4* z0 = reinterpret_cast<uint4*>(stage(s) + Cfg::OFF_P + KBS + t * 64);
+      uint4* z1 = reinterpret_cast<uint4*>(stage(s) + Cfg::OFF_DS + KBS + t * 64);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { z0[i] = make_uint4(0, 0, 0, 0); z1[i] = make_uint4(0, 0, 0, 0); }
+      for (int i = 0; i < 4; ++i) { z0[i] = make_uint4(0, 0, 0, 0); z1[i] = make_uint4(0, 0, 0, 0); }
+    }
     fence_proxy_async();
   }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDQ = tS, tDK = tDP;
+  auto tS = [&](int s) { return tmem_base + s * Cfg::TMEM_STAGE; };
+  auto tDP = [&](int s) { return tmem_base + s * Cfg::TMEM_STAGE + 128; };
+  auto tDQ = [&](int s) { return tS(s); };
+  auto tDK = [&](int s) { return tDP(s); };
+  auto tDV = [&](int s) { return HD == 64 ? tS(s) + 64 : tmem_base + 256; };
 
   if (warp == 8) {
+    // ===================== TMA producer =====================
     if (elect_one()) {
-      uint32_t ph = 0; int st = 0;
-      for (int pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
-        unsigned char* sQ = smem + st * Cfg::STAGE_BYTES + Cfg::OFF_Q;
-        unsigned char* sK = smem + st * Cfg::STAGE_BYTES + Cfg::OFF_K;
-        unsigned char* sV = smem + st * Cfg::STAGE_BYTES + Cfg::OFF_V;
-        unsigned char* sDO = smem + st * Cfg::STAGE_BYTES + Cfg::OFF_DO;
-        uint64_t* in_full_s = &in_full[st];
-        mbar_wait(&smem_free[st], ph ^ 1);
-        mbar_expect_tx(in_full_s, 4 * Cfg::T_BYTES);
+      for (int n = 0; n < n_local; ++n) {
+        const int pair = blockIdx.x + n * gridDim.x;
+        const int s = n % STAGES;
+        unsigned char* sQ = stage(s) + Cfg::OFF_Q;
+        unsigned char* sK = stage(s) + Cfg::OFF_K;
+        unsigned char* sV = stage(s) + Cfg::OFF_V;
+        unsigned char* sDO = stage(s) + Cfg::OFF_DO;
+        mbar_wait(&smem_free[s], ((n / STAGES) & 1) ^ 1);
+        mbar_expect_tx(&in_full[s], 4 * Cfg::T_BYTES);
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           int it = 2 * pair + r;
@@ -371,140 +388,216 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb) {
             const int col = h * HD + kb * 64;
-            tma_load_2d(sQ + kb * 16384 + r * 8192, &tmQKV, in_full_s, col, t0);
-            tma_load_2d(sK + kb * 16384 + r * 8192, &tmQKV, in_full_s, P.C + col, t0);
-            tma_load_2d(sV + kb * 16384 + r * 8192, &tmQKV, in_full_s, 2 * P.C + col, t0);
-            tma_load_2d(sDO + kb * 16384 + r * 8192, &tmGO, in_full_s, col, t0);
+            tma_load_2d(sQ + kb * 16384 + r * 8192, &tmQKV, &in_full[s], col, t0);
+            tma_load_2d(sK + kb * 16384 + r * 8192, &tmQKV, &in_full[s], P.C + col, t0);
+            tma_load_2d(sV + kb * 16384 + r * 8192, &tmQKV, &in_full[s], 2 * P.C + col, t0);
+            tma_load_2d(sDO + kb * 16384 + r * 8192, &tmGO, &in_full[s], col, t0);
           }
         }
-        if (++st == STAGES) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    // first half of pair a (S, dP) and second half of pair b (dQ, dV, dK) are issued in whichever order their inputs become
+    // ready, so one warp group's softmax overlaps the other group's MMAs and read-back
     if (elect_one()) {
       const uint32_t id_kk = idesc_f16(128, 128, P.fmt, 0, 0);   // S, dP
       const uint32_t id_kmn = idesc_f16(128, HD, P.fmt, 0, 1);   // dQ
       const uint32_t id_mnmn = idesc_f16(128, HD, P.fmt, 1, 1);  // dV, dK
-      uint32_t ph = 0, phs = 0; int st = 0;
-      for (int pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
-        unsigned char* sQ = smem + st * Cfg::STAGE_BYTES + Cfg::OFF_Q;
-        unsigned char* sK = smem + st * Cfg::STAGE_BYTES + Cfg::OFF_K;
-        unsigned char* sV = smem + st * Cfg::STAGE_BYTES + Cfg::OFF_V;
-        unsigned char* sDO = smem + st * Cfg::STAGE_BYTES + Cfg::OFF_DO;
-        mbar_wait(&in_full[st], phs);
-        mbar_wait(tmem_free, ph ^ 1);
-        fence_after_sync();
+      int a = 0, b = 0;
+      while (b < n_local) {
+        bool did = false;
+        if (a < n_local && a < b + STAGES) {
+          const int s = a % STAGES;
+          const uint32_t ph = (a / STAGES) & 1;
+          if (mbar_test(&in_full[s], ph) && mbar_test(&tmem_free[s], ph ^ 1)) {
+            unsigned char* sQ = stage(s) + Cfg::OFF_Q;
+            unsigned char* sK = stage(s) + Cfg::OFF_K;
+            unsigned char* sV = stage(s) + Cfg::OFF_V;
+            unsigned char* sDO = stage(s) + Cfg::OFF_DO;
+            fence_after_sync();
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb)
+            for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_f16(tS, smem_desc_k_sw128(sQ + kb * 16384 + k * 32), smem_desc_k_sw128(sK + kb * 16384 + k * 32), id_kk, (kb | k) != 0);
-            umma_f16(tDP, smem_desc_k_sw128(sDO + kb * 16384 + k * 32), smem_desc_k_sw128(sV + kb * 16384 + k * 32), id_kk, (kb | k) != 0);
+              for (int k = 0; k < 4; ++k) {
+                umma_f16(tS(s), smem_desc_k_sw128(sQ + kb * 16384 + k * 32), smem_desc_k_sw128(sK + kb * 16384 + k * 32), id_kk,
+                         (kb | k) != 0);
+                umma_f16(tDP(s), smem_desc_k_sw128(sDO + kb * 16384 + k * 32), smem_desc_k_sw128(sV + kb * 16384 + k * 32), id_kk,
+                         (kb | k) != 0);
+              }
+            umma_commit(&sdp_full[s]);
+            ++a; did = true;
           }
-        umma_commit(sdp_full);
-        mbar_wait(pds_full, ph);
-        fence_after_sync();
-        // dQ = dS K : reduction over the 128 key slots (2 key blocks x 4 k-steps of 16)
-#pragma unroll
-        for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(tDQ, smem_desc_k_sw128(sDS + kb * 16384 + k * 32), smem_desc_mn_sw128(sK + kb * 8192 + k * 2048, 16384), id_kmn,
-                     (kb | k) != 0);
-        // dV = P^T dO, dK = dS^T Q : reduction over the 128 query rows (8 k-steps of 16 rows)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          umma_f16(tDV, smem_desc_mn_sw128(sP + k * 2048, 16384), smem_desc_mn_sw128(sDO + k * 2048, 16384), id_mnmn, k != 0);
-          umma_f16(tDK, smem_desc_mn_sw128(sDS + k * 2048, 16384), smem_desc_mn_sw128(sQ + k * 2048, 16384), id_mnmn, k != 0);
         }
-        umma_commit(&smem_free[st]);
-        umma_commit(out_full);
-        ph ^= 1;
-        if (++st == STAGES) { st = 0; phs ^= 1; }
+        if (!did) {
+          const int s = b % STAGES;
+          if (mbar_test(&pds_full[s], (b / STAGES) & 1)) {
+            unsigned char* sQ = stage(s) + Cfg::OFF_Q;
+            unsigned char* sK = stage(s) + Cfg::OFF_K;
+            unsigned char* sDO = stage(s) + Cfg::OFF_DO;
+            unsigned char* sP = stage(s) + Cfg::OFF_P;
+            unsigned char* sDS = stage(s) + Cfg::OFF_DS;
+            fence_after_sync();
+            // dQ = dS K : reduction over the 128 key slots (2 key blocks x 4 k-steps of 16)
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(tDQ(s), smem_desc_k_sw128(sDS + kb * KBS + k * 32), smem_desc_mn_sw128(sK + kb * 8192 + k * 2048, 16384),
+                         id_kmn, (kb | k) != 0);
+            // dV = P^T dO, dK = dS^T Q : reduction over the 128 query rows (8 k-steps of 16 rows)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              umma_f16(tDV(s), smem_desc_mn_sw128(sP + k * 2048, KBS), smem_desc_mn_sw128(sDO + k * 2048, 16384), id_mnmn, k != 0);
+              umma_f16(tDK(s), smem_desc_mn_sw128(sDS + k * 2048, KBS), smem_desc_mn_sw128(sQ + k * 2048, 16384), id_mnmn, k != 0);
+            }
+            umma_commit(&smem_free[s]);
+            umma_commit(&out_full[s]);
+            ++b;
+          }
+        }
       }
     }
-  } else {
-    // 8 warps: warp & 3 = TMEM lane quadrant (thread = row), warp >> 2 = which half of the 64 key columns (softmax part) /
-    // of the HD output columns (epilogue) this thread converts; the row sum `delta` is completed through shared memory
-    const int q = warp & 3, hf = warp >> 2;
+  } else if ((warp >> 2) < STAGES) {
+    // ===================== softmax + read-back: warp group g = warp >> 2 owns stage g (thread = row) =====================
+    const int g = warp >> 2, q = warp & 3;
     const int row = q * 32 + lane, r = row >> 6, i = row & 63;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    uint32_t ph = 0;
-    for (int pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
+    const int s = g;
+    unsigned char* prow = stage(s) + Cfg::OFF_P + r * (2 * KBS);     // item 1's rows 64..127 live in key block 1 = +8 KB
+    unsigned char* drow = stage(s) + Cfg::OFF_DS + r * (2 * KBS);
+    const uint32_t bar_id = 1 + g * 2 + r;      // named barrier of the 64 threads (2 warps) that own one item of the pair
+    bool stores_pending = false;
+    for (int n = g; n < n_local; n += STAGES) {
+      const int pair = blockIdx.x + n * gridDim.x;
+      const uint32_t ph = (n / STAGES) & 1;
       const int it = 2 * pair + r;
       const bool valid = it < P.n_items && i < P.L;
       const int itc = it < P.n_items ? it : P.n_items - 1;
       const int win = itc / P.nh, h = itc - win * P.nh;
       const long long tok = (long long)win * P.L + i;
       const unsigned long long allowed = allowed_keys(P.mask, win, i);   // shifted-window mask (all ones when shift == 0)
-      const float l2 = valid ? P.lse[tok * P.nh + h] * 1.4426950408889634f : 0.f;
-      mbar_wait(sdp_full, ph);
+      const float lraw = valid ? P.lse[tok * P.nh + h] : 0.f;   // consumed after the wait below: the load latency hides behind it
+      mbar_wait(&sdp_full[s], ph);
       fence_after_sync();
-      uint32_t sv[32], dv[32];
-      tmem_ld32(tS + lane_sel + r * 64 + hf * 32, sv);
-      tmem_ld32(tDP + lane_sel + r * 64 + hf * 32, dv);
-      tmem_ld_wait();
-      float dpart = 0.f;
+      const float l2 = lraw * 1.4426950408889634f;
+      uint32_t sv[64];
+      float delta = 0.f;
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        const int j = hf * 32 + jj;
-        const float p = (j < P.L && valid && ((allowed >> j) & 1ull)) ? exp2f(__uint_as_float(sv[jj]) * P.scale_log2 - l2) : 0.f;
-        sv[jj] = __float_as_uint(p);
-        dpart += p * __uint_as_float(dv[jj]);
-      }
-      dsh[hf * 128 + row] = dpart;
-      named_bar_sync(1, 256);
-      const float delta = dsh[row] + dsh[128 + row];   // same order in both halves: identical value
-      unsigned char* prow = sP + r * (128 * 128);
-      unsigned char* drow = sDS + r * (128 * 128);
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t (&sh)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sv[hf * 32]);
+        uint32_t dv[32];
+        tmem_ld32(tS(s) + lane_sel + r * 64 + hf * 32, sh);
+        tmem_ld32(tDP(s) + lane_sel + r * 64 + hf * 32, dv);
+        tmem_ld_wait();
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c = hf * 4 + cc;
-        uint32_t pw[4], dw[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = cc * 8 + 2 * e;
-          const float p0 = __uint_as_float(sv[j]), p1 = __uint_as_float(sv[j + 1]);
-          pw[e] = pack2f(p0, p1, P.fmt);
-          dw[e] = pack2f(p0 * (__uint_as_float(dv[j]) - delta) * P.scale, p1 * (__uint_as_float(dv[j + 1]) - delta) * P.scale, P.fmt);
+        for (int jj = 0; jj < 32; ++jj) {
+          const int j = hf * 32 + jj;
+          const float p = (j < P.L && valid && ((allowed >> j) & 1ull)) ? exp2f(__uint_as_float(sh[jj]) * P.scale_log2 - l2) : 0.f;
+          sh[jj] = __float_as_uint(p);
+          delta += p * __uint_as_float(dv[jj]);
         }
-        *reinterpret_cast<uint4*>(prow + sw128_offset(row, c)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
-        *reinterpret_cast<uint4*>(drow + sw128_offset(row, c)) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+      }
+      if (stores_pending) {                      // the previous pair's output stores read the P / dS rows written next
+        if (i == 0) bulk_wait_read_all();
+        named_bar_sync(bar_id, 64);
+      }
+      // second pass re-reads dP from TMEM (cheaper than keeping 64 more registers live)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t dv[32];
+        tmem_ld32(tDP(s) + lane_sel + r * 64 + hf * 32, dv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = hf * 4 + cc;
+          uint32_t pw[4], dw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int jj = cc * 8 + 2 * e;
+            const float p0 = __uint_as_float(sv[hf * 32 + jj]), p1 = __uint_as_float(sv[hf * 32 + jj + 1]);
+            pw[e] = pack2f(p0, p1, P.fmt);
+            dw[e] = pack2f(p0 * (__uint_as_float(dv[jj]) - delta) * P.scale, p1 * (__uint_as_float(dv[jj + 1]) - delta) * P.scale, P.fmt);
+          }
+          *reinterpret_cast<uint4*>(prow + sw128_offset(i, c)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+          *reinterpret_cast<uint4*>(drow + sw128_offset(i, c)) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+        }
       }
       fence_proxy_async();
       fence_before_sync();
-      mbar_arrive(pds_full);
+      mbar_arrive(&pds_full[s]);
       // ---- outputs: this thread owns token `tok` as query (dQ) and as key/value (dK, dV) ----
-      mbar_wait(out_full, ph);
+      mbar_wait(&out_full[s], ph);
       fence_after_sync();
-      uint16_t* grow = reinterpret_cast<uint16_t*>(P.gqkv) + tok * 3 * P.C + h * HD;
+      if constexpr (HD == 64) {
+        // rows are staged in this thread's own (now consumed) P / dS rows in the 128-byte-swizzled layout and leave as one
+        // TMA tensor store of [L rows x 64 columns] per item and output: full-line writes instead of 16-byte row fragments
+        auto stage_rows = [&](uint32_t tsrc, unsigned char* blk, bool pre_wait) {
+          uint32_t pk[32];
 #pragma unroll
-      for (int which = 0; which < 3; ++which) {
-        const uint32_t tsrc = which == 0 ? tDQ : (which == 1 ? tDK : tDV);
+          for (int ch = 0; ch < 2; ++ch) {
+            uint32_t ov[32];
+            tmem_ld32(tsrc + lane_sel + ch * 32, ov);
+            tmem_ld_wait();
 #pragma unroll
-        for (int cq = 0; cq < HD / 64; ++cq) {
-          const int ch = hf * (HD / 64) + cq;
-          uint32_t ov[32];
-          tmem_ld32(tsrc + lane_sel + ch * 32, ov);
-          tmem_ld_wait();
-          if (valid) {
+            for (int e = 0; e < 16; ++e) pk[ch * 16 + e] = pack2f(__uint_as_float(ov[2 * e]), __uint_as_float(ov[2 * e + 1]), P.fmt);
+          }
+          if (pre_wait) {                     // the rows still hold an output whose store may be reading them
+            if (i == 0) bulk_wait_read_all();
+            named_bar_sync(bar_id, 64);
+          }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint4 st;
-              st.x = pack2f(__uint_as_float(ov[8 * c + 0]), __uint_as_float(ov[8 * c + 1]), P.fmt);
-              st.y = pack2f(__uint_as_float(ov[8 * c + 2]), __uint_as_float(ov[8 * c + 3]), P.fmt);
-              st.z = pack2f(__uint_as_float(ov[8 * c + 4]), __uint_as_float(ov[8 * c + 5]), P.fmt);
-              st.w = pack2f(__uint_as_float(ov[8 * c + 6]), __uint_as_float(ov[8 * c + 7]), P.fmt);
-              *reinterpret_cast<uint4*>(grow + which * P.C + ch * 32 + c * 8) = st;
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(blk + sw128_offset(i, c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        };
+        stage_rows(tDQ(s), prow, false);
+        stage_rows(tDK(s), drow, false);
+        fence_proxy_async();
+        named_bar_sync(bar_id, 64);
+        if (i == 0 && it < P.n_items) {
+          tma_store_2d(&tmOut, prow, h * HD, win * P.L);
+          tma_store_2d(&tmOut, drow, P.C + h * HD, win * P.L);
+          bulk_commit();
+        }
+        stage_rows(tDV(s), prow, true);
+        fence_before_sync();
+        mbar_arrive(&tmem_free[s]);           // all TMEM columns of the stage are read back
+        fence_proxy_async();
+        named_bar_sync(bar_id, 64);
+        if (i == 0 && it < P.n_items) {
+          tma_store_2d(&tmOut, prow, 2 * P.C + h * HD, win * P.L);
+          bulk_commit();
+        }
+        stores_pending = true;
+      } else {
+        uint16_t* grow = reinterpret_cast<uint16_t*>(P.gqkv) + tok * 3 * P.C + h * HD;
+#pragma unroll
+        for (int which = 0; which < 3; ++which) {
+          const uint32_t tsrc = which == 0 ? tDQ(s) : (which == 1 ? tDK(s) : tDV(s));
+#pragma unroll
+          for (int ch = 0; ch < HD / 32; ++ch) {
+            uint32_t ov[32];
+            tmem_ld32(tsrc + lane_sel + ch * 32, ov);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                uint4 st;
+                st.x = pack2f(__uint_as_float(ov[8 * c + 0]), __uint_as_float(ov[8 * c + 1]), P.fmt);
+                st.y = pack2f(__uint_as_float(ov[8 * c + 2]), __uint_as_float(ov[8 * c + 3]), P.fmt);
+                st.z = pack2f(__uint_as_float(ov[8 * c + 4]), __uint_as_float(ov[8 * c + 5]), P.fmt);
+                st.w = pack2f(__uint_as_float(ov[8 * c + 6]), __uint_as_float(ov[8 * c + 7]), P.fmt);
+                *reinterpret_cast<uint4*>(grow + which * P.C + ch * 32 + c * 8) = st;
+              }
             }
           }
         }
+        fence_before_sync();
+        mbar_arrive(&tmem_free[s]);
       }
-      fence_before_sync();
-      mbar_arrive(tmem_free);
-      ph ^= 1;
     }
   }
+  bulk_wait_all();                              // outstanding output stores (no-op for threads that issued none)
   fence_before_sync();
   __syncthreads();
   if (warp == 9) { fence_after_sync(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
@@ -516,7 +609,8 @@ int launch_bwd(const void* qkv, const float* lse, const void* go, void* gqkv, lo
   using Cfg = BCfg<HD>;
   const CUtensorMap* m = tensor_map_2d(qkv, (uint64_t)T, (uint64_t)3 * C, (uint64_t)3 * C, 64, 64, dtype);
   const CUtensorMap* mg = tensor_map_2d(go, (uint64_t)T, (uint64_t)C, (uint64_t)C, 64, 64, dtype);
-  if (!m || !mg) return B200_ERR_LAUNCH;
+  const CUtensorMap* mo = tensor_map_2d(gqkv, (uint64_t)T, (uint64_t)3 * C, (uint64_t)3 * C, (uint32_t)L, 64, dtype);
+  if (!m || !mg || !mo) return B200_ERR_LAUNCH;
   AttnBwdParams P;
   P.gqkv = gqkv; P.lse = lse; P.T = T; P.L = L; P.C = C; P.nh = nh; P.mask = M;
   P.n_items = (int)(T / L) * nh;
@@ -527,7 +621,7 @@ int launch_bwd(const void* qkv, const float* lse, const void* go, void* gqkv, lo
   auto k = swin_attn_bwd_tc_kernel<HD>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::TOTAL);
   int grid = P.n_pairs < sm_count() ? P.n_pairs : sm_count();
-  k<<<grid, kThreads10, Cfg::TOTAL, st>>>(*m, *mg, P);
+  k<<<grid, kThreads10, Cfg::TOTAL, st>>>(*m, *mg, *mo, P);
   return check_launch("swin_attn_bwd_tc");
 }
 
