@@ -49,7 +49,7 @@ __device__ __forceinline__ uint32_t pack2f(float lo, float hi, int fmt) {
 }
 
 template <int HD>
-__global__ void __launch_bounds__(kThreads10, 1) swin_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams P) {
+__global__ void __launch_bounds__(kThreads10, 1) swin_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, AttnParams P) {
   using Cfg = ACfg<HD>;
   constexpr int KB = Cfg::KB, STAGES = Cfg::STAGES;
   extern __shared__ unsigned char smem_raw_[];
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kThreads10, 1) swin_attn_fwd_tc_kernel(const _
   auto sP = [&](int s) { return smem + s * Cfg::STAGE_BYTES + 3 * Cfg::Q_BYTES; };
 
   if (warp == 8 && elect_one()) {
-    prefetch_tmap(&tmQKV);
+    prefetch_tmap(&tmQKV); prefetch_tmap(&tmO);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&qk_full[s], 1); mbar_init(&v_full[s], 1); mbar_init(&s_full[s], 1); mbar_init(&qk_free[s], 1);
       mbar_init(&p_full[s], 128); mbar_init(&o_full[s], 1); mbar_init(&v_free[s], 1);
@@ -183,6 +183,8 @@ __global__ void __launch_bounds__(kThreads10, 1) swin_attn_fwd_tc_kernel(const _
     const int row = q * 32 + lane, r = row >> 6, i = row & 63;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const int s = g;
+    const uint32_t bar_id = 1 + g * 2 + r;      // named barrier of the 64 threads (2 warps) that own one item of the pair
+    bool stores_pending = false;
     for (int n = g; n < n_local; n += STAGES) {
       const int pair = blockIdx.x + n * gridDim.x;
       const uint32_t ph = (n / STAGES) & 1;
@@ -225,6 +227,10 @@ __global__ void __launch_bounds__(kThreads10, 1) swin_attn_fwd_tc_kernel(const _
         }
       }
       unsigned char* prow = sP(s) + r * (128 * 128);
+      if (stores_pending) {                      // the previous pair's O store reads the rows written next
+        if (i == 0) bulk_wait_read_all();
+        named_bar_sync(bar_id, 64);
+      }
 #pragma unroll
       for (int c = 0; c < 8; ++c)
         *reinterpret_cast<uint4*>(prow + sw128_offset(row, c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
@@ -236,26 +242,51 @@ __global__ void __launch_bounds__(kThreads10, 1) swin_attn_fwd_tc_kernel(const _
       // ---- O ----
       mbar_wait(&o_full[s], ph);
       fence_after_sync();
-      uint16_t* orow = reinterpret_cast<uint16_t*>(P.o) + tok * P.C + h * HD;
+      if constexpr (HD == 64) {
+        // the normalised row is staged in this thread's own (consumed) P row, 128-byte swizzled, and leaves as one TMA tensor
+        // store of [L rows x 64 columns] per item: full-line writes instead of 16-byte row fragments
+        uint32_t ok[32];
 #pragma unroll
-      for (int ch = 0; ch < HD / 32; ++ch) {
-        uint32_t ov[32];
-        tmem_ld32(tO(s) + lane_sel + ch * 32, ov);
-        tmem_ld_wait();
-        if (valid) {
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t ov[32];
+          tmem_ld32(tO(s) + lane_sel + ch * 32, ov);
+          tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4 st;
-            st.x = pack2f(__uint_as_float(ov[8 * c + 0]) * inv, __uint_as_float(ov[8 * c + 1]) * inv, P.fmt);
-            st.y = pack2f(__uint_as_float(ov[8 * c + 2]) * inv, __uint_as_float(ov[8 * c + 3]) * inv, P.fmt);
-            st.z = pack2f(__uint_as_float(ov[8 * c + 4]) * inv, __uint_as_float(ov[8 * c + 5]) * inv, P.fmt);
-            st.w = pack2f(__uint_as_float(ov[8 * c + 6]) * inv, __uint_as_float(ov[8 * c + 7]) * inv, P.fmt);
-            *reinterpret_cast<uint4*>(orow + ch * 32 + c * 8) = st;
+          for (int e = 0; e < 16; ++e) ok[ch * 16 + e] = pack2f(__uint_as_float(ov[2 * e]) * inv, __uint_as_float(ov[2 * e + 1]) * inv, P.fmt);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(prow + sw128_offset(row, c)) = make_uint4(ok[4 * c], ok[4 * c + 1], ok[4 * c + 2], ok[4 * c + 3]);
+        fence_proxy_async();
+        named_bar_sync(bar_id, 64);
+        if (i == 0 && it < P.n_items) {
+          tma_store_2d(&tmO, prow + r * (64 * 128), h * HD, win * P.L);
+          bulk_commit();
+        }
+        stores_pending = true;
+      } else {
+        uint16_t* orow = reinterpret_cast<uint16_t*>(P.o) + tok * P.C + h * HD;
+#pragma unroll
+        for (int ch = 0; ch < HD / 32; ++ch) {
+          uint32_t ov[32];
+          tmem_ld32(tO(s) + lane_sel + ch * 32, ov);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4 st;
+              st.x = pack2f(__uint_as_float(ov[8 * c + 0]) * inv, __uint_as_float(ov[8 * c + 1]) * inv, P.fmt);
+              st.y = pack2f(__uint_as_float(ov[8 * c + 2]) * inv, __uint_as_float(ov[8 * c + 3]) * inv, P.fmt);
+              st.z = pack2f(__uint_as_float(ov[8 * c + 4]) * inv, __uint_as_float(ov[8 * c + 5]) * inv, P.fmt);
+              st.w = pack2f(__uint_as_float(ov[8 * c + 6]) * inv, __uint_as_float(ov[8 * c + 7]) * inv, P.fmt);
+              *reinterpret_cast<uint4*>(orow + ch * 32 + c * 8) = st;
+            }
           }
         }
       }
     }
   }
+  bulk_wait_all();                              // outstanding O stores (no-op for threads that issued none)
   fence_before_sync();
   __syncthreads();
   if (warp == 9) { fence_after_sync(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
@@ -265,7 +296,8 @@ template <int HD>
 int launch_fwd(const void* qkv, void* o, float* lse, long long T, int L, int C, int nh, const ShiftMask& M, int dtype, cudaStream_t st) {
   using Cfg = ACfg<HD>;
   const CUtensorMap* m = tensor_map_2d(qkv, (uint64_t)T, (uint64_t)3 * C, (uint64_t)3 * C, 64, 64, dtype);
-  if (!m) return B200_ERR_LAUNCH;
+  const CUtensorMap* mo = tensor_map_2d(o, (uint64_t)T, (uint64_t)C, (uint64_t)C, (uint32_t)L, 64, dtype);
+  if (!m || !mo) return B200_ERR_LAUNCH;
   AttnParams P;
   P.o = o; P.lse = lse; P.T = T; P.L = L; P.C = C; P.nh = nh; P.mask = M;
   P.n_items = (int)(T / L) * nh;
@@ -275,7 +307,7 @@ int launch_fwd(const void* qkv, void* o, float* lse, long long T, int L, int C, 
   auto k = swin_attn_fwd_tc_kernel<HD>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::TOTAL);
   int grid = P.n_pairs < sm_count() ? P.n_pairs : sm_count();
-  k<<<grid, kThreads10, Cfg::TOTAL, st>>>(*m, P);
+  k<<<grid, kThreads10, Cfg::TOTAL, st>>>(*m, *mo, P);
   return check_launch("swin_attn_fwd_tc");
 }
 
