@@ -156,42 +156,50 @@ __device__ __forceinline__ void pass1d_fast(const uint32_t* __restrict__ src, in
 // Winner-tracking 1-D pass for 16-bit types via packed integer keys: key = sortable16(value) << 16 | (0xFFFF - pos),
 // so one unsigned max picks the larger value and, among equal values, the smaller position (first occurrence).
 // Same validity condition as pass1d_fast (no NaN / -0.0 in the tile); out-of-range slots carry key 0 (never win).
+// The tile is held in the SORTABLE domain (to_sortable2 applied once at load time): an order-preserving bijection, so the
+// cascade's values never have to be decoded -- the backward only needs the winners.  The K-slot window is a ring buffer
+// (max is commutative; the position lives in the key), the loop is unrolled K times so slot indices are static.
+__device__ __forceinline__ uint32_t to_sortable2(uint32_t w) {     // per 16-bit half: negative -> ~v, else v ^ 0x8000
+  return w ^ ((((w >> 15) & 0x00010001u) * 0x7fffu) | 0x80008000u);
+}
+__device__ __forceinline__ uint32_t from_sortable2(uint32_t k) {
+  return k ^ ((((~k >> 15) & 0x00010001u) * 0x7fffu) | 0x80008000u);
+}
 template <typename T, int K>
 __device__ __forceinline__ void pass1d_key(const uint32_t* __restrict__ src, int sstride, uint32_t* __restrict__ dst,
                                            int dstride, int len, uint8_t* __restrict__ win_out, int wstride, int i0, int i1) {
   static_assert(Word<T>::EPL == 2, "key path is for 16-bit types");
   constexpr int R = K / 2;
-  auto mk = [](uint32_t b, int pos) -> uint32_t {
-    const uint32_t sk = b ^ ((b & 0x8000u) ? 0xffffu : 0x8000u);
-    return (sk << 16) | (0xffffu - (uint32_t)pos);
-  };
   uint32_t k0[K], k1[K];
+  // slot (p - (i0 - R)) mod K holds source position p
 #pragma unroll
   for (int j = 0; j < K; ++j) {
     const int p = i0 + j - R;
     if (p >= 0 && p < len) {
-      const uint32_t w = src[p * sstride];
-      k0[j] = mk(w & 0xffffu, p);
-      k1[j] = mk(w >> 16, p);
+      const uint32_t w = src[p * sstride], pinv = 0xffffu - (uint32_t)p;
+      k0[j] = (w << 16) | pinv;
+      k1[j] = (w & 0xffff0000u) | pinv;
     } else { k0[j] = 0u; k1[j] = 0u; }
   }
-  for (int i = i0; i < i1; ++i) {
-    uint32_t b0 = k0[0], b1 = k1[0];
+  for (int ib = i0; ib < i1; ib += K) {
 #pragma unroll
-    for (int j = 1; j < K; ++j) { b0 = max(b0, k0[j]); b1 = max(b1, k1[j]); }
-    const uint32_t s0 = b0 >> 16, s1 = b1 >> 16;
-    const uint32_t v0 = s0 ^ ((s0 & 0x8000u) ? 0x8000u : 0xffffu), v1 = s1 ^ ((s1 & 0x8000u) ? 0x8000u : 0xffffu);
-    dst[i * dstride] = v0 | (v1 << 16);
-    const int p0 = 0xffff - (int)(b0 & 0xffffu), p1 = 0xffff - (int)(b1 & 0xffffu);
-    win_out[i * wstride] = (uint8_t)((p0 - (i - R)) | ((p1 - (i - R)) << 4));
+    for (int u = 0; u < K; ++u) {
+      const int i = ib + u;
+      if (i < i1) {
+        uint32_t b0 = k0[0], b1 = k1[0];
 #pragma unroll
-    for (int j = 0; j < K - 1; ++j) { k0[j] = k0[j + 1]; k1[j] = k1[j + 1]; }
-    const int p = i + 1 + R;
-    if (p < len) {
-      const uint32_t w = src[p * sstride];
-      k0[K - 1] = mk(w & 0xffffu, p);
-      k1[K - 1] = mk(w >> 16, p);
-    } else { k0[K - 1] = 0u; k1[K - 1] = 0u; }
+        for (int j = 1; j < K; ++j) { b0 = max(b0, k0[j]); b1 = max(b1, k1[j]); }
+        dst[i * dstride] = __byte_perm(b0, b1, 0x7632);            // (b0 >> 16) | (b1 & 0xffff0000)
+        const uint32_t base = 0xffffu - (uint32_t)(i - R);          // offset in the window = pos - (i - R)
+        win_out[i * wstride] = (uint8_t)((base - (b0 & 0xffffu)) | ((base - (b1 & 0xffffu)) << 4));
+        const int p = i + 1 + R;                                    // replaces the oldest slot: position i - R = slot u
+        if (p < len) {
+          const uint32_t w = src[p * sstride], pinv = 0xffffu - (uint32_t)p;
+          k0[u] = (w << 16) | pinv;
+          k1[u] = (w & 0xffff0000u) | pinv;
+        } else { k0[u] = 0u; k1[u] = 0u; }
+      }
+    }
   }
 }
 template <typename T, int K, bool IS16 = (Word<T>::EPL == 2)> struct KeyPass {
@@ -520,6 +528,12 @@ __global__ void __launch_bounds__(512) sppf_pool_bwd_kernel(const T* __restrict_
   int special = tile_load_words<T, LP>(cur, reinterpret_cast<const uint32_t*>(y0 + in_img + c0), (size_t)g.C / EPL, nullptr, 0,
                                        g.H, g.W, g.Wp, valid_words, WD::neg_inf());
   special = __syncthreads_or(special);
+  if constexpr (EPL == 2) {
+    if (!special) {   // packed-key path: move the tile into the sortable domain once (see pass1d_key)
+      for (int i = threadIdx.x; i < plane * LP; i += blockDim.x) cur[i] = to_sortable2(cur[i]);
+      __syncthreads();
+    }
+  }
   // Every strip (row or column of one lane word) is split into `nseg` segments walked by different threads: the smem
   // state (74 KB per CTA) bounds the strips in flight, so segmenting is what raises the number of resident warps.
   const int nseg = g.nseg;
@@ -551,8 +565,13 @@ __global__ void __launch_bounds__(512) sppf_pool_bwd_kernel(const T* __restrict_
     if (accumulate) tile_load_f32<T, LP, true>(dstbuf, src, (size_t)4 * g.C / EPL, g.H, g.W, g.Wp, valid_words);
     else tile_load_f32<T, LP, false>(dstbuf, src, (size_t)4 * g.C / EPL, g.H, g.W, g.Wp, valid_words);
   };
-  auto zero = [&](float* buf) {
-    for (int i = threadIdx.x; i < plane * LP * EPL; i += blockDim.x) buf[i] = 0.f;
+  auto zero = [&](float* buf) {   // plane * LP * EPL floats: a multiple of 4 for every LP >= 4 (16-byte stores), scalar otherwise
+    if constexpr ((LP * EPL) % 4 == 0) {
+      uint4* b4 = reinterpret_cast<uint4*>(buf);
+      for (int i = threadIdx.x; i < plane * LP * EPL / 4; i += blockDim.x) b4[i] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+      for (int i = threadIdx.x; i < plane * LP * EPL; i += blockDim.x) buf[i] = 0.f;
+    }
   };
   load_slice(ga, 3, false);
   __syncthreads();
@@ -567,8 +586,9 @@ __global__ void __launch_bounds__(512) sppf_pool_bwd_kernel(const T* __restrict_
                         seg_lo(g.H, sg + 1));
     }
     __syncthreads();
-    // row-pass backward: gb -> ga (grad of stage input), then add the concat slice gradient g_st
-    zero(ga);
+    // row-pass backward: gb -> ga (grad of stage input).  ga starts from the concat slice gradient g_st instead of
+    // zero + a separate accumulate pass: one sweep and one barrier fewer per stage (padding columns are never touched)
+    load_slice(ga, st, false);
     __syncthreads();
     for (int u = sid; u < g.H * nseg; u += nstrips) {
       const int y = u / nseg, sg = u - y * nseg;
@@ -576,8 +596,6 @@ __global__ void __launch_bounds__(512) sppf_pool_bwd_kernel(const T* __restrict_
                         ga + ((size_t)(y * g.Wp) * LP + lane) * EPL, LP * EPL, g.W,
                         wrow + ((size_t)st * plane + y * g.Wp) * LP + lane, LP, seg_lo(g.W, sg), seg_lo(g.W, sg + 1));
     }
-    __syncthreads();
-    load_slice(ga, st, true);
     __syncthreads();
   }
   tile_store_f32<T, LP>(ga, reinterpret_cast<uint32_t*>(gy0 + in_img + c0), (size_t)g.C / EPL, g.H, g.W, g.Wp, valid_words);

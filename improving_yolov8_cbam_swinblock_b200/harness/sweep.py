@@ -58,15 +58,18 @@ def ncu_kernel_name(tag: str):
     """ABI entry point (or shape-tagged GEMM) -> kernel instantiation name used in profiles/traffic_rNN.json."""
     import re
 
-    fixed = {"b200_cbam_fwd": "b200::cbam::cbam_cluster_fwd_kernel<__nv_bfloat16, 8, 1>",
+    fixed = {"b200_cbam_fwd": "b200::cbam_cluster_fwd_kernel<__nv_bfloat16, 8, 1>",
              "b200_swin_attn_fwd_tc": "b200::swin_attn_fwd_tc_kernel<64>", "b200_swin_attn_bwd_tc": "b200::swin_attn_bwd_tc_kernel<64>",
              "b200_swin_ln1_partition": "b200::swin_ln1_partition_vec_kernel<__nv_bfloat16, 8, 2>",
              "b200_swin_res_ln2": "b200::swin_res_ln2_vec_kernel<__nv_bfloat16, 8, 2>"}
     if tag in fixed:
         return fixed[tag]
     m = re.match(r"b200_gemm_nt\[(\d+)x(\d+)x(\d+),epi(\d)\]", tag)
-    if m:
-        return f"b200::gemm_nt_kernel<{128 if int(m.group(2)) >= 128 else 64}, 4, {m.group(4)}>"
+    if m:  # the dispatch table of b200_gemm_nt (csrc/gemm_tc.cu): <BLOCK_N, STAGES, EPI, epilogue warps, staging buffers>
+        n, epi = int(m.group(2)), int(m.group(4))
+        if n >= 128:
+            return f"b200::gemm_nt_kernel<128, {4 if epi == 0 else 3}, {epi}, 8, 2>"
+        return f"b200::gemm_nt_kernel<64, 4, {epi}, 8, 1>"
     return None
 
 
