@@ -601,6 +601,150 @@ __global__ void __launch_bounds__(512) sppf_pool_bwd_kernel(const T* __restrict_
   tile_store_f32<T, LP>(ga, reinterpret_cast<uint32_t*>(gy0 + in_img + c0), (size_t)g.C / EPL, g.H, g.W, g.Wp, valid_words);
 }
 
+// ---- in-place variant (16-bit dtypes, two segments per strip) ---------------------------------------------------
+// The routing pass is written as a GATHER: target t sums, in ascending source order, the sources i in [t-R, t+R] whose
+// winner offset points at t (offset == t - i + R) -- the same values in the same order as scatter1d, so the results are
+// bit-identical -- which lets it run IN PLACE: one f32 gradient buffer instead of two (47 KB instead of 74 KB of shared
+// memory per CTA: 4 CTAs per SM = 592 slots, so the 512 work items of [64,128,20,20] are ONE wave instead of 1.15).
+// Each strip is owned by two threads that both start at the middle and walk outwards (left one descending, right one
+// ascending): everything a thread reads across the boundary is in its initial K-source window, loaded before the barrier
+// that precedes the first write; afterwards it only reads sources further out than anything it or its partner has written.
+// The window is a ring of K sources in registers; the walk is unrolled K times so ring slots are static.
+template <int K> struct Ring {
+  float2 v[K];
+  uint32_t lo[K], hi[K];   // winner offsets of the two elements of the word (15 = no source)
+};
+template <int K>
+__device__ __forceinline__ void ring_fetch(Ring<K>& rg, int slot, const float* __restrict__ buf, int stride,
+                                           const uint8_t* __restrict__ win, int wstride, int p, int len) {
+  if (p >= 0 && p < len) {
+    rg.v[slot] = *reinterpret_cast<const float2*>(buf + (size_t)p * stride);
+    const uint32_t w = win[p * wstride];
+    rg.lo[slot] = w & 15u; rg.hi[slot] = w >> 4;
+  } else {
+    rg.v[slot] = make_float2(0.f, 0.f);
+    rg.lo[slot] = 15u; rg.hi[slot] = 15u;
+  }
+}
+// window of target k = 0: logical sources -R..R in slots 0..K-1 (position = start + dir * logical index)
+template <int K>
+__device__ __forceinline__ void ring_load(Ring<K>& rg, const float* buf, int stride, const uint8_t* win, int wstride, int start,
+                                          int dir, int len) {
+#pragma unroll
+  for (int m = 0; m < K; ++m) ring_fetch<K>(rg, m, buf, stride, win, wstride, start + dir * (m - K / 2), len);
+}
+template <int K, int DIR>
+__device__ __forceinline__ void ring_walk(Ring<K>& rg, float* buf, int stride, const uint8_t* win, int wstride, int start, int n,
+                                          int len) {
+  constexpr int R = K / 2;
+  for (int k0 = 0; k0 < n; k0 += K) {
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+      const int k = k0 + u;
+      if (k < n) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int mm = 0; mm < K; ++mm) {
+          const int m = DIR > 0 ? mm : K - 1 - mm;        // ascending source POSITION in both directions
+          const int sl = (u + m) % K;                      // slot of window entry m at unrolled step u
+          const uint32_t need = DIR > 0 ? K - 1 - m : m;   // offset that makes that source's winner this target
+          if (rg.lo[sl] == need) a0 += rg.v[sl].x;
+          if (rg.hi[sl] == need) a1 += rg.v[sl].y;
+        }
+        const int t = start + DIR * k;
+        *reinterpret_cast<float2*>(buf + (size_t)t * stride) = make_float2(a0, a1);
+        ring_fetch<K>(rg, u, buf, stride, win, wstride, start + DIR * (k + R + 1), len);   // replaces logical source k - R
+      }
+    }
+  }
+}
+
+template <typename T, int K, int LP, int MAXT>   // MAXT 320: registers capped for 4 (K <= 5) / 3 CTAs per SM
+__global__ void __launch_bounds__(MAXT, MAXT <= 320 ? (K <= 5 ? 4 : 3) : 1) sppf_pool_bwd_inplace_kernel(const T* __restrict__ gcat, const T* __restrict__ y0,
+                                                                    T* __restrict__ gy0, PoolGeom g) {
+  using WD = Word<T>;
+  constexpr int EPL = WD::EPL;
+  static_assert(EPL == 2, "in-place variant: 16-bit dtypes");
+  constexpr int CC = LP * EPL;
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int plane = g.H * g.Wp;
+  float* ga = reinterpret_cast<float*>(smem);                                  // [plane][LP][2] f32 gradients
+  uint8_t* wrow = reinterpret_cast<uint8_t*>(ga + (size_t)plane * LP * EPL);   // [3][plane][LP]
+  uint8_t* wcol = wrow + (size_t)3 * plane * LP;                               // [3][plane][LP]
+  uint32_t* cur = reinterpret_cast<uint32_t*>(ga);                             // recompute phase: two word planes inside ga
+  uint32_t* tmp = cur + (size_t)plane * LP;
+
+  const int chunks = (g.C + CC - 1) / CC;
+  const int b = blockIdx.x / chunks;
+  const int c0 = (blockIdx.x % chunks) * CC;
+  const size_t in_img = (size_t)b * g.H * g.W * g.C;
+  const size_t cat_img = (size_t)b * g.H * g.W * 4 * g.C;
+  const int valid_words = min(LP, (g.C - c0) / EPL);
+  int special = tile_load_words<T, LP>(cur, reinterpret_cast<const uint32_t*>(y0 + in_img + c0), (size_t)g.C / EPL, nullptr, 0,
+                                       g.H, g.W, g.Wp, valid_words, WD::neg_inf());
+  special = __syncthreads_or(special);
+  if (!special) {
+    for (int i = threadIdx.x; i < plane * LP; i += blockDim.x) cur[i] = to_sortable2(cur[i]);
+    __syncthreads();
+  }
+  {  // winners of the three stages: strips split in two segments, interleaved over the threads
+    const int lane = threadIdx.x % LP, sid = threadIdx.x / LP, nstrips = blockDim.x / LP;
+    for (int st = 0; st < 3; ++st) {
+      for (int u = sid; u < g.H * 2; u += nstrips) {
+        const int y = u >> 1, sg = u & 1, i0 = sg ? g.W / 2 : 0, i1 = sg ? g.W : g.W / 2;
+        const uint32_t* sp = cur + (y * g.Wp) * LP + lane;
+        uint32_t* dp = tmp + (y * g.Wp) * LP + lane;
+        uint8_t* wp = wrow + ((size_t)st * plane + y * g.Wp) * LP + lane;
+        if (special) pass1d<T, K>(sp, LP, dp, LP, g.W, wp, LP, i0, i1);
+        else pass1d_key<T, K>(sp, LP, dp, LP, g.W, wp, LP, i0, i1);
+      }
+      __syncthreads();
+      for (int u = sid; u < g.W * 2; u += nstrips) {
+        const int x = u >> 1, sg = u & 1, i0 = sg ? g.H / 2 : 0, i1 = sg ? g.H : g.H / 2;
+        const uint32_t* sp = tmp + x * LP + lane;
+        uint32_t* dp = cur + x * LP + lane;
+        uint8_t* wp = wcol + ((size_t)st * plane + x) * LP + lane;
+        if (special) pass1d<T, K>(sp, g.Wp * LP, dp, g.Wp * LP, g.H, wp, g.Wp * LP, i0, i1);
+        else pass1d_key<T, K>(sp, g.Wp * LP, dp, g.Wp * LP, g.H, wp, g.Wp * LP, i0, i1);
+      }
+      __syncthreads();
+    }
+  }
+  auto load_slice = [&](int slice, bool accumulate) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(gcat + cat_img + (size_t)slice * g.C + c0);
+    if (accumulate) tile_load_f32<T, LP, true>(ga, src, (size_t)4 * g.C / EPL, g.H, g.W, g.Wp, valid_words);
+    else tile_load_f32<T, LP, false>(ga, src, (size_t)4 * g.C / EPL, g.H, g.W, g.Wp, valid_words);
+  };
+  load_slice(3, false);
+  __syncthreads();
+  // routing: first half of the CTA's threads walks the left segments (descending), second half the right ones (warp-uniform)
+  const int per = blockDim.x / 2;
+  const int sg = threadIdx.x >= per ? 1 : 0;
+  const int r_ = threadIdx.x - sg * per;
+  const int lane = r_ % LP, sid = r_ / LP;
+  Ring<K> rg;
+  auto route = [&](float* buf, int stride, const uint8_t* win, int wstride, int len, bool act) {
+    const int mid = len / 2;
+    if (act) ring_load<K>(rg, buf, stride, win, wstride, sg ? mid : mid - 1, sg ? 1 : -1, len);
+    __syncthreads();   // every thread holds its boundary window: the buffer may now be overwritten
+    if (act) {
+      if (sg) ring_walk<K, 1>(rg, buf, stride, win, wstride, mid, len - mid, len);
+      else ring_walk<K, -1>(rg, buf, stride, win, wstride, mid - 1, mid, len);
+    }
+    __syncthreads();
+  };
+  for (int st = 2; st >= 0; --st) {
+    // column-pass backward, then row-pass backward, both in place; then add the concat slice gradient g_st
+    route(ga + ((size_t)sid * LP + lane) * EPL, g.Wp * LP * EPL, wcol + ((size_t)st * plane + sid) * LP + lane, g.Wp * LP, g.H,
+          sid < g.W);
+    route(ga + ((size_t)(sid * g.Wp) * LP + lane) * EPL, LP * EPL, wrow + ((size_t)st * plane + sid * g.Wp) * LP + lane, LP, g.W,
+          sid < g.H);
+    load_slice(st, true);
+    __syncthreads();
+  }
+  tile_store_f32<T, LP>(ga, reinterpret_cast<uint32_t*>(gy0 + in_img + c0), (size_t)g.C / EPL, g.H, g.W, g.Wp, valid_words);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------------------
@@ -643,6 +787,18 @@ int launch_bwd(const void* gcat, const void* y0, void* gy0, PoolGeom g, cudaStre
   // instruction issue, and every extra segment re-scans K-1 sources
   while (g.nseg < 2 && strips * (g.nseg + 1) * LP <= 512 && (g.H < g.W ? g.H : g.W) / (g.nseg + 1) >= K) ++g.nseg;
   if (const char* ov = getenv("B200_SPPF_NSEG")) g.nseg = atoi(ov) > 0 ? atoi(ov) : g.nseg;   // tuning aid
+  if constexpr (EPL == 2) {
+    // 16-bit dtypes, two segments per strip, every strip covered in one sweep: in-place routing (one gradient buffer)
+    const int per = ((strips * LP + 31) / 32) * 32;
+    const char* off = getenv("B200_SPPF_NO_INPLACE");
+    if (g.nseg == 2 && 2 * per <= 512 && g.H >= 2 && g.W >= 2 && !(off && off[0] == '1')) {
+      const size_t smem_ip = plane * LP * EPL * 4 + plane * LP * 6;
+      auto kip = 2 * per <= 320 ? sppf_pool_bwd_inplace_kernel<T, K, LP, 320> : sppf_pool_bwd_inplace_kernel<T, K, LP, 512>;
+      cudaFuncSetAttribute(kip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ip);
+      kip<<<dim3(g.B * chunks), 2 * per, smem_ip, st>>>((const T*)gcat, (const T*)y0, (T*)gy0, g);
+      return check_launch("sppf_pool_bwd");
+    }
+  }
   int threads = ((strips * g.nseg * LP + 31) / 32) * 32;
   if (threads > 512) threads = 512;
   if (threads < 64) threads = 64;
