@@ -59,6 +59,8 @@ def ncu_kernel_name(tag: str):
     import re
 
     fixed = {"b200_cbam_fwd": "b200::cbam_cluster_fwd_kernel<__nv_bfloat16, 8, 1>",
+             "b200_sppf_pool_fwd": "b200::sppf_pool_fwd_kernel<__nv_bfloat16, 5, 16, 0>",
+             "b200_sppf_pool_bwd": "b200::sppf_pool_bwd_inplace_kernel<__nv_bfloat16, 5, 8, 320>",
              "b200_swin_attn_fwd_tc": "b200::swin_attn_fwd_tc_kernel<64>", "b200_swin_attn_bwd_tc": "b200::swin_attn_bwd_tc_kernel<64>",
              "b200_swin_ln1_partition": "b200::swin_ln1_partition_vec_kernel<__nv_bfloat16, 8, 2>",
              "b200_swin_res_ln2": "b200::swin_res_ln2_vec_kernel<__nv_bfloat16, 8, 2>"}

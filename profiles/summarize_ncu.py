@@ -17,7 +17,7 @@ def _num(v):
         return float("nan")
 
 
-MINE = re.compile(r"\b(cbam_\w+_kernel|fold_partials_kernel|bn_\w+_kernel|sppf_pool_(?:fwd|bwd)_kernel|swin_\w+_kernel|gemm_nt_kernel|"
+MINE = re.compile(r"\b(cbam_\w+_kernel|fold_partials_kernel|bn_\w+_kernel|sppf_pool_(?:fwd|bwd)(?:_inplace)?_kernel|swin_\w+_kernel|gemm_nt_kernel|"
                   r"gemm_splitk_kernel|fold_splits_kernel|fold_ln_kernel|fold_rows_kernel|colsum_partial_kernel)\b")
 
 
@@ -59,6 +59,8 @@ def launches(src, dst):
 
 def kernels(src, dst, traffic_dst):
     rows = list(csv.reader(open(src)))
+    while rows and "Kernel Name" not in rows[0]:   # `--log-file` output starts with ncu's ==PROF== lines
+        rows.pop(0)
     h = rows[0]
     want = {"dur_us": "gpu__time_duration.sum", "dram_rd": "dram__bytes_read.sum", "dram_wr": "dram__bytes_write.sum",
             "dram_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm_pct": "sm__throughput.avg.pct_of_peak_sustained_elapsed",
