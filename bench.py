@@ -119,6 +119,17 @@ def cpu_reference_leg(steps, warmup, batch=2):
 
 
 def main():
+    # stdout carries exactly ONE line (the JSON record): libraries that write to fd 1 (NCCL prints its version banner there
+    # when the first communicator is created) are sent to stderr; the record goes to a private copy of the real stdout
+    global print_record
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def print_record(line):
+        real.write(json.dumps(line) + "\n")
+        real.flush()
+
     if os.environ.get("B200_BENCH_WATCHDOG"):  # debugging aid: dump every thread's stack and exit if the run stalls
         import faulthandler
 
@@ -155,7 +166,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "inference_b1_fp32_ms")},
                 "e2e": {"value": cb["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print_record(line)
         return
 
     import torch
@@ -293,7 +304,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = {k: v for k, v in cpu_reference_leg(6, 2).items() if k != "ms_per_step"}
         line["cpu_baseline"]["sample"] += "; inference_b1_fp32_ms = configs[0] (batch 1, eval) on the same cores"
-    print(json.dumps(line))
+    print_record(line)
     if world > 1:
         dist.destroy_process_group()
 
