@@ -19,7 +19,9 @@ def test_signatures_match_reference():
     assert str(inspect.signature(P.CBAM.__init__)) == "(self, channels=None)"  # cbam.py:56
     assert str(inspect.signature(P.ChannelAttention.__init__)) == "(self, in_planes=None, ratio=16)"  # cbam.py:6
     assert str(inspect.signature(P.SpatialAttention.__init__)) == "(self, kernel_size=7)"  # cbam.py:41
-    assert str(inspect.signature(P.SwinBlock.__init__)) == "(self, dim, num_heads=2, window_size=7)"  # swin_block.py:24
+    # swin_block.py:24 -- the reference's parameters in order; `shift_size=0` is the trailing shifted-window extension
+    # (DESIGN.md section 7-4), whose default reproduces the reference block
+    assert str(inspect.signature(P.SwinBlock.__init__)) == "(self, dim, num_heads=2, window_size=7, shift_size=0)"
     assert str(inspect.signature(P.SPPF.__init__)) == "(self, c1, c2, k=5)"  # block.py:204
     with pytest.raises(AssertionError, match="3 or 7"):
         P.SpatialAttention(5)
