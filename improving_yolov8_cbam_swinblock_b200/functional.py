@@ -34,6 +34,7 @@ _lib.register("b200_bn_silu_supported", C.c_int, [_I64, _I32, _I32])
 _lib.register("b200_bn_silu_workspace_bytes", _SZ, [_I64, _I32, _I32])
 _lib.register("b200_bn_silu_fwd", C.c_int, [_VP] * 9 + [_SZ, _I64, _I32, C.c_float, C.c_float, _I32, _I32, _I32, _VP])
 _lib.register("b200_bn_silu_bwd", C.c_int, [_VP] * 10 + [_SZ, _I64, _I32, _I32, _I32, _I32, _VP])
+_lib.register("b200_nhwc_concat", C.c_int, [_VP, _VP, _VP, _I32, _VP, _I64, _I32, _VP])
 
 
 def _nhwc(x: torch.Tensor) -> torch.Tensor:
@@ -51,6 +52,94 @@ def _empty_nhwc(B, Cc, H, W, dtype, device):
 
 def _f32(w: torch.Tensor) -> torch.Tensor:
     return w.detach().to(torch.float32).contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# channel concat / chunk of channels_last maps (the seams around the blocks: C2f, Concat, Detect head)
+# --------------------------------------------------------------------------------------------------
+def _row_strided(t: torch.Tensor):
+    """Row stride S (elements) if t [B,C,H,W] is a channel slice of a dense channels_last map, else None."""
+    B, Cc, H, W = t.shape
+    S = t.stride(3) if W > 1 else (t.stride(2) if H > 1 else (t.stride(0) if B > 1 else Cc))
+    if S < Cc or (Cc > 1 and t.stride(1) != 1):
+        return None
+    if (W > 1 and t.stride(3) != S) or (H > 1 and t.stride(2) != W * S) or (B > 1 and t.stride(0) != H * W * S):
+        return None
+    return S
+
+
+def nhwc_concat_raw(tensors) -> torch.Tensor:
+    """cat(tensors, 1) into a dense channels_last tensor with one vectorised copy kernel; sources may be channel slices."""
+    t0 = tensors[0]
+    B, _, H, W = t0.shape
+    strides = [_row_strided(t) for t in tensors]
+    if any(st is None for st in strides):   # an NCHW-dense operand: convert that one, as the kernels' callers always do
+        tensors = [t if st is not None else _nhwc(t) for t, st in zip(tensors, strides)]
+        strides = [_row_strided(t) for t in tensors]
+    chans = [int(t.shape[1]) for t in tensors]
+    out = _empty_nhwc(B, sum(chans), H, W, t0.dtype, t0.device)
+    n = len(tensors)
+    srcs = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
+    cc = (C.c_int32 * n)(*chans)
+    ss = (C.c_int64 * n)(*[int(v) for v in strides])
+    call("b200_nhwc_concat", C.addressof(srcs), C.addressof(cc), C.addressof(ss), n, ptr(out), B * H * W, dtype_code(t0.dtype),
+         stream_ptr(t0.device))
+    return out
+
+
+def _concat_ok(tensors) -> bool:
+    t0 = tensors[0]
+    return (t0.is_cuda and t0.dim() == 4 and 1 <= len(tensors) <= 8 and t0.dtype in (torch.float32, torch.bfloat16, torch.float16)
+            and all(t.is_cuda and t.dim() == 4 and t.dtype == t0.dtype and t.shape[0] == t0.shape[0] and t.shape[2:] == t0.shape[2:]
+                    for t in tensors))
+
+
+class NhwcConcatFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, *tensors):
+        ctx.chans = [int(t.shape[1]) for t in tensors]
+        return nhwc_concat_raw(tensors)
+
+    @staticmethod
+    def backward(ctx, g):
+        outs, off = [], 0
+        for i, c in enumerate(ctx.chans):   # channel slices of g (views, like aten's cat backward)
+            outs.append(g.narrow(1, off, c) if ctx.needs_input_grad[i] else None)
+            off += c
+        return tuple(outs)
+
+
+class NhwcChunkFn(torch.autograd.Function):
+    """x.chunk(n, 1) whose backward is ONE concat kernel (aten: SplitBackward -> generic strided cat)."""
+
+    @staticmethod
+    def forward(ctx, x, n):
+        parts = x.chunk(n, 1)
+        ctx.meta = (x.shape, x.dtype, x.device, [int(p.shape[1]) for p in parts])
+        return parts
+
+    @staticmethod
+    def backward(ctx, *gs):
+        shape, dtype, device, chans = ctx.meta
+        B, _, H, W = shape
+        gs = [g if g is not None else torch.zeros((B, c, H, W), dtype=dtype, device=device).contiguous(memory_format=torch.channels_last)
+              for g, c in zip(gs, chans)]
+        return nhwc_concat_raw(gs), None
+
+
+def nhwc_concat(tensors) -> torch.Tensor:
+    """Drop-in for ``torch.cat(tensors, 1)`` on 4-D CUDA maps (result in channels_last memory); anything else -> torch.cat."""
+    tensors = list(tensors)
+    if not _concat_ok(tensors):
+        return torch.cat(tensors, 1)
+    return NhwcConcatFn.apply(*tensors)
+
+
+def nhwc_chunk(x: torch.Tensor, n: int):
+    """Drop-in for ``x.chunk(n, 1)`` (views of x) with the concat kernel as its backward."""
+    if not (x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16, torch.float16) and _row_strided(x) is not None):
+        return x.chunk(n, 1)
+    return NhwcChunkFn.apply(x, n)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -111,10 +111,16 @@ class C2f(nn.Module):
         self.cv2 = Conv((2 + n) * self.c, c2, 1)
         self.m = nn.ModuleList(Bottleneck(self.c, self.c, shortcut, g, k=(3, 3), e=1.0) for _ in range(n))
 
+    # DetectionGraph sets blocks["concat"] / blocks["chunk"] here (the channel concat / chunk seams);
+    # None = torch.cat / Tensor.chunk
+    concat = None
+    chunk = None
+
     def forward(self, x):
-        y = list(self.cv1(x).chunk(2, 1))
+        t = self.cv1(x)
+        y = list(t.chunk(2, 1) if self.chunk is None else self.chunk(t, 2))
         y.extend(m(y[-1]) for m in self.m)
-        return self.cv2(torch.cat(y, 1))
+        return self.cv2(torch.cat(y, 1) if self.concat is None else self.concat(y))
 
 
 class Upsample(nn.Upsample):
@@ -135,8 +141,10 @@ class Concat(nn.Module):
         super().__init__()
         self.d = dimension
 
+    concat = None
+
     def forward(self, x):
-        return torch.cat(x, self.d)
+        return torch.cat(x, self.d) if self.concat is None or self.d != 1 else self.concat(x)
 
 
 class DFL(nn.Module):
@@ -179,8 +187,11 @@ class Detect(nn.Module):
             nn.Sequential(Conv(x, c3, 3), Conv(c3, c3, 3), nn.Conv2d(c3, self.nc, 1)) for x in ch)
         self.dfl = DFL(self.reg_max)
 
+    concat = None
+
     def forward(self, x):
-        x = [torch.cat((self.cv2[i](x[i]), self.cv3[i](x[i])), 1) for i in range(self.nl)]
+        cat = (lambda ts: torch.cat(ts, 1)) if self.concat is None else self.concat
+        x = [cat((self.cv2[i](x[i]), self.cv3[i](x[i]))) for i in range(self.nl)]
         if self.training:
             return x
         shape = x[0].shape
@@ -246,6 +257,12 @@ class DetectionGraph(nn.Module):
             for m_ in self.modules():
                 if isinstance(m_, Conv):
                     m_.epilogue = epi
+        cat_, chunk_ = blocks.get("concat"), blocks.get("chunk")  # channel concat / chunk at the seams
+        for m_ in self.modules():
+            if cat_ is not None and isinstance(m_, (C2f, Concat, Detect)):
+                m_.concat = cat_
+            if chunk_ is not None and isinstance(m_, C2f):
+                m_.chunk = chunk_
         self.save = sorted(save)
         self.nc, self.scale = nc, scale
         det = self.model[-1]

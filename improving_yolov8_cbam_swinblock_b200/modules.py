@@ -204,4 +204,5 @@ def _harness_sppf():
 
 
 SPPF = _harness_sppf()
-BLOCKS = {"CBAM": CBAM, "SwinBlock": SwinBlock, "SPPF": SPPF, "conv_epilogue": conv_epilogue}
+BLOCKS = {"CBAM": CBAM, "SwinBlock": SwinBlock, "SPPF": SPPF, "conv_epilogue": conv_epilogue,
+          "concat": Fb.nhwc_concat, "chunk": Fb.nhwc_chunk}

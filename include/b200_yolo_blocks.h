@@ -148,6 +148,17 @@ B200_API int b200_colsum(const void* a, float* out, void* workspace, size_t work
                          int32_t n, int32_t dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * Channel concat of channels_last maps: the seams around the blocks -- `torch.cat(y, 1)` of
+ * C2f.forward (block.py), Concat.forward (conv.py), the Detect head (head.py:66-76), and the backward of
+ * `chunk(2, 1)`.  Source i is a row-strided view [rows, src_channels[i]] with row stride src_row_stride[i]
+ * elements (>= channels: a channel slice of a wider NHWC tensor qualifies); dst is dense [rows, sum channels].
+ * 1..8 sources; 16-byte vectors when every pointer / width / stride allows, element copies otherwise.
+ * srcs / src_channels / src_row_stride are HOST arrays.
+ * ------------------------------------------------------------------------------------------------------ */
+B200_API int b200_nhwc_concat(const void* const* srcs, const int32_t* src_channels, const int64_t* src_row_stride,
+                              int32_t n_src, void* dst, int64_t rows, int32_t dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * tcgen05 GEMM for the SwinBlock's dense contractions (torch F.linear at swin_block.py:51,53):
  *   D[M,N] = epi(A[M,K] * B[N,K]^T + bias[N]),  A/B/D/D2/R in the 16-bit activation dtype (bf16 | f16), f32 accumulate.
  *   epi 0: bias;  epi 1: D = gelu_erf(a), D2 (nullable) = a = pre-activation;  epi 2: D = a + R[M,N] (residual);
