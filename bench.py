@@ -253,11 +253,11 @@ def main():
     if ktimes:
         tot = {k: n * ms for k, (n, ms) in ktimes.items()}
         # `roofline` = the dominant kernel of the hot path proper (CBAM / SPPF / SwinBlock); the Conv-epilogue
-        # launches (SURVEY 8(f)-1 widening) are listed with their own fractions under all_kernels
-        hot = {k: v for k, v in tot.items() if not k.startswith("b200_bn_silu")} or tot
+        # and channel-concat launches (SURVEY 8(f)-1/-2 widening) are listed with their own fractions under all_kernels
+        hot = {k: v for k, v in tot.items() if not k.startswith(("b200_bn_silu", "b200_nhwc_concat"))} or tot
         top = max(hot, key=hot.get)
         n, ms = ktimes[top]
-        w = work.get(top) or sweep.gemm_work(top, peaks) or sweep.bn_work(top)
+        w = work.get(top) or sweep.gemm_work(top, peaks) or sweep.bn_work(top) or sweep.seam_work(top)
         if not w:
             roof = {"kernel": top, "avg_ms": ms, "calls": n, "note": "no algorithmic-work entry",
                     "kernels_ms_per_step": {k: v / args.steps for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
@@ -275,7 +275,7 @@ def main():
     if roof is not None:  # every hand-written kernel of the step: mean ms per launch + fraction of its roofline
         allk = {}
         for k, (n_, ms_) in ktimes.items():
-            w_ = work.get(k) or sweep.gemm_work(k, peaks) or sweep.bn_work(k)
+            w_ = work.get(k) or sweep.gemm_work(k, peaks) or sweep.bn_work(k) or sweep.seam_work(k)
             ent = {"calls_per_step": n_ / args.steps, "avg_ms": round(ms_, 5)}
             if w_:
                 pk = peaks["hbm_gbs"] if w_["bound"] == "hbm" else peaks["bf16_tflops_sustained"]

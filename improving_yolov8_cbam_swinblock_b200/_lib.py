@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200yolo.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 F32, BF16, F16 = 0, 1, 2
 CBAM_FULL, CBAM_CA, CBAM_SA = 0, 1, 2
 

@@ -227,8 +227,8 @@ template <typename T, int VW, int ACT>
 __global__ void __launch_bounds__(kT, 4) bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ gz,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                           float* __restrict__ part, const BnGeo G) {
-  constexpr bool FAST = sizeof(T) == 2;
+                                                           float* __restrict__ part, const long long gzs, const BnGeo G) {
+  constexpr bool FAST = sizeof(T) == 2;   // gzs: row stride of gz in elements (the gradient of a concat slice is a strided view)
   extern __shared__ __align__(16) float red[];   // [ngrp][2][C]
   const int C = G.C, tpr = G.tpr;
   const int rg = threadIdx.x / tpr, ch = threadIdx.x - rg * tpr;
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kT, 4) bn_bwd_reduce_kernel(const T* __restric
       a1[e] = 0.f; a2[e] = 0.f;
     }
     const T* xb = x + (size_t)r0 * C + ch * VW;
-    const T* gb = gz + (size_t)r0 * C + ch * VW;
+    const T* gb = gz + (size_t)r0 * gzs + ch * VW;
     constexpr int RB2 = RB / 2;
     for (int r = rg; r < nrows; r += RB2 * G.ngrp) {
       uint4 rx[RB2], rgz[RB2];
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(kT, 4) bn_bwd_reduce_kernel(const T* __restric
       for (int u = 0; u < RB2; ++u)
         if (r + u * G.ngrp < nrows) {
           rx[u] = ldg_stream16(xb + (size_t)(r + u * G.ngrp) * C);
-          rgz[u] = ldg_stream16(gb + (size_t)(r + u * G.ngrp) * C);
+          rgz[u] = ldg_stream16(gb + (size_t)(r + u * G.ngrp) * gzs);
         }
 #pragma unroll
       for (int u = 0; u < RB2; ++u)
@@ -310,7 +310,8 @@ template <typename T, int VW, int ACT>
 __global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ gz,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                          const float* __restrict__ coef, T* __restrict__ gx, const BnGeo G) {
+                                                          const float* __restrict__ coef, T* __restrict__ gx, const long long gzs,
+                                                          const BnGeo G) {
   constexpr bool FAST = sizeof(T) == 2;
   extern __shared__ __align__(16) float cs[];   // [5][C]: a, b (y = x*a + b), A, Bc, Cc
   const int C = G.C, tpr = G.tpr;
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const T* __restrict__ 
   const long long r0 = (long long)blockIdx.x * G.rpb;
   const int nrows = (int)min((long long)G.rpb, G.M - r0);
   const T* xb = x + (size_t)r0 * C + ch * VW;
-  const T* gb = gz + (size_t)r0 * C + ch * VW;
+  const T* gb = gz + (size_t)r0 * gzs + ch * VW;
   T* ob = gx + (size_t)r0 * C + ch * VW;
   float a[VW], b[VW], kA[VW], kB[VW], kC[VW];   // this thread's channel vector: loaded once as float4s
 #pragma unroll
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const T* __restrict__ 
     for (int u = 0; u < RB2; ++u)
       if (r + u * G.ngrp < nrows) {
         rx[u] = ldg_stream16(xb + (size_t)(r + u * G.ngrp) * C);
-        rgz[u] = ldg_stream16(gb + (size_t)(r + u * G.ngrp) * C);
+        rgz[u] = ldg_stream16(gb + (size_t)(r + u * G.ngrp) * gzs);
       }
 #pragma unroll
     for (int u = 0; u < RB2; ++u)
@@ -433,7 +434,7 @@ extern "C" B200_API int b200_bn_silu_fwd(const void* x, const float* gamma, cons
   });
 }
 
-extern "C" B200_API int b200_bn_silu_bwd(const void* gz, const void* x, const float* gamma, const float* beta,
+extern "C" B200_API int b200_bn_silu_bwd(const void* gz, int64_t gz_row_stride, const void* x, const float* gamma, const float* beta,
                                          const float* mean, const float* rstd, void* gx, float* ggamma, float* gbeta,
                                          void* workspace, size_t workspace_bytes, int64_t rows, int32_t C, int32_t training,
                                          int32_t act, int32_t dtype, void* stream) {
@@ -441,6 +442,9 @@ extern "C" B200_API int b200_bn_silu_bwd(const void* gz, const void* x, const fl
   B200_REQUIRE(gz && x && gamma && beta && mean && rstd && gx && ggamma && gbeta, B200_ERR_SHAPE, "bn_silu_bwd: null tensor pointer");
   BnGeo G;
   if (int rc = make_geo(G, rows, C, dtype, x, gz, gx)) return rc;
+  const long long gzs = gz_row_stride > 0 ? gz_row_stride : C;
+  B200_REQUIRE(gzs >= C && (gzs * (dtype == B200_F32 ? 4 : 2)) % 16 == 0, B200_ERR_ALIGN,
+               "bn_silu_bwd: gz row stride %lld must be >= C and a multiple of 16 bytes", gzs);
   const size_t need = up256((size_t)G.G * 2 * C * 4) + up256((size_t)3 * C * 4);
   B200_REQUIRE(workspace && workspace_bytes >= need, B200_ERR_WORKSPACE, "bn_silu_bwd: workspace %zu < %zu bytes", workspace_bytes, need);
   float* part = (float*)workspace;
@@ -449,12 +453,12 @@ extern "C" B200_API int b200_bn_silu_bwd(const void* gz, const void* x, const fl
   const size_t smem = (size_t)G.ngrp * 2 * C * 4;
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
     constexpr int VW = 16 / (int)sizeof(T);
-    if (act) bn_bwd_reduce_kernel<T, VW, 1><<<G.G, kT, smem, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, part, G);
-    else bn_bwd_reduce_kernel<T, VW, 0><<<G.G, kT, smem, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, part, G);
+    if (act) bn_bwd_reduce_kernel<T, VW, 1><<<G.G, kT, smem, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, part, gzs, G);
+    else bn_bwd_reduce_kernel<T, VW, 0><<<G.G, kT, smem, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, part, gzs, G);
     bn_bwd_final_kernel<<<(C + 7) / 8, kT, 0, st>>>(part, gamma, mean, rstd, ggamma, gbeta, coef, training, G);
     const size_t smc = (size_t)5 * C * 4;
-    if (act) bn_bwd_apply_kernel<T, VW, 1><<<G.G, kT, smc, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, coef, (T*)gx, G);
-    else bn_bwd_apply_kernel<T, VW, 0><<<G.G, kT, smc, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, coef, (T*)gx, G);
+    if (act) bn_bwd_apply_kernel<T, VW, 1><<<G.G, kT, smc, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, coef, (T*)gx, gzs, G);
+    else bn_bwd_apply_kernel<T, VW, 0><<<G.G, kT, smc, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, coef, (T*)gx, gzs, G);
     return check_launch("bn_silu_bwd");
   });
 }

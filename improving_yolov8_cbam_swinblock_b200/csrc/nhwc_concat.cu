@@ -113,3 +113,72 @@ extern "C" B200_API int b200_nhwc_concat(const void* const* srcs, const int32_t*
   else nhwc_concat_kernel<uint16_t><<<(unsigned)blocks, kT, 0, st>>>(P);
   return check_launch("nhwc_concat");
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Input seam: uint8 NCHW image batch -> scaled float NHWC in the compute dtype, one pass.  Replaces the trainer's
+// `img.float() / 255` (detect/train.py:100) + channels_last conversion + autocast's cast of the first conv input
+// (four full passes over a 315 MB fp32 tensor) by one read of the uint8 batch and one write of the 16-bit map.
+// Bit-identical to that chain on the GPU: ATen's CUDA division by a host scalar multiplies by the f32 reciprocal
+// (`a * (1 / b)`, BinaryDivTrueKernel.cu), so this does too, then one round-to-nearest-even conversion.
+// ---------------------------------------------------------------------------------------------------------
+namespace b200 {
+namespace {
+
+template <typename T, int CH>
+__global__ void __launch_bounds__(256) u8_to_nhwc_kernel(const uint8_t* __restrict__ img, T* __restrict__ out, long long hw,
+                                                         long long quads, float inv) {
+  // thread = 4 consecutive pixels of one image: CH uchar4 loads (one per plane), 4*CH contiguous output elements
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (long long)gridDim.x * blockDim.x) {
+    const long long hq = hw / 4;
+    const long long b = q / hq, p4 = q - b * hq;
+    const uint8_t* src = img + (size_t)b * CH * hw + (size_t)p4 * 4;
+    uchar4 v[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) v[c] = *reinterpret_cast<const uchar4*>(src + (size_t)c * hw);
+    alignas(16) T o[4 * CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      o[0 * CH + c] = DT<T>::from_f((float)v[c].x * inv);
+      o[1 * CH + c] = DT<T>::from_f((float)v[c].y * inv);
+      o[2 * CH + c] = DT<T>::from_f((float)v[c].z * inv);
+      o[3 * CH + c] = DT<T>::from_f((float)v[c].w * inv);
+    }
+    T* dst = out + ((size_t)b * hw + (size_t)p4 * 4) * CH;
+    // 4*CH elements: 8-byte aligned for every CH when T is 16-bit (4*CH*2 bytes per thread), 16-byte for f32
+    constexpr int WORDS = 4 * CH * (int)sizeof(T) / 8;
+    const uint2* ow = reinterpret_cast<const uint2*>(o);
+#pragma unroll
+    for (int w = 0; w < WORDS; ++w) reinterpret_cast<uint2*>(dst)[w] = ow[w];
+  }
+}
+
+template <typename T>
+int launch_u8(const uint8_t* img, void* out, int B, int C, long long hw, float inv, cudaStream_t st) {
+  const long long quads = (long long)B * hw / 4;
+  long long blocks = (quads + 255) / 256;
+  const long long cap = (long long)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  switch (C) {
+    case 1: u8_to_nhwc_kernel<T, 1><<<(unsigned)blocks, 256, 0, st>>>(img, (T*)out, hw, quads, inv); break;
+    case 2: u8_to_nhwc_kernel<T, 2><<<(unsigned)blocks, 256, 0, st>>>(img, (T*)out, hw, quads, inv); break;
+    case 3: u8_to_nhwc_kernel<T, 3><<<(unsigned)blocks, 256, 0, st>>>(img, (T*)out, hw, quads, inv); break;
+    default: u8_to_nhwc_kernel<T, 4><<<(unsigned)blocks, 256, 0, st>>>(img, (T*)out, hw, quads, inv); break;
+  }
+  return check_launch("u8_to_nhwc");
+}
+
+}  // namespace
+}  // namespace b200
+
+extern "C" B200_API int b200_u8_to_nhwc(const void* img, void* out, int32_t B, int32_t C, int32_t H, int32_t W, float divisor,
+                                        int32_t dtype, void* stream) {
+  B200_REQUIRE(img && out, B200_ERR_SHAPE, "u8_to_nhwc: null pointer");
+  B200_REQUIRE(B > 0 && C >= 1 && C <= 4 && H > 0 && W > 0, B200_ERR_SHAPE, "u8_to_nhwc: bad shape B=%d C=%d H=%d W=%d (1..4 channels)", B, C, H, W);
+  const long long hw = (long long)H * W;
+  B200_REQUIRE(hw % 4 == 0, B200_ERR_UNSUPPORTED, "u8_to_nhwc: H*W=%lld must be a multiple of 4", hw);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(img) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, B200_ERR_ALIGN,
+               "u8_to_nhwc: img must be 4-byte and out 16-byte aligned");
+  B200_REQUIRE(divisor != 0.f, B200_ERR_SHAPE, "u8_to_nhwc: divisor is zero");
+  cudaStream_t st = (cudaStream_t)stream;
+  return B200_DISPATCH_DTYPE(dtype, [&]() -> int { return launch_u8<T>(static_cast<const uint8_t*>(img), out, B, C, hw, 1.0f / divisor, st); });
+}

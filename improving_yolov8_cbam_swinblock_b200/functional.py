@@ -33,8 +33,9 @@ _lib.register("b200_colsum", C.c_int, [_VP] * 3 + [_SZ] + [_I64] + [_I32] * 2 + 
 _lib.register("b200_bn_silu_supported", C.c_int, [_I64, _I32, _I32])
 _lib.register("b200_bn_silu_workspace_bytes", _SZ, [_I64, _I32, _I32])
 _lib.register("b200_bn_silu_fwd", C.c_int, [_VP] * 9 + [_SZ, _I64, _I32, C.c_float, C.c_float, _I32, _I32, _I32, _VP])
-_lib.register("b200_bn_silu_bwd", C.c_int, [_VP] * 10 + [_SZ, _I64, _I32, _I32, _I32, _I32, _VP])
+_lib.register("b200_bn_silu_bwd", C.c_int, [_VP, _I64] + [_VP] * 9 + [_SZ, _I64, _I32, _I32, _I32, _I32, _VP])
 _lib.register("b200_nhwc_concat", C.c_int, [_VP, _VP, _VP, _I32, _VP, _I64, _I32, _VP])
+_lib.register("b200_u8_to_nhwc", C.c_int, [_VP, _VP] + [_I32] * 4 + [C.c_float, _I32, _VP])
 
 
 def _nhwc(x: torch.Tensor) -> torch.Tensor:
@@ -83,7 +84,7 @@ def nhwc_concat_raw(tensors) -> torch.Tensor:
     cc = (C.c_int32 * n)(*chans)
     ss = (C.c_int64 * n)(*[int(v) for v in strides])
     call("b200_nhwc_concat", C.addressof(srcs), C.addressof(cc), C.addressof(ss), n, ptr(out), B * H * W, dtype_code(t0.dtype),
-         stream_ptr(t0.device))
+         stream_ptr(t0.device), tag=f"b200_nhwc_concat[{B * H * W}x{sum(chans)}]")
     return out
 
 
@@ -133,6 +134,18 @@ def nhwc_concat(tensors) -> torch.Tensor:
     if not _concat_ok(tensors):
         return torch.cat(tensors, 1)
     return NhwcConcatFn.apply(*tensors)
+
+
+def u8_to_nhwc(img: torch.Tensor, dtype: torch.dtype = torch.float32, divisor: float = 255.0) -> torch.Tensor:
+    """uint8 NCHW image batch -> ``img.float() / divisor`` in ``dtype`` and channels_last memory, one kernel (the trainer's
+    input seam, detect/train.py:100).  Bit-identical to ATen's CUDA ``img.float() / divisor`` (a multiply by the f32 reciprocal)
+    followed by one cast to ``dtype``."""
+    if not (img.is_cuda and img.dtype == torch.uint8 and img.dim() == 4 and img.is_contiguous()):
+        raise RuntimeError("u8_to_nhwc: expected a contiguous uint8 CUDA tensor [B,C,H,W]")
+    B, Cc, H, W = img.shape
+    out = _empty_nhwc(B, Cc, H, W, dtype, img.device)
+    call("b200_u8_to_nhwc", ptr(img), ptr(out), B, Cc, H, W, float(divisor), dtype_code(dtype), stream_ptr(img.device))
+    return out
 
 
 def nhwc_chunk(x: torch.Tensor, n: int):
@@ -213,14 +226,17 @@ class BnActFn(torch.autograd.Function):
         x, wf, bf, mean, rstd = ctx.saved_tensors
         rows, Cc, training, act, wdt, bdt = ctx.cfg
         dev, code = x.device, dtype_code(x.dtype)
-        gz = _nhwc(gz.to(x.dtype))
+        gz = gz.to(x.dtype)
+        gzs = _row_strided(gz)   # a channel slice of a concat's gradient is read in place (row stride > C)
+        if gzs is None or (gzs * gz.element_size()) % 16 or gz.data_ptr() % 16:
+            gz, gzs = _nhwc(gz), Cc
         gx = torch.empty_like(x)
         gg = torch.empty(Cc, dtype=torch.float32, device=dev)
         gb = torch.empty(Cc, dtype=torch.float32, device=dev)
         nbytes = lib().b200_bn_silu_workspace_bytes(rows, Cc, code)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            call("b200_bn_silu_bwd", ptr(gz), ptr(x), ptr(wf), ptr(bf), ptr(mean), ptr(rstd), ptr(gx), ptr(gg), ptr(gb),
+            call("b200_bn_silu_bwd", ptr(gz), gzs, ptr(x), ptr(wf), ptr(bf), ptr(mean), ptr(rstd), ptr(gx), ptr(gg), ptr(gb),
                                      ptr(ws), nbytes, rows, Cc, training, act, code, stream_ptr(dev),
                                      tag=f"b200_bn_silu_bwd[{rows}x{Cc}]")
         return gx, gg.to(wdt), gb.to(bdt), None, None, None, None, None, None

@@ -119,7 +119,12 @@ class C2f(nn.Module):
     def forward(self, x):
         t = self.cv1(x)
         y = list(t.chunk(2, 1) if self.chunk is None else self.chunk(t, 2))
-        y.extend(m(y[-1]) for m in self.m)
+        # the bottlenecks' 3x3 convs and shortcut adds want a dense operand: one vectorised copy of the second half here
+        # instead of cuDNN's generic strided `.contiguous()` and a strided element-wise add per bottleneck
+        inp = y[-1] if self.concat is None else self.concat([y[-1]])
+        for m in self.m:
+            inp = m(inp)
+            y.append(inp)
         return self.cv2(torch.cat(y, 1) if self.concat is None else self.concat(y))
 
 

@@ -101,10 +101,13 @@ class DetectionLoss:
     def __call__(self, feats, batch, max_boxes=None):
         device = feats[0].device
         bs = feats[0].shape[0]
-        x = torch.cat([f.reshape(bs, self.no, -1) for f in feats], 2)
-        pred_distri, pred_scores = x.split((self.reg_max * 4, self.nc), 1)
-        pred_scores = pred_scores.permute(0, 2, 1).contiguous()
-        pred_distri = pred_distri.permute(0, 2, 1).contiguous()
+        # loss.py:207-213 builds [B, no, A] and permutes to [B, A, ·]; the same values are gathered anchor-major directly:
+        # for channels_last maps `permute(0,2,3,1).reshape(B, HW, no)` is a free view, so the three per-level reshape copies
+        # and the two permute+contiguous passes collapse into this one cat (in the activation dtype) + one cast to f32
+        xa = torch.cat([f.permute(0, 2, 3, 1).reshape(bs, -1, self.no) for f in feats], 1).float()
+        pred_distri, pred_scores = xa.split((self.reg_max * 4, self.nc), 2)
+        pred_scores = pred_scores.contiguous()
+        pred_distri = pred_distri.contiguous()
         dtype = pred_scores.dtype
         h, w = feats[0].shape[2:]
         wh = torch.stack((torch.full((), w * self.strides[0], device=device),      # fill kernels, no host->device copy:

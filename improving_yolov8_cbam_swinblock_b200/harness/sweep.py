@@ -54,6 +54,17 @@ def bn_work(tag: str, s: int = 2):
     return {"bound": "hbm", "amount": 3.0 * n * s, "note": "3*N*s: read x and g once, write g_x once (the kernel reads both twice: reduce, apply)"}
 
 
+def seam_work(tag: str, s: int = 2):
+    """Roofline entry for a shape-tagged channel-concat launch: b200_nhwc_concat[rows x C_total]."""
+    import re
+
+    m = re.match(r"b200_nhwc_concat\[(\d+)x(\d+)\]", tag)
+    if not m:
+        return None
+    n = int(m.group(1)) * int(m.group(2))
+    return {"bound": "hbm", "amount": 2.0 * n * s, "note": "2*N*s: every source element read once, written once"}
+
+
 def ncu_kernel_name(tag: str):
     """ABI entry point (or shape-tagged GEMM) -> kernel instantiation name used in profiles/traffic_rNN.json."""
     import re

@@ -80,6 +80,7 @@ class Trainer:
         self.opt = torch.optim.SGD(param_groups(model), lr=lr, momentum=momentum, nesterov=True, fused=fused)
         self.ema = EMA(model) if ema else None
         self.max_boxes = None
+        self._input_prep = blocks.get("input_prep")   # the uint8 -> float NHWC input seam (None = stock ops)
         self._params = [p for p in model.parameters() if p.requires_grad]
         self._flat = None
         if world_size > 1:
@@ -96,13 +97,19 @@ class Trainer:
 
     # ---- the step, in two halves so that the gradient exchange sits between them ---------------------------------
     def _forward_loss(self, dev_batch):
-        img = dev_batch["img"].float() / 255  # detect/train.py:100
-        if self.channels_last:
-            img = img.contiguous(memory_format=torch.channels_last)
         use_amp = self.amp_dtype is not None and self.amp_dtype != torch.float32
+        raw = dev_batch["img"]
+        if self._input_prep is not None and raw.is_cuda and raw.dtype == torch.uint8 and self.channels_last and raw.is_contiguous() \
+                and raw.shape[1] <= 4 and (raw.shape[2] * raw.shape[3]) % 4 == 0:
+            # one kernel: uint8 NCHW -> f32 division -> compute dtype, NHWC (what autocast hands the first conv anyway)
+            img = self._input_prep(raw, self.amp_dtype if use_amp else torch.float32, 255.0)
+        else:
+            img = raw.float() / 255  # detect/train.py:100
+            if self.channels_last:
+                img = img.contiguous(memory_format=torch.channels_last)
         with torch.autocast(self.device.type, dtype=self.amp_dtype or torch.bfloat16, enabled=use_amp):
             feats = self.model(img)
-            return self.criterion([f.float() for f in feats], dev_batch, max_boxes=self.max_boxes)
+            return self.criterion(feats, dev_batch, max_boxes=self.max_boxes)   # the loss casts to f32 after gathering
 
     def _fwd_bwd(self, dev_batch):
         if self._flat is not None:

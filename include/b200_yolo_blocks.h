@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 2
+#define B200_ABI_VERSION 3
 #if defined(__GNUC__)
 #define B200_API __attribute__((visibility("default")))
 #else
@@ -157,6 +157,11 @@ B200_API int b200_colsum(const void* a, float* out, void* workspace, size_t work
  * ------------------------------------------------------------------------------------------------------ */
 B200_API int b200_nhwc_concat(const void* const* srcs, const int32_t* src_channels, const int64_t* src_row_stride,
                               int32_t n_src, void* dst, int64_t rows, int32_t dtype, void* stream);
+/* Input seam: uint8 NCHW image batch -> `img.float() / divisor` in `dtype`, NHWC, one pass (detect/train.py:100 +
+ * the channels_last conversion + autocast's cast of the first conv input).  Bit-identical to ATen's CUDA division by a
+ * host scalar (multiply by the f32 reciprocal) followed by one round-to-nearest conversion.  1..4 channels, H*W % 4 == 0. */
+B200_API int b200_u8_to_nhwc(const void* img, void* out, int32_t B, int32_t C, int32_t H, int32_t W, float divisor,
+                             int32_t dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * tcgen05 GEMM for the SwinBlock's dense contractions (torch F.linear at swin_block.py:51,53):
@@ -206,8 +211,10 @@ B200_API int b200_bn_silu_fwd(const void* x, const float* gamma, const float* be
                               size_t workspace_bytes, int64_t rows, int32_t C, float eps, float momentum,
                               int32_t training, int32_t act, int32_t dtype, void* stream);
 /* backward: gx = dL/dx, ggamma / gbeta OVERWRITTEN; mean/rstd = the statistics the forward normalised with
- * (training == 0: pass running_mean and 1/sqrt(running_var + eps)).  Deterministic (no atomics). */
-B200_API int b200_bn_silu_bwd(const void* gz, const void* x, const float* gamma, const float* beta, const float* mean,
+ * (training == 0: pass running_mean and 1/sqrt(running_var + eps)).  Deterministic (no atomics).
+ * gz_row_stride: elements between consecutive rows of gz (0 = dense = C); the gradient that reaches a Conv feeding a
+ * concat is a channel slice of the concat's gradient, read in place instead of being copied first. */
+B200_API int b200_bn_silu_bwd(const void* gz, int64_t gz_row_stride, const void* x, const float* gamma, const float* beta, const float* mean,
                               const float* rstd, void* gx, float* ggamma, float* gbeta, void* workspace,
                               size_t workspace_bytes, int64_t rows, int32_t C, int32_t training, int32_t act,
                               int32_t dtype, void* stream);

@@ -23,7 +23,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     for s in syms:
         assert hasattr(h, s), f"{s} declared in the header but not exported by libb200yolo.so"
     assert sorted(_lib.declared_symbols()) == syms, "python binding table and header disagree"
-    assert _lib.lib().b200_abi_version() == 2
+    assert _lib.lib().b200_abi_version() == 3
 
 
 def test_error_convention_without_gpu():

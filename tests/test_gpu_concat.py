@@ -70,3 +70,16 @@ def test_concat_rejects_too_many_sources_by_falling_back():
 
     xs = [_cl(torch.randn(1, 8, 4, 4, device="cuda")) for _ in range(9)]   # > 8 sources: stock torch.cat
     assert torch.equal(Fb.nhwc_concat(xs), torch.cat(xs, 1))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("shape", [(2, 3, 64, 64), (3, 1, 8, 12), (1, 4, 6, 10), (2, 2, 5, 4)])
+def test_u8_to_nhwc_is_bit_identical_to_the_reference_chain(dtype, shape):
+    from improving_yolov8_cbam_swinblock_b200 import functional as Fb
+
+    torch.manual_seed(3)
+    img = torch.randint(0, 256, shape, dtype=torch.uint8, device="cuda")
+    out = Fb.u8_to_nhwc(img, dtype, 255.0)
+    ref = (img.float() / 255).to(dtype)          # detect/train.py:100, then autocast's cast of the conv input
+    assert out.is_contiguous(memory_format=torch.channels_last) or shape[1] == 1
+    assert torch.equal(out, ref)
