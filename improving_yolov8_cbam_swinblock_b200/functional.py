@@ -36,6 +36,8 @@ _lib.register("b200_bn_silu_fwd", C.c_int, [_VP] * 9 + [_SZ, _I64, _I32, C.c_flo
 _lib.register("b200_bn_silu_bwd", C.c_int, [_VP, _I64] + [_VP] * 9 + [_SZ, _I64, _I32, _I32, _I32, _I32, _VP])
 _lib.register("b200_nhwc_concat", C.c_int, [_VP, _VP, _VP, _I32, _VP, _I64, _I32, _VP])
 _lib.register("b200_u8_to_nhwc", C.c_int, [_VP, _VP] + [_I32] * 4 + [C.c_float, _I32, _VP])
+_lib.register("b200_nhwc_upsample_fwd", C.c_int, [_VP, _VP] + [_I32] * 7 + [_VP])
+_lib.register("b200_nhwc_upsample_bwd", C.c_int, [_VP, _I64, _VP] + [_I32] * 7 + [_VP])
 
 
 def _nhwc(x: torch.Tensor) -> torch.Tensor:
@@ -146,6 +148,35 @@ def u8_to_nhwc(img: torch.Tensor, dtype: torch.dtype = torch.float32, divisor: f
     out = _empty_nhwc(B, Cc, H, W, dtype, img.device)
     call("b200_u8_to_nhwc", ptr(img), ptr(out), B, Cc, H, W, float(divisor), dtype_code(dtype), stream_ptr(img.device))
     return out
+
+
+class NhwcUpsampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, sh, sw):
+        x = _nhwc(x)
+        B, Cc, H, W = x.shape
+        ctx.cfg = (B, Cc, H, W, sh, sw)
+        out = _empty_nhwc(B, Cc, H * sh, W * sw, x.dtype, x.device)
+        call("b200_nhwc_upsample_fwd", ptr(x), ptr(out), B, Cc, H, W, sh, sw, dtype_code(x.dtype), stream_ptr(x.device))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, Cc, H, W, sh, sw = ctx.cfg
+        gs = _row_strided(g)   # a channel slice of the following Concat's gradient is read in place
+        if gs is None or (gs * g.element_size()) % 16 or g.data_ptr() % 16:
+            g, gs = _nhwc(g), Cc
+        gin = _empty_nhwc(B, Cc, H, W, g.dtype, g.device)
+        call("b200_nhwc_upsample_bwd", ptr(g), gs, ptr(gin), B, Cc, H, W, sh, sw, dtype_code(g.dtype), stream_ptr(g.device))
+        return gin, None, None
+
+
+def nhwc_upsample_nearest(x: torch.Tensor, sh: int, sw: int) -> torch.Tensor:
+    """``F.interpolate(x, scale_factor=(sh, sw), mode="nearest")`` for integer factors on a CUDA map, channels_last result."""
+    if not (x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16, torch.float16)
+            and (x.shape[1] * x.element_size()) % 16 == 0):
+        return torch.nn.functional.interpolate(x, scale_factor=(float(sh), float(sw)), mode="nearest")
+    return NhwcUpsampleFn.apply(x, int(sh), int(sw))
 
 
 def nhwc_chunk(x: torch.Tensor, n: int):

@@ -134,7 +134,14 @@ class Upsample(nn.Upsample):
     nearest-neighbour upsampling only copies values, so staying in bf16/f16 is bit-identical (dtype/layout at
     the seams of the path).  Same constructor, no parameters, so state_dicts are unaffected."""
 
+    upsample = None  # DetectionGraph sets blocks["upsample"] here: callable (x, sh, sw) for integer nearest factors
+
     def forward(self, x):
+        sf = self.scale_factor
+        if self.upsample is not None and x.is_cuda and self.mode == "nearest" and self.size is None and sf is not None:
+            sh, sw = (sf, sf) if not isinstance(sf, (tuple, list)) else sf
+            if float(sh).is_integer() and float(sw).is_integer():
+                return self.upsample(x, int(sh), int(sw))   # dtype-preserving, like the branch below
         if x.is_cuda and self.mode == "nearest" and torch.is_autocast_enabled("cuda"):
             with torch.autocast("cuda", enabled=False):
                 return super().forward(x)
@@ -268,6 +275,8 @@ class DetectionGraph(nn.Module):
                 m_.concat = cat_
             if chunk_ is not None and isinstance(m_, C2f):
                 m_.chunk = chunk_
+            if blocks.get("upsample") is not None and isinstance(m_, Upsample):
+                m_.upsample = blocks["upsample"]
         self.save = sorted(save)
         self.nc, self.scale = nc, scale
         det = self.model[-1]

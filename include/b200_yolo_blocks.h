@@ -162,6 +162,14 @@ B200_API int b200_nhwc_concat(const void* const* srcs, const int32_t* src_channe
  * host scalar (multiply by the f32 reciprocal) followed by one round-to-nearest conversion.  1..4 channels, H*W % 4 == 0. */
 B200_API int b200_u8_to_nhwc(const void* img, void* out, int32_t B, int32_t C, int32_t H, int32_t W, float divisor,
                              int32_t dtype, void* stream);
+/* Nearest-neighbour up-sampling by integer factors (sh, sw) on NHWC maps -- the `nn.Upsample(None, 2, "nearest")` rows
+ * of the yaml head -- and its backward (f32 sum of the sh*sw gradients of one input pixel, fixed order).  H, W are the
+ * INPUT sizes; C must span a multiple of 16 bytes.  gout_row_stride: elements between consecutive pixels of gout
+ * (0 = dense = C; a concat-slice gradient is read in place). */
+B200_API int b200_nhwc_upsample_fwd(const void* x, void* out, int32_t B, int32_t C, int32_t H, int32_t W, int32_t sh,
+                                    int32_t sw, int32_t dtype, void* stream);
+B200_API int b200_nhwc_upsample_bwd(const void* gout, int64_t gout_row_stride, void* gin, int32_t B, int32_t C, int32_t H,
+                                    int32_t W, int32_t sh, int32_t sw, int32_t dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * tcgen05 GEMM for the SwinBlock's dense contractions (torch F.linear at swin_block.py:51,53):

@@ -83,3 +83,37 @@ def test_u8_to_nhwc_is_bit_identical_to_the_reference_chain(dtype, shape):
     ref = (img.float() / 255).to(dtype)          # detect/train.py:100, then autocast's cast of the conv input
     assert out.is_contiguous(memory_format=torch.channels_last) or shape[1] == 1
     assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("shape,sh,sw", [((2, 64, 10, 12), 2, 2), ((3, 8, 5, 7), 2, 2), ((1, 16, 4, 6), 3, 1), ((2, 24, 3, 3), 1, 2)])
+def test_nearest_upsample_forward_and_backward_match_aten(dtype, shape, sh, sw):
+    import torch.nn.functional as F
+
+    from improving_yolov8_cbam_swinblock_b200 import functional as Fb
+
+    if (shape[1] * torch.empty(0, dtype=dtype).element_size()) % 16:
+        pytest.skip("channel width below one 16-byte vector: stock op")
+    torch.manual_seed(4)
+    x = _cl(torch.randn(shape, device="cuda").to(dtype)).requires_grad_(True)
+    out = Fb.nhwc_upsample_nearest(x, sh, sw)
+    ref = F.interpolate(x.detach().float(), scale_factor=(float(sh), float(sw)), mode="nearest").to(dtype)
+    assert torch.equal(out, ref)                     # pure data movement
+    g = _cl(torch.randn_like(out))
+    out.backward(g)
+    gref = g.float().view(shape[0], shape[1], shape[2], sh, shape[3], sw).sum((3, 5))   # f32 sum of the sh*sw gradients
+    tol = 0 if dtype == torch.float32 else 2.0 ** -7
+    assert torch.allclose(x.grad.float(), gref.to(dtype).float(), rtol=tol, atol=1e-6 if tol == 0 else tol)
+
+
+def test_nearest_upsample_backward_reads_a_concat_slice_in_place():
+    from improving_yolov8_cbam_swinblock_b200 import functional as Fb
+
+    torch.manual_seed(5)
+    x = _cl(torch.randn(2, 32, 6, 6, device="cuda").bfloat16()).requires_grad_(True)
+    other = _cl(torch.randn(2, 16, 12, 12, device="cuda").bfloat16())
+    z = Fb.nhwc_concat([Fb.nhwc_upsample_nearest(x, 2, 2), other])
+    w = _cl(torch.randn_like(z))
+    (z.float() * w.float()).sum().backward()
+    gref = w[:, :32].float().view(2, 32, 6, 2, 6, 2).sum((3, 5)).bfloat16()
+    assert torch.allclose(x.grad.float(), gref.float(), rtol=2.0 ** -7, atol=2.0 ** -7)
