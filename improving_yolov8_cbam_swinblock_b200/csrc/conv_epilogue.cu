@@ -83,6 +83,7 @@ template <bool FAST> __device__ __forceinline__ float sigmoid_t(float y) {
   return __frcp_rn(1.f + __expf(-y));
 }
 
+constexpr int kFW = 4;  // finalize kernels: warps per channel
 constexpr int RB = 4;   // rows in flight per thread: RB independent 16-byte loads before any use
 
 // per-CTA additive reduction of NV values per channel held by the row groups: red[ngrp][NV][C] -> out via f(c, v[NV])
@@ -146,18 +147,30 @@ __global__ void __launch_bounds__(kT) bn_final_kernel(const T* __restrict__ x, c
                                                       float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                       float* __restrict__ scsh, float eps, float momentum, int training,
                                                       const BnGeo G) {
-  const int lane = threadIdx.x & 31, c = blockIdx.x * (kT / 32) + (threadIdx.x >> 5), C = G.C;
-  if (c >= C) return;
+  // kFW warps per channel: the G partial rows (up to 16 per SM) are summed by 128 lanes with 2 loads in flight each --
+  // one warp per channel made this 8-CTA kernel a 10 us latency chain, 59 times per step
+  __shared__ float fs[kT / 32][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = warp % kFW, C = G.C;
+  const int c = blockIdx.x * (kT / 32 / kFW) + warp / kFW;
+  const bool live = c < C;
   float mean, rstd;
   if (training) {
     float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-    int g = lane;
-    for (; g + 32 < G.G; g += 64) {
-      s0 += part[(size_t)g * 2 * C + c]; q0 += part[(size_t)g * 2 * C + C + c];
-      s1 += part[(size_t)(g + 32) * 2 * C + c]; q1 += part[(size_t)(g + 32) * 2 * C + C + c];
+    if (live) {
+      int g = sub * 32 + lane;
+      for (; g + 32 * kFW < G.G; g += 64 * kFW) {
+        s0 += part[(size_t)g * 2 * C + c]; q0 += part[(size_t)g * 2 * C + C + c];
+        s1 += part[(size_t)(g + 32 * kFW) * 2 * C + c]; q1 += part[(size_t)(g + 32 * kFW) * 2 * C + C + c];
+      }
+      if (g < G.G) { s0 += part[(size_t)g * 2 * C + c]; q0 += part[(size_t)g * 2 * C + C + c]; }
     }
-    if (g < G.G) { s0 += part[(size_t)g * 2 * C + c]; q0 += part[(size_t)g * 2 * C + C + c]; }
-    const float S = warp_sum(s0 + s1), Q = warp_sum(q0 + q1);
+    const float Sw = warp_sum(s0 + s1), Qw = warp_sum(q0 + q1);
+    if (lane == 0) { fs[warp][0] = Sw; fs[warp][1] = Qw; }
+    __syncthreads();
+    if (!live || sub != 0) return;
+    float S = 0.f, Q = 0.f;
+#pragma unroll
+    for (int k = 0; k < kFW; ++k) { S += fs[warp + k][0]; Q += fs[warp + k][1]; }
     const float dm = S * G.invM;
     mean = DT<T>::to_f(x[c]) + dm;
     const float m2 = fmaxf(Q - S * dm, 0.f);
@@ -169,6 +182,7 @@ __global__ void __launch_bounds__(kT) bn_final_kernel(const T* __restrict__ x, c
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
     }
   } else {
+    if (!live || sub != 0) return;
     mean = running_mean[c];
     rstd = rsqrtf(running_var[c] + eps);
   }
@@ -282,16 +296,26 @@ __global__ void __launch_bounds__(kT) bn_bwd_final_kernel(const float* __restric
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           float* __restrict__ ggamma, float* __restrict__ gbeta,
                                                           float* __restrict__ coef, int training, const BnGeo G) {
-  const int lane = threadIdx.x & 31, c = blockIdx.x * (kT / 32) + (threadIdx.x >> 5), C = G.C;
-  if (c >= C) return;
+  __shared__ float fs[kT / 32][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = warp % kFW, C = G.C;
+  const int c = blockIdx.x * (kT / 32 / kFW) + warp / kFW;
+  const bool live = c < C;
   float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-  int g = lane;
-  for (; g + 32 < G.G; g += 64) {
-    s0 += part[(size_t)g * 2 * C + c]; q0 += part[(size_t)g * 2 * C + C + c];
-    s1 += part[(size_t)(g + 32) * 2 * C + c]; q1 += part[(size_t)(g + 32) * 2 * C + C + c];
+  if (live) {
+    int g = sub * 32 + lane;
+    for (; g + 32 * kFW < G.G; g += 64 * kFW) {
+      s0 += part[(size_t)g * 2 * C + c]; q0 += part[(size_t)g * 2 * C + C + c];
+      s1 += part[(size_t)(g + 32 * kFW) * 2 * C + c]; q1 += part[(size_t)(g + 32 * kFW) * 2 * C + C + c];
+    }
+    if (g < G.G) { s0 += part[(size_t)g * 2 * C + c]; q0 += part[(size_t)g * 2 * C + C + c]; }
   }
-  if (g < G.G) { s0 += part[(size_t)g * 2 * C + c]; q0 += part[(size_t)g * 2 * C + C + c]; }
-  const float sgy = warp_sum(s0 + s1), sgyx = warp_sum(q0 + q1);
+  const float Sw = warp_sum(s0 + s1), Qw = warp_sum(q0 + q1);
+  if (lane == 0) { fs[warp][0] = Sw; fs[warp][1] = Qw; }
+  __syncthreads();
+  if (!live || sub != 0) return;
+  float sgy = 0.f, sgyx = 0.f;
+#pragma unroll
+  for (int k = 0; k < kFW; ++k) { sgy += fs[warp + k][0]; sgyx += fs[warp + k][1]; }
   if (lane == 0) {
     const float mu = mean[c], rs = rstd[c], ga = gamma[c];
     const float gg = rs * (sgyx - mu * sgy);
@@ -426,7 +450,7 @@ extern "C" B200_API int b200_bn_silu_fwd(const void* x, const float* gamma, cons
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
     constexpr int VW = 16 / (int)sizeof(T);
     if (training) bn_stats_kernel<T, VW><<<G.G, kT, smem, st>>>((const T*)x, part, G);
-    bn_final_kernel<T><<<(C + 7) / 8, kT, 0, st>>>((const T*)x, part, gamma, beta, running_mean, running_var, mean_out, rstd_out,
+    bn_final_kernel<T><<<(C * kFW + 7) / 8, kT, 0, st>>>((const T*)x, part, gamma, beta, running_mean, running_var, mean_out, rstd_out,
                                                   scsh, eps, momentum, training, G);
     if (act) bn_apply_kernel<T, VW, 1><<<G.G, kT, 0, st>>>((const T*)x, scsh, (T*)z, G);
     else bn_apply_kernel<T, VW, 0><<<G.G, kT, 0, st>>>((const T*)x, scsh, (T*)z, G);
@@ -455,7 +479,7 @@ extern "C" B200_API int b200_bn_silu_bwd(const void* gz, int64_t gz_row_stride, 
     constexpr int VW = 16 / (int)sizeof(T);
     if (act) bn_bwd_reduce_kernel<T, VW, 1><<<G.G, kT, smem, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, part, gzs, G);
     else bn_bwd_reduce_kernel<T, VW, 0><<<G.G, kT, smem, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, part, gzs, G);
-    bn_bwd_final_kernel<<<(C + 7) / 8, kT, 0, st>>>(part, gamma, mean, rstd, ggamma, gbeta, coef, training, G);
+    bn_bwd_final_kernel<<<(C * kFW + 7) / 8, kT, 0, st>>>(part, gamma, mean, rstd, ggamma, gbeta, coef, training, G);
     const size_t smc = (size_t)5 * C * 4;
     if (act) bn_bwd_apply_kernel<T, VW, 1><<<G.G, kT, smc, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, coef, (T*)gx, gzs, G);
     else bn_bwd_apply_kernel<T, VW, 0><<<G.G, kT, smc, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, coef, (T*)gx, gzs, G);
