@@ -83,7 +83,7 @@ template <bool FAST> __device__ __forceinline__ float sigmoid_t(float y) {
   return __frcp_rn(1.f + __expf(-y));
 }
 
-constexpr int kFW = 4;  // finalize kernels: warps per channel
+constexpr int kFT = 256, kFW = 8;   // finalize kernels: threads per CTA, warps per channel (one channel per CTA; 16 warps measured no better)
 constexpr int RB = 4;   // rows in flight per thread: RB independent 16-byte loads before any use
 
 // per-CTA additive reduction of NV values per channel held by the row groups: red[ngrp][NV][C] -> out via f(c, v[NV])
@@ -141,17 +141,17 @@ __global__ void __launch_bounds__(kT, 4) bn_stats_kernel(const T* __restrict__ x
 
 // ---- forward finalize: warp per channel sums the G partials (fixed order) -> mean, rstd, running stats, scale/shift
 template <typename T>
-__global__ void __launch_bounds__(kT) bn_final_kernel(const T* __restrict__ x, const float* __restrict__ part,
+__global__ void __launch_bounds__(kFT) bn_final_kernel(const T* __restrict__ x, const float* __restrict__ part,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       float* __restrict__ running_mean, float* __restrict__ running_var,
                                                       float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                       float* __restrict__ scsh, float eps, float momentum, int training,
                                                       const BnGeo G) {
-  // kFW warps per channel: the G partial rows (up to 16 per SM) are summed by 128 lanes with 2 loads in flight each --
-  // one warp per channel made this 8-CTA kernel a 10 us latency chain, 59 times per step
-  __shared__ float fs[kT / 32][2];
+  // kFW warps per channel: the G partial rows (up to 16 per SM) are summed by 256 lanes with 2 loads in flight each --
+  // one warp per channel made this 8-CTA kernel a 10 us latency chain, 59 times per step (2982 -> 3123 img/s)
+  __shared__ float fs[kFT / 32][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = warp % kFW, C = G.C;
-  const int c = blockIdx.x * (kT / 32 / kFW) + warp / kFW;
+  const int c = blockIdx.x * (kFT / 32 / kFW) + warp / kFW;
   const bool live = c < C;
   float mean, rstd;
   if (training) {
@@ -292,13 +292,13 @@ __global__ void __launch_bounds__(kT, 4) bn_bwd_reduce_kernel(const T* __restric
 
 // ---- backward finalize: warp per channel -> g_beta = sum(gy), g_gamma = sum(gy*xhat) = rstd*(sum(gy*x) - mean*sum(gy)),
 // and the three coefficients of g_x = A*gy + Bc*x + Cc  (coef[3][C]) --------------------------------------------------
-__global__ void __launch_bounds__(kT) bn_bwd_final_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(kFT) bn_bwd_final_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           float* __restrict__ ggamma, float* __restrict__ gbeta,
                                                           float* __restrict__ coef, int training, const BnGeo G) {
-  __shared__ float fs[kT / 32][2];
+  __shared__ float fs[kFT / 32][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = warp % kFW, C = G.C;
-  const int c = blockIdx.x * (kT / 32 / kFW) + warp / kFW;
+  const int c = blockIdx.x * (kFT / 32 / kFW) + warp / kFW;
   const bool live = c < C;
   float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
   if (live) {
@@ -450,7 +450,7 @@ extern "C" B200_API int b200_bn_silu_fwd(const void* x, const float* gamma, cons
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
     constexpr int VW = 16 / (int)sizeof(T);
     if (training) bn_stats_kernel<T, VW><<<G.G, kT, smem, st>>>((const T*)x, part, G);
-    bn_final_kernel<T><<<(C * kFW + 7) / 8, kT, 0, st>>>((const T*)x, part, gamma, beta, running_mean, running_var, mean_out, rstd_out,
+    bn_final_kernel<T><<<(C * kFW + kFT / 32 - 1) / (kFT / 32), kFT, 0, st>>>((const T*)x, part, gamma, beta, running_mean, running_var, mean_out, rstd_out,
                                                   scsh, eps, momentum, training, G);
     if (act) bn_apply_kernel<T, VW, 1><<<G.G, kT, 0, st>>>((const T*)x, scsh, (T*)z, G);
     else bn_apply_kernel<T, VW, 0><<<G.G, kT, 0, st>>>((const T*)x, scsh, (T*)z, G);
@@ -479,7 +479,7 @@ extern "C" B200_API int b200_bn_silu_bwd(const void* gz, int64_t gz_row_stride, 
     constexpr int VW = 16 / (int)sizeof(T);
     if (act) bn_bwd_reduce_kernel<T, VW, 1><<<G.G, kT, smem, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, part, gzs, G);
     else bn_bwd_reduce_kernel<T, VW, 0><<<G.G, kT, smem, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, part, gzs, G);
-    bn_bwd_final_kernel<<<(C * kFW + 7) / 8, kT, 0, st>>>(part, gamma, mean, rstd, ggamma, gbeta, coef, training, G);
+    bn_bwd_final_kernel<<<(C * kFW + kFT / 32 - 1) / (kFT / 32), kFT, 0, st>>>(part, gamma, mean, rstd, ggamma, gbeta, coef, training, G);
     const size_t smc = (size_t)5 * C * 4;
     if (act) bn_bwd_apply_kernel<T, VW, 1><<<G.G, kT, smc, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, coef, (T*)gx, gzs, G);
     else bn_bwd_apply_kernel<T, VW, 0><<<G.G, kT, smc, st>>>((const T*)x, (const T*)gz, gamma, beta, mean, rstd, coef, (T*)gx, gzs, G);
