@@ -74,7 +74,10 @@ def ncu_kernel_name(tag: str):
              "b200_sppf_pool_bwd": "b200::sppf_pool_bwd_inplace_kernel<__nv_bfloat16, 5, 8, 320>",
              "b200_swin_attn_fwd_tc": "b200::swin_attn_fwd_tc_kernel<64>", "b200_swin_attn_bwd_tc": "b200::swin_attn_bwd_tc_kernel<64>",
              "b200_swin_ln1_partition": "b200::swin_ln1_partition_vec_kernel<__nv_bfloat16, 8, 2>",
-             "b200_swin_res_ln2": "b200::swin_res_ln2_vec_kernel<__nv_bfloat16, 8, 2>"}
+             "b200_swin_res_ln2": "b200::swin_res_ln2_vec_kernel<__nv_bfloat16, 8, 2>",
+             "b200_swin_ln_bwd": "b200::swin_ln_bwd_vec_kernel<__nv_bfloat16, 8, 2, 0>",   # the norm2 instance (with the residual gradient)
+             "b200_swin_res_reverse": "b200::swin_move_vec_kernel<__nv_bfloat16, 8, 2, 0>",
+             "b200_swin_partition": "b200::swin_move_vec_kernel<__nv_bfloat16, 8, 2, 1>"}
     if tag in fixed:
         return fixed[tag]
     m = re.match(r"b200_gemm_nt\[(\d+)x(\d+)x(\d+),epi(\d)\]", tag)
@@ -184,6 +187,21 @@ def run(scale: str, B: int, peaks: dict, iters: int = 10):
         rec(f"sppf_pool_bwd_k{k}", y0.shape, _time(lambda: torch.autograd.grad(cat, yg, g, retain_graph=True), iters, flush),
             6 * n0 * 2, "hbm", "P5")
         del cat, yg
+    # ---- seams: channel concat at a P3 C2f, nearest 2x up-sampling P4 -> P3, uint8 -> NHWC input conversion
+    Bq, c3 = sh["P3"][0], sh["P3"][1]
+    wide = torch.randn((Bq, c3, 80, 80), device=dev).to(dt).contiguous(memory_format=torch.channels_last)
+    parts = list(wide.chunk(2, 1)) + [torch.randn((Bq, c3 // 2, 80, 80), device=dev).to(dt).contiguous(memory_format=torch.channels_last)]
+    ncat = sum(p_.numel() for p_ in parts)
+    with torch.no_grad():
+        rec("nhwc_concat", (Bq, 3 * (c3 // 2), 80, 80), _time(lambda: Fb.nhwc_concat(parts), iters, flush), 2 * ncat * 2, "hbm",
+            "P3 C2f: two chunk slices + one bottleneck output")
+        xu = torch.randn(sh["P4"], device=dev).to(dt).contiguous(memory_format=torch.channels_last)
+        rec("nhwc_upsample_fwd", sh["P4"], _time(lambda: Fb.nhwc_upsample_nearest(xu, 2, 2), iters, flush), 5 * xu.numel() * 2, "hbm",
+            "P4 -> P3, nearest x2")
+        img = torch.randint(0, 256, (Bq, 3, 640, 640), dtype=torch.uint8, device=dev)
+        rec("u8_to_nhwc", (Bq, 3, 640, 640), _time(lambda: Fb.u8_to_nhwc(img, dt, 255.0), iters, flush), img.numel() * 3, "hbm",
+            "uint8 NCHW -> bf16 NHWC / 255")
+    del wide, parts, xu, img
     # ---- SwinBlock at P4 (whole block vs tensor peak; FLOPs counted on un-padded tokens)
     Bs, c4, H, W = sh["P4"]
     for ws, shift in ((7, 0), (7, 3), (8, 0), (8, 4)):   # configs[4]: window 7 and 8, shift off / on (shift = extension)
