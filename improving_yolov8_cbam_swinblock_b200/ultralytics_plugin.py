@@ -21,6 +21,7 @@ from . import modules as _m
 _TARGETS = ("ultralytics.nn.tasks", "ultralytics.nn.modules", "ultralytics.nn.modules.cbam",
             "ultralytics.nn.modules.swin_block", "ultralytics.nn.modules.block")
 _saved: dict = {}
+_saved_methods: dict = {}
 
 CBAM = _m.CBAM
 ChannelAttentionMap = _m.ChannelAttention
@@ -32,11 +33,38 @@ _CONV_TARGETS = ("ultralytics.nn.tasks", "ultralytics.nn.modules", "ultralytics.
                  "ultralytics.nn.modules.block", "ultralytics.nn.modules.head")
 
 
-def install(conv_epilogue: bool = False):
+def _c2f_forward(self, x):
+    """block.py C2f.forward with the NHWC seam kernels; CPU tensors take the stock ops inside."""
+    from . import functional as Fb
+
+    y = list(Fb.nhwc_chunk(self.cv1(x), 2))
+    inp = Fb.nhwc_concat([y[-1]])   # dense second half for the bottlenecks' 3x3 convs and shortcut adds
+    for m in self.m:
+        inp = m(inp)
+        y.append(inp)
+    return self.cv2(Fb.nhwc_concat(y))
+
+
+def _concat_forward(self, x):
+    """conv.py Concat.forward: channel concat through b200_nhwc_concat, any other dimension through torch.cat."""
+    import torch
+
+    from . import functional as Fb
+
+    return Fb.nhwc_concat(x) if self.d == 1 else torch.cat(x, self.d)
+
+
+_SEAM_PATCHES = (("ultralytics.nn.modules.block", "C2f", "forward", _c2f_forward),
+                 ("ultralytics.nn.modules.conv", "Concat", "forward", _concat_forward))
+
+
+def install(conv_epilogue: bool = False, seams: bool = False):
     """Rebind CBAM / SwinBlock / SPPF in the reference's namespaces.  Returns the {name: class} table.
 
     SPPF's own cv1/cv2 always use the fused BN+SiLU epilogue; ``conv_epilogue=True`` additionally rebinds ``Conv``
-    itself (a subclass of the reference's, same state_dict / ``fuse()`` behaviour) so every Conv caller gets it."""
+    itself (a subclass of the reference's, same state_dict / ``fuse()`` behaviour) so every Conv caller gets it.
+    ``seams=True`` replaces ``C2f.forward`` and ``Concat.forward`` (same classes, same parameters) by versions that
+    move data with the NHWC concat kernel; both are undone by ``uninstall()``."""
     global SPPF, Conv
     conv_mod = importlib.import_module("ultralytics.nn.modules.conv")
     if Conv is None:
@@ -50,6 +78,11 @@ def install(conv_epilogue: bool = False):
             if hasattr(mod, "Conv"):
                 _saved.setdefault((modname, "Conv"), getattr(mod, "Conv"))
                 setattr(mod, "Conv", Conv)
+    if seams:
+        for modname, clsname, attr, fn in _SEAM_PATCHES:
+            cls_ = getattr(importlib.import_module(modname), clsname)
+            _saved_methods.setdefault((modname, clsname, attr), cls_.__dict__[attr])
+            setattr(cls_, attr, fn)
     for modname in _TARGETS:
         mod = importlib.import_module(modname)
         for name, cls in table.items():
@@ -69,3 +102,6 @@ def uninstall():
     for (modname, name), cls in list(_saved.items()):
         setattr(importlib.import_module(modname), name, cls)
     _saved.clear()
+    for (modname, clsname, attr), fn in list(_saved_methods.items()):
+        setattr(getattr(importlib.import_module(modname), clsname), attr, fn)
+    _saved_methods.clear()

@@ -63,3 +63,29 @@ def test_plugin_rebinds_reference_namespaces():
     finally:
         plugin.uninstall()
     assert tasks.CBAM is not table["CBAM"]
+
+
+def test_plugin_seams_patch_is_value_neutral_and_reversible():
+    import torch
+
+    import improving_yolov8_cbam_swinblock_b200.ultralytics_plugin as plugin
+
+    ref_loader.import_ultralytics()
+    from ultralytics.nn.modules.block import C2f
+    from ultralytics.nn.modules.conv import Concat
+
+    torch.manual_seed(0)
+    blk = C2f(16, 16, n=2, shortcut=True).eval()
+    x = torch.randn(2, 16, 8, 8)
+    ref = blk(x)
+    ref_cat = Concat(1)([x, x * 2])
+    orig = C2f.forward
+    plugin.install(seams=True)
+    try:
+        assert C2f.forward is not orig
+        assert torch.equal(blk(x), ref)                      # CPU tensors: the stock ops behind the same call sites
+        assert torch.equal(Concat(1)([x, x * 2]), ref_cat)
+        assert torch.equal(Concat(2)([x, x]), torch.cat([x, x], 2))
+    finally:
+        plugin.uninstall()
+    assert C2f.forward is orig
