@@ -118,18 +118,25 @@ def cpu_reference_leg(steps, warmup, batch=2):
                       f"{cores} torch threads", "ms_per_step": 1e3 * dt / steps}
 
 
-def main():
-    # stdout carries exactly ONE line (the JSON record): libraries that write to fd 1 (NCCL prints its version banner there
-    # when the first communicator is created) are sent to stderr; the record goes to a private copy of the real stdout
-    global print_record
+_record_out = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE line (the JSON record): libraries that write to fd 1 (NCCL prints its version banner there
+    when the first communicator is created) are sent to stderr; the record goes to a private copy of the real stdout."""
+    global _record_out
     sys.stdout.flush()
-    real = os.fdopen(os.dup(1), "w")
+    _record_out = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
 
-    def print_record(line):
-        real.write(json.dumps(line) + "\n")
-        real.flush()
 
+def print_record(line):
+    _record_out.write(json.dumps(line) + "\n")
+    _record_out.flush()
+
+
+def main():
+    _claim_stdout()
     if os.environ.get("B200_BENCH_WATCHDOG"):  # debugging aid: dump every thread's stack and exit if the run stalls
         import faulthandler
 
