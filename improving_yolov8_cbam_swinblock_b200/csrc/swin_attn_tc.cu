@@ -88,8 +88,13 @@ __global__ void __launch_bounds__(kThreads10, 1) swin_attn_fwd_tc_kernel(const _
 #pragma unroll
       for (int i = 0; i < 8; ++i) z[i] = make_uint4(0, 0, 0, 0);
     }
-    fence_proxy_async();
   }
+  // The TMA boxes carry exactly L token rows per item, so rows L..63 of every Q / K / V tile keep these zeros for the whole
+  // kernel: a non-finite value in a NEIGHBOURING window (which a 64-row box would pull in) can never meet a zero
+  // probability in the PV MMA (0 x Inf = NaN).
+  for (int s = 0; s < STAGES; ++s)
+    for (int i = threadIdx.x; i < 3 * Cfg::Q_BYTES / 16; i += kThreads10) reinterpret_cast<uint4*>(sQ(s))[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -102,6 +107,7 @@ __global__ void __launch_bounds__(kThreads10, 1) swin_attn_fwd_tc_kernel(const _
     // Q/K of a stage are reloaded as soon as the S MMAs that read them have completed, V once the PV MMAs have: the loads of
     // pair n+STAGES are in flight while pair n is still in its softmax / epilogue
     if (elect_one()) {
+      const uint32_t box_bytes = 2u * KB * (uint32_t)P.L * 128u;   // one operand tile: 2 items x KB boxes of [L rows][128 B]
       for (int n = 0; n < n_local; ++n) {
         const int pair = blockIdx.x + n * gridDim.x;
         const int s = n % STAGES;
@@ -115,7 +121,7 @@ __global__ void __launch_bounds__(kThreads10, 1) swin_attn_fwd_tc_kernel(const _
           t0[r] = win * P.L; col[r] = h * HD;
         }
         mbar_wait(&qk_free[s], ph ^ 1);
-        mbar_expect_tx(&qk_full[s], 2 * Cfg::Q_BYTES);
+        mbar_expect_tx(&qk_full[s], 2 * box_bytes);
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -124,7 +130,7 @@ __global__ void __launch_bounds__(kThreads10, 1) swin_attn_fwd_tc_kernel(const _
             tma_load_2d(sK(s) + kb * 16384 + r * 8192, &tmQKV, &qk_full[s], P.C + col[r] + kb * 64, t0[r]);
           }
         mbar_wait(&v_free[s], ph ^ 1);
-        mbar_expect_tx(&v_full[s], Cfg::Q_BYTES);
+        mbar_expect_tx(&v_full[s], box_bytes);
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -295,7 +301,7 @@ __global__ void __launch_bounds__(kThreads10, 1) swin_attn_fwd_tc_kernel(const _
 template <int HD>
 int launch_fwd(const void* qkv, void* o, float* lse, long long T, int L, int C, int nh, const ShiftMask& M, int dtype, cudaStream_t st) {
   using Cfg = ACfg<HD>;
-  const CUtensorMap* m = tensor_map_2d(qkv, (uint64_t)T, (uint64_t)3 * C, (uint64_t)3 * C, 64, 64, dtype);
+  const CUtensorMap* m = tensor_map_2d(qkv, (uint64_t)T, (uint64_t)3 * C, (uint64_t)3 * C, (uint32_t)L, 64, dtype);
   const CUtensorMap* mo = tensor_map_2d(o, (uint64_t)T, (uint64_t)C, (uint64_t)C, (uint32_t)L, 64, dtype);
   if (!m || !mo) return B200_ERR_LAUNCH;
   AttnParams P;
@@ -387,8 +393,11 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 #pragma unroll
       for (int i = 0; i < 4; ++i) { z0[i] = make_uint4(0, 0, 0, 0); z1[i] = make_uint4(0, 0, 0, 0); }
     }
-    fence_proxy_async();
   }
+  // operand tiles: rows L..63 of every item stay zero (the TMA boxes carry exactly L rows; see the forward kernel)
+  for (int s = 0; s < STAGES; ++s)
+    for (int i = threadIdx.x; i < 4 * Cfg::T_BYTES / 16; i += kThreads10) reinterpret_cast<uint4*>(stage(s))[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -410,7 +419,7 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         unsigned char* sV = stage(s) + Cfg::OFF_V;
         unsigned char* sDO = stage(s) + Cfg::OFF_DO;
         mbar_wait(&smem_free[s], ((n / STAGES) & 1) ^ 1);
-        mbar_expect_tx(&in_full[s], 4 * Cfg::T_BYTES);
+        mbar_expect_tx(&in_full[s], 4u * 2u * KB * (uint32_t)P.L * 128u);
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           int it = 2 * pair + r;
@@ -639,8 +648,8 @@ template <int HD>
 int launch_bwd(const void* qkv, const float* lse, const void* go, void* gqkv, long long T, int L, int C, int nh, const ShiftMask& M, int dtype,
                cudaStream_t st) {
   using Cfg = BCfg<HD>;
-  const CUtensorMap* m = tensor_map_2d(qkv, (uint64_t)T, (uint64_t)3 * C, (uint64_t)3 * C, 64, 64, dtype);
-  const CUtensorMap* mg = tensor_map_2d(go, (uint64_t)T, (uint64_t)C, (uint64_t)C, 64, 64, dtype);
+  const CUtensorMap* m = tensor_map_2d(qkv, (uint64_t)T, (uint64_t)3 * C, (uint64_t)3 * C, (uint32_t)L, 64, dtype);
+  const CUtensorMap* mg = tensor_map_2d(go, (uint64_t)T, (uint64_t)C, (uint64_t)C, (uint32_t)L, 64, dtype);
   const CUtensorMap* mo = tensor_map_2d(gqkv, (uint64_t)T, (uint64_t)3 * C, (uint64_t)3 * C, (uint32_t)L, 64, dtype);
   if (!m || !mg || !mo) return B200_ERR_LAUNCH;
   AttnBwdParams P;

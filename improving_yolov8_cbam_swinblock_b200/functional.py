@@ -85,16 +85,17 @@ def nhwc_concat_raw(tensors) -> torch.Tensor:
     srcs = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
     cc = (C.c_int32 * n)(*chans)
     ss = (C.c_int64 * n)(*[int(v) for v in strides])
-    call("b200_nhwc_concat", C.addressof(srcs), C.addressof(cc), C.addressof(ss), n, ptr(out), B * H * W, dtype_code(t0.dtype),
-         stream_ptr(t0.device), tag=f"b200_nhwc_concat[{B * H * W}x{sum(chans)}]")
+    with torch.cuda.device(t0.device):
+        call("b200_nhwc_concat", C.addressof(srcs), C.addressof(cc), C.addressof(ss), n, ptr(out), B * H * W, dtype_code(t0.dtype),
+             stream_ptr(t0.device), tag=f"b200_nhwc_concat[{B * H * W}x{sum(chans)}]")
     return out
 
 
 def _concat_ok(tensors) -> bool:
     t0 = tensors[0]
     return (t0.is_cuda and t0.dim() == 4 and 1 <= len(tensors) <= 8 and t0.dtype in (torch.float32, torch.bfloat16, torch.float16)
-            and all(t.is_cuda and t.dim() == 4 and t.dtype == t0.dtype and t.shape[0] == t0.shape[0] and t.shape[2:] == t0.shape[2:]
-                    for t in tensors))
+            and all(t.is_cuda and t.device == t0.device and t.dim() == 4 and t.dtype == t0.dtype and t.shape[0] == t0.shape[0]
+                    and t.shape[2:] == t0.shape[2:] for t in tensors))
 
 
 class NhwcConcatFn(torch.autograd.Function):
@@ -146,7 +147,8 @@ def u8_to_nhwc(img: torch.Tensor, dtype: torch.dtype = torch.float32, divisor: f
         raise RuntimeError("u8_to_nhwc: expected a contiguous uint8 CUDA tensor [B,C,H,W]")
     B, Cc, H, W = img.shape
     out = _empty_nhwc(B, Cc, H, W, dtype, img.device)
-    call("b200_u8_to_nhwc", ptr(img), ptr(out), B, Cc, H, W, float(divisor), dtype_code(dtype), stream_ptr(img.device))
+    with torch.cuda.device(img.device):
+        call("b200_u8_to_nhwc", ptr(img), ptr(out), B, Cc, H, W, float(divisor), dtype_code(dtype), stream_ptr(img.device))
     return out
 
 
@@ -157,7 +159,8 @@ class NhwcUpsampleFn(torch.autograd.Function):
         B, Cc, H, W = x.shape
         ctx.cfg = (B, Cc, H, W, sh, sw)
         out = _empty_nhwc(B, Cc, H * sh, W * sw, x.dtype, x.device)
-        call("b200_nhwc_upsample_fwd", ptr(x), ptr(out), B, Cc, H, W, sh, sw, dtype_code(x.dtype), stream_ptr(x.device))
+        with torch.cuda.device(x.device):
+            call("b200_nhwc_upsample_fwd", ptr(x), ptr(out), B, Cc, H, W, sh, sw, dtype_code(x.dtype), stream_ptr(x.device))
         return out
 
     @staticmethod
@@ -167,7 +170,8 @@ class NhwcUpsampleFn(torch.autograd.Function):
         if gs is None or (gs * g.element_size()) % 16 or g.data_ptr() % 16:
             g, gs = _nhwc(g), Cc
         gin = _empty_nhwc(B, Cc, H, W, g.dtype, g.device)
-        call("b200_nhwc_upsample_bwd", ptr(g), gs, ptr(gin), B, Cc, H, W, sh, sw, dtype_code(g.dtype), stream_ptr(g.device))
+        with torch.cuda.device(g.device):
+            call("b200_nhwc_upsample_bwd", ptr(g), gs, ptr(gin), B, Cc, H, W, sh, sw, dtype_code(g.dtype), stream_ptr(g.device))
         return gin, None, None
 
 

@@ -140,7 +140,9 @@ class SwinBlock(nn.Module):
             "mlp.0.weight": self.mlp[0].weight, "mlp.0.bias": self.mlp[0].bias,
             "mlp.2.weight": self.mlp[2].weight, "mlp.2.bias": self.mlp[2].bias,
         }
-        return Fb.swin_block(x, p, self.num_heads, self.window_size, getattr(self, "shift_size", 0))
+        # num_heads / shift come from state the reference class also has: a module pickled by the reference and unpickled
+        # after plugin.install() (tasks.py:1222) never ran this __init__, so it has no `num_heads` / `shift_size` attribute
+        return Fb.swin_block(x, p, self.attn.num_heads, self.window_size, getattr(self, "shift_size", 0))
 
 
 FUSE_CONV_EPILOGUE = [True]  # process-wide switch (tests / A-B timing); False = the caller's stock BatchNorm2d + SiLU
@@ -189,7 +191,8 @@ def make_sppf(conv_cls, name="SPPF", module=None):
             if not y0.is_cuda:
                 B, c_, H, W = y0.shape
                 return self.cv2(y0.new_zeros((B, 4 * c_, H, W)))
-            return self.cv2(Fb.sppf_pool(y0, self.k))
+            k = self.m.kernel_size   # not self.k: reference pickles loaded under the plugin never ran this __init__
+            return self.cv2(Fb.sppf_pool(y0, int(k[0] if isinstance(k, (tuple, list)) else k)))
 
     SPPF.__name__ = SPPF.__qualname__ = name
     if module is not None:

@@ -124,3 +124,35 @@ def test_full_size_consistency_between_modes():
     assert ca.shape == (64, 256, 1, 1) and sa.shape == (64, 1, 20, 20)
     assert float(ca.min()) > 0 and float(ca.max()) < 1 and float(sa.min()) > 0 and float(sa.max()) < 1
     assert rel_err(out, want) < 1e-2
+
+
+@pytest.mark.parametrize("shape", [(64, 256, 20, 20), (64, 128, 40, 40), (64, 64, 80, 80)])
+def test_full_size_vs_oracle_on_gpu(shape):
+    """BASELINE sizes (B=64; P5 = the model's use, P4 / P3 = the sweep shapes): the CUDA bf16 path against
+    oracle/blocks.py (pinned by the reference-generated fixtures) evaluated in fp32 on the same GPU -- output, input
+    gradient and the three weight gradients."""
+    import improving_yolov8_cbam_swinblock_b200.modules as M
+    from oracle import blocks as ob
+
+    torch.manual_seed(1)
+    B, C, H, W = shape
+    mod = M.CBAM()
+    mod(torch.zeros(1, C, 2, 2))
+    mod = mod.cuda()
+    x = torch.randn(shape, device="cuda").bfloat16()
+    g = torch.randn(shape, device="cuda").bfloat16()
+    r = mod.ca.shared_MLP[0].weight.shape[0]
+    w1 = mod.ca.shared_MLP[0].weight.detach().view(r, C).clone().requires_grad_(True)
+    w2 = mod.ca.shared_MLP[2].weight.detach().view(C, r).clone().requires_grad_(True)
+    ws = mod.sa.conv.weight.detach().clone().requires_grad_(True)
+    xo = x.float().requires_grad_(True)
+    yo = ob.cbam_forward(xo, w1, w2, ws)
+    yo.backward(g.float())
+    xi = to_cl(x).requires_grad_(True)
+    y = mod(xi)
+    y.backward(to_cl(g))
+    assert rel_err(y, yo) < 1e-2, rel_err(y, yo)
+    assert rel_err(xi.grad, xo.grad) < 1e-2, rel_err(xi.grad, xo.grad)
+    assert rel_err(mod.ca.shared_MLP[0].weight.grad.view(r, C), w1.grad) < 2e-2
+    assert rel_err(mod.ca.shared_MLP[2].weight.grad.view(C, r), w2.grad) < 2e-2
+    assert rel_err(mod.sa.conv.weight.grad, ws.grad) < 2e-2

@@ -44,6 +44,24 @@ def test_gemm_epilogues(M, N, K):
     assert rel_err(y, pre + r.float()) < 4e-3
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K", [(1024, 512, 128), (5000, 128, 512), (77, 64, 64)])
+def test_gemm_epilogue_mul_gelugrad(dtype, M, N, K):
+    """EPI_MUL_GELUGRAD (epilogue 3): D = (A W^T) * gelu'(R), the GELU backward fused into the mlp.2 data-gradient GEMM
+    (swin_block.py:53 backward), against erf-GELU's analytic derivative in fp64."""
+    from improving_yolov8_cbam_swinblock_b200 import gemm_tc
+
+    torch.manual_seed(M + N)
+    a = torch.randn(M, K, device="cuda").to(dtype)
+    w = torch.randn(N, K, device="cuda") / K ** 0.5
+    r = (2.5 * torch.randn(M, N, device="cuda")).to(dtype)
+    got = gemm_tc.gemm_nt(a, w, None, gemm_tc.EPI_MUL_GELUGRAD, residual=r)
+    rd = r.double()
+    dgelu = 0.5 * (1 + torch.erf(rd / 2 ** 0.5)) + rd * torch.exp(-0.5 * rd * rd) / (2 * torch.pi) ** 0.5
+    want = (a.double() @ w.to(dtype).double().t()) * dgelu
+    assert got.dtype == dtype and rel_err(got, want) < (4e-3 if dtype == torch.bfloat16 else 8e-4), rel_err(got, want)
+
+
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 256), (384, 128, 4096), (128, 512, 112896), (72, 200, 1000)])
 def test_gemm_splitk_all_majors(a_mn, b_mn, M, N, K):

@@ -101,6 +101,34 @@ def test_full_size_properties():
         assert torch.equal(s[3].float(), big)
 
 
+@pytest.mark.parametrize("k", [5, 7])
+@pytest.mark.parametrize("tie_stress", [False, True])
+def test_full_size_backward_vs_torch_cascade_on_gpu(k, tie_stress):
+    """BASELINE size (B=64, c_=128, 20x20, bf16): gradient routing of the cascade against autograd over three stock
+    ``F.max_pool2d`` calls on the same GPU (same strict-'>' first-occurrence rule as the oracle's scan, which the small
+    cases above pin) -- in fp32 on the bf16-representable inputs, so the only difference is the final rounding."""
+    from improving_yolov8_cbam_swinblock_b200 import functional as Fb
+
+    torch.manual_seed(k)
+    y0 = torch.randn(64, 128, 20, 20, device="cuda")
+    if tie_stress:
+        y0 = torch.relu(y0).mul(4).round().div(4)     # plateaus: ties at every stage
+    y0 = y0.bfloat16()
+    g = torch.randn(64, 512, 20, 20, device="cuda").bfloat16()
+    yo = y0.float().requires_grad_(True)
+    ys = [yo]
+    for _ in range(3):
+        ys.append(torch.nn.functional.max_pool2d(ys[-1], k, 1, k // 2))
+    torch.cat(ys, 1).backward(g.float())
+    yi = to_cl(y0).requires_grad_(True)
+    cat = Fb.sppf_pool(yi, k)
+    assert torch.equal(cat.float(), torch.cat(ys, 1).detach())
+    cat.backward(to_cl(g))
+    # every output is the bf16 rounding of an fp32 sum of bf16 terms
+    assert rel_err(yi.grad, yo.grad) < 4e-3, rel_err(yi.grad, yo.grad)
+    torch.testing.assert_close(yi.grad.float(), yo.grad, rtol=1.6e-2, atol=1e-2)
+
+
 def test_errors_are_reported_not_thrown():
     from improving_yolov8_cbam_swinblock_b200 import functional as Fb
 
