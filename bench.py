@@ -12,8 +12,11 @@ with CUDA events on the launching stream inside the timed region), ``modules`` (
 L2 flushed between launches), ``cpu_baseline`` (the oracle port of the reference blocks inside the same graph on the
 host cores, bounded sample), ``clocks``, ``gpu_launches``.
 
-``--impl reference`` times the reference's CPU implementation of the path (the oracle port: the reference package
-cannot travel to the GPU box) with all host threads on a bounded sample of the same workload.
+``--impl reference`` times the reference's own CPU implementation of the path: the UNMODIFIED ``DetectionModel`` +
+``v8DetectionLoss`` from ``oracle/_ref`` (a verbatim copy of the reference package made by ``oracle/build_ref.py``; it is
+pure Python, so this is what "compiling the reference" means here) for exactly K timed + W warm-up steps, fp32, all host
+threads, at the largest per-step batch that fits the time budget -- and prints the batch / steps / dtype it really ran.
+``gpu_eager_baseline`` (own arm, N=1) = the same unmodified reference run eagerly on the GPU: the bar to beat.
 """
 from __future__ import annotations
 
@@ -82,40 +85,210 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_leg(steps, warmup, batch=2):
-    """Reference blocks (oracle port) inside the same graph, training step on the host cores, fp32."""
+def _cpu_info():
+    model = "unknown"
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return {"nproc": os.cpu_count() or 1, "cpu_model": model}
+
+
+def _median_ms(fn, warm, reps):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(1e3 * (time.perf_counter() - t0))
+    return statistics.median(ts)
+
+
+def _ref_kind():
+    """'reference' when the unmodified reference package is importable (oracle/_ref, made by oracle/build_ref.py, or
+    /root/reference in the dev container); 'port' (oracle/modules.py in the harness graph) otherwise."""
+    from oracle import ref_step
+
+    return "reference" if ref_step.available() else "port"
+
+
+def _make_cpu_trainer(kind):
     import torch
 
+    if kind == "reference":
+        from oracle import ref_step
+
+        tr = ref_step.RefTrainer(SCALE, NC, "cpu", amp=None, ema=True)
+        return tr, tr.step, tr.model
     from improving_yolov8_cbam_swinblock_b200.harness import graph, synthetic, train
     from oracle import modules as om
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     blocks = {"CBAM": om.CBAM, "SwinBlock": om.SwinBlock, "SPPF": om.make_sppf(graph.Conv)}
     tr = train.Trainer(blocks, SCALE, NC, device="cpu", amp_dtype=None, ema=True)
     tr.max_boxes = synthetic.BOXES_PER_IMAGE
+    return tr, tr.step, tr.raw
+
+
+def cpu_reference_run(steps, warmup, batch=None, budget_s=150.0):
+    """The reference's own CPU implementation of the measured path -- the UNMODIFIED ``DetectionModel`` +
+    ``v8DetectionLoss`` + trainer-style SGD/EMA step (oracle/ref_step.py over oracle/_ref), fp32, all host threads --
+    for exactly ``warmup`` + ``steps`` steps.  ``batch=None``: the largest per-step batch in {64,32,16,8,4,2} whose
+    (warmup+steps) steps fit ``budget_s`` according to one probe step at batch 4."""
+    import torch
+
+    from improving_yolov8_cbam_swinblock_b200.harness import synthetic
+
+    kind = _ref_kind()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tr, step, _ = _make_cpu_trainer(kind)
+    if batch is None:
+        probe = synthetic.make_batch(4, IMGSZ, NC, seed=99)
+        step(probe)
+        t0 = time.perf_counter()
+        step(probe)
+        per_img = (time.perf_counter() - t0) / 4
+        batch = 2
+        for b in (64, 32, 16, 8, 4):
+            if per_img * b * (steps + warmup) <= budget_s:
+                batch = b
+                break
     host = synthetic.make_batch(batch, IMGSZ, NC, seed=1234)
     for _ in range(warmup):
-        tr.step_from_host(host)
+        step(host)
     t0 = time.perf_counter()
     for _ in range(steps):
-        tr.step_from_host(host)
+        step(host)
     dt = time.perf_counter() - t0
-    # BASELINE config 0: inference, batch 1, 640^2, fp32, eval mode on the host cores
-    tr.raw.eval()
+    what = ("unmodified reference DetectionModel + v8DetectionLoss (oracle/_ref = verbatim copy of the reference package), trainer-style "
+            "step (oracle/ref_step.py)") if kind == "reference" else "oracle/modules.py blocks in the harness graph (reference package not available)"
+    return {"value": batch * steps / dt, "unit": "img/s", "cores": cores, "kind": kind, "batch": batch, "steps": steps, "warmup": warmup,
+            "ms_per_step": 1e3 * dt / steps, **_cpu_info(),
+            "sample": f"{steps} timed (+{warmup} warm-up) fp32 training steps (fwd + v8 loss + bwd + clip + SGD + EMA) of YOLOv8{SCALE}-CBAM-Swin "
+                      f"at {IMGSZ}^2, batch {batch}, {cores} torch threads: {what}"}
+
+
+def cpu_baseline_leg(train_steps=3, train_batch=8, sweep_reps=10, sweep_batch=8):
+    """BASELINE.md section 4 items 1-3 on the box's host cores (bounded: ~30-40 s):
+    (1) configs[0]: fp32 inference, batch 1, eval + inference_mode, 3 warm-up + 10 timed, median -- at all cores and at the
+        reference's default of ONE thread (ultralytics/__init__.py:8-9 sets OMP_NUM_THREADS=1);
+    (2) training step at batch ``train_batch`` (all cores; one step at 1 thread);
+    (3) module sweep: reference CBAM / SPPF / SwinBlock modules, fwd and fwd+bwd, ``sweep_reps`` reps, median."""
+    import torch
+
+    from improving_yolov8_cbam_swinblock_b200.harness import synthetic
+
+    kind = _ref_kind()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tr, step, model = _make_cpu_trainer(kind)
+    host = synthetic.make_batch(train_batch, IMGSZ, NC, seed=1234)
+    step(host)
+    t0 = time.perf_counter()
+    for _ in range(train_steps):
+        step(host)
+    dt = time.perf_counter() - t0
+    out = {"value": train_batch * train_steps / dt, "unit": "img/s", "cores": cores, "kind": kind, **_cpu_info(),
+           "sample": f"{train_steps} fp32 training steps (fwd + v8 loss + bwd + clip + SGD + EMA) of YOLOv8{SCALE}-CBAM-Swin at {IMGSZ}^2, "
+                     f"batch {train_batch}, {cores} threads, " + ("unmodified reference (oracle/_ref)" if kind == "reference" else "oracle port")}
+    torch.set_num_threads(1)
+    small = synthetic.make_batch(2, IMGSZ, NC, seed=1)
+    t0 = time.perf_counter()
+    step(small)
+    out["train_1thread_img_s"] = round(2 / (time.perf_counter() - t0), 3)
+    # (1) configs[0]
+    model.eval()
     img1 = host["img"][:1].float() / 255
     with torch.inference_mode():
-        for _ in range(2):
-            tr.raw(img1)
-        ti = time.perf_counter()
-        n_inf = 5
-        for _ in range(n_inf):
-            tr.raw(img1)
-        inf_ms = 1e3 * (time.perf_counter() - ti) / n_inf
-    return {"value": batch * steps / dt, "unit": "img/s", "cores": cores, "kind": "port", "inference_b1_fp32_ms": round(inf_ms, 2),
-            "sample": f"{steps} fp32 training steps (fwd+loss+bwd+SGD+EMA) of YOLOv8{SCALE}-CBAM-Swin at {IMGSZ}^2, batch {batch}, "
-                      f"oracle/modules.py blocks (CPU restatement of cbam.py/swin_block.py/block.py SPPF) in the harness graph, "
-                      f"{cores} torch threads", "ms_per_step": 1e3 * dt / steps}
+        out["inference_b1_fp32_ms_1thread"] = round(_median_ms(lambda: model(img1), 1, 3), 2)
+        torch.set_num_threads(cores)
+        out["inference_b1_fp32_ms"] = round(_median_ms(lambda: model(img1), 3, 10), 2)
+    model.train()
+    out["inference_note"] = ("configs[0]: batch 1, 640^2, fp32, eval + inference_mode, median; all cores: 3 warm-up + 10 timed; "
+                             "1 thread (the reference's OMP_NUM_THREADS default): 1 warm-up + 3 timed")
+    # (3) module sweep on the reference's own module classes
+    sweep = []
+    try:
+        if kind == "reference":
+            from oracle import ref_loader
+
+            ref_loader.import_ultralytics()
+            from ultralytics.nn.modules.block import SPPF as RSPPF
+            from ultralytics.nn.modules.cbam import CBAM as RCBAM
+            from ultralytics.nn.modules.swin_block import SwinBlock as RSwin
+        else:
+            from improving_yolov8_cbam_swinblock_b200.harness import graph
+            from oracle import modules as om
+
+            RCBAM, RSwin, RSPPF = om.CBAM, om.SwinBlock, om.make_sppf(graph.Conv)
+        from improving_yolov8_cbam_swinblock_b200.harness.sweep import CHANNELS
+
+        c3, c4, c5 = CHANNELS[SCALE]
+        B = sweep_batch
+        cases = [("CBAM", lambda: RCBAM(), (B, c5, 20, 20)), ("CBAM", lambda: RCBAM(), (B, c4, 40, 40)),
+                 ("CBAM", lambda: RCBAM(), (B, c3, 80, 80)),
+                 ("SPPF_k5", lambda: RSPPF(c5, c5, 5), (B, c5, 20, 20)), ("SPPF_k7", lambda: RSPPF(c5, c5, 7), (B, c5, 20, 20)),
+                 ("SwinBlock_ws7", lambda: RSwin(c4, 2, 7), (B, c4, 40, 40)), ("SwinBlock_ws8", lambda: RSwin(c4, 2, 8), (B, c4, 40, 40))]
+        for name, mk, shape in cases:
+            torch.manual_seed(0)
+            mod = mk().train()
+            x = torch.randn(shape)
+            with torch.no_grad():
+                mod(x)   # lazy CBAM MLP
+                fwd = _median_ms(lambda: mod(x), 2, sweep_reps)
+            xg = x.clone().requires_grad_(True)
+
+            def fb():
+                y = mod(xg)
+                y.backward(torch.ones_like(y))
+
+            sweep.append({"module": name, "shape": list(shape), "fwd_ms": round(fwd, 3), "fwd_bwd_ms": round(_median_ms(fb, 2, sweep_reps), 3)})
+    except Exception as e:  # noqa: BLE001  the sweep is a reported extra: never lose the bench line over it
+        sweep.append({"error": f"{type(e).__name__}: {e}"})
+    out["module_sweep"] = {"threads": cores, "reps": sweep_reps, "dtype": "f32", "rows": sweep,
+                           "note": f"reference module classes on the host cores, batch {sweep_batch} (bounded sample), median of {sweep_reps}"}
+    return out
+
+
+def gpu_eager_baseline_leg(steps, warmup, batch, device):
+    """The honest bar: the reference ships no CUDA, so "the reference on a B200" is its
+    unmodified modules through cuDNN / cuBLAS / ATen eager.  Same synthetic batches, same step (oracle/ref_step.py), bf16
+    autocast and the trainer's native fp16 + GradScaler (trainer.py:274-276,383)."""
+    import torch
+
+    from improving_yolov8_cbam_swinblock_b200.harness import synthetic
+    from oracle import ref_step
+
+    if not ref_step.available():
+        return {"unavailable": "oracle/_ref (copy of the reference package, oracle/build_ref.py) not present"}
+    out = {"unit": "img/s", "batch": batch, "steps": steps, "warmup": warmup,
+           "what": "unmodified reference DetectionModel + v8DetectionLoss + SGD + ModelEMA, PyTorch eager on the same GPU, device-resident uint8 batches"}
+    host = [synthetic.make_batch(batch, IMGSZ, NC, seed=1234 + 100 * i) for i in range(2)]
+    for amp in ("bf16", "fp16"):
+        try:
+            tr = ref_step.RefTrainer(SCALE, NC, device, amp=amp, ema=True)
+            dev = [tr.to_device(h) for h in host]
+            for i in range(warmup):
+                tr.step(dev[i % 2])
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for i in range(steps):
+                tr.step(dev[i % 2])
+            e.record()
+            torch.cuda.synchronize()
+            ms = s.elapsed_time(e) / steps
+            out[amp] = {"value": batch / (ms * 1e-3), "ms_per_step": ms}
+            del tr, dev
+            torch.cuda.empty_cache()
+        except Exception as ex:  # noqa: BLE001
+            out[amp] = {"error": f"{type(ex).__name__}: {ex}"}
+            torch.cuda.empty_cache()
+    return out
 
 
 _record_out = None
@@ -148,6 +321,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (default = BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-eager-on-this-GPU leg")
+    ap.add_argument("--ref-batch", type=int, default=None, help="--impl reference: per-step batch (default: largest that fits the time budget)")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly (no CUDA-graph replay)")
     ap.add_argument("--scale", default=SCALE, choices=["n", "s", "m"],
@@ -167,11 +342,15 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cb = cpu_reference_leg(max(1, min(args.steps, 8)), max(1, min(args.warmup, 2)))
+        cb = cpu_reference_run(args.steps, args.warmup, batch=args.ref_batch)
+        rconfig = dict(config)   # what this arm actually ran: CPU, fp32, its own per-step batch
+        rconfig.update(per_gpu_batch=cb["batch"], global_batch=cb["batch"], parallelism="cpu", amp="none (fp32)", memory_format="contiguous (NCHW)",
+                       l2="n/a (host cores)", device=f"host CPU, {cb['cores']} threads", sample_of_workload=cb["batch"] != args.batch,
+                       steps_run=cb["steps"], warmup_run=cb["warmup"])
         line = {"impl": "reference", "metric": "train_images_per_sec", "value": cb["value"], "unit": "img/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "inference_b1_fp32_ms")},
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": rconfig,
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "nproc", "cpu_model", "batch")},
                 "e2e": {"value": cb["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print_record(line)
         return
@@ -259,9 +438,9 @@ def main():
     roof = None
     if ktimes:
         tot = {k: n * ms for k, (n, ms) in ktimes.items()}
-        # `roofline` = the dominant kernel of the hot path proper (CBAM / SPPF / SwinBlock); the Conv-epilogue
-        # and channel-concat launches (SURVEY 8(f)-1/-2 widening) are listed with their own fractions under all_kernels
-        hot = {k: v for k, v in tot.items() if not k.startswith(("b200_bn_silu", "b200_nhwc_concat"))} or tot
+        # `roofline` = the hand-written kernel with the largest share of the step among ALL of them (hot-path blocks, Conv
+        # epilogue, seams alike); every kernel's own fraction is under all_kernels, the per-block rows under blocks
+        hot = tot
         top = max(hot, key=hot.get)
         n, ms = ktimes[top]
         w = work.get(top) or sweep.gemm_work(top, peaks) or sweep.bn_work(top) or sweep.seam_work(top)
@@ -272,9 +451,10 @@ def main():
             achieved = w["amount"] / (ms * 1e-3) / (1e9 if w["bound"] == "hbm" else 1e12)
             peak = peaks["hbm_gbs"] if w["bound"] == "hbm" else peaks["bf16_tflops_sustained"]
             traffic = None  # dram__bytes_read+write per launch from the committed ncu --set full capture of this kernel
-            tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
-            if os.path.isfile(tpath):
-                traffic = json.load(open(tpath)).get(sweep.ncu_kernel_name(top) or "")
+            for tname in ("traffic_r02.json", "traffic_r01.json"):
+                tpath = os.path.join(ROOT, "profiles", tname)
+                if traffic is None and os.path.isfile(tpath):
+                    traffic = json.load(open(tpath)).get(sweep.ncu_kernel_name(top) or "")
             roof = {"kernel": top, "bound": w["bound"], "achieved": achieved, "peak": peak, "unit": "GB/s" if w["bound"] == "hbm" else "TFLOP/s",
                     "frac": achieved / peak, "traffic": traffic, "avg_ms": ms, "calls": n, "peak_source": peaks["source"] + " (sustained)",
                     "algorithmic": w["note"],
@@ -308,9 +488,21 @@ def main():
                          "config": "configs[1]: bf16 autocast, batch 64, forward only, eval mode, 1 GPU"}
     if not args.no_sweep:
         line["modules"] = sweep.run(SCALE, args.batch, peaks, iters=10)
-    if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = {k: v for k, v in cpu_reference_leg(6, 2).items() if k != "ms_per_step"}
-        line["cpu_baseline"]["sample"] += "; inference_b1_fp32_ms = configs[0] (batch 1, eval) on the same cores"
+        if roof is not None:   # per-block rows with SURVEY 8(d)'s bounds: CBAM / SPPF vs HBM, whole SwinBlock vs tensor peak
+            keep = ("cbam_fwd", "cbam_bwd", "sppf_pool_fwd_k5", "sppf_pool_bwd_k5", "sppf_pool_fwd_k7", "sppf_pool_bwd_k7",
+                    "swin_block_fwd_ws7", "swin_block_bwd_ws7")
+            roof["blocks"] = [{k: r[k] for k in ("kernel", "shape", "ms", "bound", "achieved", "peak", "unit", "frac")}
+                              for r in line["modules"] if r["kernel"] in keep and (not r["kernel"].startswith("cbam") or r["note"] == "P5")]
+    if world == 1 and not args.no_gpu_eager:
+        del tr, dev
+        torch.cuda.empty_cache()
+        line["gpu_eager_baseline"] = gpu_eager_baseline_leg(args.steps, args.warmup, args.batch, f"cuda:{local_rank}")
+        bf = line["gpu_eager_baseline"].get("bf16", {})
+        if "value" in bf:
+            line["vs_eager"] = {"value": line["value"] / bf["value"], "e2e": line["e2e"]["value"] / bf["value"],
+                                "note": "this arm / the unmodified reference run eagerly on the same GPU (bf16 autocast); >1 = faster"}
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_leg()
     print_record(line)
     if world > 1:
         dist.destroy_process_group()

@@ -19,6 +19,10 @@
 // With a stash the kernel also writes the by-products the (streaming) backward of cbam.cu consumes.
 #include <cooperative_groups.h>
 
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "cbam.cuh"
 
 namespace cg = cooperative_groups;
@@ -401,11 +405,29 @@ int launch(K kern, const Params& P, cudaStream_t st) {
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
+  // can this device co-schedule one such cluster at all (MIG slices, small GPCs, 16-CTA non-portable clusters)?  Asked once
+  // per (kernel, cluster size, smem); 0 or a failed launch -> -1 = "not taken", the caller runs the streaming chain (cbam.cu)
+  static std::mutex mu;
+  static std::map<std::tuple<const void*, int, int, int>, int> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int nclusters = 0;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_tuple((const void*)kern, L.cs, L.total, dev);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+      if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess) { nclusters = 0; cudaGetLastError(); }
+      cache.emplace(key, nclusters);
+    } else {
+      nclusters = it->second;
+    }
+  }
+  if (nclusters <= 0) return -1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, P);
   if (e != cudaSuccess) {
-    set_error("cbam: cluster launch failed (grid=%dx%d smem=%d): %s", L.cs, L.B, L.total, cudaGetErrorString(e));
     cudaGetLastError();
-    return B200_ERR_LAUNCH;
+    return -1;
   }
   return check_launch("cbam_fwd");
 }

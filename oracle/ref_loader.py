@@ -3,8 +3,9 @@
 The reference (mazouziwissem/improving_yolov8_CBAM_SwinBlock, an Ultralytics 8.3.108 fork) is pure
 Python, so it can be imported in the dev container to (a) validate the restatement in
 ``oracle/blocks.py`` and (b) generate the committed fixtures under ``tests/golden``
-(``oracle/make_golden.py``).  It does NOT exist on the GPU box: nothing on the ``-m gpu`` test path,
-``smoke()`` or ``bench.py`` may call into this file.
+(``oracle/make_golden.py``).  ``/root/reference`` does NOT exist on the GPU box; what travels there is the
+verbatim, git-ignored copy ``oracle/_ref`` made by ``oracle/build_ref.py`` (the "compiled reference" of this
+Python project).  Only checker code uses it: tests, ``bench.py --impl reference`` and its baseline legs.
 
 Recipe follows SURVEY.md section 8(c): ``cbam.py`` / ``swin_block.py`` import only torch + einops, so they
 are loaded by file path; the full ``ultralytics`` package needs permissive ``matplotlib`` stubs.
@@ -14,7 +15,18 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("B200_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    """/root/reference in the dev container; on the GPU box the verbatim copy oracle/build_ref.py made (oracle/_ref)."""
+    for cand in (os.environ.get("B200_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "ultralytics/nn/modules/cbam.py")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:

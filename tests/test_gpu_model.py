@@ -135,7 +135,10 @@ def test_graph_replayed_step_equals_eager_step(from_host):
 
 def test_whole_model_bf16_vs_oracle_blocks():
     """bf16 autocast (the benchmarked configuration): the graph with the B200 blocks against the same graph with the
-    oracle blocks evaluated in fp32 -- logits, loss items and every parameter gradient within the bf16 bar."""
+    oracle blocks evaluated in fp32 -- logits and loss items within the bf16 bar.  Whole-network bf16 back-propagation
+    through 27 randomly initialised layers amplifies rounding noise whatever implements the blocks, so the parameter
+    gradients are held to the yardstick the reference itself would meet: the error of the oracle-block graph under the
+    SAME bf16 autocast (stock PyTorch kernels) against its own fp32 run."""
     import improving_yolov8_cbam_swinblock_b200 as P
     from improving_yolov8_cbam_swinblock_b200.harness import graph, loss as hl, synthetic
     from oracle import modules as om
@@ -147,6 +150,7 @@ def test_whole_model_bf16_vs_oracle_blocks():
     mine = _build(P.BLOCKS, "n", 80, 2)
     mine.load_state_dict(ref.state_dict())
     ref, mine = ref.cuda().train(), mine.cuda().train().to(memory_format=torch.channels_last)
+    ref16 = copy.deepcopy(ref)
     batch = synthetic.make_batch(8, 320, 80, seed=9)
     dev_batch = {k: v.cuda() for k, v in batch.items()}
     img = dev_batch["img"].float() / 255
@@ -154,19 +158,27 @@ def test_whole_model_bf16_vs_oracle_blocks():
     fr = ref(img)
     with torch.autocast("cuda", dtype=torch.bfloat16):
         fm = mine(img.contiguous(memory_format=torch.channels_last))
-    for a, b in zip(fm, fr):
-        assert rel_err(a, b) < 3e-2, rel_err(a, b)
+        f16 = ref16(img)
+    for a, b, c in zip(fm, fr, f16):
+        assert rel_err(a, b) < max(3e-2, 1.5 * rel_err(c, b)), (rel_err(a, b), rel_err(c, b))
     lr, ir = crit(fr, dev_batch, max_boxes=8)
     lm, im = crit(fm, dev_batch, max_boxes=8)
+    l16, _ = crit(f16, dev_batch, max_boxes=8)
     torch.testing.assert_close(im, ir, rtol=3e-2, atol=1e-3)
     lr.sum().backward()
     lm.sum().backward()
-    gr, gm = dict(ref.named_parameters()), dict(mine.named_parameters())
-    bad = []
+    l16.sum().backward()
+    gr, gm, g16 = dict(ref.named_parameters()), dict(mine.named_parameters()), dict(ref16.named_parameters())
+    bad, num, num16, den = [], 0.0, 0.0, 0.0
     for k, p in gr.items():
         if p.grad is None:
             continue
-        e = rel_err(gm[k].grad, p.grad)
-        if e > 8e-2:   # whole-network bf16 back-propagation: rounding accumulates over 27 layers (module-level bar: 2e-2)
-            bad.append((k, round(e, 4)))
+        e, e16 = rel_err(gm[k].grad, p.grad), rel_err(g16[k].grad, p.grad)
+        num += float((gm[k].grad.double() - p.grad.double()).pow(2).sum())
+        num16 += float((g16[k].grad.double() - p.grad.double()).pow(2).sum())
+        den += float(p.grad.double().pow(2).sum())
+        if e > 3.0 * e16 + 2e-2:   # single parameters (e.g. the 98-element CBAM conv: a cancelling sum over B*H*W) are noisy in both
+            bad.append((k, round(e, 4), round(e16, 4)))
     assert not bad, bad
+    # all gradients together: the B200-block graph is as close to the fp32 truth as the stock bf16 graph is
+    assert (num / den) ** 0.5 <= 1.25 * (num16 / den) ** 0.5 + 1e-2, ((num / den) ** 0.5, (num16 / den) ** 0.5)

@@ -89,3 +89,26 @@ def test_plugin_seams_patch_is_value_neutral_and_reversible():
     finally:
         plugin.uninstall()
     assert C2f.forward is orig
+
+
+def test_reference_pickles_unpickle_as_plugin_classes_with_reference_state_only():
+    """SPPF.forward / SwinBlock.forward must not read attributes the reference classes never store (k,
+    num_heads): a module pickled by the reference and loaded after install() has run no __init__ of ours."""
+    import pickle
+
+    import improving_yolov8_cbam_swinblock_b200.ultralytics_plugin as plugin
+
+    ref_loader.import_ultralytics()
+    from ultralytics.nn.modules.block import SPPF as RSPPF
+    from ultralytics.nn.modules.swin_block import SwinBlock as RSwin
+
+    blobs = [pickle.dumps(RSwin(32, 2, 7)), pickle.dumps(RSPPF(32, 32, 7))]
+    table = plugin.install()
+    try:
+        ms, mp_ = (pickle.loads(b) for b in blobs)
+        assert type(ms) is table["SwinBlock"] and type(mp_) is table["SPPF"]
+        assert ms.attn.num_heads == 2 and ms.window_size == 7 and mp_.m.kernel_size == 7
+        x = torch.zeros(1, 32, 9, 9)   # shape probe path
+        assert ms(x).shape == x.shape and mp_(x).shape == x.shape
+    finally:
+        plugin.uninstall()
