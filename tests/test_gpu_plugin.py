@@ -48,7 +48,7 @@ def test_real_detection_model_trains_one_step_through_the_plugin(plugin):
 
     n0 = _lib.launch_count()
     loss_r, items_r = ref(dict(batch, img=img))              # BaseModel.forward(dict) -> _predict_once -> v8DetectionLoss
-    assert _lib.launch_count() - n0 > 100, "the real model's forward did not go through libb200yolo.so"
+    assert _lib.launch_count() - n0 >= 60, "the real model's forward did not go through libb200yolo.so"
     fm = mine(img)
     loss_m, items_m = hl.DetectionLoss(80, mine.stride)(fm, batch, max_boxes=8)
     torch.testing.assert_close(items_m, items_r, rtol=1e-4, atol=1e-5)
