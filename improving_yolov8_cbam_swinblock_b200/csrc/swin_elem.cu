@@ -214,9 +214,11 @@ __global__ void __launch_bounds__(256) swin_move_vec_kernel(const T* __restrict_
       if (!real) continue;
       float w[N];
       load_row<T, LPT, NV>(a + t * g.C, l, v);
-      load_row<T, LPT, NV>(b2 + t * g.C, l, w);
+      if (b2) {   // null: window_reverse + crop only
+        load_row<T, LPT, NV>(b2 + t * g.C, l, w);
 #pragma unroll
-      for (int i = 0; i < N; ++i) v[i] += w[i];
+        for (int i = 0; i < N; ++i) v[i] += w[i];
+      }
       store_row<T, LPT, NV>(out + pix * g.C, l, v);
     } else {
       if (real) load_row<T, LPT, NV>(a + pix * g.C, l, v);
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(256) swin_res_reverse_kernel(const T* __restri
   bool real;
   const long long pix = token_pixel(g, t, &real);
   if (!real) return;
-  for (int c = lane; c < g.C; c += 32) out[pix * g.C + c] = DT<T>::from_f(ldf(y1 + t * g.C + c) + ldf(m + t * g.C + c));
+  for (int c = lane; c < g.C; c += 32) out[pix * g.C + c] = DT<T>::from_f(ldf(y1 + t * g.C + c) + (m ? ldf(m + t * g.C + c) : 0.f));
 }
 
 // gy2[t,:] = g[b,y,x,:] for real tokens, 0 for padded ones (they are cropped, swin_block.py:58)
@@ -685,7 +687,7 @@ extern "C" B200_API int b200_swin_res_reverse(const void* y1, const void* m, voi
                                               int32_t W, int32_t ws, int32_t shift, int32_t dtype, void* stream) {
   WinGeom g;
   if (int rc = make_geom(&g, B, C, H, W, ws, shift)) return rc;
-  B200_REQUIRE(y1 && m && out, B200_ERR_SHAPE, "swin_res_reverse: null pointer");
+  B200_REQUIRE(y1 && out, B200_ERR_SHAPE, "swin_res_reverse: null pointer");   // m may be null: reverse + crop only
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
     int vec, iters;
     if (pick_vec<T>(C, &vec, &iters) && (((uintptr_t)y1 | (uintptr_t)m | (uintptr_t)out) & 15) == 0) {

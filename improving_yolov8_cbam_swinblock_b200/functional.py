@@ -38,6 +38,9 @@ _lib.register("b200_nhwc_concat", C.c_int, [_VP, _VP, _VP, _I32, _VP, _I64, _I32
 _lib.register("b200_u8_to_nhwc", C.c_int, [_VP, _VP] + [_I32] * 4 + [C.c_float, _I32, _VP])
 _lib.register("b200_nhwc_upsample_fwd", C.c_int, [_VP, _VP] + [_I32] * 7 + [_VP])
 _lib.register("b200_nhwc_upsample_bwd", C.c_int, [_VP, _I64, _VP] + [_I32] * 7 + [_VP])
+_lib.register("b200_swin_mlp_supported", C.c_int, [_I64, _I32, _I32])
+_lib.register("b200_swin_mlp_prep", C.c_int, [_VP] * 8 + [_I32, _I32, _VP])
+_lib.register("b200_swin_mlp_fwd", C.c_int, [_VP] * 6 + [_I64, _I32, C.c_float, _I32, _VP])
 
 
 def _nhwc(x: torch.Tensor) -> torch.Tensor:
@@ -424,6 +427,34 @@ def attn_backward(qkv, o, lse, go, T, Lw, Cc, nh, grid=(0, 0, 0, 0)):
     else:
         call("b200_swin_attn_bwd", ptr(qkv), ptr(o), ptr(lse), ptr(go), ptr(gqkv), T, Lw, Cc, nh, *grid, code, stream_ptr(dev))
     return gqkv
+
+
+USE_FUSED_MLP = True  # tests flip this to compare the fused tcgen05 MLP half with the unfused stage-by-stage path
+
+
+def fused_mlp_supported(rows: int, Cc: int, dtype) -> bool:
+    return USE_FUSED_MLP and dtype in (torch.bfloat16, torch.float16) and bool(lib().b200_swin_mlp_supported(rows, Cc, dtype_code(dtype)))
+
+
+def swin_mlp_prep(g2, b2n, w1, bb1, w2, dtype):
+    """(w1f, b1f, w2h): LayerNorm2's affine part folded into mlp.0, weights in the activation dtype (one small launch)."""
+    Cc = w1.shape[1]
+    dev = w1.device
+    w1f = torch.empty((4 * Cc, Cc), dtype=dtype, device=dev)
+    w2h = torch.empty((Cc, 4 * Cc), dtype=dtype, device=dev)
+    b1f = torch.empty(4 * Cc, dtype=torch.float32, device=dev)
+    call("b200_swin_mlp_prep", ptr(_f32(w1)), ptr(_f32(bb1)), ptr(_f32(g2)), ptr(_f32(b2n)), ptr(_f32(w2)), ptr(w1f), ptr(b1f), ptr(w2h),
+         Cc, dtype_code(dtype), stream_ptr(dev))
+    return w1f, b1f, w2h
+
+
+def swin_mlp_forward_raw(y1p, w1f, b1f, w2h, bb2, eps=1e-5):
+    """out[rows, C] = y1 + mlp.2(gelu(mlp.0(LN2(y1)))) on dense rows (pixel order), hidden activation kept on chip."""
+    rows, Cc = y1p.shape
+    out = torch.empty_like(y1p)
+    call("b200_swin_mlp_fwd", ptr(y1p), ptr(w1f), ptr(b1f), ptr(w2h), ptr(_f32(bb2)), ptr(out), rows, Cc, float(eps),
+         dtype_code(y1p.dtype), stream_ptr(y1p.device), tag=f"b200_swin_mlp_fwd[{rows}x{Cc}]")
+    return out
 
 
 class SwinBlockFn(torch.autograd.Function):

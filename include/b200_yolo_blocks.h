@@ -227,6 +227,26 @@ B200_API int b200_bn_silu_bwd(const void* gz, int64_t gz_row_stride, const void*
                               size_t workspace_bytes, int64_t rows, int32_t C, int32_t training, int32_t act,
                               int32_t dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Fused MLP half of the SwinBlock -- replaces `x_windows + self.mlp(self.norm2(x_windows))`, `window_reverse` and the
+ * crop (ultralytics/nn/modules/swin_block.py:53-58) for 16-bit activations with C = 128, in ONE tcgen05 kernel per
+ * direction: LayerNorm2 -> mlp.0 -> GELU -> mlp.2 -> + residual with the [rows, 4C] hidden activation kept on chip
+ * (TMEM / shared memory).  Rows are the real tokens in pixel order (y1 [rows = B*H*W, C], NHWC-dense).
+ *   b200_swin_mlp_prep : w1f = mlp.0.weight * norm2.weight (16-bit), b1f = mlp.0.bias + mlp.0.weight @ norm2.bias (f32),
+ *                        w2h = mlp.2.weight / 2 (16-bit; the kernels form 2 * gelu) -- LayerNorm's affine part folded
+ *                        into the first GEMM.
+ *   b200_swin_mlp_fwd  : out = y1 + mlp.2(gelu(xhat @ w1f^T + b1f)) + b2,  xhat = (y1 - mean) * rstd per row.
+ *   b200_swin_mlp_bwd  : from g_out [rows, C] and y1 recomputes xhat / the hidden pre-activation and writes
+ *                        g_y1 [rows, C] (residual + LayerNorm2 backward included) plus the three operands of the
+ *                        weight-gradient contractions: xhat [rows, C], h = gelu(a) [rows, 4C], g_a [rows, 4C]
+ *                        (d mlp.0.weight = g_a^T xhat * gamma + ..., d mlp.2.weight = g_out^T h: b200_gemm_splitk).
+ * ------------------------------------------------------------------------------------------------------ */
+B200_API int b200_swin_mlp_supported(int64_t rows, int32_t C, int32_t dtype);
+B200_API int b200_swin_mlp_prep(const float* w1, const float* b1, const float* gamma, const float* beta, const float* w2,
+                                void* w1f, float* b1f, void* w2h, int32_t C, int32_t dtype, void* stream);
+B200_API int b200_swin_mlp_fwd(const void* y1, const void* w1f, const float* b1f, const void* w2h, const float* b2, void* out,
+                               int64_t rows, int32_t C, float eps, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

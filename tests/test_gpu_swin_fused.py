@@ -1,0 +1,69 @@
+"""-m gpu: the fused tcgen05 halves of the SwinBlock (csrc/swin_mlp.cu, csrc/swin_attn_block.cu) against fp64 restatements
+of swin_block.py:50-53 on the same 16-bit inputs.  Bars: bf16 <= 2e-2 relative error (BASELINE.json), measured values are
+~10x tighter and asserted at 6e-3 / 1.5e-3 so a real regression shows."""
+import pytest
+import torch
+
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _mlp_params(C, seed):
+    g = torch.Generator().manual_seed(seed)
+    w1 = torch.randn(4 * C, C, generator=g) / C ** 0.5
+    b1 = 0.3 * torch.randn(4 * C, generator=g)
+    w2 = torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5
+    b2 = 0.3 * torch.randn(C, generator=g)
+    gamma = 1 + 0.3 * torch.randn(C, generator=g)
+    beta = 0.3 * torch.randn(C, generator=g)
+    return [t.cuda() for t in (gamma, beta, w1, b1, w2, b2)]
+
+
+def _mlp_ref(y1, gamma, beta, w1, b1, w2, b2):
+    """fp64 on the 16-bit inputs (the kernel rounds the weights to 16 bit per call: covered by the tolerance)."""
+    y = y1.double()
+    u = torch.nn.functional.layer_norm(y, (y.shape[1],), gamma.double(), beta.double(), 1e-5)
+    a = u @ w1.double().t() + b1.double()
+    h = torch.nn.functional.gelu(a)
+    return y + h @ w2.double().t() + b2.double(), u, a, h
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 6e-3), (torch.float16, 1.5e-3)])
+@pytest.mark.parametrize("rows", [128, 100, 1000, 4096 + 37, 102400])
+def test_fused_mlp_forward(dtype, tol, rows):
+    from improving_yolov8_cbam_swinblock_b200 import functional as Fb
+
+    C = 128
+    gamma, beta, w1, b1, w2, b2 = _mlp_params(C, rows)
+    torch.manual_seed(rows)
+    y1 = (1.5 * torch.randn(rows, C, device="cuda") + 0.2).to(dtype)
+    assert Fb.fused_mlp_supported(rows, C, dtype)
+    w1f, b1f, w2h = Fb.swin_mlp_prep(gamma, beta, w1, b1, w2, dtype)
+    assert rel_err(w1f, w1 * gamma[None, :]) < (4e-3 if dtype == torch.bfloat16 else 5e-4)
+    assert rel_err(b1f, b1 + w1 @ beta) < 1e-5
+    out = Fb.swin_mlp_forward_raw(y1, w1f, b1f, w2h, b2)
+    want, *_ = _mlp_ref(y1, gamma, beta, w1, b1, w2, b2)
+    assert out.shape == y1.shape and out.dtype == dtype
+    assert torch.isfinite(out).all()
+    assert rel_err(out, want) < tol, rel_err(out, want)
+    # the MLP branch alone (the residual dominates the norm above)
+    assert rel_err(out.double() - y1.double(), want - y1.double()) < 3 * tol, rel_err(out.double() - y1.double(), want - y1.double())
+    # deterministic
+    assert torch.equal(out, Fb.swin_mlp_forward_raw(y1, w1f, b1f, w2h, b2))
+
+
+def test_fused_mlp_forward_extreme_preactivations():
+    """|a| far outside the fitted range of the tanh-polynomial GELU: must saturate to 0 / a, never flip sign or NaN."""
+    from improving_yolov8_cbam_swinblock_b200 import functional as Fb
+
+    C, rows = 128, 256
+    gamma, beta, w1, b1, w2, b2 = _mlp_params(C, 3)
+    w1 = w1 * 12
+    torch.manual_seed(1)
+    y1 = torch.randn(rows, C, device="cuda").bfloat16()
+    w1f, b1f, w2h = Fb.swin_mlp_prep(gamma, beta, w1, b1, w2, torch.bfloat16)
+    out = Fb.swin_mlp_forward_raw(y1, w1f, b1f, w2h, b2)
+    want, _, a, _ = _mlp_ref(y1, gamma, beta, w1, b1, w2, b2)
+    assert float(a.abs().max()) > 30
+    assert rel_err(out, want) < 1e-2, rel_err(out, want)
