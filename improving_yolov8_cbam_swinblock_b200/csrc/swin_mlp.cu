@@ -417,6 +417,376 @@ swin_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
   if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, 512); }
 }
 
+// =====================================================================================================================
+// backward of the fused MLP half.  Per 128-row tile, with the hidden dimension in 8 chunks of 64 columns:
+//     xhat = LN2 statistics of y1 (recomputed; also written out for the weight-gradient GEMM)
+//     A(g) = xhat * W1'[chunk]^T,  G(g) = g_out * W2'[:, chunk]            (MMA_a, MMA_g -> TMEM)
+//     a = A + b1',  h = gelu(a) -> global,  g_a = G * 2 gelu'(a) -> shared (A of MMA_u) -> global (TMA store)
+//     U += g_a(g) * W1'[chunk]                                             (MMA_u; W1' = W1 gamma, so U = dL/dxhat)
+//     g_y1 = g_out + rstd * (U - mean(U) - xhat * mean(U * xhat))          (LayerNorm backward + residual)
+// The W1' chunk of a ring stage serves MMA_a (K-major B) and MMA_u (MN-major B) from the same bytes.  Parameter gradients are
+// contractions over ALL rows and are left to b200_gemm_splitk on the three tensors written here (see include/).
+// Warp roles as in the forward kernel: 0 W1' producer | 1 MMA issuer | 2-5 LayerNorm warps | 6-9 final (g_y1) warps |
+// 10-25 two groups of 8 GELU-backward warps on alternate chunks | 26 y1 / g_out tile loader | 27 W2' producer.
+// =====================================================================================================================
+constexpr int kRingW1B = 3;                                    // W1' stages are held from MMA_a(g) to MMA_u(g): a deeper ring
+struct MlpBwdSmem {
+  static constexpr int OFF_X = 0;                               // 2 x 32 KB: y1 tile -> xhat (A of MMA_a, LN backward input)
+  static constexpr int OFF_G = OFF_X + 2 * kTileBytes;          // 32 KB: g_out tile (A of MMA_g)
+  static constexpr int OFF_GA = OFF_G + kTileBytes;             // 2 x 16 KB: g_a chunk tiles (A of MMA_u, TMA store source)
+  static constexpr int OFF_W1 = OFF_GA + 2 * kHalfBytes;        // kRingW1B x 16 KB: W1' chunks [64 hidden rows][2 x 128 B]
+  static constexpr int OFF_W2 = OFF_W1 + kRingW1B * kHalfBytes; // kRing x 16 KB: W2' chunks [128 rows][128 B]
+  static constexpr int OFF_B1 = OFF_W2 + kRing * kHalfBytes;    // b1' [512] f32
+  static constexpr int OFF_RS = OFF_B1 + kHid * 4;              // rstd [2][128] f32
+  static constexpr int OFF_BAR = OFF_RS + 2 * kTileM * 4;
+  static constexpr int TOTAL = OFF_BAR + 256;
+};
+static_assert(MlpBwdSmem::TOTAL <= 232448, "shared memory budget");
+
+struct MlpBwdParams {
+  const void* gout;   // [P, 128] (also TMA-loaded as the A operand; re-read per row for the residual)
+  void* gy1;          // [P, 128]
+  void* h;            // [P, 512]
+  const float* b1f;
+  long long P;
+  int n_tiles;
+  float eps;
+};
+
+// 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kThreads, 1)
+swin_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmG,
+                    const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                    const __grid_constant__ CUtensorMap tmXhat, const __grid_constant__ CUtensorMap tmGa, MlpBwdParams P) {
+  using S = MlpBwdSmem;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  float* sb1 = reinterpret_cast<float*>(smem + S::OFF_B1);
+  float* srs = reinterpret_cast<float*>(smem + S::OFF_RS);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* y_full = bars;                 // [2] y1 tile landed
+  uint64_t* u_ready = bars + 2;            // [2] xhat written (128 LayerNorm threads)
+  uint64_t* x_free = bars + 4;             // [2] xhat tile no longer needed: 128 final threads + the xhat store's reader
+  uint64_t* g_full = bars + 6;             // g_out tile landed
+  uint64_t* g_free = bars + 7;             // the tile's eight MMA_g have read it (commit)
+  uint64_t* w1_full = bars + 8;            // [kRingW1B]
+  uint64_t* w1_empty = w1_full + kRingW1B;
+  uint64_t* w2_full = w1_empty + kRingW1B; // [kRing]
+  uint64_t* w2_empty = w2_full + kRing;
+  uint64_t* ag_full = w2_empty + kRing;    // [2] A and G accumulators of a chunk complete (commit)
+  uint64_t* ag_tfree = ag_full + 2;        // [2] ... read back (256 threads of the group)
+  uint64_t* ga_full = ag_full + 4;         // [2] g_a tile written (group leader, after the group's barrier)
+  uint64_t* ga_free = ag_full + 6;         // [2] g_a tile consumed by MMA_u (commit)
+  uint64_t* tu_full = ag_full + 8;         // [2] U accumulator of a tile complete (commit)
+  uint64_t* tu_free = ag_full + 10;        // [2] ... read back (128 final threads)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ag_full + 12);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_local = (int)blockIdx.x < P.n_tiles ? (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int n_chunks = 8 * n_local;
+  auto xbuf = [&](int b) { return smem + S::OFF_X + b * kTileBytes; };
+  unsigned char* gbuf = smem + S::OFF_G;
+  auto gabuf = [&](int i) { return smem + S::OFF_GA + i * kHalfBytes; };
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&tmY); prefetch_tmap(&tmG); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2); prefetch_tmap(&tmXhat); prefetch_tmap(&tmGa);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&y_full[i], 1); mbar_init(&u_ready[i], 32 * kLnWarps); mbar_init(&x_free[i], 32 * kOutWarps + 1);
+      mbar_init(&ag_full[i], 1); mbar_init(&ag_tfree[i], 16 * kGeluWarps); mbar_init(&ga_full[i], 1); mbar_init(&ga_free[i], 1);
+      mbar_init(&tu_full[i], 1); mbar_init(&tu_free[i], 32 * kOutWarps);
+    }
+    mbar_init(g_full, 1); mbar_init(g_free, 1);
+    for (int i = 0; i < kRingW1B; ++i) { mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1); }
+    for (int i = 0; i < kRing; ++i) { mbar_init(&w2_full[i], 1); mbar_init(&w2_empty[i], 1); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  for (int i = threadIdx.x; i < kHid; i += kThreads) sb1[i] = P.b1f[i];
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  auto tA = [&](int i) { return tmem_base + i * 64; };            // [0,128): A accumulators of the two groups
+  auto tG = [&](int i) { return tmem_base + 128 + i * 64; };      // [128,256): G accumulators
+  auto tU = [&](int b) { return tmem_base + 256 + b * 128; };     // [256,512): U accumulators of two tiles
+
+  if (warp == 0) {
+    // ===================== W1' producer: chunk g = rows (g&7)*64 .. +64, all 128 columns (two K blocks) =====================
+    if (elect_one()) {
+      int st = 0; uint32_t ph = 0;
+      for (int g = 0; g < n_chunks; ++g) {
+        unsigned char* dst = smem + S::OFF_W1 + st * kHalfBytes;
+        mbar_wait(&w1_empty[st], ph ^ 1);
+        mbar_expect_tx(&w1_full[st], kHalfBytes);
+        tma_load_2d(dst, &tmW1, &w1_full[st], 0, (g & 7) * 64);
+        tma_load_2d(dst + 64 * 128, &tmW1, &w1_full[st], 64, (g & 7) * 64);
+        if (++st == kRingW1B) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == kW2Warp) {
+    // ===================== W2' producer: chunk g = columns (g&7)*64 .. +64, all 128 rows =====================
+    if (elect_one()) {
+      int st = 0; uint32_t ph = 0;
+      for (int g = 0; g < n_chunks; ++g) {
+        mbar_wait(&w2_empty[st], ph ^ 1);
+        mbar_expect_tx(&w2_full[st], kHalfBytes);
+        tma_load_2d(smem + S::OFF_W2 + st * kHalfBytes, &tmW2, &w2_full[st], (g & 7) * 64, 0);
+        if (++st == kRing) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == kLoaderWarp) {
+    // ===================== y1 / g_out tile loader =====================
+    if (elect_one()) {
+      for (int n = 0; n < n_local; ++n) {
+        const int b = n & 1;
+        const int tile = blockIdx.x + n * gridDim.x;
+        mbar_wait(&x_free[b], ((n >> 1) & 1) ^ 1);
+        mbar_expect_tx(&y_full[b], kTileBytes);
+        tma_load_2d(xbuf(b), &tmY, &y_full[b], 0, tile * kTileM);
+        tma_load_2d(xbuf(b) + kHalfBytes, &tmY, &y_full[b], 64, tile * kTileM);
+        mbar_wait(g_free, (n & 1) ^ 1);
+        mbar_expect_tx(g_full, kTileBytes);
+        tma_load_2d(gbuf, &tmG, g_full, 0, tile * kTileM);
+        tma_load_2d(gbuf + kHalfBytes, &tmG, g_full, 64, tile * kTileM);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: stream 1 = MMA_a + MMA_g per chunk, stream 2 = MMA_u per chunk =====================
+    if (elect_one()) {
+      const uint32_t id_a = idesc_f16(128, 64, FMT, 0, 0), id_g = idesc_f16(128, 64, FMT, 0, 1), id_u = idesc_f16(128, 128, FMT, 0, 1);
+      int s1a = 0, s1u = 0, s2 = 0; uint32_t p1a = 0, p2 = 0;
+      int a = 0, b = 0;            // next chunk of stream 1 / stream 2
+      while (b < n_chunks) {
+        if (b < a && mbar_poll(&ga_full[b & 1], (b >> 1) & 1)) {
+          // ---- MMA_u(b): U[t&1] (+)= g_a(b) [128 x 64] * W1'[chunk] [64 x 128] (B MN-major, from the stage MMA_a(b) used) ----
+          const int t = b >> 3;
+          bool go = true;
+          if ((b & 7) == 0) go = mbar_poll(&tu_free[t & 1], ((t >> 1) & 1) ^ 1);   // fresh accumulator: tile t-2's final warps are done
+          if (go) {
+            fence_after_sync();
+            unsigned char* A = gabuf(b & 1);
+            unsigned char* B = smem + S::OFF_W1 + s1u * kHalfBytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(tU(t & 1), smem_desc_k_sw128(A + k * 32), smem_desc_mn_sw128(B + k * 2048, 64 * 128), id_u, ((b & 7) | k) ? 1u : 0u);
+            umma_commit(&w1_empty[s1u]);
+            umma_commit(&ga_free[b & 1]);
+            if ((b & 7) == 7) umma_commit(&tu_full[t & 1]);
+            if (++s1u == kRingW1B) s1u = 0;
+            ++b;
+          }
+        }
+        if (a < n_chunks && a < b + kRingW1B) {   // a W1' stage stays held until MMA_u of its chunk: never wait on a stage the ring cannot supply
+          const int t = a >> 3;
+          bool go = mbar_poll(&ag_tfree[a & 1], ((a >> 1) & 1) ^ 1);
+          if (go && (a & 7) == 0) go = mbar_poll(&u_ready[t & 1], (t >> 1) & 1) && mbar_poll(g_full, t & 1);
+          if (go) {
+            fence_after_sync();
+            mbar_wait(&w1_full[s1a], p1a);
+            mbar_wait(&w2_full[s2], p2);
+            fence_after_sync();
+            unsigned char* X = xbuf(t & 1);
+            unsigned char* W1s = smem + S::OFF_W1 + s1a * kHalfBytes;
+            unsigned char* W2s = smem + S::OFF_W2 + s2 * kHalfBytes;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)      // A(g) = xhat [128 x 128] * W1'[chunk]^T : B K-major [64 rows][2 K blocks]
+              umma_f16(tA(a & 1), smem_desc_k_sw128(X + (k >> 2) * kHalfBytes + (k & 3) * 32),
+                       smem_desc_k_sw128(W1s + (k >> 2) * (64 * 128) + (k & 3) * 32), id_a, k ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)      // G(g) = g_out [128 x 128] * W2'[:, chunk] : B MN-major [128 K rows][64]
+              umma_f16(tG(a & 1), smem_desc_k_sw128(gbuf + (k >> 2) * kHalfBytes + (k & 3) * 32),
+                       smem_desc_mn_sw128(W2s + k * 2048, kHalfBytes), id_g, k ? 1u : 0u);
+            umma_commit(&w2_empty[s2]);
+            umma_commit(&ag_full[a & 1]);
+            if ((a & 7) == 7) umma_commit(g_free);
+            if (++s1a == kRingW1B) { s1a = 0; p1a ^= 1; }
+            if (++s2 == kRing) { s2 = 0; p2 ^= 1; }
+            ++a;
+          }
+        }
+      }
+    }
+  } else if (warp < kFirstOutWarp) {
+    // ===================== LayerNorm warps: y1 -> xhat (in place) + rstd; the tile also leaves as xhat[P,128] =====================
+    const int q = warp & 3, row = q * 32 + lane;
+    const bool leader = (warp == 2 && lane == 0);
+    for (int n = 0; n < n_local; ++n) {
+      const int b = n & 1;
+      const int tile = blockIdx.x + n * gridDim.x;
+      unsigned char* u = xbuf(b);
+      if (leader && n > 0) {               // the previous tile's xhat store has read its buffer: one of its x_free arrivals
+        bulk_wait_read_all();
+        mbar_arrive(&x_free[(n - 1) & 1]);
+      }
+      mbar_wait(&y_full[b], (n >> 1) & 1);
+      const float x0 = up_lo<FMT>(row_chunk(u, row, 0)->x);
+      float s = 0.f, ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const uint4 w = *row_chunk(u, row, c);
+        const float d0 = up_lo<FMT>(w.x) - x0, d1 = up_hi<FMT>(w.x) - x0, d2 = up_lo<FMT>(w.y) - x0, d3 = up_hi<FMT>(w.y) - x0;
+        const float d4 = up_lo<FMT>(w.z) - x0, d5 = up_hi<FMT>(w.z) - x0, d6 = up_lo<FMT>(w.w) - x0, d7 = up_hi<FMT>(w.w) - x0;
+        s += ((d0 + d1) + (d2 + d3)) + ((d4 + d5) + (d6 + d7));
+        ss += fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3) + (fmaf(d4, d4, d5 * d5) + fmaf(d6, d6, d7 * d7));
+      }
+      const float md = s * (1.f / kC);
+      const float rstd = rsqrtf(fmaxf(ss * (1.f / kC) - md * md, 0.f) + P.eps);
+      const float shift = -(x0 + md) * rstd;
+      srs[b * kTileM + row] = rstd;
+#pragma unroll 4
+      for (int c = 0; c < 16; ++c) {
+        uint4* p = row_chunk(u, row, c);
+        const uint4 w = *p;
+        uint4 o;
+        o.x = pack2h<FMT>(fmaf(up_lo<FMT>(w.x), rstd, shift), fmaf(up_hi<FMT>(w.x), rstd, shift));
+        o.y = pack2h<FMT>(fmaf(up_lo<FMT>(w.y), rstd, shift), fmaf(up_hi<FMT>(w.y), rstd, shift));
+        o.z = pack2h<FMT>(fmaf(up_lo<FMT>(w.z), rstd, shift), fmaf(up_hi<FMT>(w.z), rstd, shift));
+        o.w = pack2h<FMT>(fmaf(up_lo<FMT>(w.w), rstd, shift), fmaf(up_hi<FMT>(w.w), rstd, shift));
+        *p = o;
+      }
+      fence_proxy_async();
+      mbar_arrive(&u_ready[b]);
+      named_bar_sync(1, 32 * kLnWarps);
+      if (leader) {
+        tma_store_2d(&tmXhat, u, 0, tile * kTileM);
+        tma_store_2d(&tmXhat, u + kHalfBytes, 64, tile * kTileM);
+        bulk_commit();
+      }
+    }
+    if (leader && n_local > 0) { bulk_wait_all(); mbar_arrive(&x_free[(n_local - 1) & 1]); }
+  } else if (warp < kFirstGeluWarp) {
+    // ===================== final warps: U = dL/dxhat -> LayerNorm backward + residual -> g_y1 row (thread = row) =====================
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    for (int n = 0; n < n_local; ++n) {
+      const int b = n & 1;
+      const long long grow = (long long)(blockIdx.x + n * gridDim.x) * kTileM + row;
+      const bool live = grow < P.P;
+      unsigned char* u = xbuf(b);
+      const uint4* grow_in = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(P.gout) + grow * kC);
+      uint4* grow_out = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(P.gy1) + grow * kC);
+      mbar_wait(&tu_full[b], (n >> 1) & 1);
+      fence_after_sync();
+      const float rstd = srs[b * kTileM + row];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tU(b) + lane_sel + ch * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 w = *row_chunk(u, row, ch * 4 + c);
+          const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float g0 = __uint_as_float(v[c * 8 + 2 * e]), g1 = __uint_as_float(v[c * 8 + 2 * e + 1]);
+            s1 += g0 + g1;
+            s2 = fmaf(g0, up_lo<FMT>(ww[e]), s2);
+            s2 = fmaf(g1, up_hi<FMT>(ww[e]), s2);
+          }
+        }
+      }
+      const float m1 = s1 * (1.f / kC), m2 = s2 * (1.f / kC);
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tU(b) + lane_sel + ch * 32, v);
+        tmem_ld_wait();
+        if (ch == 3) { fence_before_sync(); mbar_arrive(&tu_free[b]); }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 w = *row_chunk(u, row, ch * 4 + c);
+          uint4 gi = make_uint4(0, 0, 0, 0);
+          if (live) gi = ldg_stream16(grow_in + ch * 4 + c);
+          const uint32_t ww[4] = {w.x, w.y, w.z, w.w}, gg[4] = {gi.x, gi.y, gi.z, gi.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float r0 = fmaf(rstd, __uint_as_float(v[c * 8 + 2 * e]) - m1 - up_lo<FMT>(ww[e]) * m2, up_lo<FMT>(gg[e]));
+            const float r1 = fmaf(rstd, __uint_as_float(v[c * 8 + 2 * e + 1]) - m1 - up_hi<FMT>(ww[e]) * m2, up_hi<FMT>(gg[e]));
+            o[e] = pack2h<FMT>(r0, r1);
+          }
+          if (live) stg_stream16(grow_out + ch * 4 + c, make_uint4(o[0], o[1], o[2], o[3]));
+        }
+      }
+      mbar_arrive(&x_free[b]);
+    }
+  } else if (warp < kLoaderWarp) {
+    // ===================== GELU-backward warps: two groups of 8 on alternate 64-column chunks =====================
+    const int gw = warp - kFirstGeluWarp;
+    const int grp = gw >> 3;
+    const int q = warp & 3, cs = (gw >> 2) & 1;      // TMEM lane quadrant, 32-column half of the chunk
+    const int row = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const bool leader = ((gw & 7) == 0 && lane == 0);
+    unsigned char* ga = gabuf(grp);
+    bool pending = false;
+    for (int g = grp; g < n_chunks; g += 2) {
+      const uint32_t ph = (g >> 1) & 1;
+      const int t = g >> 3, j = g & 7;
+      const long long grow = (long long)(blockIdx.x + t * gridDim.x) * kTileM + row;
+      const bool live = grow < P.P;
+      const float* bias = sb1 + j * 64 + cs * 32;
+      uint16_t* hrow = reinterpret_cast<uint16_t*>(P.h) + grow * kHid + j * 64 + cs * 32;
+      mbar_wait(&ag_full[grp], ph);
+      fence_after_sync();
+      mbar_wait(&ga_free[grp], ph ^ 1);              // MMA_u(g-2) has consumed the tile ...
+      if (pending) {                                 // ... and its TMA store has read it
+        if (leader) bulk_wait_read_all();
+        named_bar_sync(2 + grp, 16 * kGeluWarps);
+      }
+#pragma unroll 1
+      for (int r2 = 0; r2 < 2; ++r2) {
+        uint32_t va[16], vg[16];
+        tmem_ld16(tA(grp) + lane_sel + cs * 32 + r2 * 16, va);
+        tmem_ld16(tG(grp) + lane_sel + cs * 32 + r2 * 16, vg);
+        tmem_ld_wait();
+        if (r2 == 1) { fence_before_sync(); mbar_arrive(&ag_tfree[grp]); }
+        uint32_t oh[8], og[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float4 bv = *reinterpret_cast<const float4*>(bias + r2 * 16 + 4 * e);
+          const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+          float hh[4], dd[4];
+#pragma unroll
+          for (int z = 0; z < 4; ++z) {
+            dd[z] = 2.f * gelu_tanh5_grad(__uint_as_float(va[4 * e + z]) + bb[z], &hh[z]) * __uint_as_float(vg[4 * e + z]);
+          }
+          oh[2 * e] = pack2h<FMT>(hh[0], hh[1]); oh[2 * e + 1] = pack2h<FMT>(hh[2], hh[3]);
+          og[2 * e] = pack2h<FMT>(dd[0], dd[1]); og[2 * e + 1] = pack2h<FMT>(dd[2], dd[3]);
+        }
+        if (live) {
+          stg_stream16(hrow + r2 * 16, make_uint4(oh[0], oh[1], oh[2], oh[3]));
+          stg_stream16(hrow + r2 * 16 + 8, make_uint4(oh[4], oh[5], oh[6], oh[7]));
+        }
+        *reinterpret_cast<uint4*>(ga + sw128_offset(row, cs * 4 + r2 * 2)) = make_uint4(og[0], og[1], og[2], og[3]);
+        *reinterpret_cast<uint4*>(ga + sw128_offset(row, cs * 4 + r2 * 2 + 1)) = make_uint4(og[4], og[5], og[6], og[7]);
+      }
+      fence_proxy_async();
+      named_bar_sync(2 + grp, 16 * kGeluWarps);
+      if (leader) {
+        mbar_arrive(&ga_full[grp]);
+        tma_store_2d(&tmGa, ga, j * 64, (blockIdx.x + t * gridDim.x) * kTileM);
+        bulk_commit();
+      }
+      pending = true;
+    }
+    if (leader) bulk_wait_all();
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) { fence_after_sync(); tmem_dealloc(tmem_base, 512); }
+}
+
 // W1' = W1 * gamma (16-bit), b1' = b1 + W1 beta (f32), W2' = W2 / 2 (16-bit; the kernels produce 2 * gelu).  One warp per W1 row; W2 converted by the same grid.
 __global__ void swin_mlp_prep_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, const float* __restrict__ w2, uint16_t* __restrict__ w1f,
@@ -483,4 +853,28 @@ extern "C" B200_API int b200_swin_mlp_fwd(const void* y1, const void* w1f, const
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::TOTAL);
   kern<<<grid, kThreads, MlpSmem::TOTAL, (cudaStream_t)stream>>>(*mY, *mO, *mW1, *mW2, P);
   return check_launch("swin_mlp_fwd");
+}
+
+extern "C" B200_API int b200_swin_mlp_bwd(const void* gout, const void* y1, const void* w1f, const float* b1f, const void* w2h, void* gy1,
+                                          void* xhat, void* h, void* ga, int64_t rows, int32_t C, float eps, int32_t dtype, void* stream) {
+  B200_REQUIRE(b200_swin_mlp_supported(rows, C, dtype), B200_ERR_UNSUPPORTED,
+               "swin_mlp_bwd: unsupported problem rows=%lld C=%d dtype=%d (16-bit dtypes, C = 128)", (long long)rows, C, dtype);
+  B200_REQUIRE(gout && y1 && w1f && b1f && w2h && gy1 && xhat && h && ga, B200_ERR_SHAPE, "swin_mlp_bwd: null pointer");
+  B200_REQUIRE((((uintptr_t)gout | (uintptr_t)y1 | (uintptr_t)w1f | (uintptr_t)w2h | (uintptr_t)gy1 | (uintptr_t)xhat | (uintptr_t)h | (uintptr_t)ga) & 15) == 0,
+               B200_ERR_ALIGN, "swin_mlp_bwd: 16-byte alignment required");
+  using namespace b200::tc;
+  const CUtensorMap* mY = tensor_map_2d(y1, (uint64_t)rows, kC, kC, kTileM, 64, dtype);
+  const CUtensorMap* mG = tensor_map_2d(gout, (uint64_t)rows, kC, kC, kTileM, 64, dtype);
+  const CUtensorMap* mW1 = tensor_map_2d(w1f, kHid, kC, kC, 64, 64, dtype);
+  const CUtensorMap* mW2 = tensor_map_2d(w2h, kC, kHid, kHid, 128, 64, dtype);
+  const CUtensorMap* mX = tensor_map_2d(xhat, (uint64_t)rows, kC, kC, kTileM, 64, dtype);
+  const CUtensorMap* mGa = tensor_map_2d(ga, (uint64_t)rows, kHid, kHid, kTileM, 64, dtype);
+  if (!mY || !mG || !mW1 || !mW2 || !mX || !mGa) return B200_ERR_LAUNCH;
+  MlpBwdParams P;
+  P.gout = gout; P.gy1 = gy1; P.h = h; P.b1f = b1f; P.P = rows; P.n_tiles = (int)((rows + kTileM - 1) / kTileM); P.eps = eps;
+  const int grid = P.n_tiles < sm_count() ? P.n_tiles : sm_count();
+  auto kern = dtype == B200_BF16 ? swin_mlp_bwd_kernel<1> : swin_mlp_bwd_kernel<0>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpBwdSmem::TOTAL);
+  kern<<<grid, kThreads, MlpBwdSmem::TOTAL, (cudaStream_t)stream>>>(*mY, *mG, *mW1, *mW2, *mX, *mGa, P);
+  return check_launch("swin_mlp_bwd");
 }

@@ -41,6 +41,7 @@ _lib.register("b200_nhwc_upsample_bwd", C.c_int, [_VP, _I64, _VP] + [_I32] * 7 +
 _lib.register("b200_swin_mlp_supported", C.c_int, [_I64, _I32, _I32])
 _lib.register("b200_swin_mlp_prep", C.c_int, [_VP] * 8 + [_I32, _I32, _VP])
 _lib.register("b200_swin_mlp_fwd", C.c_int, [_VP] * 6 + [_I64, _I32, C.c_float, _I32, _VP])
+_lib.register("b200_swin_mlp_bwd", C.c_int, [_VP] * 9 + [_I64, _I32, C.c_float, _I32, _VP])
 
 
 def _nhwc(x: torch.Tensor) -> torch.Tensor:
@@ -457,6 +458,19 @@ def swin_mlp_forward_raw(y1p, w1f, b1f, w2h, bb2, eps=1e-5):
     return out
 
 
+def swin_mlp_backward_raw(gout, y1p, w1f, b1f, w2h, eps=1e-5):
+    """-> (g_y1 [rows,C], xhat [rows,C], h = gelu(a) [rows,4C], g_a [rows,4C]): the data gradient of the fused MLP half
+    (residual + LayerNorm2 backward included) and the three operands of the weight-gradient contractions."""
+    rows, Cc = y1p.shape
+    dev, dt = y1p.device, y1p.dtype
+    gy1, xhat = torch.empty_like(y1p), torch.empty_like(y1p)
+    h = torch.empty((rows, 4 * Cc), dtype=dt, device=dev)
+    ga = torch.empty((rows, 4 * Cc), dtype=dt, device=dev)
+    call("b200_swin_mlp_bwd", ptr(gout), ptr(y1p), ptr(w1f), ptr(b1f), ptr(w2h), ptr(gy1), ptr(xhat), ptr(h), ptr(ga), rows, Cc, float(eps),
+         dtype_code(dt), stream_ptr(dev), tag=f"b200_swin_mlp_bwd[{rows}x{Cc}]")
+    return gy1, xhat, h, ga
+
+
 class SwinBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, *args):
@@ -492,15 +506,27 @@ class SwinBlockFn(torch.autograd.Function):
             qkv = gemm.linear(n1, win, bin_)
             o, lse = attn_forward(qkv, T, Lw, Cc, num_heads, grid)
             y1 = gemm.linear_res(o, wo, bo, n1)  # post-norm residual fused into the out_proj epilogue
-            u = torch.empty_like(n1)
-            mean2, rstd2 = torch.empty(T, **f32), torch.empty(T, **f32)
-            call("b200_swin_res_ln2", ptr(y1), None, ptr(g2f), ptr(b2f), None, ptr(u), ptr(mean2), ptr(rstd2), T, Cc,
-                                      code, st)
-            h, hpre = gemm.linear_gelu(u, w1, bb1)
-            m = gemm.linear(h, w2, bb2)
-            out = _empty_nhwc(B, Cc, H, W, dt, dev)
-            call("b200_swin_res_reverse", ptr(y1), ptr(m), ptr(out), B, Cc, H, W, ws, shift, code, st)
-        ctx.save_for_backward(x, g1f, g2f, win, wo, w1, w2, n1, mean1, rstd1, qkv, o, lse, y1, u, mean2, rstd2, hpre, h)
+            fused = fused_mlp_supported(B * H * W, Cc, dt)
+            if fused:
+                # MLP half in one tcgen05 kernel on the real tokens in pixel order (window_reverse + crop = the row order)
+                y1p = _empty_nhwc(B, Cc, H, W, dt, dev)
+                call("b200_swin_res_reverse", ptr(y1), None, ptr(y1p), B, Cc, H, W, ws, shift, code, st)
+                w1f, b1f, w2h = swin_mlp_prep(g2, b2, w1, bb1, w2, dt)
+                out = _empty_nhwc(B, Cc, H, W, dt, dev)
+                call("b200_swin_mlp_fwd", ptr(y1p), ptr(w1f), ptr(b1f), ptr(w2h), ptr(_f32(bb2)), ptr(out), B * H * W, Cc, 1e-5, code, st,
+                     tag=f"b200_swin_mlp_fwd[{B * H * W}x{Cc}]")
+                ctx.save_for_backward(x, g1f, g2f, b2f, win, wo, w1, n1, mean1, rstd1, qkv, o, lse, y1p, w1f, b1f, w2h)
+            else:
+                u = torch.empty_like(n1)
+                mean2, rstd2 = torch.empty(T, **f32), torch.empty(T, **f32)
+                call("b200_swin_res_ln2", ptr(y1), None, ptr(g2f), ptr(b2f), None, ptr(u), ptr(mean2), ptr(rstd2), T, Cc,
+                                          code, st)
+                h, hpre = gemm.linear_gelu(u, w1, bb1)
+                m = gemm.linear(h, w2, bb2)
+                out = _empty_nhwc(B, Cc, H, W, dt, dev)
+                call("b200_swin_res_reverse", ptr(y1), ptr(m), ptr(out), B, Cc, H, W, ws, shift, code, st)
+                ctx.save_for_backward(x, g1f, g2f, win, wo, w1, w2, n1, mean1, rstd1, qkv, o, lse, y1, u, mean2, rstd2, hpre, h)
+        ctx.fused_mlp = fused
         ctx.cfg = (B, Cc, H, W, ws, num_heads, T, shift)
         ctx.pdtypes = tuple(p.dtype for p in (g1, b1, win, bin_, wo, bo, g2, b2, w1, bb1, w2, bb2))
         return out
@@ -509,33 +535,50 @@ class SwinBlockFn(torch.autograd.Function):
     def _backward(ctx, gout):
         from . import gemm
 
-        (x, g1f, g2f, win, wo, w1, w2, n1, mean1, rstd1, qkv, o, lse, y1, u, mean2, rstd2, hpre, h) = ctx.saved_tensors
         B, Cc, H, W, ws, nh, T, shift = ctx.cfg
         grid = (-(-H // ws), -(-W // ws), ws, shift)
-        dev, dt = x.device, x.dtype
+        dev, dt = gout.device, ctx.saved_tensors[0].dtype
         code = dtype_code(dt)
         L = lib()
         st = stream_ptr(dev)
         Lw = ws * ws
         with torch.cuda.device(dev):
             gout = _nhwc(gout.to(dt))
-            gy2 = torch.empty((T, Cc), dtype=dt, device=dev)
-            call("b200_swin_partition", ptr(gout), ptr(gy2), B, Cc, H, W, ws, shift, code, st)
-            # MLP
-            gw2, gb2 = gemm.matmul_tn(gy2, h)     # [C, 4C] = gy2^T h,  [C] = sum_t gy2
-            ga = gemm.matmul_nn_gelu_bwd(gy2, w2, hpre)  # [T, 4C] = (gy2 W2) * gelu'(hpre)
-            gw1, gb1 = gemm.matmul_tn(ga, u)      # [4C, C], [4C]
-            gu = gemm.matmul_nn(ga, w1)           # [T, C]
-            del ga
-            # LN2 + residual
             nbytes = L.b200_swin_ln_bwd_workspace_bytes(T, Cc)
             wsb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            gy1 = torch.empty_like(gy2)
-            gg2 = torch.empty(Cc, dtype=torch.float32, device=dev)
-            gbt2 = torch.empty(Cc, dtype=torch.float32, device=dev)
-            call("b200_swin_ln_bwd", ptr(gu), ptr(y1), ptr(gy2), ptr(g2f), ptr(mean2), ptr(rstd2), ptr(gy1), ptr(gg2),
-                                     ptr(gbt2), ptr(wsb), nbytes, B, Cc, H, W, ws, shift, code, 0, st)
-            del gu, gy2
+            if ctx.fused_mlp:
+                (x, g1f, g2f, b2f, win, wo, w1, n1, mean1, rstd1, qkv, o, lse, y1p, w1f, b1f, w2h) = ctx.saved_tensors
+                rows = B * H * W
+                g2d = gout.permute(0, 2, 3, 1).reshape(rows, Cc)          # NHWC-dense memory viewed as [rows, C]: no copy
+                gy1p, xhat, h, ga = swin_mlp_backward_raw(g2d, y1p.permute(0, 2, 3, 1).reshape(rows, Cc), w1f, b1f, w2h)
+                gw2, gb2 = gemm.matmul_tn(g2d, h)                          # [C, 4C] = g_out^T gelu(a),  [C] = sum g_out
+                G, gb1 = gemm.matmul_tn(ga, xhat)                          # [4C, C] = g_a^T xhat,       [4C] = sum g_a
+                del h, ga, xhat
+                # LayerNorm2's affine part was folded into mlp.0 (u = xhat * gamma + beta): unfold the three gradients
+                w1d = w1.detach().float()
+                gw1 = torch.addcmul(gb1[:, None] * b2f[None, :], G, g2f[None, :])
+                gg2 = (w1d * G).sum(0)
+                gbt2 = w1d.t() @ gb1
+                gy1 = torch.empty((T, Cc), dtype=dt, device=dev)
+                call("b200_swin_partition", ptr(gy1p), ptr(gy1), B, Cc, H, W, ws, shift, code, st)
+                del gy1p
+            else:
+                (x, g1f, g2f, win, wo, w1, w2, n1, mean1, rstd1, qkv, o, lse, y1, u, mean2, rstd2, hpre, h) = ctx.saved_tensors
+                gy2 = torch.empty((T, Cc), dtype=dt, device=dev)
+                call("b200_swin_partition", ptr(gout), ptr(gy2), B, Cc, H, W, ws, shift, code, st)
+                # MLP
+                gw2, gb2 = gemm.matmul_tn(gy2, h)     # [C, 4C] = gy2^T h,  [C] = sum_t gy2
+                ga = gemm.matmul_nn_gelu_bwd(gy2, w2, hpre)  # [T, 4C] = (gy2 W2) * gelu'(hpre)
+                gw1, gb1 = gemm.matmul_tn(ga, u)      # [4C, C], [4C]
+                gu = gemm.matmul_nn(ga, w1)           # [T, C]
+                del ga
+                # LN2 + residual
+                gy1 = torch.empty_like(gy2)
+                gg2 = torch.empty(Cc, dtype=torch.float32, device=dev)
+                gbt2 = torch.empty(Cc, dtype=torch.float32, device=dev)
+                call("b200_swin_ln_bwd", ptr(gu), ptr(y1), ptr(gy2), ptr(g2f), ptr(mean2), ptr(rstd2), ptr(gy1), ptr(gg2),
+                                         ptr(gbt2), ptr(wsb), nbytes, B, Cc, H, W, ws, shift, code, 0, st)
+                del gu, gy2
             # attention
             gwo, gbo = gemm.matmul_tn(gy1, o)     # [C, C], [C]
             go = gemm.matmul_nn(gy1, wo)          # [T, C]

@@ -246,6 +246,8 @@ B200_API int b200_swin_mlp_prep(const float* w1, const float* b1, const float* g
                                 void* w1f, float* b1f, void* w2h, int32_t C, int32_t dtype, void* stream);
 B200_API int b200_swin_mlp_fwd(const void* y1, const void* w1f, const float* b1f, const void* w2h, const float* b2, void* out,
                                int64_t rows, int32_t C, float eps, int32_t dtype, void* stream);
+B200_API int b200_swin_mlp_bwd(const void* gout, const void* y1, const void* w1f, const float* b1f, const void* w2h, void* gy1,
+                               void* xhat, void* h, void* ga, int64_t rows, int32_t C, float eps, int32_t dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -67,3 +67,35 @@ def test_fused_mlp_forward_extreme_preactivations():
     want, _, a, _ = _mlp_ref(y1, gamma, beta, w1, b1, w2, b2)
     assert float(a.abs().max()) > 30
     assert rel_err(out, want) < 1e-2, rel_err(out, want)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 8e-3), (torch.float16, 2e-3)])
+@pytest.mark.parametrize("rows", [128, 100, 1000, 4096 + 37, 102400])
+def test_fused_mlp_backward(dtype, tol, rows):
+    """g_y1 and the three by-products (xhat, h, g_a) against autograd over the fp64 restatement."""
+    from improving_yolov8_cbam_swinblock_b200 import functional as Fb
+
+    C = 128
+    gamma, beta, w1, b1, w2, b2 = _mlp_params(C, rows + 1)
+    torch.manual_seed(rows + 1)
+    y1 = (1.5 * torch.randn(rows, C, device="cuda") + 0.2).to(dtype)
+    g = torch.randn(rows, C, device="cuda").to(dtype)
+    w1f, b1f, w2h = Fb.swin_mlp_prep(gamma, beta, w1, b1, w2, dtype)
+    gy1, xhat, h, ga = Fb.swin_mlp_backward_raw(g, y1, w1f, b1f, w2h)
+    yd = y1.double().requires_grad_(True)
+    xh = torch.nn.functional.layer_norm(yd, (C,), None, None, 1e-5)
+    a = (xh * gamma.double() + beta.double()) @ w1.double().t() + b1.double()
+    a.retain_grad()
+    hh = torch.nn.functional.gelu(a)
+    out = yd + hh @ w2.double().t() + b2.double()
+    out.backward(g.double())
+    for t in (gy1, xhat, h, ga):
+        assert torch.isfinite(t).all()
+    assert rel_err(xhat, xh) < (4e-3 if dtype == torch.bfloat16 else 6e-4), rel_err(xhat, xh)
+    assert rel_err(h, hh) < tol, rel_err(h, hh)
+    assert rel_err(ga, a.grad) < tol, rel_err(ga, a.grad)
+    assert rel_err(gy1, yd.grad) < tol, rel_err(gy1, yd.grad)
+    # the LayerNorm-backward part alone (the residual g dominates the norm above)
+    assert rel_err(gy1.double() - g.double(), yd.grad - g.double()) < 3 * tol
+    again = Fb.swin_mlp_backward_raw(g, y1, w1f, b1f, w2h)
+    assert all(torch.equal(u, v) for u, v in zip((gy1, xhat, h, ga), again))
