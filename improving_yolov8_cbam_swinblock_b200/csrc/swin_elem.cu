@@ -221,8 +221,15 @@ __global__ void __launch_bounds__(256) swin_move_vec_kernel(const T* __restrict_
       }
       store_row<T, LPT, NV>(out + pix * g.C, l, v);
     } else {
-      if (real) load_row<T, LPT, NV>(a + pix * g.C, l, v);
-      else {
+      if (real) {
+        load_row<T, LPT, NV>(a + pix * g.C, l, v);
+        if (b2) {   // second addend in the same pixel layout (the residual gradient of the fused MLP backward)
+          float w[N];
+          load_row<T, LPT, NV>(b2 + pix * g.C, l, w);
+#pragma unroll
+          for (int i = 0; i < N; ++i) v[i] += w[i];
+        }
+      } else {
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] = 0.f;
       }
@@ -441,13 +448,17 @@ __global__ void __launch_bounds__(256) swin_res_reverse_kernel(const T* __restri
 
 // gy2[t,:] = g[b,y,x,:] for real tokens, 0 for padded ones (they are cropped, swin_block.py:58)
 template <typename T>
-__global__ void __launch_bounds__(256) swin_partition_kernel(const T* __restrict__ gsrc, T* __restrict__ gtok, WinGeom g) {
+__global__ void __launch_bounds__(256) swin_partition_kernel(const T* __restrict__ gsrc, const T* __restrict__ gadd, T* __restrict__ gtok, WinGeom g) {
   const int lane = threadIdx.x & 31;
   const long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= g.T) return;
   bool real;
   const long long pix = token_pixel(g, t, &real);
-  for (int c = lane; c < g.C; c += 32) gtok[t * g.C + c] = real ? gsrc[pix * g.C + c] : DT<T>::from_f(0.f);
+  for (int c = lane; c < g.C; c += 32) {
+    float v = 0.f;
+    if (real) v = ldf(gsrc + pix * g.C + c) + (gadd ? ldf(gadd + pix * g.C + c) : 0.f);
+    gtok[t * g.C + c] = DT<T>::from_f(v);
+  }
 }
 
 // LayerNorm backward for a block of tokens + column partials of gamma / beta gradients.
@@ -702,23 +713,35 @@ extern "C" B200_API int b200_swin_res_reverse(const void* y1, const void* m, voi
   });
 }
 
-extern "C" B200_API int b200_swin_partition(const void* src, void* tok, int32_t B, int32_t C, int32_t H, int32_t W,
-                                            int32_t ws, int32_t shift, int32_t dtype, void* stream) {
+static int swin_partition_impl(const void* src, const void* add, void* tok, int32_t B, int32_t C, int32_t H, int32_t W, int32_t ws,
+                               int32_t shift, int32_t dtype, void* stream) {
   WinGeom g;
   if (int rc = make_geom(&g, B, C, H, W, ws, shift)) return rc;
   B200_REQUIRE(src && tok, B200_ERR_SHAPE, "swin_partition: null pointer");
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
     int vec, iters;
-    if (pick_vec<T>(C, &vec, &iters) && (((uintptr_t)src | (uintptr_t)tok) & 15) == 0) {
+    if (pick_vec<T>(C, &vec, &iters) && (((uintptr_t)src | (uintptr_t)add | (uintptr_t)tok) & 15) == 0) {
       const unsigned grid = capped_grid(g.T, 32 / vec);
       B200_DISPATCH_VEC({
-        swin_move_vec_kernel<T, VEC, ITERS, 1><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)src, nullptr, (T*)tok, g);
+        swin_move_vec_kernel<T, VEC, ITERS, 1><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)src, (const T*)add, (T*)tok, g);
         return check_launch("swin_partition");
       });
     }
-    swin_partition_kernel<T><<<warps_grid(g.T), 256, 0, (cudaStream_t)stream>>>((const T*)src, (T*)tok, g);
+    swin_partition_kernel<T><<<warps_grid(g.T), 256, 0, (cudaStream_t)stream>>>((const T*)src, (const T*)add, (T*)tok, g);
     return check_launch("swin_partition");
   });
+}
+
+extern "C" B200_API int b200_swin_partition(const void* src, void* tok, int32_t B, int32_t C, int32_t H, int32_t W,
+                                            int32_t ws, int32_t shift, int32_t dtype, void* stream) {
+  return swin_partition_impl(src, nullptr, tok, B, C, H, W, ws, shift, dtype, stream);
+}
+
+/* tok[t,:] = src[pixel(t),:] + add[pixel(t),:] for real tokens, 0 for padded ones */
+extern "C" B200_API int b200_swin_partition_add(const void* src, const void* add, void* tok, int32_t B, int32_t C, int32_t H, int32_t W,
+                                                int32_t ws, int32_t shift, int32_t dtype, void* stream) {
+  B200_REQUIRE(add, B200_ERR_SHAPE, "swin_partition_add: null pointer");
+  return swin_partition_impl(src, add, tok, B, C, H, W, ws, shift, dtype, stream);
 }
 
 extern "C" B200_API size_t b200_swin_ln_bwd_workspace_bytes(int64_t tokens, int32_t C) {

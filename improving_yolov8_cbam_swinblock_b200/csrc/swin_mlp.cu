@@ -27,6 +27,8 @@
 // (tanh.approx) per element instead of two (rcp + ex2), which halves the SFU time that bounds this epilogue.
 #include "tc.cuh"
 
+long long* g_mlp_dbg = nullptr;   // debugging aid, see b200_debug_set_mlp_timeline
+
 namespace b200 {
 namespace tc {
 namespace {
@@ -60,7 +62,7 @@ struct MlpParams {
   void* out;          // [P, 128]
   long long P;        // rows
   long long* dbg;     // optional timeline of CTA 0 (profiles/mlp_timeline.py): [role][event][index] SM clock stamps
-  int n_tiles, fmt;
+  int n_tiles, fmt, save_h;   // save_h: also write 2*gelu(a) [P, 512] (training: operand of the mlp.2 weight gradient)
   float eps;
 };
 
@@ -90,6 +92,15 @@ __device__ __forceinline__ float gelu2_tanh5(float a) {
   const float z = fminf(a * a, 64.f);
   return fmaf(a, tanh_approx(a * fmaf(z, fmaf(z, kG2, kG1), kG0)), a);
 }
+// d/da [2 gelu(a)] = d/da [a (1 + t)] of the SAME approximation: (1 + t) + a (1 - t^2) q'(a)
+__device__ __forceinline__ float gelu2_tanh5_grad(float a) {
+  const float a2 = a * a;
+  const float z = fminf(a2, 64.f);
+  const float inner = fmaf(z, fmaf(z, kG2, kG1), kG0);
+  const float t = tanh_approx(a * inner);
+  const float qd = a2 < 64.f ? fmaf(z, fmaf(z, 5.f * kG2, 3.f * kG1), kG0) : inner;   // q'(a); constant slope beyond the clamp
+  return fmaf(a * qd, fmaf(-t, t, 1.f), 1.f + t);
+}
 // d/da [a * Phi(a)] of the SAME approximation: Phi + a * 0.5 (1 - t^2) q'(a); also returns the forward value
 __device__ __forceinline__ float gelu_tanh5_grad(float a, float* fwd) {
   const float a2 = a * a;
@@ -104,7 +115,7 @@ __device__ __forceinline__ float gelu_tanh5_grad(float a, float* fwd) {
 }
 
 // debug timeline (CTA 0 only, dbg != nullptr): role r in [0,4), event e in [0,4), index i < 64
-__device__ __forceinline__ void stamp(const MlpParams& P, int r, int e, int i) {
+template <typename PT> __device__ __forceinline__ void stamp(const PT& P, int r, int e, int i) {
   if (P.dbg != nullptr && blockIdx.x == 0 && i < 64) {
     long long t;
     asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
@@ -136,7 +147,8 @@ __device__ __forceinline__ uint4* row_chunk(unsigned char* tile, int row, int c)
 template <int FMT>
 __global__ void __launch_bounds__(kThreads, 1)
 swin_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmOut,
-                    const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, MlpParams P) {
+                    const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                    const __grid_constant__ CUtensorMap tmH, MlpParams P) {
   using S = MlpSmem;
   extern __shared__ __align__(1024) unsigned char smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128-byte swizzle atoms need a 1024-byte aligned base: no slack is budgeted
@@ -165,11 +177,11 @@ swin_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
   unsigned char* obuf = smem + S::OFF_O;
 
   if (warp == 0 && elect_one()) {
-    prefetch_tmap(&tmY); prefetch_tmap(&tmOut); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2);
+    prefetch_tmap(&tmY); prefetch_tmap(&tmOut); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2); prefetch_tmap(&tmH);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&y_full[i], 1); mbar_init(&u_ready[i], 32 * kLnWarps); mbar_init(&u_free[i], 1);
       mbar_init(&h_full[i], 1); mbar_init(&h_tfree[i], 16 * kGeluWarps);     // each H accumulator belongs to one group of 8 GELU warps
-      mbar_init(&hs_full[i], 16 * kGeluWarps); mbar_init(&hs_free[i], 1); mbar_init(&o_full[i], 1);
+      mbar_init(&hs_full[i], 1); mbar_init(&hs_free[i], 1); mbar_init(&o_full[i], 1);
       mbar_init(&o_free[i], 32 * kOutWarps);
     }
     for (int i = 0; i < kRing; ++i) {
@@ -381,14 +393,20 @@ swin_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
     const int row = q * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     unsigned char* h = hbuf(grp) + cs * kHalfBytes;  // this thread's 64 columns = K-block cs of the group's A tile
+    const bool leader = ((gw & 7) == 0 && lane == 0);
+    bool pending = false;
     for (int g = grp; g < n_chunks; g += 2) {
       const uint32_t ph = (g >> 1) & 1;
       const float* bias = sb1 + (g & 3) * 128 + cs * 64;
-      if ((gw & 7) == 0 && lane == 0) stamp(P, 3, 0, g);
+      if (leader) stamp(P, 3, 0, g);
       mbar_wait(&h_full[grp], ph);
       fence_after_sync();
-      if ((gw & 7) == 0 && lane == 0) stamp(P, 3, 1, g);
+      if (leader) stamp(P, 3, 1, g);
       mbar_wait(&hs_free[grp], ph ^ 1);
+      if (pending) {                                 // the TMA store of chunk g-2 has read the tile
+        if (leader) bulk_wait_read_all();
+        named_bar_sync(2 + grp, 16 * kGeluWarps);
+      }
 #pragma unroll 1
       for (int r2 = 0; r2 < 2; ++r2) {
         uint32_t v[32];
@@ -406,11 +424,22 @@ swin_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
         for (int c = 0; c < 4; ++c)
           *reinterpret_cast<uint4*>(h + sw128_offset(row, r2 * 4 + c)) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
       }
-      if ((gw & 7) == 0 && lane == 0) stamp(P, 3, 2, g);
+      if (leader) stamp(P, 3, 2, g);
       fence_proxy_async();
-      mbar_arrive(&hs_full[grp]);
-      if ((gw & 7) == 0 && lane == 0) stamp(P, 3, 3, g);
+      named_bar_sync(2 + grp, 16 * kGeluWarps);
+      if (leader) {
+        mbar_arrive(&hs_full[grp]);
+        if (P.save_h) {
+          const int r0 = (blockIdx.x + (g >> 2) * gridDim.x) * kTileM;
+          tma_store_2d(&tmH, hbuf(grp), (g & 3) * 128, r0);
+          tma_store_2d(&tmH, hbuf(grp) + kHalfBytes, (g & 3) * 128 + 64, r0);
+          bulk_commit();
+        }
+        stamp(P, 3, 3, g);
+      }
+      pending = P.save_h != 0;
     }
+    if (leader) bulk_wait_all();
   }
   fence_before_sync();
   __syncthreads();
@@ -421,34 +450,32 @@ swin_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
 // backward of the fused MLP half.  Per 128-row tile, with the hidden dimension in 8 chunks of 64 columns:
 //     xhat = LN2 statistics of y1 (recomputed; also written out for the weight-gradient GEMM)
 //     A(g) = xhat * W1'[chunk]^T,  G(g) = g_out * W2'[:, chunk]            (MMA_a, MMA_g -> TMEM)
-//     a = A + b1',  h = gelu(a) -> global,  g_a = G * 2 gelu'(a) -> shared (A of MMA_u) -> global (TMA store)
+//     a = A + b1',  g_a = G * d[2 gelu](a) -> shared (A of MMA_u) -> global (TMA store)      (h = 2 gelu(a) was saved by the forward)
 //     U += g_a(g) * W1'[chunk]                                             (MMA_u; W1' = W1 gamma, so U = dL/dxhat)
-//     g_y1 = g_out + rstd * (U - mean(U) - xhat * mean(U * xhat))          (LayerNorm backward + residual)
+//     g_y1' = rstd * (U - mean(U) - xhat * mean(U * xhat))                 (LayerNorm backward; the residual "+ g_out" is added
+//                                                                           by the consumer, b200_swin_partition)
 // The W1' chunk of a ring stage serves MMA_a (K-major B) and MMA_u (MN-major B) from the same bytes.  Parameter gradients are
 // contractions over ALL rows and are left to b200_gemm_splitk on the three tensors written here (see include/).
 // Warp roles as in the forward kernel: 0 W1' producer | 1 MMA issuer | 2-5 LayerNorm warps | 6-9 final (g_y1) warps |
 // 10-25 two groups of 8 GELU-backward warps on alternate chunks | 26 y1 / g_out tile loader | 27 W2' producer.
 // =====================================================================================================================
-constexpr int kRingW1B = 3;                                    // W1' stages are held from MMA_a(g) to MMA_u(g): a deeper ring
+constexpr int kRingW1B = 4;                                    // W1' stages are held from MMA_a(g) to MMA_u(g): a deep ring
 struct MlpBwdSmem {
-  static constexpr int OFF_X = 0;                               // 2 x 32 KB: y1 tile -> xhat (A of MMA_a, LN backward input)
+  static constexpr int OFF_X = 0;                               // 2 x 32 KB: y1 tile -> xhat (A of MMA_a) -> g_y1 staging
   static constexpr int OFF_G = OFF_X + 2 * kTileBytes;          // 32 KB: g_out tile (A of MMA_g)
   static constexpr int OFF_GA = OFF_G + kTileBytes;             // 2 x 16 KB: g_a chunk tiles (A of MMA_u, TMA store source)
   static constexpr int OFF_W1 = OFF_GA + 2 * kHalfBytes;        // kRingW1B x 16 KB: W1' chunks [64 hidden rows][2 x 128 B]
   static constexpr int OFF_W2 = OFF_W1 + kRingW1B * kHalfBytes; // kRing x 16 KB: W2' chunks [128 rows][128 B]
-  static constexpr int OFF_B1 = OFF_W2 + kRing * kHalfBytes;    // b1' [512] f32
-  static constexpr int OFF_RS = OFF_B1 + kHid * 4;              // rstd [2][128] f32
+  static constexpr int OFF_RS = OFF_W2 + kRing * kHalfBytes;    // rstd [2][128] f32
   static constexpr int OFF_BAR = OFF_RS + 2 * kTileM * 4;
-  static constexpr int TOTAL = OFF_BAR + 256;
+  static constexpr int TOTAL = OFF_BAR + 384;   // 32 mbarriers + the TMEM slot
 };
 static_assert(MlpBwdSmem::TOTAL <= 232448, "shared memory budget");
 
 struct MlpBwdParams {
-  const void* gout;   // [P, 128] (also TMA-loaded as the A operand; re-read per row for the residual)
-  void* gy1;          // [P, 128]
-  void* h;            // [P, 512]
   const float* b1f;
   long long P;
+  long long* dbg;
   int n_tiles;
   float eps;
 };
@@ -466,16 +493,16 @@ template <int FMT>
 __global__ void __launch_bounds__(kThreads, 1)
 swin_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmG,
                     const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-                    const __grid_constant__ CUtensorMap tmXhat, const __grid_constant__ CUtensorMap tmGa, MlpBwdParams P) {
+                    const __grid_constant__ CUtensorMap tmXhat, const __grid_constant__ CUtensorMap tmGa,
+                    const __grid_constant__ CUtensorMap tmGy, MlpBwdParams P) {
   using S = MlpBwdSmem;
   extern __shared__ __align__(1024) unsigned char smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  float* sb1 = reinterpret_cast<float*>(smem + S::OFF_B1);
   float* srs = reinterpret_cast<float*>(smem + S::OFF_RS);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t* y_full = bars;                 // [2] y1 tile landed
   uint64_t* u_ready = bars + 2;            // [2] xhat written (128 LayerNorm threads)
-  uint64_t* x_free = bars + 4;             // [2] xhat tile no longer needed: 128 final threads + the xhat store's reader
+  uint64_t* x_free = bars + 4;             // [2] tile buffer reusable: the xhat store and the g_y1 store have both read it
   uint64_t* g_full = bars + 6;             // g_out tile landed
   uint64_t* g_free = bars + 7;             // the tile's eight MMA_g have read it (commit)
   uint64_t* w1_full = bars + 8;            // [kRingW1B]
@@ -498,8 +525,9 @@ swin_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
 
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmY); prefetch_tmap(&tmG); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2); prefetch_tmap(&tmXhat); prefetch_tmap(&tmGa);
+    prefetch_tmap(&tmGy);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&y_full[i], 1); mbar_init(&u_ready[i], 32 * kLnWarps); mbar_init(&x_free[i], 32 * kOutWarps + 1);
+      mbar_init(&y_full[i], 1); mbar_init(&u_ready[i], 32 * kLnWarps); mbar_init(&x_free[i], 2);
       mbar_init(&ag_full[i], 1); mbar_init(&ag_tfree[i], 16 * kGeluWarps); mbar_init(&ga_full[i], 1); mbar_init(&ga_free[i], 1);
       mbar_init(&tu_full[i], 1); mbar_init(&tu_free[i], 32 * kOutWarps);
     }
@@ -509,7 +537,6 @@ swin_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  for (int i = threadIdx.x; i < kHid; i += kThreads) sb1[i] = P.b1f[i];
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -572,6 +599,7 @@ swin_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
           if ((b & 7) == 0) go = mbar_poll(&tu_free[t & 1], ((t >> 1) & 1) ^ 1);   // fresh accumulator: tile t-2's final warps are done
           if (go) {
             fence_after_sync();
+            stamp(P, 0, 2, b);
             unsigned char* A = gabuf(b & 1);
             unsigned char* B = smem + S::OFF_W1 + s1u * kHalfBytes;
 #pragma unroll
@@ -590,9 +618,11 @@ swin_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
           if (go && (a & 7) == 0) go = mbar_poll(&u_ready[t & 1], (t >> 1) & 1) && mbar_poll(g_full, t & 1);
           if (go) {
             fence_after_sync();
+            stamp(P, 0, 0, a);
             mbar_wait(&w1_full[s1a], p1a);
             mbar_wait(&w2_full[s2], p2);
             fence_after_sync();
+            stamp(P, 0, 1, a);
             unsigned char* X = xbuf(t & 1);
             unsigned char* W1s = smem + S::OFF_W1 + s1a * kHalfBytes;
             unsigned char* W2s = smem + S::OFF_W2 + s2 * kHalfBytes;
@@ -626,7 +656,9 @@ swin_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
         bulk_wait_read_all();
         mbar_arrive(&x_free[(n - 1) & 1]);
       }
+      if (row == 0) stamp(P, 1, 0, n);
       mbar_wait(&y_full[b], (n >> 1) & 1);
+      if (row == 0) stamp(P, 1, 1, n);
       const float x0 = up_lo<FMT>(row_chunk(u, row, 0)->x);
       float s = 0.f, ss = 0.f;
 #pragma unroll
@@ -654,6 +686,7 @@ swin_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
       }
       fence_proxy_async();
       mbar_arrive(&u_ready[b]);
+      if (row == 0) stamp(P, 1, 2, n);
       named_bar_sync(1, 32 * kLnWarps);
       if (leader) {
         tma_store_2d(&tmXhat, u, 0, tile * kTileM);
@@ -663,18 +696,19 @@ swin_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
     }
     if (leader && n_local > 0) { bulk_wait_all(); mbar_arrive(&x_free[(n_local - 1) & 1]); }
   } else if (warp < kFirstGeluWarp) {
-    // ===================== final warps: U = dL/dxhat -> LayerNorm backward + residual -> g_y1 row (thread = row) =====================
+    // ===================== final warps: U = dL/dxhat -> LayerNorm backward -> g_y1 row, in place over the xhat tile =====================
+    // (thread = row = TMEM lane; the residual "+ g_out" is added by the consumer of g_y1, b200_swin_partition)
     const int q = warp & 3, row = q * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const bool leader = (warp == kFirstOutWarp && lane == 0);
     for (int n = 0; n < n_local; ++n) {
       const int b = n & 1;
-      const long long grow = (long long)(blockIdx.x + n * gridDim.x) * kTileM + row;
-      const bool live = grow < P.P;
+      const int tile = blockIdx.x + n * gridDim.x;
       unsigned char* u = xbuf(b);
-      const uint4* grow_in = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(P.gout) + grow * kC);
-      uint4* grow_out = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(P.gy1) + grow * kC);
+      if (row == 0) stamp(P, 2, 0, n);
       mbar_wait(&tu_full[b], (n >> 1) & 1);
       fence_after_sync();
+      if (row == 0) stamp(P, 2, 1, n);
       const float rstd = srs[b * kTileM + row];
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
@@ -704,22 +738,29 @@ swin_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
         if (ch == 3) { fence_before_sync(); mbar_arrive(&tu_free[b]); }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const uint4 w = *row_chunk(u, row, ch * 4 + c);
-          uint4 gi = make_uint4(0, 0, 0, 0);
-          if (live) gi = ldg_stream16(grow_in + ch * 4 + c);
-          const uint32_t ww[4] = {w.x, w.y, w.z, w.w}, gg[4] = {gi.x, gi.y, gi.z, gi.w};
+          uint4* p = row_chunk(u, row, ch * 4 + c);
+          const uint4 w = *p;
+          const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
           uint32_t o[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float r0 = fmaf(rstd, __uint_as_float(v[c * 8 + 2 * e]) - m1 - up_lo<FMT>(ww[e]) * m2, up_lo<FMT>(gg[e]));
-            const float r1 = fmaf(rstd, __uint_as_float(v[c * 8 + 2 * e + 1]) - m1 - up_hi<FMT>(ww[e]) * m2, up_hi<FMT>(gg[e]));
-            o[e] = pack2h<FMT>(r0, r1);
-          }
-          if (live) stg_stream16(grow_out + ch * 4 + c, make_uint4(o[0], o[1], o[2], o[3]));
+          for (int e = 0; e < 4; ++e)
+            o[e] = pack2h<FMT>(rstd * (__uint_as_float(v[c * 8 + 2 * e]) - m1 - up_lo<FMT>(ww[e]) * m2),
+                               rstd * (__uint_as_float(v[c * 8 + 2 * e + 1]) - m1 - up_hi<FMT>(ww[e]) * m2));
+          *p = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
-      mbar_arrive(&x_free[b]);
+      fence_proxy_async();
+      named_bar_sync(4, 32 * kOutWarps);
+      if (leader) {
+        tma_store_2d(&tmGy, u, 0, tile * kTileM);
+        tma_store_2d(&tmGy, u + kHalfBytes, 64, tile * kTileM);
+        bulk_commit();
+        bulk_wait_read_all();
+        mbar_arrive(&x_free[b]);
+      }
+      if (row == 0) stamp(P, 2, 2, n);
     }
+    if (leader) bulk_wait_all();
   } else if (warp < kLoaderWarp) {
     // ===================== GELU-backward warps: two groups of 8 on alternate 64-column chunks =====================
     const int gw = warp - kFirstGeluWarp;
@@ -733,14 +774,13 @@ swin_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
     for (int g = grp; g < n_chunks; g += 2) {
       const uint32_t ph = (g >> 1) & 1;
       const int t = g >> 3, j = g & 7;
-      const long long grow = (long long)(blockIdx.x + t * gridDim.x) * kTileM + row;
-      const bool live = grow < P.P;
-      const float* bias = sb1 + j * 64 + cs * 32;
-      uint16_t* hrow = reinterpret_cast<uint16_t*>(P.h) + grow * kHid + j * 64 + cs * 32;
+      const float4* bias = reinterpret_cast<const float4*>(P.b1f + j * 64 + cs * 32);   // 2 KB, L1 resident
+      if (leader) stamp(P, 3, 0, g);
       mbar_wait(&ag_full[grp], ph);
       fence_after_sync();
-      mbar_wait(&ga_free[grp], ph ^ 1);              // MMA_u(g-2) has consumed the tile ...
-      if (pending) {                                 // ... and its TMA store has read it
+      if (leader) stamp(P, 3, 1, g);
+      mbar_wait(&ga_free[grp], ph ^ 1);              // MMA_u(g-2) has consumed the g_a tile ...
+      if (pending) {                                 // ... and the TMA stores of chunk g-2 have read both staging tiles
         if (leader) bulk_wait_read_all();
         named_bar_sync(2 + grp, 16 * kGeluWarps);
       }
@@ -751,31 +791,28 @@ swin_mlp_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
         tmem_ld16(tG(grp) + lane_sel + cs * 32 + r2 * 16, vg);
         tmem_ld_wait();
         if (r2 == 1) { fence_before_sync(); mbar_arrive(&ag_tfree[grp]); }
-        uint32_t oh[8], og[8];
+        uint32_t og[8];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float4 bv = *reinterpret_cast<const float4*>(bias + r2 * 16 + 4 * e);
+          const float4 bv = __ldg(bias + r2 * 4 + e);
           const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
-          float hh[4], dd[4];
+          float dd[4];
 #pragma unroll
-          for (int z = 0; z < 4; ++z) {
-            dd[z] = 2.f * gelu_tanh5_grad(__uint_as_float(va[4 * e + z]) + bb[z], &hh[z]) * __uint_as_float(vg[4 * e + z]);
-          }
-          oh[2 * e] = pack2h<FMT>(hh[0], hh[1]); oh[2 * e + 1] = pack2h<FMT>(hh[2], hh[3]);
+          for (int z = 0; z < 4; ++z) dd[z] = gelu2_tanh5_grad(__uint_as_float(va[4 * e + z]) + bb[z]) * __uint_as_float(vg[4 * e + z]);
           og[2 * e] = pack2h<FMT>(dd[0], dd[1]); og[2 * e + 1] = pack2h<FMT>(dd[2], dd[3]);
         }
-        if (live) {
-          stg_stream16(hrow + r2 * 16, make_uint4(oh[0], oh[1], oh[2], oh[3]));
-          stg_stream16(hrow + r2 * 16 + 8, make_uint4(oh[4], oh[5], oh[6], oh[7]));
-        }
-        *reinterpret_cast<uint4*>(ga + sw128_offset(row, cs * 4 + r2 * 2)) = make_uint4(og[0], og[1], og[2], og[3]);
-        *reinterpret_cast<uint4*>(ga + sw128_offset(row, cs * 4 + r2 * 2 + 1)) = make_uint4(og[4], og[5], og[6], og[7]);
+        const uint32_t o0 = sw128_offset(row, cs * 4 + r2 * 2), o1 = sw128_offset(row, cs * 4 + r2 * 2 + 1);
+        *reinterpret_cast<uint4*>(ga + o0) = make_uint4(og[0], og[1], og[2], og[3]);
+        *reinterpret_cast<uint4*>(ga + o1) = make_uint4(og[4], og[5], og[6], og[7]);
       }
+      if (leader) stamp(P, 3, 2, g);
       fence_proxy_async();
       named_bar_sync(2 + grp, 16 * kGeluWarps);
       if (leader) {
+        stamp(P, 3, 3, g);
         mbar_arrive(&ga_full[grp]);
-        tma_store_2d(&tmGa, ga, j * 64, (blockIdx.x + t * gridDim.x) * kTileM);
+        const int r0 = (blockIdx.x + t * gridDim.x) * kTileM;
+        tma_store_2d(&tmGa, ga, j * 64, r0);
         bulk_commit();
       }
       pending = true;
@@ -814,7 +851,6 @@ __global__ void swin_mlp_prep_kernel(const float* __restrict__ w1, const float* 
 
 using namespace b200;
 
-static long long* g_mlp_dbg = nullptr;
 /* debugging aid (not part of the public header): device buffer of 16*64 int64 receiving CTA 0's event clock stamps */
 extern "C" B200_API void b200_debug_set_mlp_timeline(void* buf) { g_mlp_dbg = (long long*)buf; }
 
@@ -834,7 +870,7 @@ extern "C" B200_API int b200_swin_mlp_prep(const float* w1, const float* b1, con
 }
 
 extern "C" B200_API int b200_swin_mlp_fwd(const void* y1, const void* w1f, const float* b1f, const void* w2h, const float* b2, void* out,
-                                          int64_t rows, int32_t C, float eps, int32_t dtype, void* stream) {
+                                          void* h2, int64_t rows, int32_t C, float eps, int32_t dtype, void* stream) {
   B200_REQUIRE(b200_swin_mlp_supported(rows, C, dtype), B200_ERR_UNSUPPORTED,
                "swin_mlp_fwd: unsupported problem rows=%lld C=%d dtype=%d (16-bit dtypes, C = 128)", (long long)rows, C, dtype);
   B200_REQUIRE(y1 && w1f && b1f && w2h && b2 && out, B200_ERR_SHAPE, "swin_mlp_fwd: null pointer");
@@ -845,22 +881,25 @@ extern "C" B200_API int b200_swin_mlp_fwd(const void* y1, const void* w1f, const
   const CUtensorMap* mO = tensor_map_2d(out, (uint64_t)rows, kC, kC, kTileM, 64, dtype);
   const CUtensorMap* mW1 = tensor_map_2d(w1f, kHid, kC, kC, 128, 64, dtype);
   const CUtensorMap* mW2 = tensor_map_2d(w2h, kC, kHid, kHid, 128, 64, dtype);
-  if (!mY || !mO || !mW1 || !mW2) return B200_ERR_LAUNCH;
+  const CUtensorMap* mH = h2 ? tensor_map_2d(h2, (uint64_t)rows, kHid, kHid, kTileM, 64, dtype) : mO;
+  if (!mY || !mO || !mW1 || !mW2 || !mH) return B200_ERR_LAUNCH;
+  B200_REQUIRE(((uintptr_t)h2 & 15) == 0, B200_ERR_ALIGN, "swin_mlp_fwd: 16-byte alignment required");
   MlpParams P;
+  P.save_h = h2 != nullptr;
   P.b1f = b1f; P.b2 = b2; P.out = out; P.P = rows; P.dbg = g_mlp_dbg; P.n_tiles = (int)((rows + kTileM - 1) / kTileM); P.fmt = dtype == B200_BF16 ? 1 : 0; P.eps = eps;
   const int grid = P.n_tiles < sm_count() ? P.n_tiles : sm_count();
   auto kern = dtype == B200_BF16 ? swin_mlp_fwd_kernel<1> : swin_mlp_fwd_kernel<0>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::TOTAL);
-  kern<<<grid, kThreads, MlpSmem::TOTAL, (cudaStream_t)stream>>>(*mY, *mO, *mW1, *mW2, P);
+  kern<<<grid, kThreads, MlpSmem::TOTAL, (cudaStream_t)stream>>>(*mY, *mO, *mW1, *mW2, *mH, P);
   return check_launch("swin_mlp_fwd");
 }
 
 extern "C" B200_API int b200_swin_mlp_bwd(const void* gout, const void* y1, const void* w1f, const float* b1f, const void* w2h, void* gy1,
-                                          void* xhat, void* h, void* ga, int64_t rows, int32_t C, float eps, int32_t dtype, void* stream) {
+                                          void* xhat, void* ga, int64_t rows, int32_t C, float eps, int32_t dtype, void* stream) {
   B200_REQUIRE(b200_swin_mlp_supported(rows, C, dtype), B200_ERR_UNSUPPORTED,
                "swin_mlp_bwd: unsupported problem rows=%lld C=%d dtype=%d (16-bit dtypes, C = 128)", (long long)rows, C, dtype);
-  B200_REQUIRE(gout && y1 && w1f && b1f && w2h && gy1 && xhat && h && ga, B200_ERR_SHAPE, "swin_mlp_bwd: null pointer");
-  B200_REQUIRE((((uintptr_t)gout | (uintptr_t)y1 | (uintptr_t)w1f | (uintptr_t)w2h | (uintptr_t)gy1 | (uintptr_t)xhat | (uintptr_t)h | (uintptr_t)ga) & 15) == 0,
+  B200_REQUIRE(gout && y1 && w1f && b1f && w2h && gy1 && xhat && ga, B200_ERR_SHAPE, "swin_mlp_bwd: null pointer");
+  B200_REQUIRE((((uintptr_t)gout | (uintptr_t)y1 | (uintptr_t)w1f | (uintptr_t)w2h | (uintptr_t)gy1 | (uintptr_t)xhat | (uintptr_t)ga) & 15) == 0,
                B200_ERR_ALIGN, "swin_mlp_bwd: 16-byte alignment required");
   using namespace b200::tc;
   const CUtensorMap* mY = tensor_map_2d(y1, (uint64_t)rows, kC, kC, kTileM, 64, dtype);
@@ -869,12 +908,13 @@ extern "C" B200_API int b200_swin_mlp_bwd(const void* gout, const void* y1, cons
   const CUtensorMap* mW2 = tensor_map_2d(w2h, kC, kHid, kHid, 128, 64, dtype);
   const CUtensorMap* mX = tensor_map_2d(xhat, (uint64_t)rows, kC, kC, kTileM, 64, dtype);
   const CUtensorMap* mGa = tensor_map_2d(ga, (uint64_t)rows, kHid, kHid, kTileM, 64, dtype);
-  if (!mY || !mG || !mW1 || !mW2 || !mX || !mGa) return B200_ERR_LAUNCH;
+  const CUtensorMap* mGy = tensor_map_2d(gy1, (uint64_t)rows, kC, kC, kTileM, 64, dtype);
+  if (!mY || !mG || !mW1 || !mW2 || !mX || !mGa || !mGy) return B200_ERR_LAUNCH;
   MlpBwdParams P;
-  P.gout = gout; P.gy1 = gy1; P.h = h; P.b1f = b1f; P.P = rows; P.n_tiles = (int)((rows + kTileM - 1) / kTileM); P.eps = eps;
+  P.b1f = b1f; P.P = rows; P.dbg = g_mlp_dbg; P.n_tiles = (int)((rows + kTileM - 1) / kTileM); P.eps = eps;
   const int grid = P.n_tiles < sm_count() ? P.n_tiles : sm_count();
   auto kern = dtype == B200_BF16 ? swin_mlp_bwd_kernel<1> : swin_mlp_bwd_kernel<0>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpBwdSmem::TOTAL);
-  kern<<<grid, kThreads, MlpBwdSmem::TOTAL, (cudaStream_t)stream>>>(*mY, *mG, *mW1, *mW2, *mX, *mGa, P);
+  kern<<<grid, kThreads, MlpBwdSmem::TOTAL, (cudaStream_t)stream>>>(*mY, *mG, *mW1, *mW2, *mX, *mGa, *mGy, P);
   return check_launch("swin_mlp_bwd");
 }

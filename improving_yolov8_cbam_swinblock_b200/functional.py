@@ -26,6 +26,7 @@ _lib.register("b200_swin_res_ln2", C.c_int, [_VP] * 8 + [_I64] + [_I32] * 2 + [_
 _lib.register("b200_swin_gelu", C.c_int, [_VP] * 3 + [_I64] + [_I32] * 2 + [_VP])
 _lib.register("b200_swin_res_reverse", C.c_int, [_VP] * 3 + [_I32] * 7 + [_VP])
 _lib.register("b200_swin_partition", C.c_int, [_VP] * 2 + [_I32] * 7 + [_VP])
+_lib.register("b200_swin_partition_add", C.c_int, [_VP] * 3 + [_I32] * 7 + [_VP])
 _lib.register("b200_swin_ln_bwd_workspace_bytes", _SZ, [_I64, _I32])
 _lib.register("b200_swin_ln_bwd", C.c_int, [_VP] * 10 + [_SZ] + [_I32] * 8 + [_VP])
 _lib.register("b200_colsum_workspace_bytes", _SZ, [_I64, _I32])
@@ -40,8 +41,8 @@ _lib.register("b200_nhwc_upsample_fwd", C.c_int, [_VP, _VP] + [_I32] * 7 + [_VP]
 _lib.register("b200_nhwc_upsample_bwd", C.c_int, [_VP, _I64, _VP] + [_I32] * 7 + [_VP])
 _lib.register("b200_swin_mlp_supported", C.c_int, [_I64, _I32, _I32])
 _lib.register("b200_swin_mlp_prep", C.c_int, [_VP] * 8 + [_I32, _I32, _VP])
-_lib.register("b200_swin_mlp_fwd", C.c_int, [_VP] * 6 + [_I64, _I32, C.c_float, _I32, _VP])
-_lib.register("b200_swin_mlp_bwd", C.c_int, [_VP] * 9 + [_I64, _I32, C.c_float, _I32, _VP])
+_lib.register("b200_swin_mlp_fwd", C.c_int, [_VP] * 7 + [_I64, _I32, C.c_float, _I32, _VP])
+_lib.register("b200_swin_mlp_bwd", C.c_int, [_VP] * 8 + [_I64, _I32, C.c_float, _I32, _VP])
 
 
 def _nhwc(x: torch.Tensor) -> torch.Tensor:
@@ -449,26 +450,28 @@ def swin_mlp_prep(g2, b2n, w1, bb1, w2, dtype):
     return w1f, b1f, w2h
 
 
-def swin_mlp_forward_raw(y1p, w1f, b1f, w2h, bb2, eps=1e-5):
-    """out[rows, C] = y1 + mlp.2(gelu(mlp.0(LN2(y1)))) on dense rows (pixel order), hidden activation kept on chip."""
+def swin_mlp_forward_raw(y1p, w1f, b1f, w2h, bb2, eps=1e-5, save_h=False):
+    """out[rows, C] = y1 + mlp.2(gelu(mlp.0(LN2(y1)))) on dense rows (pixel order), hidden activation kept on chip.
+    save_h: also return h2 = 2*gelu(a) [rows, 4C] (the 16-bit tiles the second GEMM consumed) for the backward."""
     rows, Cc = y1p.shape
     out = torch.empty_like(y1p)
-    call("b200_swin_mlp_fwd", ptr(y1p), ptr(w1f), ptr(b1f), ptr(w2h), ptr(_f32(bb2)), ptr(out), rows, Cc, float(eps),
+    h2 = torch.empty((rows, 4 * Cc), dtype=y1p.dtype, device=y1p.device) if save_h else None
+    call("b200_swin_mlp_fwd", ptr(y1p), ptr(w1f), ptr(b1f), ptr(w2h), ptr(_f32(bb2)), ptr(out), ptr(h2), rows, Cc, float(eps),
          dtype_code(y1p.dtype), stream_ptr(y1p.device), tag=f"b200_swin_mlp_fwd[{rows}x{Cc}]")
-    return out
+    return (out, h2) if save_h else out
 
 
 def swin_mlp_backward_raw(gout, y1p, w1f, b1f, w2h, eps=1e-5):
-    """-> (g_y1 [rows,C], xhat [rows,C], h = gelu(a) [rows,4C], g_a [rows,4C]): the data gradient of the fused MLP half
-    (residual + LayerNorm2 backward included) and the three operands of the weight-gradient contractions."""
+    """-> (g_y1' [rows,C], xhat [rows,C], g_a [rows,4C]): the LayerNorm2-backward term of the data gradient of the fused
+    MLP half (the full gradient is g_y1' + gout: the residual is added by the consumer, b200_swin_partition_add) and the
+    operands of the mlp.0 weight-gradient contraction (mlp.2's uses the forward's saved h2)."""
     rows, Cc = y1p.shape
     dev, dt = y1p.device, y1p.dtype
     gy1, xhat = torch.empty_like(y1p), torch.empty_like(y1p)
-    h = torch.empty((rows, 4 * Cc), dtype=dt, device=dev)
     ga = torch.empty((rows, 4 * Cc), dtype=dt, device=dev)
-    call("b200_swin_mlp_bwd", ptr(gout), ptr(y1p), ptr(w1f), ptr(b1f), ptr(w2h), ptr(gy1), ptr(xhat), ptr(h), ptr(ga), rows, Cc, float(eps),
+    call("b200_swin_mlp_bwd", ptr(gout), ptr(y1p), ptr(w1f), ptr(b1f), ptr(w2h), ptr(gy1), ptr(xhat), ptr(ga), rows, Cc, float(eps),
          dtype_code(dt), stream_ptr(dev), tag=f"b200_swin_mlp_bwd[{rows}x{Cc}]")
-    return gy1, xhat, h, ga
+    return gy1, xhat, ga
 
 
 class SwinBlockFn(torch.autograd.Function):
@@ -513,9 +516,11 @@ class SwinBlockFn(torch.autograd.Function):
                 call("b200_swin_res_reverse", ptr(y1), None, ptr(y1p), B, Cc, H, W, ws, shift, code, st)
                 w1f, b1f, w2h = swin_mlp_prep(g2, b2, w1, bb1, w2, dt)
                 out = _empty_nhwc(B, Cc, H, W, dt, dev)
-                call("b200_swin_mlp_fwd", ptr(y1p), ptr(w1f), ptr(b1f), ptr(w2h), ptr(_f32(bb2)), ptr(out), B * H * W, Cc, 1e-5, code, st,
-                     tag=f"b200_swin_mlp_fwd[{B * H * W}x{Cc}]")
-                ctx.save_for_backward(x, g1f, g2f, b2f, win, wo, w1, n1, mean1, rstd1, qkv, o, lse, y1p, w1f, b1f, w2h)
+                need_grad = any(ctx.needs_input_grad)
+                h2 = torch.empty((B * H * W, 4 * Cc), dtype=dt, device=dev) if need_grad else None   # 2*gelu(a), for d mlp.2.weight
+                call("b200_swin_mlp_fwd", ptr(y1p), ptr(w1f), ptr(b1f), ptr(w2h), ptr(_f32(bb2)), ptr(out), ptr(h2), B * H * W, Cc, 1e-5,
+                     code, st, tag=f"b200_swin_mlp_fwd[{B * H * W}x{Cc}]")
+                ctx.save_for_backward(x, g1f, g2f, b2f, win, wo, w1, n1, mean1, rstd1, qkv, o, lse, y1p, w1f, b1f, w2h, h2)
             else:
                 u = torch.empty_like(n1)
                 mean2, rstd2 = torch.empty(T, **f32), torch.empty(T, **f32)
@@ -547,20 +552,21 @@ class SwinBlockFn(torch.autograd.Function):
             nbytes = L.b200_swin_ln_bwd_workspace_bytes(T, Cc)
             wsb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             if ctx.fused_mlp:
-                (x, g1f, g2f, b2f, win, wo, w1, n1, mean1, rstd1, qkv, o, lse, y1p, w1f, b1f, w2h) = ctx.saved_tensors
+                (x, g1f, g2f, b2f, win, wo, w1, n1, mean1, rstd1, qkv, o, lse, y1p, w1f, b1f, w2h, h2) = ctx.saved_tensors
                 rows = B * H * W
                 g2d = gout.permute(0, 2, 3, 1).reshape(rows, Cc)          # NHWC-dense memory viewed as [rows, C]: no copy
-                gy1p, xhat, h, ga = swin_mlp_backward_raw(g2d, y1p.permute(0, 2, 3, 1).reshape(rows, Cc), w1f, b1f, w2h)
-                gw2, gb2 = gemm.matmul_tn(g2d, h)                          # [C, 4C] = g_out^T gelu(a),  [C] = sum g_out
+                gy1p, xhat, ga = swin_mlp_backward_raw(g2d, y1p.permute(0, 2, 3, 1).reshape(rows, Cc), w1f, b1f, w2h)
+                gw2, gb2 = gemm.matmul_tn(g2d, h2)                         # 2 * [C, 4C] = g_out^T (2 gelu(a)),  [C] = sum g_out
+                gw2 = gw2.mul_(0.5)
                 G, gb1 = gemm.matmul_tn(ga, xhat)                          # [4C, C] = g_a^T xhat,       [4C] = sum g_a
-                del h, ga, xhat
+                del ga, xhat
                 # LayerNorm2's affine part was folded into mlp.0 (u = xhat * gamma + beta): unfold the three gradients
                 w1d = w1.detach().float()
                 gw1 = torch.addcmul(gb1[:, None] * b2f[None, :], G, g2f[None, :])
                 gg2 = (w1d * G).sum(0)
                 gbt2 = w1d.t() @ gb1
                 gy1 = torch.empty((T, Cc), dtype=dt, device=dev)
-                call("b200_swin_partition", ptr(gy1p), ptr(gy1), B, Cc, H, W, ws, shift, code, st)
+                call("b200_swin_partition_add", ptr(gy1p), ptr(gout), ptr(gy1), B, Cc, H, W, ws, shift, code, st)   # + residual
                 del gy1p
             else:
                 (x, g1f, g2f, win, wo, w1, w2, n1, mean1, rstd1, qkv, o, lse, y1, u, mean2, rstd2, hpre, h) = ctx.saved_tensors

@@ -134,6 +134,10 @@ B200_API int b200_swin_res_reverse(const void* y1, const void* m, void* out, int
 /* tok[T,C] = partition(pad(src)) without normalisation (used for the upstream gradient) */
 B200_API int b200_swin_partition(const void* src, void* tok, int32_t B, int32_t C, int32_t H, int32_t W,
                                  int32_t ws, int32_t shift, int32_t dtype, void* stream);
+/* the same with a second addend in pixel layout: tok = partition(src + add) -- used to add the residual gradient g_out to the
+ * LayerNorm-backward term that b200_swin_mlp_bwd leaves in g_y1 */
+B200_API int b200_swin_partition_add(const void* src, const void* add, void* tok, int32_t B, int32_t C, int32_t H, int32_t W,
+                                     int32_t ws, int32_t shift, int32_t dtype, void* stream);
 /* LayerNorm backward.  mode 0 (LN2): token-major, gin = LN^T(gout) + gres.  mode 1 (LN1): xin = x (NHWC, gathered
  * through the window map), gin = gx scattered back to NHWC; ggamma/gbeta [C] f32 overwritten; norm1.bias receives
  * gradient from padded tokens too. */
@@ -235,19 +239,22 @@ B200_API int b200_bn_silu_bwd(const void* gz, int64_t gz_row_stride, const void*
  *   b200_swin_mlp_prep : w1f = mlp.0.weight * norm2.weight (16-bit), b1f = mlp.0.bias + mlp.0.weight @ norm2.bias (f32),
  *                        w2h = mlp.2.weight / 2 (16-bit; the kernels form 2 * gelu) -- LayerNorm's affine part folded
  *                        into the first GEMM.
- *   b200_swin_mlp_fwd  : out = y1 + mlp.2(gelu(xhat @ w1f^T + b1f)) + b2,  xhat = (y1 - mean) * rstd per row.
+ *   b200_swin_mlp_fwd  : out = y1 + mlp.2(gelu(xhat @ w1f^T + b1f)) + b2,  xhat = (y1 - mean) * rstd per row; in training
+ *                        the 16-bit tiles 2*gelu(a) that feed the second GEMM are also stored (h2) for the backward.
  *   b200_swin_mlp_bwd  : from g_out [rows, C] and y1 recomputes xhat / the hidden pre-activation and writes
- *                        g_y1 [rows, C] (residual + LayerNorm2 backward included) plus the three operands of the
- *                        weight-gradient contractions: xhat [rows, C], h = gelu(a) [rows, 4C], g_a [rows, 4C]
- *                        (d mlp.0.weight = g_a^T xhat * gamma + ..., d mlp.2.weight = g_out^T h: b200_gemm_splitk).
+ *                        g_y1 [rows, C] (the LayerNorm2-backward term; the residual "+ g_out" is added by the consumer,
+ *                        b200_swin_partition_add) plus the operands of the weight-gradient contractions it owns:
+ *                        xhat [rows, C] and g_a [rows, 4C]   (d mlp.0.weight = g_a^T xhat * gamma + ...,
+ *                        d mlp.2.weight = g_out^T h2 / 2 with the forward's h2: b200_gemm_splitk).
  * ------------------------------------------------------------------------------------------------------ */
 B200_API int b200_swin_mlp_supported(int64_t rows, int32_t C, int32_t dtype);
 B200_API int b200_swin_mlp_prep(const float* w1, const float* b1, const float* gamma, const float* beta, const float* w2,
                                 void* w1f, float* b1f, void* w2h, int32_t C, int32_t dtype, void* stream);
 B200_API int b200_swin_mlp_fwd(const void* y1, const void* w1f, const float* b1f, const void* w2h, const float* b2, void* out,
-                               int64_t rows, int32_t C, float eps, int32_t dtype, void* stream);
+                               void* h2 /* optional [rows, 4C]: 2*gelu(a), saved for the backward */, int64_t rows, int32_t C,
+                               float eps, int32_t dtype, void* stream);
 B200_API int b200_swin_mlp_bwd(const void* gout, const void* y1, const void* w1f, const float* b1f, const void* w2h, void* gy1,
-                               void* xhat, void* h, void* ga, int64_t rows, int32_t C, float eps, int32_t dtype, void* stream);
+                               void* xhat, void* ga, int64_t rows, int32_t C, float eps, int32_t dtype, void* stream);
 
 #ifdef __cplusplus
 }

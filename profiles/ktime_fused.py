@@ -27,6 +27,8 @@ def main():
     out = {}
     w1f, b1f, w2h = Fb.swin_mlp_prep(gamma, beta, w1, b1, w2, dt)
     out["swin_mlp_prep_us"] = 1e3 * _time(lambda: Fb.swin_mlp_prep(gamma, beta, w1, b1, w2, dt), 10, flush)
+    ms_t = _time(lambda: Fb.swin_mlp_forward_raw(y1, w1f, b1f, w2h, b2, save_h=True), 20, flush)
+    out["swin_mlp_fwd_train_us"] = 1e3 * ms_t
     ms = _time(lambda: Fb.swin_mlp_forward_raw(y1, w1f, b1f, w2h, b2), 20, flush)
     flops = 2.0 * rows * C * 4 * C * 2
     out["swin_mlp_fwd_us"] = 1e3 * ms

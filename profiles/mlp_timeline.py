@@ -19,13 +19,16 @@ w2 = torch.randn(Cc, 4 * Cc, device=dev) / (4 * Cc) ** 0.5
 b1, b2 = torch.randn(4 * Cc, device=dev), torch.randn(Cc, device=dev)
 gamma, beta = torch.ones(Cc, device=dev), torch.zeros(Cc, device=dev)
 w1f, b1f, w2h = Fb.swin_mlp_prep(gamma, beta, w1, b1, w2, dt)
+BWD = len(sys.argv) > 1 and sys.argv[1] == "bwd"
+g = torch.randn(rows, Cc, device=dev).to(dt)
+run = (lambda: Fb.swin_mlp_backward_raw(g, y1, w1f, b1f, w2h)) if BWD else (lambda: Fb.swin_mlp_forward_raw(y1, w1f, b1f, w2h, b2))
 for _ in range(3):
-    Fb.swin_mlp_forward_raw(y1, w1f, b1f, w2h, b2)
+    run()
 buf = torch.zeros(16 * 64, dtype=torch.int64, device=dev)
 L = _lib.lib()
 L.b200_debug_set_mlp_timeline.argtypes = [C.c_void_p]
 L.b200_debug_set_mlp_timeline(C.c_void_p(buf.data_ptr()))
-Fb.swin_mlp_forward_raw(y1, w1f, b1f, w2h, b2)
+run()
 torch.cuda.synchronize()
 L.b200_debug_set_mlp_timeline(C.c_void_p(0))
 t = buf.cpu().view(4, 4, 64)
@@ -39,5 +42,5 @@ for r in range(4):
             v = int(t[r, e, i])
             if v > 0:
                 ev.append((v - t0, names[r][0], names[r][1][e], i))
-for v, role, e, i in sorted(ev)[:260]:
+for v, role, e, i in sorted(ev)[:400]:
     print(f"{v:8d} {role:5s} {e:12s} {i}")
