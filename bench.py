@@ -325,6 +325,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=None, help="--impl reference: per-step batch (default: largest that fits the time budget)")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly (no CUDA-graph replay)")
+    ap.add_argument("--cudnn-benchmark", type=int, default=0, help="torch.backends.cudnn.benchmark for the stock convolutions (A/B switch)")
     ap.add_argument("--scale", default=SCALE, choices=["n", "s", "m"],
                     help="width/depth variant (BASELINE configs[3]: s/m with SwinBlock [256]/[384]); default n = the headline config")
     args = ap.parse_args()
@@ -365,6 +366,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the B200 kernels have no CPU path)")
     torch.cuda.set_device(local_rank)
+    torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     _lib.lib()  # fail loudly here if libb200yolo.so is missing
