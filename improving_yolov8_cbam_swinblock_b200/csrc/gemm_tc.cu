@@ -82,6 +82,37 @@ const CUtensorMap* tensor_map_2d(const void* base, uint64_t rows, uint64_t cols,
   return m;
 }
 
+const CUtensorMap* tensor_map_nhwc(const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t box_h, uint32_t box_w,
+                                   int dtype) {
+  // shares the 2-D cache: (rows, cols, stride) = (B*H, W, C) cannot collide with a 2-D key of the same base because box_cols = 0 marks it
+  Key key{base, B * H, W, C | (H << 32), box_h * 1024u + box_w, 0u, dtype};
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) return it->second;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (driver too old?)"); return nullptr; }
+  if (g_maps.size() > 4096) {
+    for (auto& kv : g_maps) delete kv.second;
+    g_maps.clear();
+  }
+  CUtensorMap* m = new CUtensorMap;
+  cuuint64_t dims[4] = {C, W, H, B};
+  cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[4] = {64, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, dtype == B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (NHWC) failed (%d) B=%llu H=%llu W=%llu C=%llu box=%ux%u", (int)r, (unsigned long long)B,
+              (unsigned long long)H, (unsigned long long)W, (unsigned long long)C, box_h, box_w);
+    delete m;
+    return nullptr;
+  }
+  g_maps.emplace(key, m);
+  return m;
+}
+
 namespace {
 
 constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;

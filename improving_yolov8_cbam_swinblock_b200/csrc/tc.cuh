@@ -13,6 +13,12 @@ namespace tc {
 const CUtensorMap* tensor_map_2d(const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                                  uint32_t box_rows, uint32_t box_cols, int dtype);
 
+// NHWC map [B, H, W, C] of 16-bit elements as a 4-D tensor, box = [1, box_h, box_w, 64 channels], 128-byte swizzle: one box
+// is a window of box_h x box_w pixels landing as box_h*box_w consecutive 128-byte rows (a K-major UMMA operand block).
+// Out-of-bounds pixels read as zero and are skipped on store -- the zero padding / crop of swin_block.py:41-45,58.
+const CUtensorMap* tensor_map_nhwc(const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t box_h, uint32_t box_w,
+                                   int dtype);
+
 // ---- device ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -39,6 +45,19 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* m
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src_smem, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(smem_u32(src_smem))
+               : "memory");
+}
+
+// 4-D variants (coordinates innermost first: channel, x, y, image)
+__device__ __forceinline__ void tma_load_4d(void* dst_smem, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src_smem, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(src_smem))
                : "memory");
 }
 

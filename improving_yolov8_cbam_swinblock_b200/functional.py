@@ -39,6 +39,8 @@ _lib.register("b200_nhwc_concat", C.c_int, [_VP, _VP, _VP, _I32, _VP, _I64, _I32
 _lib.register("b200_u8_to_nhwc", C.c_int, [_VP, _VP] + [_I32] * 4 + [C.c_float, _I32, _VP])
 _lib.register("b200_nhwc_upsample_fwd", C.c_int, [_VP, _VP] + [_I32] * 7 + [_VP])
 _lib.register("b200_nhwc_upsample_bwd", C.c_int, [_VP, _I64, _VP] + [_I32] * 7 + [_VP])
+_lib.register("b200_swin_attn_block_supported", C.c_int, [_I32] * 8)
+_lib.register("b200_swin_attn_block_fwd", C.c_int, [_VP] * 14 + [_I32] * 6 + [C.c_float, _I32, _VP])
 _lib.register("b200_swin_mlp_supported", C.c_int, [_I64, _I32, _I32])
 _lib.register("b200_swin_mlp_prep", C.c_int, [_VP] * 8 + [_I32, _I32, _VP])
 _lib.register("b200_swin_mlp_fwd", C.c_int, [_VP] * 7 + [_I64, _I32, C.c_float, _I32, _VP])
@@ -431,6 +433,36 @@ def attn_backward(qkv, o, lse, go, T, Lw, Cc, nh, grid=(0, 0, 0, 0)):
     return gqkv
 
 
+USE_FUSED_ATTN = True  # tests flip this to compare the fused tcgen05 attention half with the unfused stage-by-stage path
+
+
+def fused_attn_supported(B, Cc, H, W, heads, ws, shift, dtype) -> bool:
+    return (USE_FUSED_ATTN and dtype in (torch.bfloat16, torch.float16)
+            and bool(lib().b200_swin_attn_block_supported(B, Cc, H, W, heads, ws, shift, dtype_code(dtype))))
+
+
+def swin_attn_block_forward_raw(x, g1, b1, win, bin_, wo, bo, heads, ws, train=False, eps=1e-5):
+    """y1 [B,C,H,W] (channels_last) = n1 + out_proj(MHSA(n1)), n1 = LN1(window tokens of zero-padded x), in one kernel.
+    train: also returns (n1 [T,C], qkv [T,3C], o [T,C], lse [T,heads], mean [T], rstd [T]) in window-token order."""
+    x = _nhwc(x)
+    B, Cc, H, W = x.shape
+    dev, dt = x.device, x.dtype
+    y1 = _empty_nhwc(B, Cc, H, W, dt, dev)
+    extra = None
+    if train:
+        T = int(lib().b200_swin_num_tokens(B, H, W, ws))
+        f32 = dict(dtype=torch.float32, device=dev)
+        extra = (torch.empty((T, Cc), dtype=dt, device=dev), torch.empty((T, 3 * Cc), dtype=dt, device=dev),
+                 torch.empty((T, Cc), dtype=dt, device=dev), torch.empty((T, heads), **f32), torch.empty(T, **f32), torch.empty(T, **f32))
+    e = extra or (None,) * 6
+    wi, wod = win.detach().to(dt).contiguous(), wo.detach().to(dt).contiguous()
+    with torch.cuda.device(dev):
+        call("b200_swin_attn_block_fwd", ptr(x), ptr(_f32(g1)), ptr(_f32(b1)), ptr(wi), ptr(_f32(bin_)), ptr(wod), ptr(_f32(bo)), ptr(y1),
+             ptr(e[0]), ptr(e[1]), ptr(e[2]), ptr(e[3]), ptr(e[4]), ptr(e[5]), B, Cc, H, W, heads, ws, float(eps), dtype_code(dt),
+             stream_ptr(dev), tag=f"b200_swin_attn_block_fwd[{B}x{Cc}x{H}x{W},ws{ws}]")
+    return (y1, *extra) if train else y1
+
+
 USE_FUSED_MLP = True  # tests flip this to compare the fused tcgen05 MLP half with the unfused stage-by-stage path
 
 
@@ -500,23 +532,34 @@ class SwinBlockFn(torch.autograd.Function):
         st = stream_ptr(dev)
         f32 = dict(dtype=torch.float32, device=dev)
         g1f, b1f, g2f, b2f = _f32(g1), _f32(b1), _f32(g2), _f32(b2)
+        need_grad = any(ctx.needs_input_grad)
         with torch.cuda.device(dev):
-            n1 = torch.empty((T, Cc), dtype=dt, device=dev)
-            mean1, rstd1 = torch.empty(T, **f32), torch.empty(T, **f32)
             grid = (-(-H // ws), -(-W // ws), ws, shift)
-            call("b200_swin_ln1_partition", ptr(x), ptr(g1f), ptr(b1f), ptr(n1), ptr(mean1), ptr(rstd1), B, Cc, H, W, ws,
-                                            shift, code, st)
-            qkv = gemm.linear(n1, win, bin_)
-            o, lse = attn_forward(qkv, T, Lw, Cc, num_heads, grid)
-            y1 = gemm.linear_res(o, wo, bo, n1)  # post-norm residual fused into the out_proj epilogue
+            fused_attn = fused_attn_supported(B, Cc, H, W, num_heads, ws, shift, dt) and fused_mlp_supported(B * H * W, Cc, dt)
+            if fused_attn:
+                # attention half in one tcgen05 kernel: x -> y1 in pixel order (+ the backward's by-products when training)
+                if need_grad:
+                    y1p, n1, qkv, o, lse, mean1, rstd1 = swin_attn_block_forward_raw(x, g1, b1, win, bin_, wo, bo, num_heads, ws, train=True)
+                else:
+                    y1p = swin_attn_block_forward_raw(x, g1, b1, win, bin_, wo, bo, num_heads, ws, train=False)
+                    n1 = qkv = o = lse = mean1 = rstd1 = None
+                y1 = None
+            else:
+                n1 = torch.empty((T, Cc), dtype=dt, device=dev)
+                mean1, rstd1 = torch.empty(T, **f32), torch.empty(T, **f32)
+                call("b200_swin_ln1_partition", ptr(x), ptr(g1f), ptr(b1f), ptr(n1), ptr(mean1), ptr(rstd1), B, Cc, H, W, ws,
+                                                shift, code, st)
+                qkv = gemm.linear(n1, win, bin_)
+                o, lse = attn_forward(qkv, T, Lw, Cc, num_heads, grid)
+                y1 = gemm.linear_res(o, wo, bo, n1)  # post-norm residual fused into the out_proj epilogue
             fused = fused_mlp_supported(B * H * W, Cc, dt)
             if fused:
                 # MLP half in one tcgen05 kernel on the real tokens in pixel order (window_reverse + crop = the row order)
-                y1p = _empty_nhwc(B, Cc, H, W, dt, dev)
-                call("b200_swin_res_reverse", ptr(y1), None, ptr(y1p), B, Cc, H, W, ws, shift, code, st)
+                if not fused_attn:
+                    y1p = _empty_nhwc(B, Cc, H, W, dt, dev)
+                    call("b200_swin_res_reverse", ptr(y1), None, ptr(y1p), B, Cc, H, W, ws, shift, code, st)
                 w1f, b1f, w2h = swin_mlp_prep(g2, b2, w1, bb1, w2, dt)
                 out = _empty_nhwc(B, Cc, H, W, dt, dev)
-                need_grad = any(ctx.needs_input_grad)
                 h2 = torch.empty((B * H * W, 4 * Cc), dtype=dt, device=dev) if need_grad else None   # 2*gelu(a), for d mlp.2.weight
                 call("b200_swin_mlp_fwd", ptr(y1p), ptr(w1f), ptr(b1f), ptr(w2h), ptr(_f32(bb2)), ptr(out), ptr(h2), B * H * W, Cc, 1e-5,
                      code, st, tag=f"b200_swin_mlp_fwd[{B * H * W}x{Cc}]")

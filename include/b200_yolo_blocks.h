@@ -256,6 +256,22 @@ B200_API int b200_swin_mlp_fwd(const void* y1, const void* w1f, const float* b1f
 B200_API int b200_swin_mlp_bwd(const void* gout, const void* y1, const void* w1f, const float* b1f, const void* w2h, void* gy1,
                                void* xhat, void* ga, int64_t rows, int32_t C, float eps, int32_t dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Fused attention half of the SwinBlock -- replaces F.pad, rearrange, window_partition, norm1, nn.MultiheadAttention and the
+ * first residual add (ultralytics/nn/modules/swin_block.py:41-52) plus window_reverse / crop for that half (:55-58), for
+ * 16-bit activations with C = 128, 2 heads, window <= 8 and no shift, in ONE tcgen05 kernel:
+ *     y1 [B,H,W,C] (pixel order) = n1 + out_proj(MHSA(n1)),  n1 = LayerNorm1(window tokens of the zero-padded x).
+ * w_in [3C,C] / w_out [C,C] are the 16-bit copies of attn.in_proj_weight / attn.out_proj.weight; biases and LayerNorm
+ * parameters f32.  Training (n1 != NULL): the by-products the backward consumes are written too, in window-token order
+ * (T = b200_swin_num_tokens rows): n1 [T,C], qkv [T,3C], o [T,C], lse [T,2], mean / rstd [T].
+ * ------------------------------------------------------------------------------------------------------ */
+B200_API int b200_swin_attn_block_supported(int32_t B, int32_t C, int32_t H, int32_t W, int32_t heads, int32_t ws, int32_t shift,
+                                            int32_t dtype);
+B200_API int b200_swin_attn_block_fwd(const void* x, const float* gamma, const float* beta, const void* w_in, const float* b_in,
+                                      const void* w_out, const float* b_out, void* y1, void* n1, void* qkv, void* o, float* lse,
+                                      float* mean, float* rstd, int32_t B, int32_t C, int32_t H, int32_t W, int32_t heads,
+                                      int32_t ws, float eps, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,18 @@ def main():
         ms = _time(lambda: Fb.swin_mlp_backward_raw(g, y1, w1f, b1f, w2h), 20, flush)
         out["swin_mlp_bwd_us"] = 1e3 * ms
         out["swin_mlp_bwd_tflops"] = 1.5 * flops / (ms * 1e-3) / 1e12
+    # attention half: x -> y1 (pixel order), one kernel
+    B, H, W, ws = 64, 40, 40, 7
+    x = torch.randn(B, C, H, W, device=dev).to(dt).contiguous(memory_format=torch.channels_last)
+    g1, bt1 = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+    win = torch.randn(3 * C, C, device=dev) / C ** 0.5
+    wo = torch.randn(C, C, device=dev) / C ** 0.5
+    bi, bo = torch.randn(3 * C, device=dev), torch.randn(C, device=dev)
+    for train in (False, True):
+        ms = _time(lambda: Fb.swin_attn_block_forward_raw(x, g1, bt1, win, bi, wo, bo, 2, ws, train=train), 20, flush)
+        out["swin_attn_block_fwd_%s_us" % ("train" if train else "infer")] = 1e3 * ms
+    fl = B * H * W * (8 * C * C + 4 * ws * ws * C)
+    out["swin_attn_block_fwd_infer_tflops"] = fl / (out["swin_attn_block_fwd_infer_us"] * 1e-6) / 1e12
     print(json.dumps(out))
 
 

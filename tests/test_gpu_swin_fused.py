@@ -99,3 +99,51 @@ def test_fused_mlp_backward(dtype, tol, rows):
     assert rel_err(gy1, yd.grad - g.double()) < 3 * tol, rel_err(gy1, yd.grad - g.double())
     again = Fb.swin_mlp_backward_raw(g, y1, w1f, b1f, w2h)
     assert all(torch.equal(u, v) for u, v in zip((gy1, xhat, ga), again))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 8e-3), (torch.float16, 1.5e-3)])
+@pytest.mark.parametrize("shape,ws", [((1, 128, 7, 7), 7), ((2, 128, 14, 7), 7), ((2, 128, 40, 40), 7), ((3, 128, 23, 9), 7),
+                                      ((1, 128, 24, 16), 8), ((2, 128, 5, 6), 3), ((64, 128, 40, 40), 7)])
+def test_fused_attention_half_forward(dtype, tol, shape, ws):
+    """y1 and every training by-product (n1, qkv, o, lse, mean, rstd) against an fp64 restatement of swin_block.py:41-52
+    (zero padding BEFORE LayerNorm, packed in_proj, per-window 2-head softmax attention, out_proj, post-norm residual)."""
+    from improving_yolov8_cbam_swinblock_b200 import functional as Fb
+    from oracle import blocks as ob
+
+    B, C, H, W = shape
+    heads = 2
+    torch.manual_seed(H * W + ws)
+    g1 = (1 + 0.3 * torch.randn(C)).cuda()
+    b1 = (0.3 * torch.randn(C)).cuda()
+    win = (torch.randn(3 * C, C) / C ** 0.5).cuda()
+    bin_ = (0.3 * torch.randn(3 * C)).cuda()
+    wo = (torch.randn(C, C) / C ** 0.5).cuda()
+    bo = (0.3 * torch.randn(C)).cuda()
+    x = torch.randn(shape, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    assert Fb.fused_attn_supported(B, C, H, W, heads, ws, 0, dtype)
+    y1, n1, qkv, o, lse, mean, rstd = Fb.swin_attn_block_forward_raw(x, g1, b1, win, bin_, wo, bo, heads, ws, train=True)
+    y1_inf = Fb.swin_attn_block_forward_raw(x, g1, b1, win, bin_, wo, bo, heads, ws, train=False)
+    assert torch.equal(y1, y1_inf)
+    # fp64 restatement on the same 16-bit input
+    L = ws * ws
+    xd = x.double()
+    ph, pw = (ws - H % ws) % ws, (ws - W % ws) % ws
+    xp = torch.nn.functional.pad(xd, (0, pw, 0, ph))
+    Hp, Wp = H + ph, W + pw
+    t = xp.permute(0, 2, 3, 1).reshape(B, Hp // ws, ws, Wp // ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, L, C)
+    n1r = torch.nn.functional.layer_norm(t, (C,), g1.double(), b1.double(), 1e-5)
+    qkvr = n1r @ win.double().t() + bin_.double()
+    q, k, v = qkvr.split(C, -1)
+    hd = C // heads
+    sh = lambda z: z.reshape(-1, L, heads, hd).transpose(1, 2)   # noqa: E731
+    s = (sh(q) @ sh(k).transpose(-1, -2)) / hd ** 0.5
+    orr = (s.softmax(-1) @ sh(v)).transpose(1, 2).reshape(-1, L, C)
+    y1r = n1r + orr @ wo.double().t() + bo.double()
+    y1r = y1r.reshape(B, Hp // ws, Wp // ws, ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B, Hp, Wp, C)[:, :H, :W].permute(0, 3, 1, 2)
+    assert rel_err(n1, n1r.reshape(-1, C)) < (5e-3 if dtype == torch.bfloat16 else 8e-4)
+    assert rel_err(qkv, qkvr.reshape(-1, 3 * C)) < tol
+    assert rel_err(o, orr.reshape(-1, C)) < tol
+    assert rel_err(lse, torch.logsumexp(s, -1).transpose(1, 2).reshape(-1, heads)) < 2e-3
+    assert rel_err(mean, t.mean(-1).reshape(-1)) < 1e-4 or float(t.mean(-1).abs().max()) < 1e-6
+    assert rel_err(y1, y1r) < tol, rel_err(y1, y1r)
+    assert torch.isfinite(y1).all()
