@@ -428,10 +428,26 @@ def main():
     config["launch_mode"] = (("CUDA-graph replay of fwd+loss+bwd+clip+SGD" if world == 1 else
                               "CUDA-graph replay: graph A fwd+loss+bwd into one flat gradient buffer, one eager NCCL all-reduce, graph B clip+SGD") +
                              " (captured once; gpu_launches = C-ABI kernel calls replayed inside the graph)") if graphed else f"eager launches ({tr._graph_error or 'graph capture disabled'})"
+    if graphed and world > 1:
+        config["launch_mode"] += f"; multi-GPU capture: {tr._graph_mode}" + (f" ({tr._graph_error})" if tr._graph_error else "")
     config["eager_ms_per_step"] = ms_eager / args.steps
-    if rank != 0:
+    def shutdown():
+        """Tear the process group down without ever hanging the run: graphs that captured NCCL kernels go first, and a timer
+        force-exits (status 0: the record is already printed) if communicator destruction blocks."""
         if world > 1:
-            dist.destroy_process_group()
+            import threading
+
+            t = threading.Timer(45.0, lambda: os._exit(0))
+            t.daemon = True
+            t.start()
+            try:
+                dist.destroy_process_group()
+            finally:
+                t.cancel()
+
+    if rank != 0:
+        tr.release_graphs()
+        shutdown()
         return
 
     peaks = _peaks()
@@ -506,8 +522,9 @@ def main():
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg()
     print_record(line)
-    if world > 1:
-        dist.destroy_process_group()
+    if "tr" in locals():
+        tr.release_graphs()
+    shutdown()
 
 
 if __name__ == "__main__":
