@@ -461,7 +461,7 @@ def main():
         hot = tot
         top = max(hot, key=hot.get)
         n, ms = ktimes[top]
-        w = work.get(top) or sweep.gemm_work(top, peaks) or sweep.bn_work(top) or sweep.seam_work(top)
+        w = work.get(top) or sweep.gemm_work(top, peaks) or sweep.fused_work(top) or sweep.bn_work(top) or sweep.seam_work(top)
         if not w:
             roof = {"kernel": top, "avg_ms": ms, "calls": n, "note": "no algorithmic-work entry",
                     "kernels_ms_per_step": {k: v / args.steps for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
@@ -480,7 +480,7 @@ def main():
     if roof is not None:  # every hand-written kernel of the step: mean ms per launch + fraction of its roofline
         allk = {}
         for k, (n_, ms_) in ktimes.items():
-            w_ = work.get(k) or sweep.gemm_work(k, peaks) or sweep.bn_work(k) or sweep.seam_work(k)
+            w_ = work.get(k) or sweep.gemm_work(k, peaks) or sweep.fused_work(k) or sweep.bn_work(k) or sweep.seam_work(k)
             ent = {"calls_per_step": n_ / args.steps, "avg_ms": round(ms_, 5)}
             if w_:
                 pk = peaks["hbm_gbs"] if w_["bound"] == "hbm" else peaks["bf16_tflops_sustained"]

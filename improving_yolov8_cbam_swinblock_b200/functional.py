@@ -39,6 +39,9 @@ _lib.register("b200_nhwc_concat", C.c_int, [_VP, _VP, _VP, _I32, _VP, _I64, _I32
 _lib.register("b200_u8_to_nhwc", C.c_int, [_VP, _VP] + [_I32] * 4 + [C.c_float, _I32, _VP])
 _lib.register("b200_nhwc_upsample_fwd", C.c_int, [_VP, _VP] + [_I32] * 7 + [_VP])
 _lib.register("b200_nhwc_upsample_bwd", C.c_int, [_VP, _I64, _VP] + [_I32] * 7 + [_VP])
+_lib.register("b200_bce_logits_workspace_bytes", _SZ, [])
+_lib.register("b200_bce_logits_fwd", C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _SZ, _I32, _I32, _I32, _VP])
+_lib.register("b200_bce_logits_bwd", C.c_int, [_VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _I32, _I32, _I32, _VP])
 _lib.register("b200_swin_attn_block_supported", C.c_int, [_I32] * 8)
 _lib.register("b200_swin_attn_block_fwd", C.c_int, [_VP] * 14 + [_I32] * 6 + [C.c_float, _I32, _VP])
 _lib.register("b200_swin_mlp_supported", C.c_int, [_I64, _I32, _I32])
@@ -195,6 +198,61 @@ def nhwc_chunk(x: torch.Tensor, n: int):
     if not (x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16, torch.float16) and _row_strided(x) is not None):
         return x.chunk(n, 1)
     return NhwcChunkFn.apply(x, n)
+
+
+# --------------------------------------------------------------------------------------------------
+# classification term of the detection loss   (utils/loss.py:235 + the dense one-hot target of tal.py:98-107)
+# --------------------------------------------------------------------------------------------------
+def _level_args(maps):
+    n = len(maps)
+    ptrs = (C.c_void_p * n)(*[m.data_ptr() for m in maps])
+    anchors = (C.c_int32 * n)(*[int(m.shape[2] * m.shape[3]) for m in maps])
+    strides = (C.c_int64 * n)(*[int(m.shape[1]) for m in maps])
+    return n, ptrs, anchors, strides
+
+
+class ClsLossFn(torch.autograd.Function):
+    """sum_{b,a,c} BCEWithLogits(x, t) with t[b,a,c] = value[b,a] * (c == label[b,a]) over the Detect class maps
+    (one [B,nc,H,W] channels_last map per level), read in place: no cat / permute / float copies, no dense target."""
+
+    @staticmethod
+    def forward(ctx, label, value, *maps):
+        maps = tuple(_nhwc(m) for m in maps)
+        m0 = maps[0]
+        B, nc = m0.shape[0], m0.shape[1]
+        dev, code = m0.device, dtype_code(m0.dtype)
+        label = label.to(torch.int32).contiguous()
+        value = value.to(torch.float32).contiguous()
+        n, ptrs, anchors, strides = _level_args(maps)
+        nbytes = lib().b200_bce_logits_workspace_bytes()
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            call("b200_bce_logits_fwd", C.addressof(ptrs), C.addressof(anchors), C.addressof(strides), n, ptr(label), ptr(value), ptr(out),
+                 ptr(ws), nbytes, B, nc, code, stream_ptr(dev))
+        ctx.save_for_backward(label, value, *maps)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        label, value, *maps = ctx.saved_tensors
+        m0 = maps[0]
+        B, nc = m0.shape[0], m0.shape[1]
+        dev, code = m0.device, dtype_code(m0.dtype)
+        grads = [torch.empty_like(m) for m in maps]   # channels_last, like the maps
+        n, ptrs, anchors, strides = _level_args(maps)
+        gptrs = (C.c_void_p * n)(*[t.data_ptr() for t in grads])
+        scale = g.detach().to(torch.float32).reshape(1).contiguous()
+        with torch.cuda.device(dev):
+            call("b200_bce_logits_bwd", C.addressof(ptrs), C.addressof(gptrs), C.addressof(anchors), C.addressof(strides), n, ptr(label),
+                 ptr(value), ptr(scale), B, nc, code, stream_ptr(dev))
+        return (None, None, *grads)
+
+
+def cls_bce_sum(maps, label, value):
+    """BCEWithLogits(reduction='sum') of the class maps against the (label, value) targets of the task-aligned assigner."""
+    return ClsLossFn.apply(label, value, *maps)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -200,9 +200,13 @@ class Detect(nn.Module):
         self.dfl = DFL(self.reg_max)
 
     concat = None
+    split_outputs = False   # training: hand the loss the (box, cls) maps of each level separately (no channel concat: the fused
+                            # classification-loss kernel reads the class maps in place and the gradients stay dense)
 
     def forward(self, x):
         cat = (lambda ts: torch.cat(ts, 1)) if self.concat is None else self.concat
+        if self.training and self.split_outputs:
+            return [(self.cv2[i](x[i]), self.cv3[i](x[i])) for i in range(self.nl)]
         x = [cat((self.cv2[i](x[i]), self.cv3[i](x[i]))) for i in range(self.nl)]
         if self.training:
             return x

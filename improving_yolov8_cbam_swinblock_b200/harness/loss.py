@@ -39,16 +39,24 @@ def _ciou(b1, b2, eps=1e-7):
 
 @torch.no_grad()
 def task_aligned_assign(pd_scores, pd_bboxes, anc_points, gt_labels, gt_bboxes, mask_gt,
-                        topk=10, alpha=0.5, beta=6.0, eps=1e-9):
-    """Dense TaskAlignedAssigner (utils/tal.py:52-130): returns target_bboxes, target_scores, fg_mask."""
-    bs, na, nc = pd_scores.shape
+                        topk=10, alpha=0.5, beta=6.0, eps=1e-9, bbox_scores=None, nc=None, sparse=False):
+    """Dense TaskAlignedAssigner (utils/tal.py:52-130): returns target_bboxes, target_scores, fg_mask.
+    ``bbox_scores`` [bs, nmax, na] (optional): the predicted score of every anchor for each GT's own class, gathered by the
+    caller (then ``pd_scores`` may be None).  ``sparse``: return the targets as (label [bs,na], value [bs,na]) instead of the
+    dense one-hot ``target_scores`` -- target_scores[b,a,c] = value[b,a] * (c == label[b,a])."""
+    if pd_scores is not None:
+        bs, na, nc = pd_scores.shape
+    else:
+        bs, _, na = bbox_scores.shape
     nmax = gt_bboxes.shape[1]
     lt, rb = gt_bboxes.view(bs, nmax, 1, 4).chunk(2, -1)
     deltas = torch.cat((anc_points.view(1, 1, na, 2) - lt, rb - anc_points.view(1, 1, na, 2)), -1)
-    mask_in_gts = deltas.amin(-1).gt(eps).to(pd_scores.dtype)  # [bs, nmax, na]
+    mask_in_gts = deltas.amin(-1).gt(eps).to(pd_bboxes.dtype)  # [bs, nmax, na]
     m = mask_in_gts * mask_gt  # mask_gt: [bs, nmax, 1]
-    lbl = gt_labels.long().clamp(0, nc - 1).view(bs, nmax, 1).expand(bs, nmax, na)
-    bbox_scores = pd_scores.transpose(1, 2).gather(1, lbl) * m  # pd_scores[b, a, label[b, j]]
+    if bbox_scores is None:
+        lbl = gt_labels.long().clamp(0, nc - 1).view(bs, nmax, 1).expand(bs, nmax, na)
+        bbox_scores = pd_scores.transpose(1, 2).gather(1, lbl)  # pd_scores[b, a, label[b, j]]
+    bbox_scores = bbox_scores * m
     overlaps = _ciou(gt_bboxes.view(bs, nmax, 1, 4), pd_bboxes.view(bs, 1, na, 4)).clamp(0) * m
     align = bbox_scores.pow(alpha) * overlaps.pow(beta)
     _, topk_idx = torch.topk(align, topk, dim=-1)
@@ -63,11 +71,14 @@ def task_aligned_assign(pd_scores, pd_bboxes, anc_points, gt_labels, gt_bboxes, 
     flat_idx = tgt_idx + torch.arange(bs, device=tgt_idx.device).view(-1, 1) * nmax
     target_labels = gt_labels.long().flatten()[flat_idx].clamp(0)
     target_bboxes = gt_bboxes.reshape(-1, 4)[flat_idx]
-    target_scores = F.one_hot(target_labels, nc).to(pd_scores.dtype) * (fg > 0).unsqueeze(-1)
     align = align * mask_pos
     pos_align = align.amax(-1, keepdim=True)
     pos_ovl = (overlaps * mask_pos).amax(-1, keepdim=True)
     norm = (align * pos_ovl / (pos_align + eps)).amax(-2).unsqueeze(-1)
+    if sparse:   # (label, value) per anchor: background anchors get label -1 / value 0
+        fgm = fg > 0
+        return target_bboxes, (torch.where(fgm, target_labels, -1), norm.squeeze(-1) * fgm), fgm
+    target_scores = F.one_hot(target_labels, nc).to(pd_bboxes.dtype) * (fg > 0).unsqueeze(-1)
     return target_bboxes, target_scores * norm, fg > 0
 
 
@@ -98,7 +109,57 @@ class DetectionLoss:
         out[..., 1:5] = torch.cat((xy - half, xy + half), -1)
         return out
 
+    cls_loss = None   # optional fused classification term: callable(cls_maps, label [B,A], value [B,A]) -> BCE sum
+
+    def _call_split(self, pairs, batch, max_boxes):
+        """The same loss on the Detect head's un-concatenated (box, cls) maps: the class logits are never gathered into a
+        [B, 8400, nc] tensor -- the assigner gathers the nmax scores it needs per anchor, the BCE term is one fused kernel
+        over the class maps (utils/loss.py:207-255 computes the same three numbers)."""
+        boxes, clss = [p[0] for p in pairs], [p[1] for p in pairs]
+        device, bs = boxes[0].device, boxes[0].shape[0]
+        pred_distri = torch.cat([f.permute(0, 2, 3, 1).reshape(bs, -1, self.reg_max * 4) for f in boxes], 1).float()
+        dtype = pred_distri.dtype
+        h, w = boxes[0].shape[2:]
+        wh = torch.stack((torch.full((), w * self.strides[0], device=device), torch.full((), h * self.strides[0], device=device)))
+        anchor_points, stride_tensor = make_anchors(boxes, self.strides, 0.5)
+        t = self.targets_dense(batch, bs, max_boxes, wh, device)
+        gt_labels, gt_bboxes = t[..., :1], t[..., 1:5]
+        mask_gt = gt_bboxes.sum(2, keepdim=True).gt(0.0).to(torch.float32)
+        b, a, c = pred_distri.shape
+        proj = torch.arange(self.reg_max, dtype=dtype, device=device)
+        dist = pred_distri.view(b, a, 4, c // 4).softmax(3).matmul(proj)
+        pred_bboxes = torch.cat((anchor_points - dist[..., :2], anchor_points + dist[..., 2:]), -1)
+        nmax = gt_bboxes.shape[1]
+        with torch.no_grad():   # sigmoid(logit[b, a, label[b, j]]) for every GT j: the only class scores the assigner reads
+            lbl = gt_labels.long().clamp(0, self.nc - 1).view(bs, 1, nmax)
+            raw = torch.cat([f.permute(0, 2, 3, 1).reshape(bs, -1, self.nc).gather(2, lbl.expand(bs, f.shape[2] * f.shape[3], nmax))
+                             for f in clss], 1)
+            bbox_scores = raw.float().sigmoid().transpose(1, 2)
+        target_bboxes, (tlabel, tval), fg = task_aligned_assign(
+            None, (pred_bboxes.detach() * stride_tensor).float(), (anchor_points * stride_tensor).float(), gt_labels, gt_bboxes, mask_gt,
+            topk=self.topk, bbox_scores=bbox_scores, nc=self.nc, sparse=True)
+        tss = tval.sum().clamp(min=1.0)
+        lcls = self.cls_loss(clss, tlabel, tval) / tss
+        target_bboxes = target_bboxes / stride_tensor
+        weight = tval * fg
+        iou = _ciou(pred_bboxes.float(), target_bboxes)
+        lbox = ((1.0 - iou) * weight).sum() / tss
+        ltrb = torch.cat((anchor_points - target_bboxes[..., :2], target_bboxes[..., 2:] - anchor_points), -1)
+        ltrb = ltrb.clamp(0, self.reg_max - 1 - 0.01)
+        tl = ltrb.long()
+        wl = (tl + 1) - ltrb
+        logp = F.log_softmax(pred_distri.view(b, a, 4, self.reg_max).float(), -1)
+        ce_l = -logp.gather(-1, tl.unsqueeze(-1)).squeeze(-1)
+        ce_r = -logp.gather(-1, (tl + 1).unsqueeze(-1)).squeeze(-1)
+        ldfl = (((ce_l * wl + ce_r * (1 - wl)).mean(-1)) * weight).sum() / tss
+        loss = torch.stack((lbox * self.gains[0], lcls.float() * self.gains[1], ldfl * self.gains[2]))
+        return loss * bs, loss.detach()
+
     def __call__(self, feats, batch, max_boxes=None):
+        if isinstance(feats[0], (tuple, list)):
+            if self.cls_loss is not None and max_boxes:
+                return self._call_split(feats, batch, max_boxes)
+            feats = [torch.cat(p, 1) for p in feats]
         device = feats[0].device
         bs = feats[0].shape[0]
         # loss.py:207-213 builds [B, no, A] and permutes to [B, A, ·]; the same values are gathered anchor-major directly:

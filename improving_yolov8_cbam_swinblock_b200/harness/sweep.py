@@ -65,6 +65,26 @@ def seam_work(tag: str, s: int = 2):
     return {"bound": "hbm", "amount": 2.0 * n * s, "note": "2*N*s: every source element read once, written once"}
 
 
+def fused_work(tag: str):
+    """Roofline entry for the fused SwinBlock launches: tensor-core FLOPs on UN-PADDED tokens (the SwinBlock is
+    bounded by the tensor pipe; padding / recompute show up as lost efficiency)."""
+    import re
+
+    m = re.match(r"b200_swin_mlp_(fwd|bwd)\[(\d+)x(\d+)\]", tag)
+    if m:
+        rows, C = int(m.group(2)), int(m.group(3))
+        if m.group(1) == "fwd":
+            return {"bound": "tensor", "amount": 16.0 * rows * C * C, "note": "mlp.0 + mlp.2: 2 x 2*rows*C*4C FLOP (LN2 / GELU / residual ride along)"}
+        return {"bound": "tensor", "amount": 24.0 * rows * C * C,
+                "note": "recompute mlp.0, d hidden = g W2, d xhat = g_a W1: 3 x 2*rows*C*4C FLOP (the two weight gradients are b200_gemm_splitk launches)"}
+    m = re.match(r"b200_swin_attn_block_fwd\[(\d+)x(\d+)x(\d+)x(\d+),ws(\d+)\]", tag)
+    if m:
+        B, C, H, W, ws = (int(v) for v in m.groups())
+        return {"bound": "tensor", "amount": float(B * H * W) * (8.0 * C * C + 4.0 * ws * ws * C),
+                "note": "in_proj + QK^T + PV + out_proj on un-padded tokens: B*H*W*(8C^2 + 4*ws^2*C) FLOP"}
+    return None
+
+
 def ncu_kernel_name(tag: str):
     """ABI entry point (or shape-tagged GEMM) -> kernel instantiation name used in profiles/traffic_rNN.json."""
     import re
@@ -80,6 +100,10 @@ def ncu_kernel_name(tag: str):
              "b200_swin_partition": "b200::swin_move_vec_kernel<__nv_bfloat16, 8, 2, 1>"}
     if tag in fixed:
         return fixed[tag]
+    for pre, name in (("b200_swin_mlp_fwd[", "b200::swin_mlp_fwd_kernel<1>"), ("b200_swin_mlp_bwd[", "b200::swin_mlp_bwd_kernel<1>"),
+                      ("b200_swin_attn_block_fwd[", "b200::swin_attn_block_fwd_kernel<1>")):
+        if tag.startswith(pre):
+            return name
     m = re.match(r"b200_gemm_nt\[(\d+)x(\d+)x(\d+),epi(\d)\]", tag)
     if m:  # the dispatch table of b200_gemm_nt (csrc/gemm_tc.cu): <BLOCK_N, STAGES, EPI, epilogue warps, staging buffers>
         n, epi = int(m.group(2)), int(m.group(4))

@@ -76,6 +76,10 @@ class Trainer:
             model = model.to(memory_format=torch.channels_last)
         self.raw = self.model = model
         self.criterion = hloss.DetectionLoss(nc, model.stride)
+        # fused classification term (the kernel moves 16-byte vectors of class logits: nc a multiple of 8)
+        if blocks.get("cls_loss") is not None and self.device.type == "cuda" and nc % 8 == 0:
+            self.criterion.cls_loss = blocks["cls_loss"]
+            model.model[-1].split_outputs = True
         fused = self.device.type == "cuda"
         self.opt = torch.optim.SGD(param_groups(model), lr=lr, momentum=momentum, nesterov=True, fused=fused)
         self.ema = EMA(model) if ema else None

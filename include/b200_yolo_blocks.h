@@ -272,6 +272,23 @@ B200_API int b200_swin_attn_block_fwd(const void* x, const float* gamma, const f
                                       float* mean, float* rstd, int32_t B, int32_t C, int32_t H, int32_t W, int32_t heads,
                                       int32_t ws, float eps, int32_t dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Classification term of the v8 detection loss -- replaces, for the class logits of
+ * ultralytics/utils/loss.py:207-213,235 (`self.bce(pred_scores, target_scores.to(dtype)).sum()`), the cat / permute /
+ * contiguous / float copies of the three Detect levels, the dense one-hot target of TaskAlignedAssigner (tal.py:98-107)
+ * and BCEWithLogits forward + backward, by one streaming read of the logits per direction.
+ *   logits[l]  : class map of level l, NHWC-dense (or row-strided) [B * anchors[l], C] with row stride row_stride[l] elements
+ *   label,value: [B, sum(anchors)] target of each anchor: t[b,a,c] = value * (c == label); label < 0 = background
+ *   fwd: loss_sum[0] = sum softplus(x) - x*t (f32, deterministic).   bwd: grads[l] = (sigmoid(x) - t) * scale[0], same layout.
+ * ------------------------------------------------------------------------------------------------------ */
+B200_API size_t b200_bce_logits_workspace_bytes(void);
+B200_API int b200_bce_logits_fwd(const void* const* logits, const int32_t* anchors, const int64_t* row_stride, int32_t n_levels,
+                                 const int32_t* label, const float* value, float* loss_sum, void* workspace, size_t workspace_bytes,
+                                 int32_t B, int32_t C, int32_t dtype, void* stream);
+B200_API int b200_bce_logits_bwd(const void* const* logits, void* const* grads, const int32_t* anchors, const int64_t* row_stride,
+                                 int32_t n_levels, const int32_t* label, const float* value, const float* scale, int32_t B, int32_t C,
+                                 int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,7 +17,7 @@ def _num(v):
         return float("nan")
 
 
-MINE = re.compile(r"\b(cbam_\w+_kernel|fold_partials_kernel|bn_\w+_kernel|sppf_pool_(?:fwd|bwd)(?:_inplace)?_kernel|swin_\w+_kernel|gemm_nt_kernel|"
+MINE = re.compile(r"\b(swin_mlp_\w+_kernel|swin_attn_block_\w+_kernel|cbam_\w+_kernel|fold_partials_kernel|bn_\w+_kernel|sppf_pool_(?:fwd|bwd)(?:_inplace)?_kernel|swin_\w+_kernel|gemm_nt_kernel|"
                   r"gemm_splitk_kernel|fold_splits_kernel|fold_ln_kernel|fold_rows_kernel|colsum_partial_kernel|nhwc_concat_kernel|"
                   r"u8_to_nhwc_kernel|upsample_(?:fwd|bwd)_kernel)\b")
 
