@@ -30,7 +30,8 @@ struct BceParams {
   long long vec_total;    // total 16-byte vectors over all levels
 };
 
-__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x))); }
+// max(x,0) + log(1 + exp(-|x|)): the argument of the log lies in (1, 2], so the fast log has no cancellation problem
+__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x))); }
 
 template <typename T, int VE, bool BWD>
 __global__ void __launch_bounds__(256) bce_kernel(const BceParams P) {

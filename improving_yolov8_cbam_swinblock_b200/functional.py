@@ -229,7 +229,7 @@ class ClsLossFn(torch.autograd.Function):
         out = torch.empty((), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             call("b200_bce_logits_fwd", C.addressof(ptrs), C.addressof(anchors), C.addressof(strides), n, ptr(label), ptr(value), ptr(out),
-                 ptr(ws), nbytes, B, nc, code, stream_ptr(dev))
+                 ptr(ws), nbytes, B, nc, code, stream_ptr(dev), tag=f"b200_bce_logits_fwd[{B * sum(anchors)}x{nc}]")
         ctx.save_for_backward(label, value, *maps)
         return out
 
@@ -246,7 +246,7 @@ class ClsLossFn(torch.autograd.Function):
         scale = g.detach().to(torch.float32).reshape(1).contiguous()
         with torch.cuda.device(dev):
             call("b200_bce_logits_bwd", C.addressof(ptrs), C.addressof(gptrs), C.addressof(anchors), C.addressof(strides), n, ptr(label),
-                 ptr(value), ptr(scale), B, nc, code, stream_ptr(dev))
+                 ptr(value), ptr(scale), B, nc, code, stream_ptr(dev), tag=f"b200_bce_logits_bwd[{B * sum(anchors)}x{nc}]")
         return (None, None, *grads)
 
 
@@ -289,6 +289,59 @@ class SPPFPoolFn(torch.autograd.Function):
             call("b200_sppf_pool_bwd", ptr(gcat), ptr(y0), ptr(gy0), B, Cc, H, W, ctx.k, dtype_code(y0.dtype),
                                            stream_ptr(y0.device))
         return gy0, None
+
+
+class Conv1x1Fn(torch.autograd.Function):
+    """1x1 stride-1 convolution without bias (SPPF's cv1 / cv2, block.py:218-219) as a plain GEMM over the NHWC rows on the
+    hand-written tcgen05 kernels: y[rows, c2] = x[rows, c1] @ W^T (b200_gemm_nt); backward: dX = dY @ W (b200_gemm_nt),
+    dW = dY^T X (b200_gemm_splitk: split-K over the rows, both operands MN-major, f32)."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        from . import gemm_tc as tc
+
+        x = _nhwc(x)
+        B, c1, H, W = x.shape
+        c2 = w.shape[0]
+        a = x.permute(0, 2, 3, 1).reshape(B * H * W, c1)       # NHWC-dense memory as [rows, c1]: a view
+        wt = w.detach().reshape(c2, c1)
+        with torch.cuda.device(x.device):
+            y = tc.gemm_nt(a, wt, None, tc.EPI_BIAS)
+        ctx.save_for_backward(a, wt)
+        ctx.meta = (B, c1, c2, H, W, w.shape, w.stride(), w.dtype)
+        return y.view(B, H, W, c2).permute(0, 3, 1, 2)         # logical NCHW over NHWC memory = channels_last
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        from . import gemm_tc as tc
+
+        a, wt = ctx.saved_tensors
+        B, c1, c2, H, W, wshape, wstride, wdtype = ctx.meta
+        g = _nhwc(gy.to(a.dtype)).permute(0, 2, 3, 1).reshape(B * H * W, c2)
+        with torch.cuda.device(a.device):
+            gx = tc.gemm_nt(g, wt.t().contiguous(), None, tc.EPI_BIAS) if ctx.needs_input_grad[0] else None
+            gw = tc.gemm_splitk(g, a, True, True)               # [c2, c1] f32 = sum_rows g(r, :)^T a(r, :)
+        if gx is not None:
+            gx = gx.view(B, H, W, c1).permute(0, 3, 1, 2)
+        return gx, gw.to(wdtype).as_strided(wshape, wstride)
+
+
+def conv1x1_supported(x: torch.Tensor, conv) -> bool:
+    """True for a bias-free 1x1 / stride 1 / ungrouped nn.Conv2d on a 16-bit CUDA map whose widths the tcgen05 GEMM tiles."""
+    from . import gemm_tc as tc
+
+    if not (x.is_cuda and x.dim() == 4 and x.dtype in (torch.bfloat16, torch.float16) and type(conv) is torch.nn.Conv2d):
+        return False
+    if conv.kernel_size != (1, 1) or conv.stride != (1, 1) or conv.padding != (0, 0) or conv.groups != 1 or conv.bias is not None:
+        return False
+    c2, c1 = conv.weight.shape[:2]
+    rows = x.shape[0] * x.shape[2] * x.shape[3]
+    return c1 % 64 == 0 and c2 % 64 == 0 and rows % 8 == 0 and x.shape[1] == c1
+
+
+def conv1x1(x: torch.Tensor, conv) -> torch.Tensor:
+    return Conv1x1Fn.apply(x, conv.weight)
 
 
 def sppf_pool(y0: torch.Tensor, k: int) -> torch.Tensor:

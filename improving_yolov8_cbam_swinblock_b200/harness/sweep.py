@@ -77,6 +77,12 @@ def fused_work(tag: str):
             return {"bound": "tensor", "amount": 16.0 * rows * C * C, "note": "mlp.0 + mlp.2: 2 x 2*rows*C*4C FLOP (LN2 / GELU / residual ride along)"}
         return {"bound": "tensor", "amount": 24.0 * rows * C * C,
                 "note": "recompute mlp.0, d hidden = g W2, d xhat = g_a W1: 3 x 2*rows*C*4C FLOP (the two weight gradients are b200_gemm_splitk launches)"}
+    m = re.match(r"b200_bce_logits_(fwd|bwd)\[(\d+)x(\d+)\]", tag)
+    if m:
+        n = int(m.group(2)) * int(m.group(3))
+        if m.group(1) == "fwd":
+            return {"bound": "hbm", "amount": 2.0 * n, "note": "N*s: the class logits read once (16-bit)"}
+        return {"bound": "hbm", "amount": 4.0 * n, "note": "2*N*s: logits read once, gradient written once"}
     m = re.match(r"b200_swin_attn_block_fwd\[(\d+)x(\d+)x(\d+)x(\d+),ws(\d+)\]", tag)
     if m:
         B, C, H, W, ws = (int(v) for v in m.groups())

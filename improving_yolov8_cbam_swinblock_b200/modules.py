@@ -173,6 +173,20 @@ def make_conv(conv_cls, name="Conv", module=None):
     return Conv
 
 
+GEMM_1X1 = [True]  # SPPF's cv1 / cv2 (1x1 convolutions = GEMMs over the NHWC rows) on the hand-written tcgen05 GEMM
+
+
+def conv_block(conv_module, x):
+    """``Conv.forward`` (conv.py:65-79) of a 1x1 Conv: the convolution itself as ``b200_gemm_nt`` when the layer is a plain
+    1x1 GEMM the kernel tiles (16-bit activations under autocast, widths multiples of 64), followed by the fused BN + SiLU
+    epilogue; anything else (f32, fused-BN ``forward_fuse`` after ``fuse()``, odd widths, CPU) takes the module's own forward."""
+    if GEMM_1X1[0] and hasattr(conv_module, "bn") and x.is_cuda and torch.is_autocast_enabled("cuda") and x.dtype == torch.float32:
+        x = x.to(torch.get_autocast_dtype("cuda"))
+    if GEMM_1X1[0] and hasattr(conv_module, "bn") and Fb.conv1x1_supported(x, conv_module.conv):
+        return conv_epilogue(conv_module, Fb.conv1x1(x, conv_module.conv))
+    return conv_module(x)
+
+
 def make_sppf(conv_cls, name="SPPF", module=None):
     """SPPF bound to the caller's stock ``Conv`` (cv1/cv2 stay Conv instances so ``BaseModel.fuse`` keeps folding
     their BN, tasks.py:219-225); only the pooling cascade + concat (block.py:224-226) runs in our kernel."""
@@ -187,12 +201,13 @@ def make_sppf(conv_cls, name="SPPF", module=None):
             self.k = k
 
         def forward(self, x):
-            y0 = self.cv1(x)
-            if not y0.is_cuda:
+            if not x.is_cuda:
+                y0 = self.cv1(x)
                 B, c_, H, W = y0.shape
                 return self.cv2(y0.new_zeros((B, 4 * c_, H, W)))
+            y0 = conv_block(self.cv1, x)
             k = self.m.kernel_size   # not self.k: reference pickles loaded under the plugin never ran this __init__
-            return self.cv2(Fb.sppf_pool(y0, int(k[0] if isinstance(k, (tuple, list)) else k)))
+            return conv_block(self.cv2, Fb.sppf_pool(y0, int(k[0] if isinstance(k, (tuple, list)) else k)))
 
     SPPF.__name__ = SPPF.__qualname__ = name
     if module is not None:

@@ -136,3 +136,42 @@ def test_errors_are_reported_not_thrown():
         Fb.sppf_pool_forward_raw(to_cl(torch.zeros(1, 8, 4, 4, device="cuda")), 4)
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         Fb.sppf_pool_forward_raw(torch.zeros(1, 8, 4, 4), 5)
+
+
+@pytest.mark.parametrize("k", [5, 7])
+@pytest.mark.parametrize("train", [True, False])
+def test_sppf_module_1x1_convs_on_the_tcgen05_gemm(k, train):
+    """SPPF's cv1 / cv2 (block.py:218-219) run as GEMMs over the NHWC rows on b200_gemm_nt / b200_gemm_splitk.
+    Truth = the same module in fp32 (stock convolutions, TF32 off); the bf16 module must meet the 2e-2 bar with the GEMM path and
+    be as close to the truth as the bf16 module with the stock cuDNN 1x1 convolutions is (outputs, input and parameter gradients)."""
+    import improving_yolov8_cbam_swinblock_b200.modules as M
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(k)
+    mod = M.SPPF(256, 256, k).cuda().to(memory_format=torch.channels_last).train(train)
+    x = to_cl(torch.randn(8, 256, 20, 20, device="cuda"))
+    g = to_cl(torch.randn(8, 256, 20, 20, device="cuda"))
+
+    def run(flag, amp):
+        M.GEMM_1X1[0] = flag
+        try:
+            mod.zero_grad()
+            for b in mod.modules():
+                if isinstance(b, torch.nn.BatchNorm2d):
+                    b.reset_running_stats()
+            xi = x.clone().requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                y = mod(xi)
+            y.backward(g.to(y.dtype))
+            return (y.detach().float(), xi.grad.float(), {n: p.grad.float().clone() for n, p in mod.named_parameters()})
+        finally:
+            M.GEMM_1X1[0] = True
+
+    y32, gx32, gp32 = run(False, False)
+    yg, gxg, gpg = run(True, True)
+    ys, gxs, gps = run(False, True)
+    for got, stock, want, what in [(yg, ys, y32, "y"), (gxg, gxs, gx32, "gx")] + [(gpg[n], gps[n], gp32[n], n) for n in gp32]:
+        e, es = rel_err(got, want), rel_err(stock, want)
+        # (bf16 rounding of y0 changes which elements win the max-pools, so BOTH bf16 modules' gradients sit ~10 % from the fp32
+        # ones: the yardstick for the gradients is the stock bf16 module, the 2e-2 bar applies to the output)
+        assert e < 1.5 * es + 2e-3 and (what != "y" or e < 2e-2), (what, e, es)
