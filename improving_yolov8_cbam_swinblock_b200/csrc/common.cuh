@@ -127,15 +127,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
+// With a suspend-time hint the hardware may park the waiting thread until the phase completes (the hint is an upper bound).  Half of
+// the executed instructions of the fused SwinBlock kernels are such try_wait + branch spins of idle roles; the hint was measured to
+// change neither that count's effect nor the kernel times (the working warps are latency-, not issue-bound) -- kept as the idiom.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}"
-      :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+      :: "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 // non-blocking probe (may suspend for the hardware's try_wait time limit): true once the phase with `parity` has completed
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {

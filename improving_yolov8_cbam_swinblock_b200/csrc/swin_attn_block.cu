@@ -49,9 +49,19 @@ static_assert(ABSmem::TOTAL <= 232448, "shared memory budget");
 struct ABParams {
   const float *gamma, *beta, *b_in, *b_out;
   float *lse, *mean, *rstd;     // training by-products (null: inference)
+  long long* dbg;               // optional timeline of CTA 0 (profiles/attn_block_timeline.py)
   int nwin, n_tiles, L, ws, nWh, nWw, train;
   float scale_log2, eps;
 };
+
+// debug timeline (CTA 0 only, dbg != nullptr): event e in [0,16), tile index i < 16
+__device__ __forceinline__ void stamp(const ABParams& P, int e, int i) {
+  if (P.dbg != nullptr && blockIdx.x == 0 && i < 16) {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+    P.dbg[e * 16 + i] = t;
+  }
+}
 
 template <int FMT> __device__ __forceinline__ uint32_t pack2h(float lo, float hi) {
   if (FMT == 1) {
@@ -174,6 +184,7 @@ swin_attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
         // ---- QKV = n1 * W_in^T ----
         mbar_wait(&n1_ready[b], (n >> 1) & 1);
         fence_after_sync();
+        stamp(P, 0, n);
         for (int c = 0; c < 6; ++c) {
           mbar_wait(&w_full[st], ph);
           fence_after_sync();
@@ -184,9 +195,11 @@ swin_attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
           if (++st == kRing) { st = 0; ph ^= 1; }
         }
         umma_commit(qkv_full);
+        stamp(P, 1, n);
         // ---- S_h = Q_h K_h^T ----
         mbar_wait(qk_ready, tp);
         fence_after_sync();
+        stamp(P, 2, n);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const uint64_t da = smem_desc_k_sw128(tbuf(h)), db = smem_desc_k_sw128(tbuf(2 + h));
@@ -197,6 +210,7 @@ swin_attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
         // ---- O_h = P_h V_h : P_h = [K-block 0 over Q_h | K-block 1 over K_h], V_h [128 keys x 64] MN-major ----
         mbar_wait(p_ready, tp);
         fence_after_sync();
+        stamp(P, 3, n);
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -211,6 +225,7 @@ swin_attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
         mbar_wait(o_ready, tp);
         mbar_wait(y_free, tp ^ 1);
         fence_after_sync();
+        stamp(P, 4, n);
         for (int kb = 0; kb < 2; ++kb) {
           mbar_wait(&w_full[st], ph);
           fence_after_sync();
@@ -221,6 +236,7 @@ swin_attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
           if (++st == kRing) { st = 0; ph ^= 1; }
         }
         umma_commit(y_full);
+        stamp(P, 5, n);
       }
     }
   } else if (warp >= kFirstLnWarp && warp < kFirstFinWarp) {
@@ -234,7 +250,9 @@ swin_attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
       const int win = 2 * tile + w;
       const bool live = i < L && win < P.nwin;
       unsigned char* u = abuf(b);
+      if (row == 0) stamp(P, 6, n);
       mbar_wait(&x_full[b], (n >> 1) & 1);
+      if (row == 0) stamp(P, 7, n);
       if (live) {
         const float x0 = up_lo<FMT>(row_chunk(u, row, 0)->x);
         float s = 0.f, ss = 0.f;
@@ -269,6 +287,7 @@ swin_attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
       }
       fence_proxy_async();
       mbar_arrive(&n1_ready[b]);
+      if (row == 0) stamp(P, 8, n);
       if (P.train) {              // n1 in token order for the backward: boxes [L rows x 64 columns] straight from the A tile
         named_bar_sync(1, 32 * kLnWarps);
         if (leader) {
@@ -298,6 +317,7 @@ swin_attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
       unsigned char* u = abuf(b);
       mbar_wait(y_full, n & 1);
       fence_after_sync();
+      if (row == 0) stamp(P, 9, n);
       mbar_wait(&n1_stored[b], (n >> 1) & 1);
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
@@ -334,6 +354,7 @@ swin_attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
         bulk_commit();
         bulk_wait_read_all();
         mbar_arrive(&a_free[b]);
+        stamp(P, 10, n);
       }
     }
     if (leader) bulk_wait_all();
@@ -353,6 +374,7 @@ swin_attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
       // ---- QKV accumulator -> + b_in -> 16 bit -> Q/K/V tiles: this thread's 96 columns = 3 x 32 ----
       mbar_wait(qkv_full, tp);
       fence_after_sync();
+      if (leader) stamp(P, 11, n);
       if (n > 0) {
         mbar_wait(y_full, tp ^ 1);                     // out_proj of the previous tile has read the O (= V) tiles
         if (P.train) {                                 // ... and the previous tile's o stores have read them too
@@ -383,6 +405,7 @@ swin_attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
       fence_before_sync();
       fence_proxy_async();
       mbar_arrive(qk_ready);
+      if (leader) stamp(P, 12, n);
       if (P.train) {             // qkv rows in token order: six [L x 64] boxes per window
         named_bar_sync(3, 32 * kWorkWarps);
         if (leader) {
@@ -397,6 +420,7 @@ swin_attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
         const int h = cg;
         mbar_wait(s_full, tp);
         fence_after_sync();
+        if (leader) stamp(P, 13, n);
         uint32_t sa[32], sb[32];
         tmem_ld32(tS + lane_sel + h * 128 + w * 64, sa);
         tmem_ld32(tS + lane_sel + h * 128 + w * 64 + 32, sb);
@@ -433,6 +457,7 @@ swin_attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
         fence_before_sync();
         fence_proxy_async();
         mbar_arrive(p_ready);
+        if (leader) stamp(P, 14, n);
         const bool live = i < L && win < P.nwin;
         if (P.train && live) P.lse[((long long)win * L + i) * 2 + h] = (m + log2f(sum)) * 0.69314718055994530942f;
         const float inv = 1.f / sum;
@@ -462,6 +487,7 @@ swin_attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
         fence_before_sync();
         fence_proxy_async();
         mbar_arrive(o_ready);
+        if (leader) stamp(P, 15, n);
         if (P.train) {           // o rows in token order: [L x 64] boxes per (window, head)
           named_bar_sync(4, 16 * kWorkWarps);
           if (leader) {
@@ -485,6 +511,10 @@ swin_attn_block_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
 }  // namespace b200
 
 using namespace b200;
+
+static long long* g_ab_dbg = nullptr;
+/* debugging aid (not part of the public header): device buffer of 16*16 int64 receiving CTA 0's event clock stamps */
+extern "C" B200_API void b200_debug_set_attn_block_timeline(void* buf) { g_ab_dbg = (long long*)buf; }
 
 extern "C" B200_API int b200_swin_attn_block_supported(int32_t B, int32_t C, int32_t H, int32_t W, int32_t heads, int32_t ws, int32_t shift,
                                                        int32_t dtype) {
@@ -519,7 +549,7 @@ extern "C" B200_API int b200_swin_attn_block_fwd(const void* x, const float* gam
   ABParams P;
   P.gamma = gamma; P.beta = beta; P.b_in = b_in; P.b_out = b_out; P.lse = lse; P.mean = mean; P.rstd = rstd;
   P.nwin = (int)nwin; P.n_tiles = (int)((nwin + 1) / 2); P.L = L; P.ws = ws; P.nWh = nWh; P.nWw = nWw; P.train = train ? 1 : 0;
-  P.scale_log2 = 1.4426950408889634f / sqrtf((float)kHD); P.eps = eps;
+  P.scale_log2 = 1.4426950408889634f / sqrtf((float)kHD); P.eps = eps; P.dbg = g_ab_dbg;
   const int grid = P.n_tiles < sm_count() ? P.n_tiles : sm_count();
   auto kern = dtype == B200_BF16 ? swin_attn_block_fwd_kernel<1> : swin_attn_block_fwd_kernel<0>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ABSmem::TOTAL);
