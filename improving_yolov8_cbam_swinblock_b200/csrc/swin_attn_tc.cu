@@ -343,13 +343,20 @@ template <int HD> struct BCfg {
   static constexpr int P_BYTES = 3 * 64 * 128;
   static constexpr int KB_STRIDE = 64 * 128;       // byte distance between the two key blocks of P / dS
   static constexpr int STAGES = HD == 64 ? 2 : 1;  // a stage = operand tiles + P/dS + TMEM columns of one pair in flight
-  static constexpr int OFF_Q = 0, OFF_K = T_BYTES, OFF_V = 2 * T_BYTES, OFF_DO = 3 * T_BYTES;
-  static constexpr int OFF_P = 4 * T_BYTES, OFF_DS = OFF_P + P_BYTES;
-  static constexpr int STAGE_BYTES = OFF_DS + P_BYTES;
+  // HD 192: four 48 KB operand tiles leave no room for P / dS (2 x 24 KB): they overlay the V tile, which is dead once the
+  // dP MMAs have completed (exactly 48 KB).  The overlay's zero rows are re-zeroed for every pair; rows L..63 of the V tile stay
+  // zero because the rows of P / dS that fall there belong to padded query rows, which write zeros.
+  static constexpr bool OVERLAY = HD == 192;
+  static constexpr int OFF_Q = 0, OFF_K = T_BYTES, OFF_DO = 2 * T_BYTES, OFF_V = 3 * T_BYTES;
+  static constexpr int OFF_P = OVERLAY ? OFF_V : 4 * T_BYTES, OFF_DS = OFF_P + P_BYTES;
+  static constexpr int STAGE_BYTES = OVERLAY ? 4 * T_BYTES : OFF_DS + P_BYTES;
   static constexpr int OFF_BAR = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = OFF_BAR + 128 + 1024;
+  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+  static_assert(TOTAL <= 232448, "shared memory budget");
   // HD 64: per stage S 128 (dQ aliases columns 0..63, dV columns 64..127) | dP 128 (dK aliases 0..63)  -> 2 x 256
   // HD 128: S 128 (= dQ) | dP 128 (= dK) | dV 128
+  // HD 192: S 128 | dP 128 during the first half; then dQ 0..191 | dK 192..383 | dV[:, 0:128] 384..511, and dV[:, 128:192] in
+  //         columns 0..63 in a third round once dQ has been read back (3 x 192 fp32 columns do not fit in 512)
   static constexpr int TMEM_STAGE = 256;
   static constexpr int TMEM_COLS = 512;
 };
@@ -370,7 +377,9 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   uint64_t* pds_full = in_full + 6;
   uint64_t* out_full = in_full + 8;
   uint64_t* tmem_free = in_full + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + 12);
+  uint64_t* dq_read = in_full + 12;     // HD 192: dQ read back (128 threads) -> its columns may take the last third of dV
+  uint64_t* out2_full = in_full + 13;   // HD 192: that third is complete (commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + 14);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_local = blockIdx.x < P.n_pairs ? (P.n_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   auto stage = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
@@ -381,6 +390,7 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       mbar_init(&in_full[s], 1); mbar_init(&smem_free[s], 1); mbar_init(&sdp_full[s], 1); mbar_init(&pds_full[s], 128);
       mbar_init(&out_full[s], 1); mbar_init(&tmem_free[s], 128);
     }
+    mbar_init(dq_read, 128); mbar_init(out2_full, 1);
     fence_mbar_init();
   }
   if (warp == 9) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
@@ -405,8 +415,8 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   auto tS = [&](int s) { return tmem_base + s * Cfg::TMEM_STAGE; };
   auto tDP = [&](int s) { return tmem_base + s * Cfg::TMEM_STAGE + 128; };
   auto tDQ = [&](int s) { return tS(s); };
-  auto tDK = [&](int s) { return tDP(s); };
-  auto tDV = [&](int s) { return HD == 64 ? tS(s) + 64 : tmem_base + 256; };
+  auto tDK = [&](int s) { return HD == 192 ? tmem_base + 192 : tDP(s); };
+  auto tDV = [&](int s) { return HD == 64 ? tS(s) + 64 : (HD == 192 ? tmem_base + 384 : tmem_base + 256); };
 
   if (warp == 8) {
     // ===================== TMA producer =====================
@@ -487,13 +497,31 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
                 umma_f16(tDQ(s), smem_desc_k_sw128(sDS + kb * KBS + k * 32), smem_desc_mn_sw128(sK + kb * 8192 + k * 2048, 16384),
                          id_kmn, (kb | k) != 0);
             // dV = P^T dO, dK = dS^T Q : reduction over the 128 query rows (8 k-steps of 16 rows)
+            if constexpr (HD == 192) {
+              const uint32_t id_v128 = idesc_f16(128, 128, P.fmt, 1, 1), id_v64 = idesc_f16(128, 64, P.fmt, 1, 1);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              umma_f16(tDV(s), smem_desc_mn_sw128(sP + k * 2048, KBS), smem_desc_mn_sw128(sDO + k * 2048, 16384), id_mnmn, k != 0);
-              umma_f16(tDK(s), smem_desc_mn_sw128(sDS + k * 2048, KBS), smem_desc_mn_sw128(sQ + k * 2048, 16384), id_mnmn, k != 0);
+              for (int k = 0; k < 8; ++k) {
+                umma_f16(tDV(s), smem_desc_mn_sw128(sP + k * 2048, KBS), smem_desc_mn_sw128(sDO + k * 2048, 16384), id_v128, k != 0);
+                umma_f16(tDK(s), smem_desc_mn_sw128(sDS + k * 2048, KBS), smem_desc_mn_sw128(sQ + k * 2048, 16384), id_mnmn, k != 0);
+              }
+              umma_commit(&out_full[s]);
+              mbar_wait(dq_read, b & 1);          // third round: dV[:, 128:192] over the columns dQ occupied
+              fence_after_sync();
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                umma_f16(tmem_base, smem_desc_mn_sw128(sP + k * 2048, KBS), smem_desc_mn_sw128(sDO + 2 * 16384 + k * 2048, 16384),
+                         id_v64, k != 0);
+              umma_commit(&smem_free[s]);
+              umma_commit(out2_full);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                umma_f16(tDV(s), smem_desc_mn_sw128(sP + k * 2048, KBS), smem_desc_mn_sw128(sDO + k * 2048, 16384), id_mnmn, k != 0);
+                umma_f16(tDK(s), smem_desc_mn_sw128(sDS + k * 2048, KBS), smem_desc_mn_sw128(sQ + k * 2048, 16384), id_mnmn, k != 0);
+              }
+              umma_commit(&smem_free[s]);
+              umma_commit(&out_full[s]);
             }
-            umma_commit(&smem_free[s]);
-            umma_commit(&out_full[s]);
             ++b;
           }
         }
@@ -543,6 +571,12 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         if (i == 0) bulk_wait_read_all();
         named_bar_sync(bar_id, 64);
       }
+      if constexpr (Cfg::OVERLAY) {               // the shared zero rows were overwritten by this pair's V tile
+        uint4* z0 = reinterpret_cast<uint4*>(stage(s) + Cfg::OFF_P + KBS + row * 64);
+        uint4* z1 = reinterpret_cast<uint4*>(stage(s) + Cfg::OFF_DS + KBS + row * 64);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { z0[e] = make_uint4(0, 0, 0, 0); z1[e] = make_uint4(0, 0, 0, 0); }
+      }
       // second pass re-reads dP from TMEM (cheaper than keeping 64 more registers live)
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
@@ -558,7 +592,10 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
             const int jj = cc * 8 + 2 * e;
             const float p0 = __uint_as_float(sv[hf * 32 + jj]), p1 = __uint_as_float(sv[hf * 32 + jj + 1]);
             pw[e] = pack2f(p0, p1, P.fmt);
-            dw[e] = pack2f(p0 * (__uint_as_float(dv[jj]) - delta) * P.scale, p1 * (__uint_as_float(dv[jj + 1]) - delta) * P.scale, P.fmt);
+            // padded rows write exact zeros (their dP may be 0 x Inf = NaN): with the overlay these bytes are rows L..63 of
+            // the next pair's V tile
+            dw[e] = valid ? pack2f(p0 * (__uint_as_float(dv[jj]) - delta) * P.scale, p1 * (__uint_as_float(dv[jj + 1]) - delta) * P.scale, P.fmt)
+                          : 0u;
           }
           *reinterpret_cast<uint4*>(prow + sw128_offset(i, c)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
           *reinterpret_cast<uint4*>(drow + sw128_offset(i, c)) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
@@ -618,7 +655,19 @@ swin_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 #pragma unroll
           for (int ch = 0; ch < HD / 32; ++ch) {
             uint32_t ov[32];
-            tmem_ld32(tsrc + lane_sel + ch * 32, ov);
+            uint32_t taddr = tsrc + lane_sel + ch * 32;
+            if constexpr (HD == 192) {
+              if (which == 1 && ch == 0) {          // dQ is out of TMEM: release its columns for the last third of dV
+                fence_before_sync();
+                mbar_arrive(dq_read);
+              }
+              if (which == 2 && ch == 4) {
+                mbar_wait(out2_full, (n / STAGES) & 1);
+                fence_after_sync();
+              }
+              if (which == 2 && ch >= 4) taddr = tmem_base + lane_sel + (ch - 4) * 32;
+            }
+            tmem_ld32(taddr, ov);
             tmem_ld_wait();
             if (valid) {
 #pragma unroll
@@ -676,7 +725,7 @@ extern "C" B200_API int b200_swin_attn_tc_supported(int64_t tokens, int32_t L, i
   if (dtype != B200_BF16 && dtype != B200_F16) return 0;
   if (tokens <= 0 || L <= 0 || L > 64 || tokens % L != 0 || nh <= 0 || C % nh != 0) return 0;
   const int hd = C / nh;
-  return (hd == 64 || hd == 128) && (3 * C) % 8 == 0;
+  return (hd == 64 || hd == 128 || hd == 192) && (3 * C) % 8 == 0;
 }
 
 extern "C" B200_API int b200_swin_attn_fwd_tc(const void* qkv, void* o, float* lse, int64_t tokens, int32_t L, int32_t C,
@@ -685,11 +734,12 @@ extern "C" B200_API int b200_swin_attn_fwd_tc(const void* qkv, void* o, float* l
   if (int rc = check_shift(tokens, L, nWh, nWw, ws, shift)) return rc;
   const ShiftMask M = make_shift_mask(nWh, nWw, ws, shift);
   B200_REQUIRE(b200_swin_attn_tc_supported(tokens, L, C, nh, dtype), B200_ERR_UNSUPPORTED,
-               "swin_attn_fwd_tc: unsupported problem (16-bit dtype, L<=64, head dim 64 or 128)");
+               "swin_attn_fwd_tc: unsupported problem (16-bit dtype, L<=64, head dim 64, 128 or 192)");
   B200_REQUIRE(qkv && o, B200_ERR_SHAPE, "swin_attn_fwd_tc: null pointer");
   B200_REQUIRE((((uintptr_t)qkv | (uintptr_t)o) & 15) == 0, B200_ERR_ALIGN, "swin_attn_fwd_tc: 16-byte alignment required");
   cudaStream_t st = (cudaStream_t)stream;
   if (C / nh == 64) return tc::launch_fwd<64>(qkv, o, lse, tokens, L, C, nh, M, dtype, st);
+  if (C / nh == 192) return tc::launch_fwd<192>(qkv, o, lse, tokens, L, C, nh, M, dtype, st);
   return tc::launch_fwd<128>(qkv, o, lse, tokens, L, C, nh, M, dtype, st);
 }
 
@@ -699,10 +749,11 @@ extern "C" B200_API int b200_swin_attn_bwd_tc(const void* qkv, const float* lse,
   if (int rc = check_shift(tokens, L, nWh, nWw, ws, shift)) return rc;
   const ShiftMask M = make_shift_mask(nWh, nWw, ws, shift);
   B200_REQUIRE(b200_swin_attn_tc_supported(tokens, L, C, nh, dtype), B200_ERR_UNSUPPORTED,
-               "swin_attn_bwd_tc: unsupported problem (16-bit dtype, L<=64, head dim 64 or 128)");
+               "swin_attn_bwd_tc: unsupported problem (16-bit dtype, L<=64, head dim 64, 128 or 192)");
   B200_REQUIRE(qkv && lse && go && gqkv, B200_ERR_SHAPE, "swin_attn_bwd_tc: null pointer");
   B200_REQUIRE((((uintptr_t)qkv | (uintptr_t)go | (uintptr_t)gqkv) & 15) == 0, B200_ERR_ALIGN, "swin_attn_bwd_tc: 16-byte alignment required");
   cudaStream_t st = (cudaStream_t)stream;
   if (C / nh == 64) return tc::launch_bwd<64>(qkv, lse, go, gqkv, tokens, L, C, nh, M, dtype, st);
+  if (C / nh == 192) return tc::launch_bwd<192>(qkv, lse, go, gqkv, tokens, L, C, nh, M, dtype, st);
   return tc::launch_bwd<128>(qkv, lse, go, gqkv, tokens, L, C, nh, M, dtype, st);
 }
