@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kFT) bn_final_kernel(const T* __restrict__ x, 
                                                       float* __restrict__ running_mean, float* __restrict__ running_var,
                                                       float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                       float* __restrict__ scsh, float eps, float momentum, int training,
-                                                      const BnGeo G) {
+                                                      long long* __restrict__ num_batches_tracked, const BnGeo G) {
   // kFW warps per channel: the G partial rows (up to 16 per SM) are summed by 256 lanes with 2 loads in flight each --
   // one warp per channel made this 8-CTA kernel a 10 us latency chain, 59 times per step (2982 -> 3123 img/s)
   __shared__ float fs[kFT / 32][2];
@@ -154,6 +154,8 @@ __global__ void __launch_bounds__(kFT) bn_final_kernel(const T* __restrict__ x, 
   const int c = blockIdx.x * (kFT / 32 / kFW) + warp / kFW;
   const bool live = c < C;
   float mean, rstd;
+  // nn.BatchNorm2d.forward's bookkeeping, folded in here instead of one more launch per layer (59 per step)
+  if (training && num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;
   if (training) {
     float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
     if (live) {
@@ -432,10 +434,25 @@ extern "C" B200_API size_t b200_bn_silu_workspace_bytes(int64_t rows, int32_t C,
   return b200::up256((size_t)G.G * 2 * C * 4) + b200::up256((size_t)3 * C * 4);   // per-CTA partials + scale/shift | bwd coefficients
 }
 
+extern "C" B200_API int b200_bn_silu_fwd_tracked(const void* x, const float* gamma, const float* beta, float* running_mean,
+                                                 float* running_var, int64_t* num_batches_tracked, void* z, float* mean_out,
+                                                 float* rstd_out, void* workspace, size_t workspace_bytes, int64_t rows, int32_t C,
+                                                 float eps, float momentum, int32_t training, int32_t act, int32_t dtype,
+                                                 void* stream);
+
 extern "C" B200_API int b200_bn_silu_fwd(const void* x, const float* gamma, const float* beta, float* running_mean,
                                          float* running_var, void* z, float* mean_out, float* rstd_out, void* workspace,
                                          size_t workspace_bytes, int64_t rows, int32_t C, float eps, float momentum,
                                          int32_t training, int32_t act, int32_t dtype, void* stream) {
+  return b200_bn_silu_fwd_tracked(x, gamma, beta, running_mean, running_var, nullptr, z, mean_out, rstd_out, workspace, workspace_bytes,
+                                  rows, C, eps, momentum, training, act, dtype, stream);
+}
+
+extern "C" B200_API int b200_bn_silu_fwd_tracked(const void* x, const float* gamma, const float* beta, float* running_mean,
+                                                 float* running_var, int64_t* num_batches_tracked, void* z, float* mean_out,
+                                                 float* rstd_out, void* workspace, size_t workspace_bytes, int64_t rows, int32_t C,
+                                                 float eps, float momentum, int32_t training, int32_t act, int32_t dtype,
+                                                 void* stream) {
   using namespace b200;
   B200_REQUIRE(x && gamma && beta && z, B200_ERR_SHAPE, "bn_silu_fwd: null tensor pointer");
   B200_REQUIRE(training || (running_mean && running_var), B200_ERR_SHAPE, "bn_silu_fwd: eval mode needs running statistics");
@@ -451,7 +468,7 @@ extern "C" B200_API int b200_bn_silu_fwd(const void* x, const float* gamma, cons
     constexpr int VW = 16 / (int)sizeof(T);
     if (training) bn_stats_kernel<T, VW><<<G.G, kT, smem, st>>>((const T*)x, part, G);
     bn_final_kernel<T><<<(C * kFW + kFT / 32 - 1) / (kFT / 32), kFT, 0, st>>>((const T*)x, part, gamma, beta, running_mean, running_var, mean_out, rstd_out,
-                                                  scsh, eps, momentum, training, G);
+                                                  scsh, eps, momentum, training, (long long*)num_batches_tracked, G);
     if (act) bn_apply_kernel<T, VW, 1><<<G.G, kT, 0, st>>>((const T*)x, scsh, (T*)z, G);
     else bn_apply_kernel<T, VW, 0><<<G.G, kT, 0, st>>>((const T*)x, scsh, (T*)z, G);
     return check_launch("bn_silu_fwd");

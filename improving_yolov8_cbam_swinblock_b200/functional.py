@@ -34,6 +34,7 @@ _lib.register("b200_colsum", C.c_int, [_VP] * 3 + [_SZ] + [_I64] + [_I32] * 2 + 
 _lib.register("b200_bn_silu_supported", C.c_int, [_I64, _I32, _I32])
 _lib.register("b200_bn_silu_workspace_bytes", _SZ, [_I64, _I32, _I32])
 _lib.register("b200_bn_silu_fwd", C.c_int, [_VP] * 9 + [_SZ, _I64, _I32, C.c_float, C.c_float, _I32, _I32, _I32, _VP])
+_lib.register("b200_bn_silu_fwd_tracked", C.c_int, [_VP] * 10 + [_SZ, _I64, _I32, C.c_float, C.c_float, _I32, _I32, _I32, _VP])
 _lib.register("b200_bn_silu_bwd", C.c_int, [_VP, _I64] + [_VP] * 9 + [_SZ, _I64, _I32, _I32, _I32, _I32, _VP])
 _lib.register("b200_nhwc_concat", C.c_int, [_VP, _VP, _VP, _I32, _VP, _I64, _I32, _VP])
 _lib.register("b200_u8_to_nhwc", C.c_int, [_VP, _VP] + [_I32] * 4 + [C.c_float, _I32, _VP])
@@ -292,12 +293,13 @@ class SPPFPoolFn(torch.autograd.Function):
 
 
 class Conv1x1Fn(torch.autograd.Function):
-    """1x1 stride-1 convolution without bias (SPPF's cv1 / cv2, block.py:218-219) as a plain GEMM over the NHWC rows on the
-    hand-written tcgen05 kernels: y[rows, c2] = x[rows, c1] @ W^T (b200_gemm_nt); backward: dX = dY @ W (b200_gemm_nt),
-    dW = dY^T X (b200_gemm_splitk: split-K over the rows, both operands MN-major, f32)."""
+    """1x1 stride-1 convolution (SPPF's cv1 / cv2, block.py:218-219: no bias; the Detect head's last convolutions, head.py:45-62:
+    with bias) as a plain GEMM over the NHWC rows on the hand-written tcgen05 kernels: y[rows, c2] = x[rows, c1] @ W^T + b
+    (b200_gemm_nt, bias in the epilogue); backward: dX = dY @ W (b200_gemm_nt), dW = dY^T X and db = column sums of dY in the same
+    pass (b200_gemm_splitk: split-K over the rows, both operands MN-major, f32)."""
 
     @staticmethod
-    def forward(ctx, x, w):
+    def forward(ctx, x, w, bias=None):
         from . import gemm_tc as tc
 
         x = _nhwc(x)
@@ -306,9 +308,9 @@ class Conv1x1Fn(torch.autograd.Function):
         a = x.permute(0, 2, 3, 1).reshape(B * H * W, c1)       # NHWC-dense memory as [rows, c1]: a view
         wt = w.detach().reshape(c2, c1)
         with torch.cuda.device(x.device):
-            y = tc.gemm_nt(a, wt, None, tc.EPI_BIAS)
+            y = tc.gemm_nt(a, wt, bias, tc.EPI_BIAS)
         ctx.save_for_backward(a, wt)
-        ctx.meta = (B, c1, c2, H, W, w.shape, w.stride(), w.dtype)
+        ctx.meta = (B, c1, c2, H, W, w.shape, w.stride(), w.dtype, None if bias is None else bias.dtype)
         return y.view(B, H, W, c2).permute(0, 3, 1, 2)         # logical NCHW over NHWC memory = channels_last
 
     @staticmethod
@@ -317,31 +319,48 @@ class Conv1x1Fn(torch.autograd.Function):
         from . import gemm_tc as tc
 
         a, wt = ctx.saved_tensors
-        B, c1, c2, H, W, wshape, wstride, wdtype = ctx.meta
+        B, c1, c2, H, W, wshape, wstride, wdtype, bdtype = ctx.meta
         g = _nhwc(gy.to(a.dtype)).permute(0, 2, 3, 1).reshape(B * H * W, c2)
+        gb = None
         with torch.cuda.device(a.device):
             gx = tc.gemm_nt(g, wt.t().contiguous(), None, tc.EPI_BIAS) if ctx.needs_input_grad[0] else None
-            gw = tc.gemm_splitk(g, a, True, True)               # [c2, c1] f32 = sum_rows g(r, :)^T a(r, :)
+            if bdtype is not None:
+                gw, gb = tc.gemm_splitk(g, a, True, True, want_colsum=True)   # [c2, c1] f32 = sum_rows g(r, :)^T a(r, :); [c2]
+                gb = gb.to(bdtype)
+            else:
+                gw = tc.gemm_splitk(g, a, True, True)
         if gx is not None:
             gx = gx.view(B, H, W, c1).permute(0, 3, 1, 2)
-        return gx, gw.to(wdtype).as_strided(wshape, wstride)
+        return gx, gw.to(wdtype).as_strided(wshape, wstride), gb
 
 
-def conv1x1_supported(x: torch.Tensor, conv) -> bool:
-    """True for a bias-free 1x1 / stride 1 / ungrouped nn.Conv2d on a 16-bit CUDA map whose widths the tcgen05 GEMM tiles."""
-    from . import gemm_tc as tc
-
+def conv1x1_supported(x: torch.Tensor, conv, allow_bias: bool = False) -> bool:
+    """True for a 1x1 / stride 1 / ungrouped nn.Conv2d on a 16-bit CUDA map whose widths the tcgen05 GEMM tiles."""
     if not (x.is_cuda and x.dim() == 4 and x.dtype in (torch.bfloat16, torch.float16) and type(conv) is torch.nn.Conv2d):
         return False
-    if conv.kernel_size != (1, 1) or conv.stride != (1, 1) or conv.padding != (0, 0) or conv.groups != 1 or conv.bias is not None:
+    if conv.kernel_size != (1, 1) or conv.stride != (1, 1) or conv.padding != (0, 0) or conv.groups != 1:
+        return False
+    if conv.bias is not None and not allow_bias:
         return False
     c2, c1 = conv.weight.shape[:2]
     rows = x.shape[0] * x.shape[2] * x.shape[3]
-    return c1 % 64 == 0 and c2 % 64 == 0 and rows % 8 == 0 and x.shape[1] == c1
+    ok = (c1 % 64 == 0 and c2 % 64 == 0) or (allow_bias and c1 % 8 == 0 and c2 % 8 == 0 and c1 >= 16 and c2 >= 16)
+    return ok and rows % 8 == 0 and x.shape[1] == c1
 
 
 def conv1x1(x: torch.Tensor, conv) -> torch.Tensor:
-    return Conv1x1Fn.apply(x, conv.weight)
+    return Conv1x1Fn.apply(x, conv.weight, conv.bias)
+
+
+def head_conv(conv, x: torch.Tensor) -> torch.Tensor:
+    """The Detect head's last 1x1 convolution of a branch (head.py:45-62: ``nn.Conv2d(c, 4*reg_max | nc, 1)`` with bias) on the
+    tcgen05 GEMM with the bias in its epilogue and the bias gradient out of the weight-gradient pass; the module's own forward
+    for anything the kernel does not tile (f32, CPU, odd widths)."""
+    if x.is_cuda and torch.is_autocast_enabled("cuda") and x.dtype == torch.float32:
+        x = x.to(torch.get_autocast_dtype("cuda"))
+    if conv1x1_supported(x, conv, allow_bias=True):
+        return conv1x1(x, conv)
+    return conv(x)
 
 
 def sppf_pool(y0: torch.Tensor, k: int) -> torch.Tensor:
@@ -354,7 +373,7 @@ def sppf_pool(y0: torch.Tensor, k: int) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------------
 class BnActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, act):
+    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, act, tracked=None):
         x = _nhwc(x)
         B, Cc, H, W = x.shape
         rows, dev, code = B * H * W, x.device, dtype_code(x.dtype)
@@ -366,9 +385,9 @@ class BnActFn(torch.autograd.Function):
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         wf, bf = _f32(weight), _f32(bias)
         with torch.cuda.device(dev):
-            call("b200_bn_silu_fwd", ptr(x), ptr(wf), ptr(bf), ptr(running_mean), ptr(running_var), ptr(z), ptr(mean),
-                                     ptr(rstd), ptr(ws), nbytes, rows, Cc, float(eps), float(momentum), int(training), int(act),
-                                     code, stream_ptr(dev), tag=f"b200_bn_silu_fwd[{rows}x{Cc}]")
+            call("b200_bn_silu_fwd_tracked", ptr(x), ptr(wf), ptr(bf), ptr(running_mean), ptr(running_var), ptr(tracked), ptr(z),
+                 ptr(mean), ptr(rstd), ptr(ws), nbytes, rows, Cc, float(eps), float(momentum), int(training), int(act), code,
+                 stream_ptr(dev), tag=f"b200_bn_silu_fwd[{rows}x{Cc}]")
         ctx.save_for_backward(x, wf, bf, mean, rstd)
         ctx.cfg = (rows, Cc, int(training), int(act), weight.dtype, bias.dtype)
         return z
@@ -392,7 +411,7 @@ class BnActFn(torch.autograd.Function):
             call("b200_bn_silu_bwd", ptr(gz), gzs, ptr(x), ptr(wf), ptr(bf), ptr(mean), ptr(rstd), ptr(gx), ptr(gg), ptr(gb),
                                      ptr(ws), nbytes, rows, Cc, training, act, code, stream_ptr(dev),
                                      tag=f"b200_bn_silu_bwd[{rows}x{Cc}]")
-        return gx, gg.to(wdt), gb.to(bdt), None, None, None, None, None, None
+        return gx, gg.to(wdt), gb.to(bdt), None, None, None, None, None, None, None
 
 
 def bn_act_supported(x: torch.Tensor, bn) -> bool:
@@ -410,12 +429,15 @@ def bn_act_supported(x: torch.Tensor, bn) -> bool:
 def bn_act(x: torch.Tensor, bn, silu: bool) -> torch.Tensor:
     """act(bn(x)) for the conv output x [B,C,H,W] with `bn` an nn.BatchNorm2d (conv.py:65-79); batch statistics and
     the running-stat update in training mode, running statistics in eval mode."""
-    if bn.training:
-        bn.num_batches_tracked.add_(1)   # nn.BatchNorm2d.forward bookkeeping (state_dict parity)
     rm, rv = bn.running_mean, bn.running_var
     if rm.dtype != torch.float32:   # eval mode of a .half()-ed module (validator.py:147-149): read-only f32 copies
         rm, rv = rm.float(), rv.float()
-    return BnActFn.apply(x, bn.weight, bn.bias, rm, rv, bn.training, bn.momentum, bn.eps, silu)
+    # nn.BatchNorm2d.forward's `num_batches_tracked.add_(1)` (state_dict parity) happens inside the finalize kernel
+    nbt = bn.num_batches_tracked if bn.training and bn.num_batches_tracked is not None else None
+    if nbt is not None and not (nbt.is_cuda and nbt.dtype == torch.int64):
+        nbt.add_(1)
+        nbt = None
+    return BnActFn.apply(x, bn.weight, bn.bias, rm, rv, bn.training, bn.momentum, bn.eps, silu, nbt)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -200,14 +200,20 @@ class Detect(nn.Module):
         self.dfl = DFL(self.reg_max)
 
     concat = None
+    head_conv = None        # the last 1x1 convolution (+ bias) of every branch as a fused GEMM (None = nn.Conv2d)
     split_outputs = False   # training: hand the loss the (box, cls) maps of each level separately (no channel concat: the fused
                             # classification-loss kernel reads the class maps in place and the gradients stay dense)
+
+    def _branch(self, seq, x):
+        if self.head_conv is None:
+            return seq(x)
+        return self.head_conv(seq[2], seq[1](seq[0](x)))
 
     def forward(self, x):
         cat = (lambda ts: torch.cat(ts, 1)) if self.concat is None else self.concat
         if self.training and self.split_outputs:
-            return [(self.cv2[i](x[i]), self.cv3[i](x[i])) for i in range(self.nl)]
-        x = [cat((self.cv2[i](x[i]), self.cv3[i](x[i]))) for i in range(self.nl)]
+            return [(self._branch(self.cv2[i], x[i]), self._branch(self.cv3[i], x[i])) for i in range(self.nl)]
+        x = [cat((self._branch(self.cv2[i], x[i]), self._branch(self.cv3[i], x[i]))) for i in range(self.nl)]
         if self.training:
             return x
         shape = x[0].shape
@@ -281,6 +287,8 @@ class DetectionGraph(nn.Module):
                 m_.chunk = chunk_
             if blocks.get("upsample") is not None and isinstance(m_, Upsample):
                 m_.upsample = blocks["upsample"]
+            if blocks.get("head_conv") is not None and isinstance(m_, Detect):
+                m_.head_conv = blocks["head_conv"]
         self.save = sorted(save)
         self.nc, self.scale = nc, scale
         det = self.model[-1]

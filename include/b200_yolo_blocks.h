@@ -222,6 +222,12 @@ B200_API int b200_bn_silu_fwd(const void* x, const float* gamma, const float* be
                               float* running_var, void* z, float* mean_out, float* rstd_out, void* workspace,
                               size_t workspace_bytes, int64_t rows, int32_t C, float eps, float momentum,
                               int32_t training, int32_t act, int32_t dtype, void* stream);
+/* Same, plus nn.BatchNorm2d.forward's bookkeeping (torch/nn/modules/batchnorm.py: `self.num_batches_tracked.add_(1)` in training
+ * mode) folded into the finalize kernel: `num_batches_tracked` is the module's int64 device scalar (NULL: not touched). */
+B200_API int b200_bn_silu_fwd_tracked(const void* x, const float* gamma, const float* beta, float* running_mean,
+                                      float* running_var, int64_t* num_batches_tracked, void* z, float* mean_out, float* rstd_out,
+                                      void* workspace, size_t workspace_bytes, int64_t rows, int32_t C, float eps, float momentum,
+                                      int32_t training, int32_t act, int32_t dtype, void* stream);
 /* backward: gx = dL/dx, ggamma / gbeta OVERWRITTEN; mean/rstd = the statistics the forward normalised with
  * (training == 0: pass running_mean and 1/sqrt(running_var + eps)).  Deterministic (no atomics).
  * gz_row_stride: elements between consecutive rows of gz (0 = dense = C); the gradient that reaches a Conv feeding a

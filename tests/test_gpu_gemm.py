@@ -78,3 +78,41 @@ def test_gemm_splitk_all_majors(a_mn, b_mn, M, N, K):
     want = A.double() @ Bm.double().t()
     assert rel_err(got, want) < 1e-5, rel_err(got, want)
     assert rel_err(cs, A.double().sum(1)) < 1e-5, rel_err(cs, A.double().sum(1))  # fused bias-gradient column sums
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 1e-2), (torch.float16, 2e-3)])
+@pytest.mark.parametrize("shape,c2", [((2, 64, 20, 20), 64), ((3, 80, 40, 40), 80), ((2, 80, 20, 20), 80), ((1, 64, 80, 80), 64),
+                                      ((2, 96, 12, 10), 144)])
+def test_head_conv_with_bias_matches_conv2d(dtype, tol, shape, c2):
+    """the Detect head's last 1x1 convolution (+ bias, head.py:45-62) as b200_gemm_nt (bias in the epilogue) with
+    dW and db out of one b200_gemm_splitk pass; truth = F.conv2d in fp32 on the same (rounded) inputs."""
+    from improving_yolov8_cbam_swinblock_b200 import functional as Fb
+
+    torch.manual_seed(sum(shape) + c2)
+    conv = torch.nn.Conv2d(shape[1], c2, 1).cuda()
+    with torch.no_grad():
+        conv.bias.normal_()
+    x = torch.randn(shape, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    g = torch.randn(shape[0], c2, *shape[2:], device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    assert Fb.conv1x1_supported(x, conv, allow_bias=True) and not Fb.conv1x1_supported(x, conv)
+    from improving_yolov8_cbam_swinblock_b200 import _lib
+
+    _launches = _lib.launch_count
+    launches = _launches()
+    xg = x.clone().requires_grad_(True)
+    y = Fb.head_conv(conv, xg)
+    y.backward(g)
+    assert _launches() - launches >= 3, "head_conv did not run the hand-written GEMMs"
+    got = (y.detach().float(), xg.grad.float(), conv.weight.grad.clone(), conv.bias.grad.clone())
+    conv.zero_grad()
+    w32 = conv.weight.detach().to(dtype).float().requires_grad_(True)   # the GEMM consumes the rounded weight
+    b32 = conv.bias.detach().clone().requires_grad_(True)
+    x32 = x.float().requires_grad_(True)
+    y32 = torch.nn.functional.conv2d(x32, w32, b32)
+    y32.backward(g.float())
+    for name, a, b in zip(("y", "gx", "gw", "gb"), got, (y32.detach(), x32.grad, w32.grad, b32.grad)):
+        assert rel_err(a, b) <= tol, f"{name}: {rel_err(a, b):.2e}"
+    # under autocast the f32 feature map is cast first, exactly as F.conv2d would
+    with torch.autocast("cuda", dtype=dtype):
+        y2 = Fb.head_conv(conv, x.float())
+    assert y2.dtype == dtype and rel_err(y2.float(), y32.detach()) <= tol
