@@ -175,3 +175,42 @@ def test_sppf_module_1x1_convs_on_the_tcgen05_gemm(k, train):
         # (bf16 rounding of y0 changes which elements win the max-pools, so BOTH bf16 modules' gradients sit ~10 % from the fp32
         # ones: the yardstick for the gradients is the stock bf16 module, the 2e-2 bar applies to the output)
         assert e < 1.5 * es + 2e-3 and (what != "y" or e < 2e-2), (what, e, es)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("k", [3, 5, 7, 9, 11, 13])
+@pytest.mark.parametrize("kind", ["rand", "ties", "special"])
+def test_strip_kernels_equal_generic_kernels(dtype, k, kind, monkeypatch):
+    """The 20x20 / 16-bit kernels with strips in registers (csrc/sppf_strip.cu) against the generic shared-memory kernels
+    (csrc/sppf_pool.cu, pinned above by the oracle and the reference fixtures): concat bit-identical, gradient bit-identical
+    (same routing, same summation order: sources ascending, then + the slice gradient).  `special` = NaN / -0.0 / +-inf planes,
+    which take the exact scalar passes inside the strip kernels."""
+    from improving_yolov8_cbam_swinblock_b200 import functional as Fb
+
+    torch.manual_seed(k)
+    y0 = torch.randn(3, 64, 20, 20, device="cuda")
+    if kind == "ties":
+        y0 = torch.relu(y0).mul(2).round().div(2)
+    if kind == "special":
+        y0[0, :8, 3, 4] = float("nan")
+        y0[1, 40:, 10:14, 2:9] = -0.0
+        y0[1, 3, 0, 0] = float("inf")
+        y0[2, 5, :, :] = float("-inf")
+        y0[2, 33, 19, 19] = float("nan")
+    y0 = to_cl(y0.to(dtype))
+    g = to_cl(torch.randn(3, 256, 20, 20, device="cuda").to(dtype))
+
+    def run():
+        y = y0.clone().requires_grad_(True)
+        cat = Fb.sppf_pool(y, k)
+        cat.backward(g)
+        return cat.detach(), y.grad
+
+    cat_s, gy_s = run()
+    monkeypatch.setenv("B200_SPPF_NO_STRIP", "1")
+    cat_g, gy_g = run()
+    monkeypatch.delenv("B200_SPPF_NO_STRIP")
+    assert torch.equal(_bits(cat_s.contiguous()), _bits(cat_g.contiguous()))
+    both_nan = gy_s.isnan() & gy_g.isnan()
+    assert torch.equal(_bits(gy_s.contiguous())[~both_nan], _bits(gy_g.contiguous())[~both_nan])
+    assert torch.equal(gy_s.isnan(), gy_g.isnan())
