@@ -36,6 +36,12 @@ _lib.register("b200_bn_silu_workspace_bytes", _SZ, [_I64, _I32, _I32])
 _lib.register("b200_bn_silu_fwd", C.c_int, [_VP] * 9 + [_SZ, _I64, _I32, C.c_float, C.c_float, _I32, _I32, _I32, _VP])
 _lib.register("b200_bn_silu_fwd_tracked", C.c_int, [_VP] * 10 + [_SZ, _I64, _I32, C.c_float, C.c_float, _I32, _I32, _I32, _VP])
 _lib.register("b200_bn_silu_bwd", C.c_int, [_VP, _I64] + [_VP] * 9 + [_SZ, _I64, _I32, _I32, _I32, _I32, _VP])
+_lib.register("b200_det_decode", C.c_int, [_VP] * 5 + [_I32] + [_VP] * 3 + [_I32] * 4 + [_VP])
+_lib.register("b200_tal_workspace_bytes", _SZ, [_I32] * 4)
+_lib.register("b200_tal_assign", C.c_int, [_VP] * 6 + [_I32] + [_VP] * 4 + [_SZ] + [_I32] * 3 + [C.c_float] * 3 + [_VP])
+_lib.register("b200_box_dfl_workspace_bytes", _SZ, [])
+_lib.register("b200_box_dfl_fwd", C.c_int, [_VP] * 3 + [_I32] + [_VP] * 4 + [_SZ, _I32, _I32, _VP])
+_lib.register("b200_box_dfl_bwd", C.c_int, [_VP] * 4 + [_I32] + [_VP] * 3 + [_I32, _I32, _VP])
 _lib.register("b200_nhwc_concat", C.c_int, [_VP, _VP, _VP, _I32, _VP, _I64, _I32, _VP])
 _lib.register("b200_u8_to_nhwc", C.c_int, [_VP, _VP] + [_I32] * 4 + [C.c_float, _I32, _VP])
 _lib.register("b200_nhwc_upsample_fwd", C.c_int, [_VP, _VP] + [_I32] * 7 + [_VP])
@@ -254,6 +260,116 @@ class ClsLossFn(torch.autograd.Function):
 def cls_bce_sum(maps, label, value):
     """BCEWithLogits(reduction='sum') of the class maps against the (label, value) targets of the task-aligned assigner."""
     return ClsLossFn.apply(label, value, *maps)
+
+
+# --------------------------------------------------------------------------------------------------
+# task-aligned assigner + box / DFL terms of the detection loss   (utils/loss.py:199-255, utils/tal.py:41-327)
+# --------------------------------------------------------------------------------------------------
+def _geom_args(maps, strides):
+    n = len(maps)
+    Hs = (C.c_int32 * n)(*[int(m.shape[2]) for m in maps])
+    Ws = (C.c_int32 * n)(*[int(m.shape[3]) for m in maps])
+    st = (C.c_float * n)(*[float(s) for s in strides])
+    return n, Hs, Ws, st
+
+
+def _box_maps_ok(maps, reg_max=16):
+    m0 = maps[0]
+    return all(m.is_cuda and m.dim() == 4 and m.shape[1] == 4 * reg_max and m.dtype == m0.dtype and m.device == m0.device
+               for m in maps) and m0.dtype in (torch.float32, torch.bfloat16, torch.float16)
+
+
+def det_decode(box_maps, cls_maps, strides, gt):
+    """pred_boxes [B, A, 4] (grid units) and scores [B, nmax, A] = sigmoid of every GT's own class logit (no autograd)."""
+    box_maps = [_nhwc(m.detach()) for m in box_maps]
+    cls_maps = [_nhwc(m.detach()) for m in cls_maps]
+    m0 = box_maps[0]
+    B, nc, nmax, dev = m0.shape[0], cls_maps[0].shape[1], gt.shape[1], m0.device
+    A = sum(int(m.shape[2] * m.shape[3]) for m in box_maps)
+    gt = gt.detach().to(torch.float32).contiguous()
+    pred = torch.empty((B, A, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((B, nmax, A), dtype=torch.float32, device=dev)
+    n, Hs, Ws, st = _geom_args(box_maps, strides)
+    bp = (C.c_void_p * n)(*[m.data_ptr() for m in box_maps])
+    cp = (C.c_void_p * n)(*[m.data_ptr() for m in cls_maps])
+    with torch.cuda.device(dev):
+        call("b200_det_decode", C.addressof(bp), C.addressof(cp), C.addressof(Hs), C.addressof(Ws), C.addressof(st), n, ptr(gt),
+             ptr(pred), ptr(scores), B, nc, nmax, dtype_code(m0.dtype), stream_ptr(dev), tag=f"b200_det_decode[{B * A}x{4 * 16}]")
+    return pred, scores
+
+
+def tal_assign(pred, scores, gt, shapes, strides, topk=10, alpha=0.5, beta=6.0, eps=1e-9):
+    """TaskAlignedAssigner on the decoded boxes: (target_label [B,A] int32, target_value [B,A], target_box [B,A,4] grid units)."""
+    B, A, _ = pred.shape
+    nmax, dev = gt.shape[1], pred.device
+    gt = gt.detach().to(torch.float32).contiguous()
+    n = len(shapes)
+    Hs = (C.c_int32 * n)(*[int(s[0]) for s in shapes])
+    Ws = (C.c_int32 * n)(*[int(s[1]) for s in shapes])
+    st = (C.c_float * n)(*[float(s) for s in strides])
+    tlabel = torch.empty((B, A), dtype=torch.int32, device=dev)
+    tvalue = torch.empty((B, A), dtype=torch.float32, device=dev)
+    tbox = torch.empty((B, A, 4), dtype=torch.float32, device=dev)
+    nbytes = lib().b200_tal_workspace_bytes(B, nmax, A, int(topk))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        call("b200_tal_assign", ptr(pred), ptr(scores), ptr(gt), C.addressof(Hs), C.addressof(Ws), C.addressof(st), n, ptr(tlabel),
+             ptr(tvalue), ptr(tbox), ptr(ws), nbytes, B, nmax, int(topk), float(alpha), float(beta), float(eps), stream_ptr(dev),
+             tag=f"b200_tal_assign[{B}x{nmax}x{A}]")
+    return tlabel, tvalue, tbox
+
+
+class BoxDflLossFn(torch.autograd.Function):
+    """(sum (1 - CIoU) * weight, sum DFL * weight) over the positive anchors, straight from the Detect box maps
+    (one [B, 64, H, W] channels_last map per level); gradient written in the layout of the maps."""
+
+    @staticmethod
+    def forward(ctx, tbox, weight, *maps):
+        maps = tuple(_nhwc(m) for m in maps)
+        m0 = maps[0]
+        B, dev, code = m0.shape[0], m0.device, dtype_code(m0.dtype)
+        tbox = tbox.detach().to(torch.float32).contiguous()
+        weight = weight.detach().to(torch.float32).contiguous()
+        n, Hs, Ws, _ = _geom_args(maps, [1.0] * len(maps))
+        bp = (C.c_void_p * n)(*[m.data_ptr() for m in maps])
+        nbytes = lib().b200_box_dfl_workspace_bytes()
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        rows = B * sum(int(m.shape[2] * m.shape[3]) for m in maps)
+        with torch.cuda.device(dev):
+            call("b200_box_dfl_fwd", C.addressof(bp), C.addressof(Hs), C.addressof(Ws), n, ptr(tbox), ptr(weight), ptr(out), ptr(ws),
+                 nbytes, B, code, stream_ptr(dev), tag=f"b200_box_dfl_fwd[{rows}x64]")
+        ctx.save_for_backward(tbox, weight, *maps)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        tbox, weight, *maps = ctx.saved_tensors
+        m0 = maps[0]
+        B, dev, code = m0.shape[0], m0.device, dtype_code(m0.dtype)
+        grads = [torch.empty_like(m) for m in maps]
+        n, Hs, Ws, _ = _geom_args(maps, [1.0] * len(maps))
+        bp = (C.c_void_p * n)(*[m.data_ptr() for m in maps])
+        gp = (C.c_void_p * n)(*[t.data_ptr() for t in grads])
+        gs = g.detach().to(torch.float32).reshape(2).contiguous()
+        rows = B * sum(int(m.shape[2] * m.shape[3]) for m in maps)
+        with torch.cuda.device(dev):
+            call("b200_box_dfl_bwd", C.addressof(bp), C.addressof(gp), C.addressof(Hs), C.addressof(Ws), n, ptr(tbox), ptr(weight),
+                 ptr(gs), B, code, stream_ptr(dev), tag=f"b200_box_dfl_bwd[{rows}x64]")
+        return (None, None, *grads)
+
+
+def box_dfl_sums(maps, tbox, weight):
+    return BoxDflLossFn.apply(tbox, weight, *maps)
+
+
+class DetLossKernels:
+    """What harness/loss.py:DetectionLoss calls when the fused path is on (BLOCKS["det_loss"])."""
+    supported = staticmethod(_box_maps_ok)
+    decode = staticmethod(det_decode)
+    assign = staticmethod(tal_assign)
+    box_dfl = staticmethod(box_dfl_sums)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -111,6 +111,26 @@ class DetectionLoss:
 
     cls_loss = None   # optional fused classification term: callable(cls_maps, label [B,A], value [B,A]) -> BCE sum
 
+    det_kernels = None   # optional fused decode / assigner / box+DFL kernels (functional.DetLossKernels): SURVEY 8(f)-4
+
+    def _call_fused(self, pairs, batch, max_boxes):
+        """The whole loss on kernels: decode -> task-aligned assignment -> (box, DFL) sums and the classification sum, all read
+        from the Detect head's maps in place (utils/loss.py:207-255 computes the same three numbers)."""
+        K = self.det_kernels
+        boxes, clss = [p[0] for p in pairs], [p[1] for p in pairs]
+        device, bs = boxes[0].device, boxes[0].shape[0]
+        h, w = boxes[0].shape[2:]
+        wh = torch.stack((torch.full((), w * self.strides[0], device=device), torch.full((), h * self.strides[0], device=device)))
+        gt = self.targets_dense(batch, bs, max_boxes, wh, device)        # [B, nmax, 5]: class, xyxy (pixels)
+        with torch.no_grad():
+            pred, scores = K.decode(boxes, clss, self.strides, gt)
+            tlabel, tval, tbox = K.assign(pred, scores, gt, [f.shape[2:] for f in boxes], self.strides, topk=self.topk)
+        tss = tval.sum().clamp(min=1.0)
+        lcls = self.cls_loss(clss, tlabel, tval) / tss
+        sums = K.box_dfl(boxes, tbox, tval) / tss
+        loss = torch.stack((sums[0] * self.gains[0], lcls.float() * self.gains[1], sums[1] * self.gains[2]))
+        return loss * bs, loss.detach()
+
     def _call_split(self, pairs, batch, max_boxes):
         """The same loss on the Detect head's un-concatenated (box, cls) maps: the class logits are never gathered into a
         [B, 8400, nc] tensor -- the assigner gathers the nmax scores it needs per anchor, the BCE term is one fused kernel
@@ -158,6 +178,8 @@ class DetectionLoss:
     def __call__(self, feats, batch, max_boxes=None):
         if isinstance(feats[0], (tuple, list)):
             if self.cls_loss is not None and max_boxes:
+                if self.det_kernels is not None and self.det_kernels.supported([p[0] for p in feats], self.reg_max):
+                    return self._call_fused(feats, batch, max_boxes)
                 return self._call_split(feats, batch, max_boxes)
             feats = [torch.cat(p, 1) for p in feats]
         device = feats[0].device

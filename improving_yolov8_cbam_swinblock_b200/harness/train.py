@@ -80,6 +80,8 @@ class Trainer:
         if blocks.get("cls_loss") is not None and self.device.type == "cuda" and nc % 8 == 0:
             self.criterion.cls_loss = blocks["cls_loss"]
             model.model[-1].split_outputs = True
+            if blocks.get("det_loss") is not None:   # assigner + box / DFL terms as kernels too
+                self.criterion.det_kernels = blocks["det_loss"]
         fused = self.device.type == "cuda"
         self.opt = torch.optim.SGD(param_groups(model), lr=lr, momentum=momentum, nesterov=True, fused=fused)
         self.ema = EMA(model) if ema else None

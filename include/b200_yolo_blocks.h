@@ -295,6 +295,39 @@ B200_API int b200_bce_logits_bwd(const void* const* logits, void* const* grads, 
                                  int32_t n_levels, const int32_t* label, const float* value, const float* scale, int32_t B, int32_t C,
                                  int32_t dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Task-aligned assigner + box / DFL terms of the v8 detection loss on the Detect head's un-concatenated maps.
+ * Replaces ultralytics/utils/loss.py:207-255 (`v8DetectionLoss.__call__`: `bbox_decode` :199, the assigner call :224-232,
+ * `BboxLoss.forward` :84-107 = CIoU + DFL) and ultralytics/utils/tal.py:41-327 (`TaskAlignedAssigner.forward`, `get_pos_mask`,
+ * `get_box_metrics`, `select_topk_candidates`, `select_highest_overlaps`, `get_targets`).
+ *   box_maps[l] : DFL logits of level l, NHWC-dense [B * H[l] * W[l], 64] (4 sides x reg_max 16); cls_maps[l]: [B * H*W, nc]
+ *   gt          : [B, nmax, 5] f32 rows (class, x1, y1, x2, y2 in pixels); an all-zero box is padding (loss.py:175-190)
+ *   anchors of all levels are concatenated level-major: A = sum H[l] * W[l]; anchor centre = (x + 0.5, y + 0.5) grid units
+ * b200_det_decode : pred_boxes [B, A, 4] f32 = anchor -/+ softmax-expectation of the DFL logits (grid units);
+ *                   scores [B, nmax, A] f32 = sigmoid(class logit of GT j's own class) -- all the assigner reads of the class maps
+ * b200_tal_assign : target_label [B, A] (int32, -1 = background), target_value [B, A] (the normalised alignment metric =
+ *                   the value of the one-hot target_scores row), target_box [B, A, 4] (grid units).  top-k ties: lower anchor
+ *                   index; anchors with a zero metric are never selected (they carry a zero target either way)
+ * b200_box_dfl_fwd: sums[0] = sum_a (1 - CIoU(pred_a, target_a)) * weight_a, sums[1] = sum_a DFL(a) * weight_a  (weight = target_value)
+ * b200_box_dfl_bwd: grad_maps[l] = grad_sums[0] * d sums[0] / d logits + grad_sums[1] * d sums[1] / d logits, layout of box_maps
+ * No atomics on floating-point sums (per-GT maxima use an order-free integer atomicMax): deterministic.
+ * ------------------------------------------------------------------------------------------------------ */
+B200_API int b200_det_decode(const void* const* box_maps, const void* const* cls_maps, const int32_t* H, const int32_t* W,
+                             const float* strides, int32_t n_levels, const float* gt, float* pred_boxes, float* scores, int32_t B,
+                             int32_t nc, int32_t nmax, int32_t dtype, void* stream);
+B200_API size_t b200_tal_workspace_bytes(int32_t B, int32_t nmax, int32_t A_total, int32_t topk);
+B200_API int b200_tal_assign(const float* pred_boxes, const float* scores, const float* gt, const int32_t* H, const int32_t* W,
+                             const float* strides, int32_t n_levels, int32_t* target_label, float* target_value, float* target_box,
+                             void* workspace, size_t workspace_bytes, int32_t B, int32_t nmax, int32_t topk, float alpha, float beta,
+                             float eps, void* stream);
+B200_API size_t b200_box_dfl_workspace_bytes(void);
+B200_API int b200_box_dfl_fwd(const void* const* box_maps, const int32_t* H, const int32_t* W, int32_t n_levels, const float* target_box,
+                              const float* weight, float* sums, void* workspace, size_t workspace_bytes, int32_t B, int32_t dtype,
+                              void* stream);
+B200_API int b200_box_dfl_bwd(const void* const* box_maps, void* const* grad_maps, const int32_t* H, const int32_t* W, int32_t n_levels,
+                              const float* target_box, const float* weight, const float* grad_sums, int32_t B, int32_t dtype,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif
