@@ -42,6 +42,10 @@ _lib.register("b200_tal_assign", C.c_int, [_VP] * 6 + [_I32] + [_VP] * 4 + [_SZ]
 _lib.register("b200_box_dfl_workspace_bytes", _SZ, [])
 _lib.register("b200_box_dfl_fwd", C.c_int, [_VP] * 3 + [_I32] + [_VP] * 4 + [_SZ, _I32, _I32, _VP])
 _lib.register("b200_box_dfl_bwd", C.c_int, [_VP] * 4 + [_I32] + [_VP] * 3 + [_I32, _I32, _VP])
+_lib.register("b200_stem_conv_supported", C.c_int, [_I32] * 4)
+_lib.register("b200_stem_conv_fwd", C.c_int, [_VP] * 3 + [_I32] * 5 + [_VP])
+_lib.register("b200_stem_conv_wgrad_workspace_bytes", _SZ, [_I32])
+_lib.register("b200_stem_conv_wgrad", C.c_int, [_VP] * 4 + [_SZ] + [_I32] * 5 + [_VP])
 _lib.register("b200_nhwc_concat", C.c_int, [_VP, _VP, _VP, _I32, _VP, _I64, _I32, _VP])
 _lib.register("b200_u8_to_nhwc", C.c_int, [_VP, _VP] + [_I32] * 4 + [C.c_float, _I32, _VP])
 _lib.register("b200_nhwc_upsample_fwd", C.c_int, [_VP, _VP] + [_I32] * 7 + [_VP])
@@ -476,6 +480,57 @@ def head_conv(conv, x: torch.Tensor) -> torch.Tensor:
         x = x.to(torch.get_autocast_dtype("cuda"))
     if conv1x1_supported(x, conv, allow_bias=True):
         return conv1x1(x, conv)
+    return conv(x)
+
+
+class StemConvFn(torch.autograd.Function):
+    """The model's first convolution Conv2d(3, c2, 3, 2, 1, bias=False) on a 16-bit channels_last image (hand-written mma kernels,
+    csrc/stem_conv.cu): y = conv(x, w); backward: the weight gradient only -- the image needs none (an input gradient, if ever
+    asked for, comes from ATen)."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x = _nhwc(x)
+        B, _, H, W = x.shape
+        c2 = w.shape[0]
+        wf = _f32(w.detach())
+        y = _empty_nhwc(B, c2, H // 2, W // 2, x.dtype, x.device)
+        with torch.cuda.device(x.device):
+            call("b200_stem_conv_fwd", ptr(x), ptr(wf), ptr(y), B, H, W, c2, dtype_code(x.dtype), stream_ptr(x.device),
+                 tag=f"b200_stem_conv_fwd[{B}x{H}x{W}x3->{c2}]")
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        B, _, H, W = x.shape
+        c2 = w.shape[0]
+        gy = _nhwc(gy.to(x.dtype))
+        gw = torch.empty(w.shape, dtype=torch.float32, device=x.device)
+        nbytes = lib().b200_stem_conv_wgrad_workspace_bytes(c2)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            call("b200_stem_conv_wgrad", ptr(gy), ptr(x), ptr(gw), ptr(ws), nbytes, B, H, W, c2, dtype_code(x.dtype),
+                 stream_ptr(x.device), tag=f"b200_stem_conv_wgrad[{B}x{H}x{W}x3->{c2}]")
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.nn.grad.conv2d_input(x.shape, w.to(x.dtype), gy, stride=2, padding=1)
+        return gx, gw.to(w.dtype)
+
+
+def stem_conv(conv, x: torch.Tensor) -> torch.Tensor:
+    """``conv(x)`` for the first layer's nn.Conv2d: the hand-written kernels when it is Conv2d(3, c2, 3, 2, 1, bias=False) on a
+    16-bit CUDA image they tile, the module's own forward otherwise."""
+    if x.is_cuda and x.dim() == 4 and torch.is_autocast_enabled("cuda") and x.dtype == torch.float32:
+        x = x.to(torch.get_autocast_dtype("cuda"))
+    if (x.is_cuda and x.dim() == 4 and x.dtype in (torch.bfloat16, torch.float16) and type(conv) is torch.nn.Conv2d
+            and conv.in_channels == 3 and x.shape[1] == 3 and conv.kernel_size == (3, 3) and conv.stride == (2, 2)
+            and conv.padding == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is None
+            and conv.padding_mode == "zeros"
+            and lib().b200_stem_conv_supported(int(x.shape[2]), int(x.shape[3]), int(conv.out_channels), dtype_code(x.dtype))):
+        return StemConvFn.apply(x, conv.weight)
     return conv(x)
 
 

@@ -84,9 +84,10 @@ class Conv(nn.Module):
         self.act = nn.SiLU() if act is True else act if isinstance(act, nn.Module) else nn.Identity()
 
     epilogue = None  # DetectionGraph sets blocks["conv_epilogue"] here: callable (conv_module, y) -> act(bn(y))
+    conv_fn = None   # per instance: callable (nn.Conv2d, x) -> conv(x); set on the first layer from blocks["stem_conv"]
 
     def forward(self, x):
-        y = self.conv(x)
+        y = self.conv(x) if self.conv_fn is None else self.conv_fn(self.conv, x)
         return self.act(self.bn(y)) if self.epilogue is None else self.epilogue(self, y)
 
 
@@ -289,6 +290,8 @@ class DetectionGraph(nn.Module):
                 m_.upsample = blocks["upsample"]
             if blocks.get("head_conv") is not None and isinstance(m_, Detect):
                 m_.head_conv = blocks["head_conv"]
+        if blocks.get("stem_conv") is not None and isinstance(self.model[0], Conv):   # the 3-channel first layer (yaml backbone row 0)
+            self.model[0].conv_fn = blocks["stem_conv"]
         self.save = sorted(save)
         self.nc, self.scale = nc, scale
         det = self.model[-1]

@@ -328,6 +328,19 @@ B200_API int b200_box_dfl_bwd(const void* const* box_maps, void* const* grad_map
                               const float* target_box, const float* weight, const float* grad_sums, int32_t B, int32_t dtype,
                               void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * The model's first convolution: Conv(3, c2, k=3, s=2, p=1), bias-free (yaml backbone row 0: `[-1, 1, Conv, [64, 3, 2]]` scaled;
+ * ultralytics/nn/modules/conv.py:37-91 `self.conv`), on a 16-bit NHWC image x [B, H, W, 3] -> y [B, H/2, W/2, c2], and its weight
+ * gradient (the input needs none).  w / gw: [c2, 3, 3, 3] f32 (OIHW, as nn.Conv2d.weight).  H even, W % 32 == 0, c2 in {16, 32, 48}.
+ * Deterministic (per-CTA partial matrices folded in a fixed order).
+ * ------------------------------------------------------------------------------------------------------ */
+B200_API int b200_stem_conv_supported(int32_t H, int32_t W, int32_t c2, int32_t dtype);
+B200_API int b200_stem_conv_fwd(const void* x, const float* w, void* y, int32_t B, int32_t H, int32_t W, int32_t c2, int32_t dtype,
+                                void* stream);
+B200_API size_t b200_stem_conv_wgrad_workspace_bytes(int32_t c2);
+B200_API int b200_stem_conv_wgrad(const void* gy, const void* x, float* gw, void* workspace, size_t workspace_bytes, int32_t B, int32_t H,
+                                  int32_t W, int32_t c2, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,58 @@
+"""-m gpu: the first layer's convolution Conv2d(3, c2, 3, 2, 1, bias=False) (csrc/stem_conv.cu) against F.conv2d in fp32 on the same
+(rounded) image and weight: output and weight gradient; module hook falls back to the stock convolution for anything else."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 1e-2), (torch.float16, 2e-3)])
+@pytest.mark.parametrize("B,H,W,c2", [(2, 64, 64, 16), (3, 70, 96, 16), (2, 128, 160, 32), (1, 32, 32, 48), (8, 640, 640, 16)])
+def test_stem_conv_matches_conv2d(dtype, tol, B, H, W, c2):
+    from improving_yolov8_cbam_swinblock_b200 import _lib, functional as Fb
+
+    torch.manual_seed(B + H + c2)
+    conv = torch.nn.Conv2d(3, c2, 3, 2, 1, bias=False).cuda()
+    x = torch.rand(B, 3, H, W, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    g = torch.randn(B, c2, H // 2, W // 2, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    n0 = _lib.launch_count()
+    y = Fb.stem_conv(conv, x)
+    y.backward(g)
+    assert _lib.launch_count() - n0 >= 2, "stem_conv did not run the hand-written kernels"
+    assert y.is_contiguous(memory_format=torch.channels_last) and y.dtype == dtype
+    gw = conv.weight.grad.clone()
+    w32 = conv.weight.detach().to(dtype).float().requires_grad_(True)   # the kernel consumes the rounded weight (as autocast does)
+    y32 = F.conv2d(x.float(), w32, None, 2, 1)
+    y32.backward(g.float())
+    assert rel_err(y.float(), y32) <= tol, rel_err(y.float(), y32)
+    assert rel_err(gw, w32.grad) <= 1e-4, rel_err(gw, w32.grad)          # bf16 products are exact in f32; only the order differs
+    # deterministic
+    conv.weight.grad = None
+    y2 = Fb.stem_conv(conv, x)
+    y2.backward(g)
+    assert torch.equal(y2, y) and torch.equal(conv.weight.grad, gw)
+
+
+def test_stem_conv_hook_falls_back():
+    from improving_yolov8_cbam_swinblock_b200 import _lib, functional as Fb
+
+    x = torch.rand(2, 3, 64, 64, device="cuda")
+    for conv, inp in [(torch.nn.Conv2d(3, 16, 3, 2, 1, bias=False).cuda(), x),                      # f32, no autocast
+                      (torch.nn.Conv2d(3, 24, 3, 2, 1, bias=False).cuda(), x.bfloat16()),          # width the kernel does not tile
+                      (torch.nn.Conv2d(3, 16, 3, 1, 1, bias=False).cuda(), x.bfloat16()),          # stride 1
+                      (torch.nn.Conv2d(3, 16, 3, 2, 1, bias=True).cuda(), x.bfloat16())]:          # bias
+        n0 = _lib.launch_count()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=inp.dtype != torch.float32):
+            y = Fb.stem_conv(conv, inp)
+        assert _lib.launch_count() == n0
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=inp.dtype != torch.float32):
+            assert torch.equal(y, conv(inp))
+    # under autocast an f32 image is cast first, exactly as F.conv2d would
+    conv = torch.nn.Conv2d(3, 16, 3, 2, 1, bias=False).cuda()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = Fb.stem_conv(conv, x)
+        want = conv(x)
+    assert y.dtype == torch.bfloat16 and rel_err(y.float(), want.float()) < 1e-2
