@@ -83,6 +83,14 @@ __device__ __forceinline__ void stg_stream16(void* p, uint4 v) {
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS, L1 bypassed); !valid zero-fills the destination (src-size 0: nothing is read).
+// A thread can have any number in flight -- no staging registers -- which is what lets a CTA request a whole tile at once.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---- shifted-window mask (SwinBlock extension; the reference block is unshifted: shift == 0 disables it) ----------
 // After the cyclic shift by `shift` only the windows of the last window row / column mix image regions; inside them a
 // query attends to the keys on its own side of the seam (row/col index >= ws-shift or not).  ra / ca: bit j = key j

@@ -63,26 +63,19 @@ __device__ __forceinline__ float k_weight(const float* __restrict__ w, int n, in
 // stage the kIR input rows of tile (b, oy0) : row i <-> input row 2*oy0 - 1 + i (zero outside the image)
 template <typename T, int IR>
 __device__ __forceinline__ void stage_input(unsigned char* xs, const T* __restrict__ x, int b, int oy0, int H, int W, int pitch) {
-  const int vpr = W * 6 / 16 + 1, total = IR * vpr;   // + 1: the zero pad in front of the row (v == 0)
-  for (int it0 = threadIdx.x; it0 < total; it0 += 4 * blockDim.x) {   // four 16-byte loads in flight per thread
-    uint4 val[4];
+  // asynchronous copies: the whole tile is requested at once (register-staged batches of four loads were four DRAM round trips per
+  // tile and left the kernels latency-bound at a third of the HBM rate); the caller waits with cp_async_wait_all + __syncthreads
+  const int vpr = W * 6 / 16 + 1;   // + 1: the zero pad in front of the row (v == 0)
+  const unsigned char* xb = reinterpret_cast<const unsigned char*>(x);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int it = it0 + u * blockDim.x;
-      val[u] = make_uint4(0u, 0u, 0u, 0u);
-      if (it < total) {
-        const int i = it / vpr, v = it - i * vpr, iy = 2 * oy0 - 1 + i;
-        if (v > 0 && iy >= 0 && iy < H)
-          val[u] = ldg_stream16(reinterpret_cast<const unsigned char*>(x) + ((size_t)(b * H + iy) * W) * 6 + (size_t)(v - 1) * 16);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int it = it0 + u * blockDim.x;
-      if (it < total) {
-        const int i = it / vpr, v = it - i * vpr;
-        *reinterpret_cast<uint4*>(xs + (size_t)i * pitch + (size_t)v * 16) = val[u];
-      }
+  for (int i = 0; i < IR; ++i) {   // row by row: no integer division per copy
+    const int iy = 2 * oy0 - 1 + i;
+    const bool row_ok = iy >= 0 && iy < H;
+    const unsigned char* rsrc = xb + ((size_t)(b * H + (row_ok ? iy : 0)) * W) * 6;
+    unsigned char* rdst = xs + (size_t)i * pitch;
+    for (int v = threadIdx.x; v < vpr; v += blockDim.x) {
+      const bool ok = row_ok && v > 0;
+      cp_async16(rdst + (size_t)v * 16, ok ? rsrc + (size_t)(v - 1) * 16 : xb, ok);
     }
   }
 }
@@ -110,6 +103,7 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const T* __restrict__ x, 
 #pragma unroll
     for (int h = 0; h < 2; ++h) koff[s][h] = k_offset(16 * s + 2 * q + 8 * h, pitch);
   stage_input<T, 2 * kR + 1>(xs, x, b, oy0, H, W, pitch);
+  cp_async_wait_all();
   __syncthreads();
   const int gpr = Wo / 16;   // 16-pixel groups per output row
   const int rows = min(kR, Ho - oy0);
@@ -165,14 +159,9 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const T* __restrict__ g
     {
       const int vecs = rows * Wo * OC * 2 / 16;
       const unsigned char* src = reinterpret_cast<const unsigned char*>(gy) + ((size_t)(b * Ho + oy0) * Wo) * OC * 2;
-      for (int v0 = threadIdx.x; v0 < vecs; v0 += 4 * blockDim.x) {
-        uint4 val[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) if (v0 + u * (int)blockDim.x < vecs) val[u] = ldg_stream16(src + (size_t)(v0 + u * blockDim.x) * 16);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) if (v0 + u * (int)blockDim.x < vecs) *reinterpret_cast<uint4*>(gs + (size_t)(v0 + u * blockDim.x) * 16) = val[u];
-      }
+      for (int v = threadIdx.x; v < vecs; v += blockDim.x) cp_async16(gs + (size_t)v * 16, src + (size_t)v * 16, true);
     }
+    cp_async_wait_all();
     __syncthreads();
     for (int g = warp; g < rows * gpr; g += (int)(blockDim.x >> 5)) {
       const int orow = g / gpr, ox0 = (g - orow * gpr) * 16;
@@ -283,16 +272,19 @@ extern "C" B200_API int b200_stem_conv_wgrad(const void* gy, const void* x, floa
   const size_t smem_in = (size_t)(2 * kRW + 1) * pitch + (size_t)kRW * Wo * c2 * 2, smem_red = (size_t)8 * c2 * 32 * 4;
   const size_t smem = smem_in > smem_red ? smem_in : smem_red;
   B200_REQUIRE(smem <= (size_t)max_smem_optin(), B200_ERR_UNSUPPORTED, "stem_conv_wgrad: W=%d does not fit in shared memory", W);
-  int per_sm = (int)((size_t)max_smem_optin() / (smem + 1024));
-  per_sm = per_sm < 1 ? 1 : per_sm > 5 ? 5 : per_sm;
-  int grid = sm_count() * per_sm;
-  if (grid > n_tiles) grid = n_tiles;
+  int grid = 0;
   float* part = (float*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
+  // persistent CTAs: exactly one resident wave (the occupancy query accounts for registers as well as shared memory)
 #define B200_STEM_WG(TT, OCC)                                                                                  \
   {                                                                                                            \
     auto kern = stem_wgrad_kernel<TT, OCC>;                                                                    \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
+    int per_sm = 1;                                                                                            \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);                                   \
+    per_sm = per_sm < 1 ? 1 : per_sm > 5 ? 5 : per_sm;                                                         \
+    grid = sm_count() * per_sm;                                                                                \
+    if (grid > n_tiles) grid = n_tiles;                                                                        \
     kern<<<grid, 256, smem, st>>>((const TT*)gy, (const TT*)x, part, H, W, Ho, Wo, tpi, n_tiles, pitch);       \
   }
   if (dtype == B200_BF16) {

@@ -46,6 +46,9 @@ _lib.register("b200_stem_conv_supported", C.c_int, [_I32] * 4)
 _lib.register("b200_stem_conv_fwd", C.c_int, [_VP] * 3 + [_I32] * 5 + [_VP])
 _lib.register("b200_stem_conv_wgrad_workspace_bytes", _SZ, [_I32])
 _lib.register("b200_stem_conv_wgrad", C.c_int, [_VP] * 4 + [_SZ] + [_I32] * 5 + [_VP])
+_lib.register("b200_conv3x3_wgrad_supported", C.c_int, [_I32] * 6)
+_lib.register("b200_conv3x3_wgrad_workspace_bytes", _SZ, [_I32] * 2)
+_lib.register("b200_conv3x3_wgrad", C.c_int, [_VP] * 4 + [_SZ] + [_I32] * 7 + [_VP])
 _lib.register("b200_nhwc_concat", C.c_int, [_VP, _VP, _VP, _I32, _VP, _I64, _I32, _VP])
 _lib.register("b200_u8_to_nhwc", C.c_int, [_VP, _VP] + [_I32] * 4 + [C.c_float, _I32, _VP])
 _lib.register("b200_nhwc_upsample_fwd", C.c_int, [_VP, _VP] + [_I32] * 7 + [_VP])
@@ -531,6 +534,56 @@ def stem_conv(conv, x: torch.Tensor) -> torch.Tensor:
             and conv.padding_mode == "zeros"
             and lib().b200_stem_conv_supported(int(x.shape[2]), int(x.shape[3]), int(conv.out_channels), dtype_code(x.dtype))):
         return StemConvFn.apply(x, conv.weight)
+    return conv(x)
+
+
+class Conv3x3WgradFn(torch.autograd.Function):
+    """A narrow 3x3 nn.Conv2d (bias-free, padding 1, stride 1 or 2) whose WEIGHT GRADIENT runs on the hand-written mma kernel
+    (csrc/conv_wgrad.cu); the forward and the input gradient stay ATen's (cuDNN) -- for 16 / 32 input channels cuDNN's wgrad
+    falls back to sm80 legacy kernels (1.5 ms per step in the round-2 launch list)."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride):
+        x = _nhwc(x)
+        wl = w.detach().to(x.dtype)
+        y = torch.nn.functional.conv2d(x, wl, None, stride, 1)
+        ctx.save_for_backward(x, wl)
+        ctx.meta = (int(stride), w.dtype)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, wl = ctx.saved_tensors
+        stride, wdtype = ctx.meta
+        B, cin, H, W = x.shape
+        cout = wl.shape[0]
+        gy = _nhwc(gy.to(x.dtype))
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.ops.aten.convolution_backward(gy, x, wl, None, [stride, stride], [1, 1], [1, 1], False, [0, 0], 1,
+                                                     [True, False, False])[0]
+        gw = torch.empty(wl.shape, dtype=torch.float32, device=x.device)
+        nbytes = lib().b200_conv3x3_wgrad_workspace_bytes(cin, cout)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            call("b200_conv3x3_wgrad", ptr(gy), ptr(x), ptr(gw), ptr(ws), nbytes, B, H, W, cin, cout, stride, dtype_code(x.dtype),
+                 stream_ptr(x.device), tag=f"b200_conv3x3_wgrad[{B}x{H}x{W}x{cin}->{cout},s{stride}]")
+        return gx, gw.to(wdtype), None
+
+
+def conv3x3(conv, x: torch.Tensor) -> torch.Tensor:
+    """``conv(x)`` with the weight gradient of a narrow 3x3 convolution on the hand-written kernel when the layer qualifies
+    (training, 16-bit CUDA map, cin = 16, cout in {16, 32}); the module's own forward otherwise."""
+    if x.is_cuda and x.dim() == 4 and torch.is_autocast_enabled("cuda") and x.dtype == torch.float32:
+        x = x.to(torch.get_autocast_dtype("cuda"))
+    if (x.is_cuda and x.dim() == 4 and torch.is_grad_enabled() and conv.weight.requires_grad and x.dtype in (torch.bfloat16, torch.float16)
+            and type(conv) is torch.nn.Conv2d and conv.kernel_size == (3, 3) and conv.stride in ((1, 1), (2, 2))
+            and conv.padding == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is None
+            and conv.padding_mode == "zeros" and x.shape[1] == conv.in_channels
+            and lib().b200_conv3x3_wgrad_supported(int(x.shape[2]), int(x.shape[3]), int(conv.in_channels), int(conv.out_channels),
+                                                   int(conv.stride[0]), dtype_code(x.dtype))):
+        return Conv3x3WgradFn.apply(x, conv.weight, int(conv.stride[0]))
     return conv(x)
 
 

@@ -290,6 +290,11 @@ class DetectionGraph(nn.Module):
                 m_.upsample = blocks["upsample"]
             if blocks.get("head_conv") is not None and isinstance(m_, Detect):
                 m_.head_conv = blocks["head_conv"]
+        if blocks.get("conv3x3") is not None:   # narrow 3x3 convolutions: weight gradient on the hand-written kernel
+            for m_ in self.modules():
+                if isinstance(m_, Conv) and m_.conv.kernel_size == (3, 3) and m_.conv.in_channels == 16 \
+                        and m_.conv.out_channels in (16, 32):
+                    m_.conv_fn = blocks["conv3x3"]
         if blocks.get("stem_conv") is not None and isinstance(self.model[0], Conv):   # the 3-channel first layer (yaml backbone row 0)
             self.model[0].conv_fn = blocks["stem_conv"]
         self.save = sorted(save)

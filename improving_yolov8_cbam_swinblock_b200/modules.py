@@ -224,4 +224,4 @@ def _harness_sppf():
 SPPF = _harness_sppf()
 BLOCKS = {"CBAM": CBAM, "SwinBlock": SwinBlock, "SPPF": SPPF, "conv_epilogue": conv_epilogue,
           "concat": Fb.nhwc_concat, "chunk": Fb.nhwc_chunk, "input_prep": Fb.u8_to_nhwc, "cls_loss": Fb.cls_bce_sum,
-          "upsample": Fb.nhwc_upsample_nearest, "head_conv": Fb.head_conv, "det_loss": Fb.DetLossKernels, "stem_conv": Fb.stem_conv}
+          "upsample": Fb.nhwc_upsample_nearest, "head_conv": Fb.head_conv, "det_loss": Fb.DetLossKernels, "stem_conv": Fb.stem_conv, "conv3x3": Fb.conv3x3}

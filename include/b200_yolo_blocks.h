@@ -341,6 +341,17 @@ B200_API size_t b200_stem_conv_wgrad_workspace_bytes(int32_t c2);
 B200_API int b200_stem_conv_wgrad(const void* gy, const void* x, float* gw, void* workspace, size_t workspace_bytes, int32_t B, int32_t H,
                                   int32_t W, int32_t c2, int32_t dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Weight gradient of the narrow 3x3 convolutions at the top of the model (yaml backbone rows 1-2 at scale n: the 16 -> 32 stride-2
+ * Conv and the 16 -> 16 C2f bottleneck convolutions: nn.Conv2d(16, cout, 3, stride, 1, bias=False), cout in {16, 32}, stride 1 or 2;
+ * conv.py:37-91 `self.conv`; wider layers stay on cuDNN, whose sm100 kernels are faster there): gw [cout, cin, 3, 3] f32 = d loss / d weight from x [B, H, W, cin] and gy [B, H/stride, W/stride, cout] (16-bit NHWC).
+ * (W / stride) % 16 == 0.  Deterministic.  The forward and the input gradient stay the caller's (cuDNN).
+ * ------------------------------------------------------------------------------------------------------ */
+B200_API int b200_conv3x3_wgrad_supported(int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t stride, int32_t dtype);
+B200_API size_t b200_conv3x3_wgrad_workspace_bytes(int32_t cin, int32_t cout);
+B200_API int b200_conv3x3_wgrad(const void* gy, const void* x, float* gw, void* workspace, size_t workspace_bytes, int32_t B, int32_t H,
+                                int32_t W, int32_t cin, int32_t cout, int32_t stride, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

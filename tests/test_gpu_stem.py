@@ -56,3 +56,38 @@ def test_stem_conv_hook_falls_back():
         y = Fb.stem_conv(conv, x)
         want = conv(x)
     assert y.dtype == torch.bfloat16 and rel_err(y.float(), want.float()) < 1e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,H,W,cin,cout,stride", [(2, 32, 32, 16, 16, 1), (3, 38, 64, 16, 32, 2), (2, 20, 48, 16, 32, 1), (2, 64, 96, 16, 16, 2),
+                                                   (1, 6, 16, 16, 16, 1), (8, 160, 160, 16, 16, 1), (8, 320, 320, 16, 32, 2)])
+def test_conv3x3_wgrad_matches_conv2d(dtype, B, H, W, cin, cout, stride):
+    """csrc/conv_wgrad.cu against autograd of F.conv2d in fp32 on the same rounded tensors; output and input gradient are ATen's."""
+    from improving_yolov8_cbam_swinblock_b200 import _lib, functional as Fb
+
+    torch.manual_seed(H + cin + cout)
+    conv = torch.nn.Conv2d(cin, cout, 3, stride, 1, bias=False).cuda()
+    x = torch.randn(B, cin, H, W, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    g = torch.randn(B, cout, H // stride, W // stride, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    n0 = _lib.launch_count()
+    y = Fb.conv3x3(conv, x)
+    y.backward(g)
+    assert _lib.launch_count() - n0 >= 1, "conv3x3 did not run the hand-written weight-gradient kernel"
+    gw, gx = conv.weight.grad.clone(), x.grad.clone()
+    w32 = conv.weight.detach().to(dtype).float().requires_grad_(True)
+    x32 = x.detach().float().requires_grad_(True)
+    y32 = F.conv2d(x32, w32, None, stride, 1)
+    y32.backward(g.float())
+    assert rel_err(gw, w32.grad) <= 1e-4, rel_err(gw, w32.grad)
+    assert rel_err(y.float(), y32) <= (1e-2 if dtype == torch.bfloat16 else 2e-3)
+    assert rel_err(gx.float(), x32.grad) <= (1e-2 if dtype == torch.bfloat16 else 2e-3)
+    conv.weight.grad = None
+    Fb.conv3x3(conv, x.detach()).backward(g)
+    assert torch.equal(conv.weight.grad, gw)   # deterministic
+    # layers the kernel does not serve keep the stock path (other widths: cuDNN's sm100 wgrad kernels are the faster ones there)
+    for other, inp in [(torch.nn.Conv2d(cin, 24, 3, stride, 1, bias=False).cuda(), x.detach()),
+                       (torch.nn.Conv2d(32, 32, 3, stride, 1, bias=False).cuda(), torch.cat((x.detach(), x.detach()), 1))]:
+        n0 = _lib.launch_count()
+        with torch.autocast("cuda", dtype=dtype):
+            Fb.conv3x3(other, inp).float().sum().backward()
+        assert _lib.launch_count() == n0 and other.weight.grad is not None
