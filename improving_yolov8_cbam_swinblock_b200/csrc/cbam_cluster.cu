@@ -110,6 +110,7 @@ __device__ __forceinline__ void channel_partials(const T* xc, int np, int p0, in
 
 template <typename T, int VW, bool IDX>
 __global__ void __launch_bounds__(kT) cbam_cluster_fwd_kernel(const __grid_constant__ Params P) {
+  pdl_enter();
   cg::cluster_group cluster = cg::this_cluster();
   const Plan& L = P.pl;
   const int CS = L.cs, rank = blockIdx.x, b = blockIdx.y;
@@ -398,13 +399,15 @@ int launch(K kern, const Params& P, cudaStream_t st) {
   cfg.blockDim = dim3(kT);
   cfg.dynamicSmemBytes = L.total;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = L.cs;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see common.cuh: the kernel starts with pdl_enter()
+  at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   // can this device co-schedule one such cluster at all (MIG slices, small GPCs, 16-CTA non-portable clusters)?  Asked once
   // per (kernel, cluster size, smem); 0 or a failed launch -> -1 = "not taken", the caller runs the streaming chain (cbam.cu)
   static std::mutex mu;

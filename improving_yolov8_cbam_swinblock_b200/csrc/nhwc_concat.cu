@@ -43,6 +43,7 @@ struct CatParams {
 
 template <typename V>   // V = uint4 (16-byte vectors) or a 2/4-byte scalar
 __global__ void __launch_bounds__(kT) nhwc_concat_kernel(const __grid_constant__ CatParams P) {
+  pdl_enter();
   const uint32_t step = gridDim.x * kT;
   for (uint32_t i0 = blockIdx.x * kT + threadIdx.x; i0 < P.items; i0 += kInFlight * step) {
     V v[kInFlight];
@@ -108,10 +109,142 @@ extern "C" B200_API int b200_nhwc_concat(const void* const* srcs, const int32_t*
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   cudaStream_t st = (cudaStream_t)stream;
-  if (vec) nhwc_concat_kernel<uint4><<<(unsigned)blocks, kT, 0, st>>>(P);
-  else if (es == 4) nhwc_concat_kernel<uint32_t><<<(unsigned)blocks, kT, 0, st>>>(P);
-  else nhwc_concat_kernel<uint16_t><<<(unsigned)blocks, kT, 0, st>>>(P);
+  if (vec) launch_k(nhwc_concat_kernel<uint4>, (unsigned)blocks, kT, 0, st, P);
+  else if (es == 4) launch_k(nhwc_concat_kernel<uint32_t>, (unsigned)blocks, kT, 0, st, P);
+  else launch_k(nhwc_concat_kernel<uint16_t>, (unsigned)blocks, kT, 0, st, P);
   return check_launch("nhwc_concat");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Gradient fan-in at the seams: a feature map with several consumers (a bottleneck output inside `C2f` feeds the next
+// bottleneck AND the concat -- block.py C2f.forward `y.extend(m(y[-1]) for m in self.m)`; a saved layer `y[j]` of
+// `_predict_once`, tasks.py:171-176, feeds the next layer AND a later `Concat`) receives one gradient per consumer and
+// autograd sums them.  One of them is a channel slice of a concat's gradient (a row-strided view), which sends ATen's add
+// down its generic strided path (one element per thread, ~2 TB/s).  Here: 2..4 row-strided `[rows, C]` sources of one
+// dtype -> dense `[rows, C]`, 16-byte vectors, summed in f32 in source order and rounded once (for two sources that is
+// exactly ATen's `a + b` on 16-bit tensors).
+// ---------------------------------------------------------------------------------------------------------
+namespace b200 {
+namespace {
+
+constexpr int kMaxAdd = 4;
+struct AddParams {
+  const unsigned char* src[kMaxAdd];
+  long long stride[kMaxAdd];   // source row stride in bytes
+  unsigned char* dst;
+  uint32_t n, upr, items;      // sources, 16-byte vectors per row, rows * upr
+  FastDiv dupr;
+};
+
+template <typename T> __device__ __forceinline__ void add_unpack(const uint4& r, float* v) {
+  if constexpr (sizeof(T) == 4) {
+    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+  } else {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if constexpr (sizeof(T) == 2 && DT<T>::code == B200_BF16) {
+        v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+      } else {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        v[2 * i] = f.x; v[2 * i + 1] = f.y;
+      }
+    }
+  }
+}
+template <typename T> __device__ __forceinline__ uint4 add_pack(const float* v) {
+  if constexpr (sizeof(T) == 4) {
+    return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+  } else {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if constexpr (DT<T>::code == B200_BF16) {
+        const __nv_bfloat162 p = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&p);
+      } else {
+        const __half2 p = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&p);
+      }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+template <typename T, int N>
+__global__ void __launch_bounds__(kT) nhwc_add_kernel(const __grid_constant__ AddParams P) {
+  pdl_enter();
+  constexpr int VW = 16 / (int)sizeof(T);
+  constexpr int U = N <= 2 ? 4 : 2;   // vectors in flight per thread and source
+  const uint32_t step = gridDim.x * kT;
+  for (uint32_t i0 = blockIdx.x * kT + threadIdx.x; i0 < P.items; i0 += U * step) {
+    uint4 raw[U][N];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t i = i0 + u * step;
+      if (i < P.items) {
+        const uint32_t row = P.dupr.div(i), col = i - row * P.upr;
+#pragma unroll
+        for (int k = 0; k < N; ++k) raw[u][k] = ldg_stream16(P.src[k] + (long long)row * P.stride[k] + (size_t)col * 16);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t i = i0 + u * step;
+      if (i < P.items) {
+        float acc[VW], v[VW];
+        add_unpack<T>(raw[u][0], acc);
+#pragma unroll
+        for (int k = 1; k < N; ++k) {
+          add_unpack<T>(raw[u][k], v);
+#pragma unroll
+          for (int e = 0; e < VW; ++e) acc[e] += v[e];
+        }
+        stg_stream16(P.dst + (size_t)i * 16, add_pack<T>(acc));
+      }
+    }
+  }
+}
+
+}  // namespace
+}  // namespace b200
+
+extern "C" B200_API int b200_nhwc_add(const void* const* srcs, const int64_t* src_row_stride, int32_t n_src, void* dst, int64_t rows,
+                                      int32_t cols, int32_t dtype, void* stream) {
+  B200_REQUIRE(srcs && src_row_stride && dst, B200_ERR_SHAPE, "nhwc_add: null pointer");
+  B200_REQUIRE(n_src >= 2 && n_src <= kMaxAdd, B200_ERR_UNSUPPORTED, "nhwc_add: %d sources (2..%d supported)", n_src, kMaxAdd);
+  B200_REQUIRE(dtype == B200_F32 || dtype == B200_BF16 || dtype == B200_F16, B200_ERR_DTYPE, "nhwc_add: unsupported dtype code %d", dtype);
+  B200_REQUIRE(rows > 0 && cols > 0, B200_ERR_SHAPE, "nhwc_add: rows=%lld cols=%d", (long long)rows, cols);
+  const int es = dtype == B200_F32 ? 4 : 2;
+  B200_REQUIRE(((long long)cols * es) % 16 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0, B200_ERR_ALIGN,
+               "nhwc_add: rows of %d elements / the destination are not 16-byte multiples", cols);
+  AddParams P;
+  for (int i = 0; i < kMaxAdd; ++i) {
+    const int k = i < n_src ? i : n_src - 1;
+    B200_REQUIRE(srcs[k] && src_row_stride[k] >= cols, B200_ERR_SHAPE, "nhwc_add: source %d: row stride %lld < %d", k,
+                 (long long)src_row_stride[k], cols);
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(srcs[k]) & 15) == 0 && ((long long)src_row_stride[k] * es) % 16 == 0, B200_ERR_ALIGN,
+                 "nhwc_add: source %d is not 16-byte aligned / strided", k);
+    P.src[i] = static_cast<const unsigned char*>(srcs[k]);
+    P.stride[i] = (long long)src_row_stride[k] * es;
+  }
+  const long long upr = (long long)cols * es / 16;
+  B200_REQUIRE(rows * upr < (1ll << 31), B200_ERR_UNSUPPORTED, "nhwc_add: %lld x %lld vectors exceed the 31-bit item range",
+               (long long)rows, upr);
+  P.dst = static_cast<unsigned char*>(dst);
+  P.n = (uint32_t)n_src; P.upr = (uint32_t)upr; P.items = (uint32_t)(rows * upr);
+  P.dupr.init((uint32_t)upr);
+  const int per = n_src <= 2 ? 4 : 2;
+  long long blocks = ((long long)P.items + (long long)kT * per - 1) / ((long long)kT * per);
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
+    if (n_src == 2) launch_k(nhwc_add_kernel<T, 2>, (unsigned)blocks, kT, 0, st, P);
+    else if (n_src == 3) launch_k(nhwc_add_kernel<T, 3>, (unsigned)blocks, kT, 0, st, P);
+    else launch_k(nhwc_add_kernel<T, 4>, (unsigned)blocks, kT, 0, st, P);
+    return check_launch("nhwc_add");
+  });
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -127,6 +260,7 @@ namespace {
 template <typename T, int CH>
 __global__ void __launch_bounds__(256) u8_to_nhwc_kernel(const uint8_t* __restrict__ img, T* __restrict__ out, long long hw,
                                                          long long quads, float inv) {
+  pdl_enter();
   // thread = 4 consecutive pixels of one image: CH uchar4 loads (one per plane), 4*CH contiguous output elements
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (long long)gridDim.x * blockDim.x) {
     const long long hq = hw / 4;
@@ -159,10 +293,10 @@ int launch_u8(const uint8_t* img, void* out, int B, int C, long long hw, float i
   const long long cap = (long long)sm_count() * 32;
   if (blocks > cap) blocks = cap;
   switch (C) {
-    case 1: u8_to_nhwc_kernel<T, 1><<<(unsigned)blocks, 256, 0, st>>>(img, (T*)out, hw, quads, inv); break;
-    case 2: u8_to_nhwc_kernel<T, 2><<<(unsigned)blocks, 256, 0, st>>>(img, (T*)out, hw, quads, inv); break;
-    case 3: u8_to_nhwc_kernel<T, 3><<<(unsigned)blocks, 256, 0, st>>>(img, (T*)out, hw, quads, inv); break;
-    default: u8_to_nhwc_kernel<T, 4><<<(unsigned)blocks, 256, 0, st>>>(img, (T*)out, hw, quads, inv); break;
+    case 1: launch_k(u8_to_nhwc_kernel<T, 1>, (unsigned)blocks, 256, 0, st, img, (T*)out, hw, quads, inv); break;
+    case 2: launch_k(u8_to_nhwc_kernel<T, 2>, (unsigned)blocks, 256, 0, st, img, (T*)out, hw, quads, inv); break;
+    case 3: launch_k(u8_to_nhwc_kernel<T, 3>, (unsigned)blocks, 256, 0, st, img, (T*)out, hw, quads, inv); break;
+    default: launch_k(u8_to_nhwc_kernel<T, 4>, (unsigned)blocks, 256, 0, st, img, (T*)out, hw, quads, inv); break;
   }
   return check_launch("u8_to_nhwc");
 }
@@ -199,6 +333,7 @@ struct UpGeo {
 };
 
 __global__ void __launch_bounds__(256) upsample_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, const __grid_constant__ UpGeo G) {
+  pdl_enter();
   const uint32_t step = gridDim.x * 256;
   for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < G.items; i += step) {
     const uint32_t pix = G.dvpp.div(i), v = i - pix * G.vpp;
@@ -212,6 +347,7 @@ __global__ void __launch_bounds__(256) upsample_fwd_kernel(const uint4* __restri
 template <typename T>
 __global__ void __launch_bounds__(256) upsample_bwd_kernel(const unsigned char* __restrict__ g, uint4* __restrict__ gin,
                                                            const __grid_constant__ UpGeo G) {
+  pdl_enter();
   constexpr int VW = 16 / (int)sizeof(T);
   const uint32_t step = gridDim.x * 256;
   for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < G.items; i += step) {
@@ -266,7 +402,7 @@ extern "C" B200_API int b200_nhwc_upsample_fwd(const void* x, void* out, int32_t
   B200_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, B200_ERR_ALIGN, "nhwc_upsample_fwd: tensors must be 16-byte aligned");
   UpGeo G;
   if (int rc = up_geo(G, B, C, H, W, sh, sw, dtype, false, 0)) return rc;
-  upsample_fwd_kernel<<<up_blocks(G.items), 256, 0, (cudaStream_t)stream>>>(static_cast<const uint4*>(x), static_cast<uint4*>(out), G);
+  launch_k(upsample_fwd_kernel, up_blocks(G.items), 256, 0, (cudaStream_t)stream, static_cast<const uint4*>(x), static_cast<uint4*>(out), G);
   return check_launch("nhwc_upsample_fwd");
 }
 
@@ -278,7 +414,7 @@ extern "C" B200_API int b200_nhwc_upsample_bwd(const void* gout, int64_t gout_ro
   if (int rc = up_geo(G, B, C, H, W, sh, sw, dtype, true, gout_row_stride)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {
-    upsample_bwd_kernel<T><<<up_blocks(G.items), 256, 0, st>>>(static_cast<const unsigned char*>(gout), static_cast<uint4*>(gin), G);
+    launch_k(upsample_bwd_kernel<T>, up_blocks(G.items), 256, 0, st, static_cast<const unsigned char*>(gout), static_cast<uint4*>(gin), G);
     return check_launch("nhwc_upsample_bwd");
   });
 }

@@ -276,6 +276,7 @@ struct PoolGeom {
 template <typename T, int K, int LP, bool WITH_IDX>
 __global__ void __launch_bounds__(512) sppf_pool_fwd_kernel(const T* __restrict__ y0, T* __restrict__ cat,
                                                             int32_t* __restrict__ idx, PoolGeom g) {
+  pdl_enter();
   using WD = Word<T>;
   constexpr int EPL = WD::EPL;
   constexpr int CC = LP * EPL;
@@ -396,6 +397,7 @@ __device__ __forceinline__ void scatter1d(const float* __restrict__ src, int sst
 template <typename T, int K, int LP>
 __global__ void __launch_bounds__(512) sppf_pool_bwd_kernel(const T* __restrict__ gcat, const T* __restrict__ y0,
                                                             T* __restrict__ gy0, PoolGeom g) {
+  pdl_enter();
   using WD = Word<T>;
   constexpr int EPL = WD::EPL;
   constexpr int CC = LP * EPL;
@@ -558,6 +560,7 @@ __device__ __forceinline__ void ring_walk(Ring<K>& rg, float* buf, int stride, c
 template <typename T, int K, int LP, int MAXT>   // MAXT 320: registers capped for 4 (K <= 5) / 3 CTAs per SM
 __global__ void __launch_bounds__(MAXT, MAXT <= 320 ? (K <= 5 ? 4 : 3) : 1) sppf_pool_bwd_inplace_kernel(const T* __restrict__ gcat, const T* __restrict__ y0,
                                                                     T* __restrict__ gy0, PoolGeom g) {
+  pdl_enter();
   using WD = Word<T>;
   constexpr int EPL = WD::EPL;
   static_assert(EPL == 2, "in-place variant: 16-bit dtypes");
@@ -660,11 +663,11 @@ int launch_fwd(const void* y0, void* cat, int32_t* idx, PoolGeom g, cudaStream_t
   if (idx) {
     auto kern = sppf_pool_fwd_kernel<T, K, LP, true>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, threads, smem, st>>>((const T*)y0, (T*)cat, idx, g);
+    launch_k(kern, grid, threads, smem, st, (const T*)y0, (T*)cat, idx, g);
   } else {
     auto kern = sppf_pool_fwd_kernel<T, K, LP, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, threads, smem, st>>>((const T*)y0, (T*)cat, idx, g);
+    launch_k(kern, grid, threads, smem, st, (const T*)y0, (T*)cat, idx, g);
   }
   return check_launch("sppf_pool_fwd");
 }
@@ -691,7 +694,7 @@ int launch_bwd(const void* gcat, const void* y0, void* gy0, PoolGeom g, cudaStre
       const size_t smem_ip = plane * LP * EPL * 4 + plane * LP * 6;
       auto kip = 2 * per <= 320 ? sppf_pool_bwd_inplace_kernel<T, K, LP, 320> : sppf_pool_bwd_inplace_kernel<T, K, LP, 512>;
       cudaFuncSetAttribute(kip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ip);
-      kip<<<dim3(g.B * chunks), 2 * per, smem_ip, st>>>((const T*)gcat, (const T*)y0, (T*)gy0, g);
+      launch_k(kip, dim3(g.B * chunks), 2 * per, smem_ip, st, (const T*)gcat, (const T*)y0, (T*)gy0, g);
       return check_launch("sppf_pool_bwd");
     }
   }
@@ -700,7 +703,7 @@ int launch_bwd(const void* gcat, const void* y0, void* gy0, PoolGeom g, cudaStre
   if (threads < 64) threads = 64;
   auto kern = sppf_pool_bwd_kernel<T, K, LP>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  kern<<<dim3(g.B * chunks), threads, smem, st>>>((const T*)gcat, (const T*)y0, (T*)gy0, g);
+  launch_k(kern, dim3(g.B * chunks), threads, smem, st, (const T*)gcat, (const T*)y0, (T*)gy0, g);
   return check_launch("sppf_pool_bwd");
 }
 

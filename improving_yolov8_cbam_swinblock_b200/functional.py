@@ -50,6 +50,7 @@ _lib.register("b200_conv3x3_wgrad_supported", C.c_int, [_I32] * 6)
 _lib.register("b200_conv3x3_wgrad_workspace_bytes", _SZ, [_I32] * 2)
 _lib.register("b200_conv3x3_wgrad", C.c_int, [_VP] * 4 + [_SZ] + [_I32] * 7 + [_VP])
 _lib.register("b200_nhwc_concat", C.c_int, [_VP, _VP, _VP, _I32, _VP, _I64, _I32, _VP])
+_lib.register("b200_nhwc_add", C.c_int, [_VP, _VP, _I32, _VP, _I64, _I32, _I32, _VP])
 _lib.register("b200_u8_to_nhwc", C.c_int, [_VP, _VP] + [_I32] * 4 + [C.c_float, _I32, _VP])
 _lib.register("b200_nhwc_upsample_fwd", C.c_int, [_VP, _VP] + [_I32] * 7 + [_VP])
 _lib.register("b200_nhwc_upsample_bwd", C.c_int, [_VP, _I64, _VP] + [_I32] * 7 + [_VP])
@@ -212,6 +213,69 @@ def nhwc_chunk(x: torch.Tensor, n: int):
     if not (x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16, torch.float16) and _row_strided(x) is not None):
         return x.chunk(n, 1)
     return NhwcChunkFn.apply(x, n)
+
+
+# --------------------------------------------------------------------------------------------------
+# gradient fan-in: a map with several consumers (C2f bottleneck outputs, the saved layers of `_predict_once`)
+# --------------------------------------------------------------------------------------------------
+def _add_ok(gs) -> bool:
+    g0 = gs[0]
+    es = g0.element_size()
+    if not (g0.is_cuda and g0.dim() == 4 and 2 <= len(gs) <= 4 and g0.dtype in (torch.float32, torch.bfloat16, torch.float16)
+            and (g0.shape[1] * es) % 16 == 0):
+        return False
+    for g in gs:
+        if not (g.is_cuda and g.device == g0.device and g.dtype == g0.dtype and g.shape == g0.shape):
+            return False
+        S = _row_strided(g)
+        if S is None or (S * es) % 16 or g.data_ptr() % 16:
+            return False
+    return True
+
+
+def nhwc_add(gs) -> torch.Tensor:
+    """Sum of 2..4 same-shape maps (dense channels_last or channel slices of one) in ONE vectorised kernel: f32 sum in list
+    order, one rounding (two operands: bit-identical to ``a + b``).  Anything else -> torch adds."""
+    gs = list(gs)
+    if not _add_ok(gs):
+        out = gs[0]
+        for g in gs[1:]:
+            out = out + g
+        return out
+    g0 = gs[0]
+    B, Cc, H, W = g0.shape
+    out = _empty_nhwc(B, Cc, H, W, g0.dtype, g0.device)
+    n = len(gs)
+    srcs = (C.c_void_p * n)(*[g.data_ptr() for g in gs])
+    ss = (C.c_int64 * n)(*[int(_row_strided(g)) for g in gs])
+    with torch.cuda.device(g0.device):
+        call("b200_nhwc_add", C.addressof(srcs), C.addressof(ss), n, ptr(out), B * H * W, Cc, dtype_code(g0.dtype),
+             stream_ptr(g0.device), tag=f"b200_nhwc_add[{B * H * W}x{Cc}x{n}]")
+    return out
+
+
+class NhwcForkFn(torch.autograd.Function):
+    """x -> n aliases of x, one per consumer.  Backward: ONE fan-in kernel over the consumers' gradients (a concat-slice
+    gradient is read in place as a row-strided view) instead of autograd's pairwise accumulation, which runs ATen's generic
+    strided add as soon as one operand is such a slice."""
+
+    @staticmethod
+    def forward(ctx, x, n):
+        return tuple(x.view_as(x) for _ in range(n))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        gs = [g for g in gs if g is not None]
+        if not gs:
+            return None, None
+        return (gs[0] if len(gs) == 1 else nhwc_add(gs)), None
+
+
+def nhwc_fork(x: torch.Tensor, n: int = 2):
+    """n aliases of ``x`` for n consumers (see NhwcForkFn); plain repetition when no gradient will flow."""
+    if n <= 1 or not (x.is_cuda and x.requires_grad and torch.is_grad_enabled()):
+        return (x,) * max(n, 1)
+    return NhwcForkFn.apply(x, n)
 
 
 # --------------------------------------------------------------------------------------------------

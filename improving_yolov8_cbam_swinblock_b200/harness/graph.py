@@ -116,16 +116,26 @@ class C2f(nn.Module):
     # None = torch.cat / Tensor.chunk
     concat = None
     chunk = None
+    fork = None   # blocks["fork"]: (x, n) -> n aliases of x whose gradients are summed by ONE fan-in kernel (None = autograd's adds)
 
     def forward(self, x):
         t = self.cv1(x)
         y = list(t.chunk(2, 1) if self.chunk is None else self.chunk(t, 2))
         # the bottlenecks' 3x3 convs and shortcut adds want a dense operand: one vectorised copy of the second half here
         # instead of cuDNN's generic strided `.contiguous()` and a strided element-wise add per bottleneck
-        inp = y[-1] if self.concat is None else self.concat([y[-1]])
-        for m in self.m:
+        if self.fork is not None:   # y[1] feeds the concat and the first bottleneck
+            y[-1], inp = self.fork(y[-1], 2)
+        else:
+            inp = y[-1]
+        inp = inp if self.concat is None else self.concat([inp])
+        last = len(self.m) - 1
+        for k, m in enumerate(self.m):
             inp = m(inp)
-            y.append(inp)
+            if self.fork is not None and k < last:   # a bottleneck output feeds the concat and the next bottleneck
+                a, inp = self.fork(inp, 2)
+                y.append(a)
+            else:
+                y.append(inp)
         return self.cv2(torch.cat(y, 1) if self.concat is None else self.concat(y))
 
 
@@ -286,6 +296,8 @@ class DetectionGraph(nn.Module):
                 m_.concat = cat_
             if chunk_ is not None and isinstance(m_, C2f):
                 m_.chunk = chunk_
+            if blocks.get("fork") is not None and isinstance(m_, C2f):
+                m_.fork = blocks["fork"]
             if blocks.get("upsample") is not None and isinstance(m_, Upsample):
                 m_.upsample = blocks["upsample"]
             if blocks.get("head_conv") is not None and isinstance(m_, Detect):
@@ -298,6 +310,15 @@ class DetectionGraph(nn.Module):
         if blocks.get("stem_conv") is not None and isinstance(self.model[0], Conv):   # the 3-channel first layer (yaml backbone row 0)
             self.model[0].conv_fn = blocks["stem_conv"]
         self.save = sorted(save)
+        # consumers per layer output (the next layer when its `from` is -1, plus every later row that names it): a saved layer
+        # with several consumers hands each its own alias, so that their gradients meet in one fan-in kernel
+        self._fork = blocks.get("fork")
+        self._consumers = [0] * len(layers)
+        for mod in layers:
+            for j in ([mod.f] if isinstance(mod.f, int) else mod.f):
+                src = mod.i - 1 if j == -1 else j % mod.i
+                if src >= 0:
+                    self._consumers[src] += 1
         self.nc, self.scale = nc, scale
         det = self.model[-1]
         # stride pass on CPU zeros (tasks.py:350-364); CBAM creates its lazy MLP here (cbam.py:31-33)
@@ -312,12 +333,18 @@ class DetectionGraph(nn.Module):
                 mm.eps, mm.momentum = 1e-3, 0.03
 
     def _predict_once(self, x):
-        y = []
+        y = []   # per layer: the aliases of its output not yet handed to a consumer (tasks.py:171-176 keeps `y[j]` itself)
         for m in self.model:
-            if m.f != -1:
-                x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
+            if m.i > 0:
+                src = [m.f] if isinstance(m.f, int) else m.f
+                ins = [y[m.i - 1 if j == -1 else j].pop() for j in src]
+                x = ins[0] if isinstance(m.f, int) else ins
             x = m(x)
-            y.append(x if m.i in self.save else None)
+            n = self._consumers[m.i]
+            if self._fork is not None and n > 1 and torch.is_tensor(x):
+                y.append(list(self._fork(x, n)))
+            else:
+                y.append([x] * max(n, 1))
         return x
 
     def forward(self, x):

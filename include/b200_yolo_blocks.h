@@ -161,6 +161,14 @@ B200_API int b200_colsum(const void* a, float* out, void* workspace, size_t work
  * ------------------------------------------------------------------------------------------------------ */
 B200_API int b200_nhwc_concat(const void* const* srcs, const int32_t* src_channels, const int64_t* src_row_stride,
                               int32_t n_src, void* dst, int64_t rows, int32_t dtype, void* stream);
+/* Gradient fan-in at the seams: dst[rows, cols] (dense) = sum of 2..4 row-strided sources [rows, cols] of one dtype
+ * (row stride src_row_stride[i] >= cols elements), summed in f32 in source order and rounded once.  Replaces the adds
+ * autograd issues where a map has several consumers -- a bottleneck output inside C2f (block.py C2f.forward:
+ * `y.extend(m(y[-1]) for m in self.m)` feeds the next bottleneck AND the concat) and the saved layers `y[j]` of
+ * `_predict_once` (tasks.py:171-176) -- one operand there is a channel slice of a concat's gradient, which ATen adds
+ * through its generic strided kernel.  Rows, pointers and strides must be 16-byte multiples.  HOST arrays. */
+B200_API int b200_nhwc_add(const void* const* srcs, const int64_t* src_row_stride, int32_t n_src, void* dst, int64_t rows,
+                           int32_t cols, int32_t dtype, void* stream);
 /* Input seam: uint8 NCHW image batch -> `img.float() / divisor` in `dtype`, NHWC, one pass (detect/train.py:100 +
  * the channels_last conversion + autocast's cast of the first conv input).  Bit-identical to ATen's CUDA division by a
  * host scalar (multiply by the f32 reciprocal) followed by one round-to-nearest conversion.  1..4 channels, H*W % 4 == 0. */

@@ -117,3 +117,61 @@ def test_nearest_upsample_backward_reads_a_concat_slice_in_place():
     (z.float() * w.float()).sum().backward()
     gref = w[:, :32].float().view(2, 32, 6, 2, 6, 2).sum((3, 5)).bfloat16()
     assert torch.allclose(x.grad.float(), gref.float(), rtol=2.0 ** -7, atol=2.0 ** -7)
+
+
+# ---- gradient fan-in (b200_nhwc_add) and the fork that routes a multi-consumer map's gradients through it ---------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("n", [2, 3, 4])
+def test_fan_in_add_of_dense_and_sliced_sources(dtype, n):
+    from improving_yolov8_cbam_swinblock_b200 import functional as Fb
+
+    torch.manual_seed(10 + n)
+    wide = _cl(torch.randn(3, 160, 9, 11, device="cuda").to(dtype))
+    srcs = [wide[:, 32:96], _cl(torch.randn(3, 64, 9, 11, device="cuda").to(dtype)), wide[:, 96:160], wide[:, 0:64]][:n]
+    assert Fb._add_ok(srcs)
+    out = Fb.nhwc_add(srcs)
+    acc = srcs[0].float()
+    for s in srcs[1:]:
+        acc = acc + s.float()          # f32 sum in list order, one rounding
+    assert out.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(out, acc.to(dtype))
+    if n == 2:
+        assert torch.equal(out, srcs[0] + srcs[1])   # two operands: exactly ATen's a + b
+
+
+def test_fan_in_add_full_size_and_fallback():
+    from improving_yolov8_cbam_swinblock_b200 import functional as Fb
+
+    torch.manual_seed(3)
+    g_cat = _cl(torch.randn(64, 96, 80, 80, device="cuda").bfloat16())     # the P3 C2f concat's gradient
+    dense = _cl(torch.randn(64, 32, 80, 80, device="cuda").bfloat16())
+    sl = g_cat[:, 64:96]
+    assert torch.equal(Fb.nhwc_add([sl, dense]), sl + dense)
+    odd = [torch.randn(2, 7, 5, 5, device="cuda"), torch.randn(2, 7, 5, 5, device="cuda")]   # 28-byte rows: stock adds
+    assert not Fb._add_ok(odd)
+    assert torch.equal(Fb.nhwc_add(odd), odd[0] + odd[1])
+
+
+def test_fork_gradient_equals_autograd_accumulation():
+    from improving_yolov8_cbam_swinblock_b200 import functional as Fb
+
+    torch.manual_seed(4)
+    x = _cl(torch.randn(4, 64, 12, 12, device="cuda").bfloat16()).requires_grad_(True)
+    other = _cl(torch.randn(4, 32, 12, 12, device="cuda").bfloat16())
+    w_cat = torch.randn(4, 96, 12, 12, device="cuda").bfloat16()
+    w_b = _cl(torch.randn(4, 64, 12, 12, device="cuda").bfloat16())
+
+    def run(fork):
+        a, b = fork(x)
+        z = Fb.nhwc_concat([other, a])          # a's gradient: a channel slice of z's gradient (row-strided view)
+        ((z * w_cat).sum() + (b * w_b).sum()).backward()
+        g = x.grad.clone()
+        x.grad = None
+        return g
+
+    g_ref = run(lambda t: (t, t))
+    g = run(lambda t: Fb.nhwc_fork(t, 2))
+    assert torch.equal(g, g_ref)
+    with torch.no_grad():
+        a, b = Fb.nhwc_fork(x, 2)
+    assert a is x and b is x                    # no gradient: plain repetition
