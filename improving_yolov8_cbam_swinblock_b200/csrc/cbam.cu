@@ -26,6 +26,7 @@
 // same conv window) -- the result is NaN in exactly the positions where the reference's is.
 #include "cbam.cuh"
 
+
 namespace b200 {
 namespace {
 using namespace cbam;

@@ -18,6 +18,7 @@
 // owns ~50 pixels at the model's shape, so scalar set-up code is what the kernel's latency is made of.
 // With a stash the kernel also writes the by-products the (streaming) backward of cbam.cu consumes.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -248,17 +249,24 @@ __global__ void __launch_bounds__(kT) cbam_cluster_fwd_kernel(const __grid_const
           }
         }
       }
+      // lmx = this lane's own maximum.  The lanes hold ascending channel ranges, so the FIRST lane whose own maximum equals
+      // the reduced one owns the first arg-max channel: one ballot instead of an index butterfly
+      float lmx[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) lmx[u] = mx[u];
       for (int o = LPP >> 1; o > 0; o >>= 1) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
-          const float tm = __shfl_xor_sync(0xffffffffu, mx[u], o);
-          if (IDX) {
-            const int ti = __shfl_xor_sync(0xffffffffu, mi[u], o);
-            if (tm > mx[u] || (tm == mx[u] && ti < mi[u])) { mx[u] = tm; mi[u] = ti; }  // larger, then first channel
-          } else {
-            mx[u] = fmaxf(mx[u], tm);
-          }
+          mx[u] = fmaxf(mx[u], __shfl_xor_sync(0xffffffffu, mx[u], o));
+        }
+      }
+      if (IDX) {
+        const unsigned submask = (LPP == 32 ? 0xffffffffu : ((1u << LPP) - 1u)) << (sub * LPP);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const unsigned hit = __ballot_sync(0xffffffffu, lmx[u] == mx[u]) & submask;
+          mi[u] = __shfl_sync(0xffffffffu, mi[u], hit ? __ffs(hit) - 1 : (int)(sub * LPP));
         }
       }
       if (sl == 0) {
@@ -449,16 +457,19 @@ int cluster_fwd(const void* x, const float* w1, const float* w2, const float* ws
   L.lpp = 1;
   while (L.lpp < L.nch && L.lpp < 32) L.lpp <<= 1;
   L.groups = L.nch >= kT ? 1 : std::min(kT / L.nch, std::max(1, 13312 / (C * 12)));   // keeps 4 CTAs per SM at C=256
+  { static const int fg = [] { const char* e = getenv("B200_CBAM_GROUPS"); return e ? atoi(e) : 0; }(); if (fg > 0 && L.nch < kT) L.groups = std::min(kT / L.nch, fg); }
   L.invC = 1.f / (float)C;
   L.invHW = 1.f / (float)L.HW;
   // whole image in the shared memory of one cluster, at least two CTAs per SM so the phases of different clusters
   // overlap; bulk copies need 16-byte chunk sizes
   bool ok = false;
+  static const int forced = [] { const char* e = getenv("B200_CBAM_CS"); return e ? atoi(e) : 0; }();   // tuning aid: force the cluster size
   for (int c : {8, 16}) {
+    if (forced > 0) c = forced;
     L.cs = c; L.pchunk = (L.HW + c - 1) / c; L.cper = (C + c - 1) / c;
     if (((size_t)L.pchunk * C * esize) % 16) continue;
     layout(L, esize);
-    if ((size_t)L.total <= (size_t)100 * 1024) { ok = true; break; }
+    if ((size_t)L.total <= (size_t)(forced > 0 ? 220 : 100) * 1024) { ok = true; break; }
   }
   if (!ok) return -1;
   return B200_DISPATCH_DTYPE(dtype, [&]() -> int {

@@ -85,8 +85,14 @@ class Conv(nn.Module):
 
     epilogue = None  # DetectionGraph sets blocks["conv_epilogue"] here: callable (conv_module, y) -> act(bn(y))
     conv_fn = None   # per instance: callable (nn.Conv2d, x) -> conv(x); set on the first layer from blocks["stem_conv"]
+    w16 = None       # per instance, set by the Trainer: a 16-bit LEAF copy of conv.weight, refreshed once per step for all layers
+                     # together; its gradient is copied back the same way (instead of autocast's cast kernel per layer and direction)
 
     def forward(self, x):
+        if self.w16 is not None and self.conv_fn is None and self.training and x.dtype == self.w16.dtype and torch.is_grad_enabled():
+            c = self.conv
+            y = nn.functional.conv2d(x, self.w16, None, c.stride, c.padding, c.dilation, c.groups)
+            return self.act(self.bn(y)) if self.epilogue is None else self.epilogue(self, y)
         y = self.conv(x) if self.conv_fn is None else self.conv_fn(self.conv, x)
         return self.act(self.bn(y)) if self.epilogue is None else self.epilogue(self, y)
 

@@ -49,8 +49,8 @@ class EMA:
         self.updates += 1
         d = self.decay * (1 - math.exp(-self.updates / self.tau))
         cur = [p.detach() for p in model.state_dict().values() if p.dtype.is_floating_point]
-        torch._foreach_mul_(self.shadow, d)
-        torch._foreach_add_(self.shadow, cur, alpha=1 - d)
+        # v = d*v + (1-d)*p in ONE multi-tensor pass (the two-op form read and wrote every shadow tensor twice per step)
+        torch._foreach_lerp_(self.shadow, cur, 1 - d)
 
 
 class Trainer:
@@ -95,6 +95,20 @@ class Trainer:
             for p in self._params:
                 p.grad = self._flat[off:off + p.numel()].as_strided(p.shape, p.stride())  # same memory order as the parameter
                 off += p.numel()
+        # under autocast every stock convolution casts its f32 weight to the compute dtype in the forward and its
+        # 16-bit weight gradient back to f32 in the backward -- two tiny kernels per layer and step (~100 launches).  Instead: one
+        # 16-bit leaf per layer, all refreshed by ONE multi-tensor copy at the start of the step and all gradients copied back by
+        # ONE multi-tensor copy after the backward.  Same values as autocast's casts (bit-identical step).
+        self._w16 = []   # (Conv module, f32 parameter, 16-bit leaf, f32 gradient buffer)
+        if self.device.type == "cuda" and amp_dtype in (torch.bfloat16, torch.float16) and os.environ.get("B200_W16", "1") != "0":
+            for m_ in model.modules():
+                if isinstance(m_, graph.Conv) and m_.conv_fn is None and m_.conv.bias is None and m_.conv.weight.requires_grad \
+                        and m_.conv.padding_mode == "zeros":
+                    p = m_.conv.weight
+                    leaf = p.detach().to(amp_dtype).requires_grad_(True)   # keeps the parameter's (channels_last) strides
+                    g32 = p.grad if p.grad is not None else torch.zeros_like(p)
+                    m_.w16 = leaf
+                    self._w16.append((m_, p, leaf, g32))
         self._graph, self._graph_b, self._graph_error, self._static, self._static_items = None, None, None, None, None
         self._graph_mode = None
         self._prefetched, self._copy_stream = None, None
@@ -121,8 +135,19 @@ class Trainer:
     def _fwd_bwd(self, dev_batch):
         if self._flat is not None:
             self._flat.zero_()              # grads are views of the flat buffer: autograd accumulates in place
+        if self._w16:
+            with torch.no_grad():
+                torch._foreach_copy_([t[2] for t in self._w16], [t[1] for t in self._w16])   # f32 weights -> 16-bit leaves
+            for t in self._w16:
+                t[2].grad = None
         loss, items = self._forward_loss(dev_batch)
         loss.sum().backward()
+        if self._w16:
+            live = [t for t in self._w16 if t[2].grad is not None]
+            with torch.no_grad():
+                torch._foreach_copy_([t[3] for t in live], [t[2].grad for t in live])       # 16-bit gradients -> f32 .grad
+            for _, p, _, g32 in live:
+                p.grad = g32
         return items
 
     def _exchange(self):

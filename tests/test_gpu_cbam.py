@@ -40,7 +40,11 @@ def test_golden_fp32(name, ctor):
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 2e-2), (torch.float16, 4e-3)])
-@pytest.mark.parametrize("shape", [(4, 256, 20, 20), (2, 64, 40, 40), (2, 128, 80, 80), (3, 48, 9, 7), (1, 576, 20, 20)])
+# (4,256,20,20), (2,64,40,40) and the odd-sized (3,128,13,11), (2,256,9,8), (5,64,17,19) fit one SM's shared memory: in 16-bit
+# dtypes they run the one-CTA-per-image kernel (csrc/cbam_image.cu; 32 / 8 / 16 lanes per pixel), the others the cluster kernel or
+# the streaming chain
+@pytest.mark.parametrize("shape", [(4, 256, 20, 20), (2, 64, 40, 40), (2, 128, 80, 80), (3, 48, 9, 7), (1, 576, 20, 20),
+                                   (3, 128, 13, 11), (2, 256, 9, 8), (5, 64, 17, 19)])
 def test_vs_oracle(dtype, tol, shape):
     """Same seeded input through the CUDA module and the fp64 oracle; 16-bit error is measured vs the oracle."""
     import improving_yolov8_cbam_swinblock_b200.modules as M

@@ -182,3 +182,30 @@ def test_whole_model_bf16_vs_oracle_blocks():
     assert not bad, bad
     # all gradients together: the B200-block graph is as close to the fp32 truth as the stock bf16 graph is
     assert (num / den) ** 0.5 <= 1.25 * (num16 / den) ** 0.5 + 1e-2, ((num / den) ** 0.5, (num16 / den) ** 0.5)
+
+
+def test_weight_leaves_step_is_bit_identical_to_autocast_casts(monkeypatch):
+    """The Trainer hands every stock convolution a 16-bit leaf copy of its weight (one multi-tensor refresh per step, one
+    multi-tensor copy of the gradients back) instead of autocast's per-layer cast kernels: same values, so three steps must
+    leave bit-identical parameters and loss items (cuDNN deterministic, same algorithms for the same shapes)."""
+    import improving_yolov8_cbam_swinblock_b200 as P
+    from improving_yolov8_cbam_swinblock_b200.harness import synthetic, train
+
+    torch.backends.cudnn.deterministic = True
+    try:
+        monkeypatch.setenv("B200_W16", "1")
+        a = train.Trainer(P.BLOCKS, "n", 80, device="cuda:0", amp_dtype=torch.bfloat16, seed=5)
+        monkeypatch.setenv("B200_W16", "0")
+        b = train.Trainer(P.BLOCKS, "n", 80, device="cuda:0", amp_dtype=torch.bfloat16, seed=5)
+        assert len(a._w16) > 30 and not b._w16
+        for t in (a, b):
+            t.max_boxes = synthetic.BOXES_PER_IMAGE
+        for i in range(3):
+            batch = synthetic.make_batch(4, 256, 80, seed=40 + i)
+            la = a.step(a.to_device(batch))
+            lb = b.step(b.to_device(batch))
+            assert torch.equal(la, lb), f"step {i}: {la} vs {lb}"
+        for (k, va), vb in zip(a.raw.state_dict().items(), b.raw.state_dict().values()):
+            assert torch.equal(va, vb), k
+    finally:
+        torch.backends.cudnn.deterministic = False
