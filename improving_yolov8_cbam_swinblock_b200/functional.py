@@ -49,6 +49,8 @@ _lib.register("b200_stem_conv_wgrad", C.c_int, [_VP] * 4 + [_SZ] + [_I32] * 5 + 
 _lib.register("b200_conv3x3_wgrad_supported", C.c_int, [_I32] * 6)
 _lib.register("b200_conv3x3_wgrad_workspace_bytes", _SZ, [_I32] * 2)
 _lib.register("b200_conv3x3_wgrad", C.c_int, [_VP] * 4 + [_SZ] + [_I32] * 7 + [_VP])
+_lib.register("b200_conv3x3_dgrad_s2_supported", C.c_int, [_I32] * 5)
+_lib.register("b200_conv3x3_dgrad_s2", C.c_int, [_VP, _VP, _VP, _VP] + [_I32] * 6 + [_VP])
 _lib.register("b200_nhwc_concat", C.c_int, [_VP, _VP, _VP, _I32, _VP, _I64, _I32, _VP])
 _lib.register("b200_nhwc_add", C.c_int, [_VP, _VP, _I32, _VP, _I64, _I32, _I32, _VP])
 _lib.register("b200_u8_to_nhwc", C.c_int, [_VP, _VP] + [_I32] * 4 + [C.c_float, _I32, _VP])
@@ -601,6 +603,9 @@ def stem_conv(conv, x: torch.Tensor) -> torch.Tensor:
     return conv(x)
 
 
+DGRAD_S2 = [True]   # process-wide switch (tests / A-B timing): False = ATen's (cuDNN) input gradient for the stride-2 layer
+
+
 class Conv3x3WgradFn(torch.autograd.Function):
     """A narrow 3x3 nn.Conv2d (bias-free, padding 1, stride 1 or 2) whose WEIGHT GRADIENT runs on the hand-written mma kernel
     (csrc/conv_wgrad.cu); the forward and the input gradient stay ATen's (cuDNN) -- for 16 / 32 input channels cuDNN's wgrad
@@ -625,8 +630,17 @@ class Conv3x3WgradFn(torch.autograd.Function):
         gy = _nhwc(gy.to(x.dtype))
         gx = None
         if ctx.needs_input_grad[0]:
-            gx = torch.ops.aten.convolution_backward(gy, x, wl, None, [stride, stride], [1, 1], [1, 1], False, [0, 0], 1,
-                                                     [True, False, False])[0]
+            code = dtype_code(x.dtype)
+            if stride == 2 and DGRAD_S2[0] and lib().b200_conv3x3_dgrad_s2_supported(H, W, cin, cout, code):
+                # the 16 -> 32 stride-2 layer: cuDNN's generic strided dgrad takes 0.38 ms there (csrc/conv_dgrad.cu)
+                gx = torch.empty_like(x)
+                wst = (C.c_int64 * 4)(*[int(v) for v in wl.stride()])
+                with torch.cuda.device(x.device):
+                    call("b200_conv3x3_dgrad_s2", ptr(gy), ptr(wl), C.addressof(wst), ptr(gx), B, H, W, cin, cout, code,
+                         stream_ptr(x.device), tag=f"b200_conv3x3_dgrad_s2[{B}x{H}x{W}x{cin}<-{cout}]")
+            else:
+                gx = torch.ops.aten.convolution_backward(gy, x, wl, None, [stride, stride], [1, 1], [1, 1], False, [0, 0], 1,
+                                                         [True, False, False])[0]
         gw = torch.empty(wl.shape, dtype=torch.float32, device=x.device)
         nbytes = lib().b200_conv3x3_wgrad_workspace_bytes(cin, cout)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)

@@ -360,6 +360,16 @@ B200_API size_t b200_conv3x3_wgrad_workspace_bytes(int32_t cin, int32_t cout);
 B200_API int b200_conv3x3_wgrad(const void* gy, const void* x, float* gw, void* workspace, size_t workspace_bytes, int32_t B, int32_t H,
                                 int32_t W, int32_t cin, int32_t cout, int32_t stride, int32_t dtype, void* stream);
 
+/* Input gradient of the stride-2 member of that family (yaml backbone row 1 at scale n: nn.Conv2d(16, 32, 3, 2, 1, bias=False);
+ * autograd of F.conv2d w.r.t. the input, conv.py:37-91 `self.conv`): gx [B, H, W, 16] from gy [B, H/2, W/2, 32] (16-bit NHWC) and
+ * the weight w [32, 16, 3, 3] in the same 16-bit dtype, read through its element strides (w_stride = {oc, ci, ky, kx}: the
+ * parameter is channels_last in the harness).  cuDNN runs its generic strided-dgrad kernel there (0.38 ms, 8x its HBM time);
+ * here each of the four input-pixel parities is its own small implicit GEMM (1, 2, 2 and 4 taps) on mma.sync.
+ * H, W even, (W / 2) % 16 == 0, cin == 16, cout == 32. */
+B200_API int b200_conv3x3_dgrad_s2_supported(int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t dtype);
+B200_API int b200_conv3x3_dgrad_s2(const void* gy, const void* w, const int64_t* w_stride, void* gx, int32_t B, int32_t H, int32_t W,
+                                   int32_t cin, int32_t cout, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,3 +91,43 @@ def test_conv3x3_wgrad_matches_conv2d(dtype, B, H, W, cin, cout, stride):
         with torch.autocast("cuda", dtype=dtype):
             Fb.conv3x3(other, inp).float().sum().backward()
         assert _lib.launch_count() == n0 and other.weight.grad is not None
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (3, 38, 64), (1, 2, 32), (2, 66, 160), (16, 320, 320)])
+@pytest.mark.parametrize("cl_weight", [False, True])
+def test_conv3x3_dgrad_s2_matches_aten(dtype, B, H, W, cl_weight):
+    """csrc/conv_dgrad.cu (input gradient of the 16 -> 32 stride-2 layer) against ATen's convolution_backward on the same 16-bit
+    tensors and against the fp32 gradient: no further from fp32 than cuDNN is, ragged row tiles (H/2 % 4 != 0), a one-row map,
+    both weight layouts (the harness keeps parameters channels_last), deterministic."""
+    from improving_yolov8_cbam_swinblock_b200 import _lib, functional as Fb
+
+    torch.manual_seed(H + W)
+    conv = torch.nn.Conv2d(16, 32, 3, 2, 1, bias=False).cuda()
+    if cl_weight:
+        conv = conv.to(memory_format=torch.channels_last)
+    x = torch.randn(B, 16, H, W, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    g = torch.randn(B, 32, H // 2, W // 2, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+
+    def grad(mine):
+        Fb.DGRAD_S2[0] = mine
+        try:
+            n0 = _lib.launch_count()
+            Fb.conv3x3(conv, x).backward(g)
+            n = _lib.launch_count() - n0
+        finally:
+            Fb.DGRAD_S2[0] = True
+        gx = x.grad.clone()
+        x.grad = None
+        return gx, n
+
+    gx, n_mine = grad(True)
+    gx_aten, n_aten = grad(False)
+    assert n_mine == n_aten + 1, "the hand-written input-gradient kernel did not run"
+    assert gx.is_contiguous(memory_format=torch.channels_last) and gx.dtype == dtype
+    w32 = conv.weight.detach().to(dtype).float()
+    ref = torch.nn.grad.conv2d_input(x.shape, w32, g.float(), stride=2, padding=1)
+    e_mine, e_aten = rel_err(gx.float(), ref), rel_err(gx_aten.float(), ref)
+    assert e_mine <= max(1.05 * e_aten, 1e-6), (e_mine, e_aten)
+    assert rel_err(gx.float(), gx_aten.float()) <= (8e-3 if dtype == torch.bfloat16 else 1e-3)
+    assert torch.equal(grad(True)[0], gx)   # deterministic
