@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(kFT) bn_bwd_final_kernel(const float* __restri
 
 // ---- backward apply: g_x = A*gy + Bc*x + Cc -----------------------------------------------------------------------
 template <typename T, int VW, int ACT>
-__global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ gz,
+__global__ void __launch_bounds__(kT, 4) bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ gz,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           const float* __restrict__ coef, T* __restrict__ gx, const long long gzs,
@@ -363,20 +363,9 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const T* __restrict__ 
   const T* xb = x + (size_t)r0 * C + ch * VW;
   const T* gb = gz + (size_t)r0 * gzs + ch * VW;
   T* ob = gx + (size_t)r0 * C + ch * VW;
-  float a[VW], b[VW], kA[VW], kB[VW], kC[VW];   // this thread's channel vector: loaded once as float4s
-#pragma unroll
-  for (int q = 0; q < VW / 4; ++q) {
-    const float4 t0 = *reinterpret_cast<const float4*>(cs + ch * VW + 4 * q);
-    const float4 t1 = *reinterpret_cast<const float4*>(cs + C + ch * VW + 4 * q);
-    const float4 t2 = *reinterpret_cast<const float4*>(cs + 2 * C + ch * VW + 4 * q);
-    const float4 t3 = *reinterpret_cast<const float4*>(cs + 3 * C + ch * VW + 4 * q);
-    const float4 t4 = *reinterpret_cast<const float4*>(cs + 4 * C + ch * VW + 4 * q);
-    a[4 * q] = t0.x; a[4 * q + 1] = t0.y; a[4 * q + 2] = t0.z; a[4 * q + 3] = t0.w;
-    b[4 * q] = t1.x; b[4 * q + 1] = t1.y; b[4 * q + 2] = t1.z; b[4 * q + 3] = t1.w;
-    kA[4 * q] = t2.x; kA[4 * q + 1] = t2.y; kA[4 * q + 2] = t2.z; kA[4 * q + 3] = t2.w;
-    kB[4 * q] = t3.x; kB[4 * q + 1] = t3.y; kB[4 * q + 2] = t3.z; kB[4 * q + 3] = t3.w;
-    kC[4 * q] = t4.x; kC[4 * q + 1] = t4.y; kC[4 * q + 2] = t4.z; kC[4 * q + 3] = t4.w;
-  }
+  // The five per-channel constants of this thread's channel vector stay in shared memory and are re-read four channels at a
+  // time (5 LDS.128 per half vector): holding all 5 x VW of them in registers cost 80 registers = 3 CTAs per SM
+  const float* cv = cs + ch * VW;
   constexpr int RB2 = RB / 2;
   for (int r = rg; r < nrows; r += RB2 * G.ngrp) {
     uint4 rx[RB2], rgz[RB2];
@@ -386,19 +375,33 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const T* __restrict__ 
         rx[u] = ldg_stream16(xb + (size_t)(r + u * G.ngrp) * C);
         rgz[u] = ldg_stream16(gb + (size_t)(r + u * G.ngrp) * gzs);
       }
+    float v[RB2][VW], g[RB2][VW];
+#pragma unroll
+    for (int u = 0; u < RB2; ++u) {
+      unpack<T, VW>(rx[u], v[u]);
+      unpack<T, VW>(rgz[u], g[u]);
+    }
+#pragma unroll
+    for (int q = 0; q < VW / 4; ++q) {
+      const float4 t0 = *reinterpret_cast<const float4*>(cv + 4 * q);
+      const float4 t1 = *reinterpret_cast<const float4*>(cv + C + 4 * q);
+      const float4 t2 = *reinterpret_cast<const float4*>(cv + 2 * C + 4 * q);
+      const float4 t3 = *reinterpret_cast<const float4*>(cv + 3 * C + 4 * q);
+      const float4 t4 = *reinterpret_cast<const float4*>(cv + 4 * C + 4 * q);
+      const float a[4] = {t0.x, t0.y, t0.z, t0.w}, b[4] = {t1.x, t1.y, t1.z, t1.w}, kA[4] = {t2.x, t2.y, t2.z, t2.w},
+                  kB[4] = {t3.x, t3.y, t3.z, t3.w}, kC[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+      for (int u = 0; u < RB2; ++u)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float xe = v[u][4 * q + e];
+          const float gy = grad_y<FAST, ACT>(g[u][4 * q + e], fmaf(xe, a[e], b[e]));
+          v[u][4 * q + e] = fmaf(kA[e], gy, fmaf(kB[e], xe, kC[e]));
+        }
+    }
 #pragma unroll
     for (int u = 0; u < RB2; ++u)
-      if (r + u * G.ngrp < nrows) {
-        float v[VW], g[VW];
-        unpack<T, VW>(rx[u], v);
-        unpack<T, VW>(rgz[u], g);
-#pragma unroll
-        for (int e = 0; e < VW; ++e) {
-          const float gy = grad_y<FAST, ACT>(g[e], fmaf(v[e], a[e], b[e]));
-          v[e] = fmaf(kA[e], gy, fmaf(kB[e], v[e], kC[e]));
-        }
-        stg_stream16(ob + (size_t)(r + u * G.ngrp) * C, pack<T, VW>(v));
-      }
+      if (r + u * G.ngrp < nrows) stg_stream16(ob + (size_t)(r + u * G.ngrp) * C, pack<T, VW>(v[u]));
   }
 }
 
