@@ -105,7 +105,14 @@ class Bottleneck(nn.Module):
         self.cv2 = Conv(c_, c2, k[1], 1, g=g)
         self.add = shortcut and c1 == c2
 
+    fork = None   # blocks["fork"] (see C2f.fork): with a shortcut, x feeds cv1 AND the residual add
+
     def forward(self, x):
+        if self.add and self.fork is not None:
+            # the add's gradient can be a channel slice of the C2f concat's gradient (last bottleneck): summed with cv1's input
+            # gradient by the fan-in kernel instead of ATen's generic strided add
+            xa, xb = self.fork(x, 2)
+            return xa + self.cv2(self.cv1(xb))
         y = self.cv2(self.cv1(x))
         return x + y if self.add else y
 
@@ -302,7 +309,7 @@ class DetectionGraph(nn.Module):
                 m_.concat = cat_
             if chunk_ is not None and isinstance(m_, C2f):
                 m_.chunk = chunk_
-            if blocks.get("fork") is not None and isinstance(m_, C2f):
+            if blocks.get("fork") is not None and isinstance(m_, (C2f, Bottleneck)):
                 m_.fork = blocks["fork"]
             if blocks.get("upsample") is not None and isinstance(m_, Upsample):
                 m_.upsample = blocks["upsample"]

@@ -59,10 +59,31 @@ def seam_work(tag: str, s: int = 2):
     import re
 
     m = re.match(r"b200_nhwc_concat\[(\d+)x(\d+)\]", tag)
-    if not m:
-        return None
-    n = int(m.group(1)) * int(m.group(2))
-    return {"bound": "hbm", "amount": 2.0 * n * s, "note": "2*N*s: every source element read once, written once"}
+    if m:
+        n = int(m.group(1)) * int(m.group(2))
+        return {"bound": "hbm", "amount": 2.0 * n * s, "note": "2*N*s: every source element read once, written once"}
+    m = re.match(r"b200_nhwc_add\[(\d+)x(\d+)x(\d+)\]", tag)
+    if m:   # gradient fan-in: n sources read once, the dense sum written once
+        n, k = int(m.group(1)) * int(m.group(2)), int(m.group(3))
+        return {"bound": "hbm", "amount": (k + 1.0) * n * s, "note": "(n+1)*N*s: n gradient maps read once, their sum written once"}
+    # the callers' convolutions served by hand-written kernels: one pass over the operands (the tensor-core work is negligible
+    # at 3 / 16 input channels: these launches are bounded by HBM)
+    m = re.match(r"b200_conv3x3_dgrad_s2\[(\d+)x(\d+)x(\d+)x(\d+)<-(\d+)\]", tag)
+    if m:
+        B, H, W, cin, cout = (int(v) for v in m.groups())
+        return {"bound": "hbm", "amount": (B * H * W * cin + B * (H // 2) * (W // 2) * cout) * float(s),
+                "note": "read gy once, write gx once (weights negligible)"}
+    m = re.match(r"b200_conv3x3_wgrad\[(\d+)x(\d+)x(\d+)x(\d+)->(\d+),s(\d)\]", tag)
+    if m:
+        B, H, W, cin, cout, st = (int(v) for v in m.groups())
+        return {"bound": "hbm", "amount": (B * H * W * cin + B * (H // st) * (W // st) * cout) * float(s),
+                "note": "read x and gy once (the weight gradient is a few KB)"}
+    m = re.match(r"b200_stem_conv_(fwd|wgrad)\[(\d+)x(\d+)x(\d+)x(\d+)->(\d+)\]", tag)
+    if m:
+        B, H, W, cin, cout = (int(v) for v in m.groups()[1:])
+        return {"bound": "hbm", "amount": (B * H * W * cin + B * (H // 2) * (W // 2) * cout) * float(s),
+                "note": "one pass over the input and the output (forward) / the output gradient (weight gradient)"}
+    return None
 
 
 def fused_work(tag: str):
