@@ -92,9 +92,15 @@ class Trainer:
         if world_size > 1:
             self._flat = torch.zeros(sum(p.numel() for p in self._params), dtype=torch.float32, device=self.device)
             off = 0
+            self._views = []
             for p in self._params:
                 p.grad = self._flat[off:off + p.numel()].as_strided(p.shape, p.stride())  # same memory order as the parameter
+                self._views.append(p.grad)
                 off += p.numel()
+            # Autograd ACCUMULATES into an existing .grad (one add kernel per parameter and step, ~160 launches, plus the zero fill).
+            # Default: let the backward produce fresh gradients and move them into the flat buffer with ONE multi-tensor copy
+            # (B200_FLAT_COPY=0: the accumulate-in-place form).
+            self._flat_copy = os.environ.get("B200_FLAT_COPY", "1") != "0"
         # under autocast every stock convolution casts its f32 weight to the compute dtype in the forward and its
         # 16-bit weight gradient back to f32 in the backward -- two tiny kernels per layer and step (~100 launches).  Instead: one
         # 16-bit leaf per layer, all refreshed by ONE multi-tensor copy at the start of the step and all gradients copied back by
@@ -134,7 +140,11 @@ class Trainer:
 
     def _fwd_bwd(self, dev_batch):
         if self._flat is not None:
-            self._flat.zero_()              # grads are views of the flat buffer: autograd accumulates in place
+            if self._flat_copy:
+                for p in self._params:
+                    p.grad = None           # fresh gradients from the backward, gathered into the flat buffer below
+            else:
+                self._flat.zero_()          # grads are views of the flat buffer: autograd accumulates in place
         if self._w16:
             with torch.no_grad():
                 torch._foreach_copy_([t[2] for t in self._w16], [t[1] for t in self._w16])   # f32 weights -> 16-bit leaves
@@ -148,6 +158,21 @@ class Trainer:
                 torch._foreach_copy_([t[3] for t in live], [t[2].grad for t in live])       # 16-bit gradients -> f32 .grad
             for _, p, _, g32 in live:
                 p.grad = g32
+        if self._flat is not None and self._flat_copy:
+            src, dst, missing = [], [], []
+            for p, v in zip(self._params, self._views):
+                if p.grad is None:
+                    missing.append(v)       # a parameter the loss did not reach: its slot must read zero
+                elif p.grad is not v:
+                    src.append(p.grad)
+                    dst.append(v)
+            with torch.no_grad():
+                if dst:
+                    torch._foreach_copy_(dst, src)
+                if missing:
+                    torch._foreach_zero_(missing)
+            for p, v in zip(self._params, self._views):
+                p.grad = v
         return items
 
     def _exchange(self):
