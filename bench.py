@@ -500,10 +500,23 @@ def main():
         imgf = (dev[0]["img"].float() / 255).contiguous(memory_format=torch.channels_last)
         for _ in range(3):
             tr.raw(imgf)
-        ms_inf = timed(lambda i: tr.raw(imgf), args.steps, collective=False)
+        inf_fn, inf_mode, g_inf = (lambda i: tr.raw(imgf)), "eager launches", None
+        if graphed:   # the eager forward is host-bound (~400 launches in < 8 ms): replay it as a CUDA graph like the training step
+            try:
+                torch.cuda.synchronize()
+                g_inf = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_inf):
+                    inf_out = tr.raw(imgf)  # noqa: F841  (kept alive: the graph's output buffers)
+                inf_fn, inf_mode = (lambda i: g_inf.replay()), "CUDA-graph replay"
+            except Exception as e:  # noqa: BLE001  capture is an optimisation; the eager forward stays correct
+                sys.stderr.write(f"[bench] inference graph capture failed: {type(e).__name__}: {e}\n")
+                torch.cuda.synchronize()
+                inf_fn, g_inf = (lambda i: tr.raw(imgf)), None
+        ms_inf = timed(inf_fn, args.steps, collective=False)
+        del g_inf
     tr.raw.train()
     line["inference"] = {"value": args.batch * args.steps / (ms_inf * 1e-3), "unit": "img/s", "ms_per_batch": ms_inf / args.steps,
-                         "config": "configs[1]: bf16 autocast, batch 64, forward only, eval mode, 1 GPU"}
+                         "config": f"configs[1]: bf16 autocast, batch 64, forward only, eval mode, 1 GPU, {inf_mode}"}
     if not args.no_sweep:
         line["modules"] = sweep.run(SCALE, args.batch, peaks, iters=10)
         if roof is not None:   # per-block rows with SURVEY 8(d)'s bounds: CBAM / SPPF vs HBM, whole SwinBlock vs tensor peak
