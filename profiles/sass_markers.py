@@ -1,6 +1,7 @@
 """Per-kernel SASS marker counts of libb200yolo.so (what proves a Blackwell-native kernel, B200_PROFILING.md):
 UTC*MMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG/UTMASTG = TMA tensor load/store, UBLKCP = cp.async.bulk,
-HMMA = legacy mma.sync (must be 0).  usage: python profiles/sass_markers.py > profiles/sass_markers_rNN.md"""
+HMMA = legacy mma.sync: 0 in every SwinBlock / GEMM kernel (those are tcgen05); the narrow-channel convolution kernels of the
+callers (stem 3 -> 16, 3x3 wgrad / stride-2 dgrad at 16 channels: HBM-bound, K = 27..288, tensor work negligible) use it on purpose.  usage: python profiles/sass_markers.py > profiles/sass_markers_rNN.md"""
 import collections
 import os
 import re
