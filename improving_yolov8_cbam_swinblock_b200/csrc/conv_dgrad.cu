@@ -12,6 +12,11 @@
 // re-laid as [tap][ci][oc] in shared memory.  A warp owns 16 consecutive px of one py row = a 2 x 32 block of input pixels: its
 // four accumulator sets are interleaved through a per-warp staging tile and leave as 16-byte stores of whole pixel rows.
 // No atomics, every output element written exactly once: deterministic.
+//
+// Measured (profiles/README.md): 103-105 us for this kernel AND for the forward kernel below, whatever the tile height, the CTAs per
+// SM (2 or 3) or the staging (single- or double-buffered cp.async): both issue the same 3.69 M mma.sync.m16n8k16 (15.1 GFLOP), i.e.
+// both sit at ~147 TFLOP/s -- the rate of the legacy HMMA path on this GPU (one HMMA.16816 per ~32 cycles and SM sub-partition).
+// Going below needs the tcgen05 path (an implicit-GEMM convolution on UMMA), not a better mma.sync schedule.
 #include <type_traits>
 
 #include "common.cuh"
@@ -147,12 +152,107 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_dgrad_s2_kernel(const T* __
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Forward of the same layer: y[b, oy, ox, oc] = sum over (ky, kx, ci) of x[b, 2*oy - 1 + ky, 2*ox - 1 + kx, ci] * w[oc, ci, ky, kx].
+// cuDNN picks an sm80 legacy fprop here (0.14 ms for 210 MB in / 105 MB out: 3x the HBM time).  Implicit GEMM per 16 output pixels:
+// M = 16, N = 32 oc, K = 9 taps x 16 ci = 36 MMAs.  The A fragment of tap (ky, kx) is ONE ldmatrix.x4 on the staged NHWC input
+// row 2*orow + ky: matrix rows = the 16-byte halves of pixels 2*(ox0 + m) + kx (pixel 0 of a staged row is x = -1, a zero pixel).
+// Rows 64 bytes apart would hit four banks eight times; the 16-byte chunks of every 128-byte line (4 pixels) are therefore XOR-
+// swizzled with the line index (chunk ^= line & 3), which makes the eight rows of a matrix land in eight different chunks.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int kFR = 2, kFWarps = 10, kFThreads = kFWarps * 32;   // 2 output rows x 10 groups of 16 pixels at W/2 = 160: 2 groups per warp
+constexpr int kFWP = 48;   // bytes per (tap, oc) weight row: 16 ci + padding
+constexpr int kFSP = 80;   // bytes per staged output pixel: 32 oc + padding
+
+__device__ __host__ __forceinline__ int fwd_phys(int p, int h) {   // byte offset of half h of pixel slot p inside a staged row
+  return (p >> 2) * 128 + (((((p & 3) << 1) | h) ^ ((p >> 2) & 3)) << 4);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kFThreads, 2) conv3_fwd_s2_kernel(const T* __restrict__ x, const T* __restrict__ w, const WStride ws,
+                                                                     T* __restrict__ y, int H, int W, int Ho, int Wo, int tiles_per_img,
+                                                                     int n_tiles) {
+  pdl_enter();
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int IR = 2 * kFR + 1;
+  const int RPB = ((W + 1 + 3) / 4) * 128;             // bytes per staged input row: slot 0 = x = -1, slots 1..W, rounded up to a line
+  unsigned char* xs = smem;                            // [IR][slots][32 B], swizzled
+  unsigned char* wsm = xs + (size_t)IR * RPB;          // [9][kOc][kFWP]
+  unsigned char* stage = wsm + 9 * kOc * kFWP;         // [kFWarps][16][kFSP]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = lane & 3, r = lane >> 2;
+  for (int i = tid; i < 9 * kOc * kCi; i += kFThreads) {
+    const int tap = i / (kOc * kCi), rem = i - tap * kOc * kCi, oc = rem / kCi, ci = rem - oc * kCi;
+    const int ky = tap / 3, kx = tap - ky * 3;
+    *reinterpret_cast<T*>(wsm + (size_t)(tap * kOc + oc) * kFWP + ci * 2) = w[oc * ws.oc + ci * ws.ci + ky * ws.ky + kx * ws.kx];
+  }
+  for (int i = tid; i < IR * 2; i += kFThreads)        // the zero pixel in front of every staged row
+    *reinterpret_cast<uint4*>(xs + (size_t)(i >> 1) * RPB + fwd_phys(0, i & 1)) = make_uint4(0, 0, 0, 0);
+
+  const uint32_t xs_u = smem_u32(xs), ws_u = smem_u32(wsm);
+  const int m_l = (lane & 7) + ((lane & 8) ? 8 : 0), h_l = (lane & 16) ? 1 : 0;
+  uint32_t a_off[3];
+#pragma unroll
+  for (int kx = 0; kx < 3; ++kx) a_off[kx] = (uint32_t)fwd_phys(2 * m_l + kx, h_l);   // + og * 1024 per group (16 pixels = 8 lines)
+  const uint32_t b_lane = (uint32_t)(((lane & 7) + ((lane & 16) ? 8 : 0)) * kFWP + ((lane & 8) ? 16 : 0));
+  unsigned char* st = stage + (size_t)warp * (16 * kFSP);
+  const int gpr = Wo / 16;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_img, oy0 = (tile - b * tiles_per_img) * kFR;
+    __syncthreads();   // previous tile consumed (first pass: weights / zero pixels written)
+#pragma unroll
+    for (int i = 0; i < IR; ++i) {
+      const int iy = 2 * oy0 - 1 + i;
+      const bool ok = iy >= 0 && iy < H;
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(x) + ((size_t)(b * H + (ok ? iy : 0)) * W) * (kCi * 2);
+      unsigned char* dst = xs + (size_t)i * RPB;
+      for (int v = tid; v < W * 2; v += kFThreads) cp_async16(dst + fwd_phys((v >> 1) + 1, v & 1), src + (size_t)v * 16, ok);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    for (int g = warp; g < kFR * gpr; g += kFWarps) {
+      const int orow = g / gpr, og = g - orow * gpr;
+      if (oy0 + orow >= Ho) break;
+      float acc[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int ky = t / 3, kx = t - ky * 3;
+        uint32_t A[4], B0[4], B1[4];
+        ldsm_x4(A, xs_u + (uint32_t)((2 * orow + ky) * RPB + og * 1024) + a_off[kx]);
+        ldsm_x4(B0, ws_u + (uint32_t)((t * kOc) * kFWP) + b_lane);          // oc 0-15: b0/b1 of n-tiles 0, 1
+        ldsm_x4(B1, ws_u + (uint32_t)((t * kOc + 16) * kFWP) + b_lane);     // oc 16-31: n-tiles 2, 3
+        MmaD<T>::run(acc[0], A, B0[0], B0[1]);
+        MmaD<T>::run(acc[1], A, B0[2], B0[3]);
+        MmaD<T>::run(acc[2], A, B1[0], B1[1]);
+        MmaD<T>::run(acc[3], A, B1[2], B1[3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        unsigned char* o = st + r * kFSP + (nt * 8 + 2 * q) * 2;
+        *reinterpret_cast<uint32_t*>(o) = MmaD<T>::pack(acc[nt][0], acc[nt][1]);
+        *reinterpret_cast<uint32_t*>(o + 8 * kFSP) = MmaD<T>::pack(acc[nt][2], acc[nt][3]);
+      }
+      __syncwarp();
+      unsigned char* orow_g = reinterpret_cast<unsigned char*>(y) + (((size_t)b * Ho + oy0 + orow) * Wo + og * 16) * (kOc * 2);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = lane + 32 * j;   // 64 16-byte chunks = 16 pixels x 32 oc, contiguous in y
+        stg_stream16(orow_g + (size_t)c * 16, *reinterpret_cast<const uint4*>(st + (c >> 2) * kFSP + (c & 3) * 16));
+      }
+      __syncwarp();
+    }
+  }
+}
+
+size_t fwd_smem_bytes(int W) { return (size_t)(2 * kFR + 1) * (((W + 1 + 3) / 4) * 128) + 9 * kOc * kFWP + kFWarps * 16 * kFSP; }
+
 bool dgrad_shape_ok(int H, int W, int cin, int cout, int dtype) {
   if (!(dtype == B200_BF16 || dtype == B200_F16) || cin != kCi || cout != kOc) return false;
   if (H <= 0 || W <= 0 || ((H | W) & 1)) return false;
   const int Wo = W / 2;
   const size_t smem = (size_t)(kR + 1) * (Wo + 1) * kGP + 9 * kCi * kWP + kWarps * kStageWarp;
-  return Wo % 16 == 0 && smem <= (size_t)max_smem_optin();
+  return Wo % 16 == 0 && smem <= (size_t)max_smem_optin() && fwd_smem_bytes(W) <= (size_t)max_smem_optin();
 }
 
 }  // namespace
@@ -187,4 +287,29 @@ extern "C" B200_API int b200_conv3x3_dgrad_s2(const void* gy, const void* w, con
   };
   if (dtype == B200_BF16) return go(conv3_dgrad_s2_kernel<__nv_bfloat16>, (__nv_bfloat16*)nullptr);
   return go(conv3_dgrad_s2_kernel<__half>, (__half*)nullptr);
+}
+
+extern "C" B200_API int b200_conv3x3_fwd_s2(const void* x, const void* w, const int64_t* w_stride, void* y, int32_t B, int32_t H, int32_t W,
+                                            int32_t cin, int32_t cout, int32_t dtype, void* stream) {
+  B200_REQUIRE(x && w && w_stride && y, B200_ERR_SHAPE, "conv3x3_fwd_s2: null pointer");
+  B200_REQUIRE(B > 0 && dgrad_shape_ok(H, W, cin, cout, dtype), B200_ERR_UNSUPPORTED,
+               "conv3x3_fwd_s2: unsupported shape H=%d W=%d cin=%d cout=%d dtype=%d", H, W, cin, cout, dtype);
+  B200_REQUIRE((((uintptr_t)x | (uintptr_t)y) & 15) == 0, B200_ERR_ALIGN, "conv3x3_fwd_s2: tensors must be 16-byte aligned");
+  const int Ho = H / 2, Wo = W / 2, tpi = (Ho + kFR - 1) / kFR, n_tiles = B * tpi;
+  const size_t smem = fwd_smem_bytes(W);
+  const WStride ws{w_stride[0], w_stride[1], w_stride[2], w_stride[3]};
+  cudaStream_t st = (cudaStream_t)stream;
+  auto go = [&](auto kern, auto* tag) -> int {
+    using T = typename std::remove_pointer<decltype(tag)>::type;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFThreads, smem);
+    per_sm = per_sm < 1 ? 1 : per_sm > 4 ? 4 : per_sm;
+    int grid = sm_count() * per_sm;   // persistent CTAs: one resident wave
+    if (grid > n_tiles) grid = n_tiles;
+    launch_k(kern, grid, kFThreads, smem, st, (const T*)x, (const T*)w, ws, (T*)y, H, W, Ho, Wo, tpi, n_tiles);
+    return check_launch("conv3x3_fwd_s2");
+  };
+  if (dtype == B200_BF16) return go(conv3_fwd_s2_kernel<__nv_bfloat16>, (__nv_bfloat16*)nullptr);
+  return go(conv3_fwd_s2_kernel<__half>, (__half*)nullptr);
 }

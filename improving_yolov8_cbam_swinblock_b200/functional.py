@@ -51,6 +51,7 @@ _lib.register("b200_conv3x3_wgrad_workspace_bytes", _SZ, [_I32] * 2)
 _lib.register("b200_conv3x3_wgrad", C.c_int, [_VP] * 4 + [_SZ] + [_I32] * 7 + [_VP])
 _lib.register("b200_conv3x3_dgrad_s2_supported", C.c_int, [_I32] * 5)
 _lib.register("b200_conv3x3_dgrad_s2", C.c_int, [_VP, _VP, _VP, _VP] + [_I32] * 6 + [_VP])
+_lib.register("b200_conv3x3_fwd_s2", C.c_int, [_VP, _VP, _VP, _VP] + [_I32] * 6 + [_VP])
 _lib.register("b200_nhwc_concat", C.c_int, [_VP, _VP, _VP, _I32, _VP, _I64, _I32, _VP])
 _lib.register("b200_nhwc_add", C.c_int, [_VP, _VP, _I32, _VP, _I64, _I32, _I32, _VP])
 _lib.register("b200_u8_to_nhwc", C.c_int, [_VP, _VP] + [_I32] * 4 + [C.c_float, _I32, _VP])
@@ -603,6 +604,7 @@ def stem_conv(conv, x: torch.Tensor) -> torch.Tensor:
     return conv(x)
 
 
+FWD_S2 = [True]     # the same switch for the forward of that layer
 DGRAD_S2 = [True]   # process-wide switch (tests / A-B timing): False = ATen's (cuDNN) input gradient for the stride-2 layer
 
 
@@ -615,7 +617,17 @@ class Conv3x3WgradFn(torch.autograd.Function):
     def forward(ctx, x, w, stride):
         x = _nhwc(x)
         wl = w.detach().to(x.dtype)
-        y = torch.nn.functional.conv2d(x, wl, None, stride, 1)
+        B, cin, H, W = x.shape
+        cout, code = int(wl.shape[0]), dtype_code(x.dtype)
+        if stride == 2 and FWD_S2[0] and lib().b200_conv3x3_dgrad_s2_supported(H, W, cin, cout, code):
+            # the 16 -> 32 stride-2 layer: cuDNN picks an sm80 legacy fprop there (csrc/conv_dgrad.cu: conv3_fwd_s2_kernel)
+            y = _empty_nhwc(B, cout, H // 2, W // 2, x.dtype, x.device)
+            wst = (C.c_int64 * 4)(*[int(v) for v in wl.stride()])
+            with torch.cuda.device(x.device):
+                call("b200_conv3x3_fwd_s2", ptr(x), ptr(wl), C.addressof(wst), ptr(y), B, H, W, cin, cout, code,
+                     stream_ptr(x.device), tag=f"b200_conv3x3_fwd_s2[{B}x{H}x{W}x{cin}->{cout}]")
+        else:
+            y = torch.nn.functional.conv2d(x, wl, None, stride, 1)
         ctx.save_for_backward(x, wl)
         ctx.meta = (int(stride), w.dtype)
         return y

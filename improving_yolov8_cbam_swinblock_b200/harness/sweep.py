@@ -73,6 +73,11 @@ def seam_work(tag: str, s: int = 2):
         B, H, W, cin, cout = (int(v) for v in m.groups())
         return {"bound": "hbm", "amount": (B * H * W * cin + B * (H // 2) * (W // 2) * cout) * float(s),
                 "note": "read gy once, write gx once (weights negligible)"}
+    m = re.match(r"b200_conv3x3_fwd_s2\[(\d+)x(\d+)x(\d+)x(\d+)->(\d+)\]", tag)
+    if m:
+        B, H, W, cin, cout = (int(v) for v in m.groups())
+        return {"bound": "hbm", "amount": (B * H * W * cin + B * (H // 2) * (W // 2) * cout) * float(s),
+                "note": "read x once, write y once (weights negligible)"}
     m = re.match(r"b200_conv3x3_wgrad\[(\d+)x(\d+)x(\d+)x(\d+)->(\d+),s(\d)\]", tag)
     if m:
         B, H, W, cin, cout, st = (int(v) for v in m.groups())

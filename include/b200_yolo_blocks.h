@@ -369,6 +369,13 @@ B200_API int b200_conv3x3_wgrad(const void* gy, const void* x, float* gw, void* 
 B200_API int b200_conv3x3_dgrad_s2_supported(int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t dtype);
 B200_API int b200_conv3x3_dgrad_s2(const void* gy, const void* w, const int64_t* w_stride, void* gx, int32_t B, int32_t H, int32_t W,
                                    int32_t cin, int32_t cout, int32_t dtype, void* stream);
+/* Forward of the same layer (nn.Conv2d(16, 32, 3, 2, 1, bias=False) on 16-bit NHWC maps): y [B, H/2, W/2, 32] from x [B, H, W, 16]
+ * and w [32, 16, 3, 3] (16-bit, element strides as for the input gradient).  cuDNN picks an sm80 legacy fprop there (0.14 ms, 3x the HBM time).
+ * Implicit GEMM on mma.sync: M = 16 output pixels, N = 32, K = 9 taps x 16 channels, the A operand read by ldmatrix straight from
+ * the staged NHWC input rows (stride-2 pixel addresses, XOR-swizzled 16-byte chunks).  Same shape limits as the input gradient
+ * (b200_conv3x3_dgrad_s2_supported answers for both). */
+B200_API int b200_conv3x3_fwd_s2(const void* x, const void* w, const int64_t* w_stride, void* y, int32_t B, int32_t H, int32_t W,
+                                 int32_t cin, int32_t cout, int32_t dtype, void* stream);
 
 #ifdef __cplusplus
 }

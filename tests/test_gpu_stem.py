@@ -131,3 +131,37 @@ def test_conv3x3_dgrad_s2_matches_aten(dtype, B, H, W, cl_weight):
     assert e_mine <= max(1.05 * e_aten, 1e-6), (e_mine, e_aten)
     assert rel_err(gx.float(), gx_aten.float()) <= (8e-3 if dtype == torch.bfloat16 else 1e-3)
     assert torch.equal(grad(True)[0], gx)   # deterministic
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (3, 38, 64), (1, 2, 32), (2, 66, 160), (16, 320, 320)])
+@pytest.mark.parametrize("cl_weight", [False, True])
+def test_conv3x3_fwd_s2_matches_aten(dtype, B, H, W, cl_weight):
+    """csrc/conv_dgrad.cu conv3_fwd_s2_kernel (forward of the 16 -> 32 stride-2 layer) against F.conv2d on the same 16-bit tensors and
+    against the fp32 convolution: no further from fp32 than cuDNN is; ragged row tiles (H/2 odd), a one-row map, both weight layouts."""
+    from improving_yolov8_cbam_swinblock_b200 import _lib, functional as Fb
+
+    torch.manual_seed(H * 3 + W)
+    conv = torch.nn.Conv2d(16, 32, 3, 2, 1, bias=False).cuda()
+    if cl_weight:
+        conv = conv.to(memory_format=torch.channels_last)
+    x = torch.randn(B, 16, H, W, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+
+    def fwd(mine):
+        Fb.FWD_S2[0] = mine
+        try:
+            n0 = _lib.launch_count()
+            y = Fb.conv3x3(conv, x)
+            return y.detach(), _lib.launch_count() - n0
+        finally:
+            Fb.FWD_S2[0] = True
+
+    y, n_mine = fwd(True)
+    y_aten, n_aten = fwd(False)
+    assert n_mine == n_aten + 1, "the hand-written forward kernel did not run"
+    assert y.shape == (B, 32, H // 2, W // 2) and y.dtype == dtype and y.is_contiguous(memory_format=torch.channels_last)
+    ref = F.conv2d(x.detach().float(), conv.weight.detach().to(dtype).float(), None, 2, 1)
+    e_mine, e_aten = rel_err(y.float(), ref), rel_err(y_aten.float(), ref)
+    assert e_mine <= max(1.05 * e_aten, 1e-6), (e_mine, e_aten)
+    assert rel_err(y.float(), y_aten.float()) <= (8e-3 if dtype == torch.bfloat16 else 1e-3)
+    assert torch.equal(fwd(True)[0], y)   # deterministic
