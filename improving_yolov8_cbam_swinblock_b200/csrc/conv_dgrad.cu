@@ -13,10 +13,11 @@
 // four accumulator sets are interleaved through a per-warp staging tile and leave as 16-byte stores of whole pixel rows.
 // No atomics, every output element written exactly once: deterministic.
 //
-// Measured (profiles/README.md): 103-105 us for this kernel AND for the forward kernel below, whatever the tile height, the CTAs per
-// SM (2 or 3) or the staging (single- or double-buffered cp.async): both issue the same 3.69 M mma.sync.m16n8k16 (15.1 GFLOP), i.e.
-// both sit at ~147 TFLOP/s -- the rate of the legacy HMMA path on this GPU (one HMMA.16816 per ~32 cycles and SM sub-partition).
-// Going below needs the tcgen05 path (an implicit-GEMM convolution on UMMA), not a better mma.sync schedule.
+// Measured (profiles/README.md): the first version of this kernel and of the forward kernel below took 103-105 us whatever the tile
+// height, the CTAs per SM (2 or 3) or the staging (single- or double-buffered cp.async).  ncu named the limiter: the shared-memory
+// pipe (stall reasons mio_throttle / short_scoreboard in front; HMMA at 26 % of its rate, DRAM at 30 %, 0.24 instructions issued per
+// cycle and scheduler) -- 26 ldmatrix per 36 MMAs, 18 of them re-reading the weight fragments.  With the weights of 7 of the 9 taps
+// resident in registers and one parity class accumulated at a time: 105 -> 86 us (forward: 6 taps resident, 102 -> 93 us).
 #include <type_traits>
 
 #include "common.cuh"
@@ -29,6 +30,7 @@ constexpr int kGP = 80;    // bytes per gy pixel in shared memory: 64 of data + 
 constexpr int kWP = 80;    // bytes per (tap, ci) weight row: 32 oc + padding
 constexpr int kSP = 48;    // bytes per staged output pixel: 32 of data + 16 of padding
 constexpr int kStageWarp = 2 * 32 * kSP;
+constexpr int kDBReg = 7;  // taps of the input-gradient kernel whose weight fragments stay in registers (8 registers each)
 
 template <typename T> struct MmaD;
 template <> struct MmaD<__nv_bfloat16> {
@@ -54,6 +56,12 @@ template <> struct MmaD<__half> {
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+// four 8x8 16-bit matrices from the accumulator fragment layout to shared memory in one instruction (lane l supplies the address of
+// row l % 8 of matrix l / 8)
+__device__ __forceinline__ void stsm_x4(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
 
 struct WStride { long long oc, ci, ky, kx; };
@@ -87,10 +95,21 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_dgrad_s2_kernel(const T* __
   const uint32_t a_lane = (uint32_t)(((lane & 7) + ((lane & 8) ? 8 : 0)) * kGP + ((lane & 16) ? 16 : 0));
   const uint32_t b_lane = (uint32_t)(((lane & 7) + ((lane & 16) ? 8 : 0)) * kWP + ((lane & 8) ? 16 : 0));
   unsigned char* st = stage + (size_t)warp * kStageWarp;
+  const uint32_t st_u = smem_u32(st);
   const int gpr = Wo / 16;
+  // The weight fragments of the first kDBReg taps (in kTaps order) stay in registers for the whole kernel: re-reading all 18 of
+  // them per 16-pixel group kept the kernel on the shared-memory pipe (ncu: mio_throttle / short_scoreboard lead the stalls; HMMA
+  // at 26 % of its rate, DRAM at 30 %)
+  __syncthreads();
+  uint32_t Bf[kDBReg][2][4];
+#pragma unroll
+  for (int t = 0; t < kDBReg; ++t)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+      ldsm_x4(Bf[t][ks], ws_u + (uint32_t)((kTaps[t].ky * 3 + kTaps[t].kx) * kCi * kWP + ks * 32) + b_lane);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int b = tile / tiles_per_img, py0 = (tile - b * tiles_per_img) * kR;
-    __syncthreads();   // previous tile consumed (first pass: weights / zero pixels written)
+    __syncthreads();   // previous tile consumed
     for (int i = 0; i <= kR; ++i) {
       const int oy = py0 + i;
       const bool ok = oy < Ho;
@@ -111,33 +130,34 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_dgrad_s2_kernel(const T* __
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks)
             ldsm_x4(A[a][bb][ks], gs_u + (uint32_t)((pr + a) * RP + (px0 + bb) * kGP + ks * 32) + a_lane);
-      float acc[4][2][4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) acc[c][nt][0] = acc[c][nt][1] = acc[c][nt][2] = acc[c][nt][3] = 0.f;
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const Tap tp = kTaps[t];
-        const int tap = tp.ky * 3 + tp.kx;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          uint32_t B[4];   // b0 / b1 of ci 0-7, b0 / b1 of ci 8-15
-          ldsm_x4(B, ws_u + (uint32_t)(tap * kCi * kWP + ks * 32) + b_lane);
-          MmaD<T>::run(acc[tp.cls][0], A[tp.a][tp.b][ks], B[0], B[1]);
-          MmaD<T>::run(acc[tp.cls][1], A[tp.a][tp.b][ks], B[2], B[3]);
-        }
-      }
-      // interleave the four parity classes: staged pixel (dy, 2*m + dx), m = the warp's px index
+      // one parity class at a time (8 accumulator registers live instead of 32), staged pixel (dy, 2*m + dx), m = the warp's px index
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const int dy = c >> 1, dx = c & 1;
+        float acc[2][4];
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          unsigned char* o = st + dy * (32 * kSP) + (2 * r + dx) * kSP + (nt * 8 + 2 * q) * 2;
-          *reinterpret_cast<uint32_t*>(o) = MmaD<T>::pack(acc[c][nt][0], acc[c][nt][1]);
-          *reinterpret_cast<uint32_t*>(o + 16 * kSP) = MmaD<T>::pack(acc[c][nt][2], acc[c][nt][3]);   // rows r + 8: 16 staged pixels on
+        for (int nt = 0; nt < 2; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          if (kTaps[t].cls != c) continue;
+          const Tap tp = kTaps[t];
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            if (t < kDBReg) {
+              MmaD<T>::run(acc[0], A[tp.a][tp.b][ks], Bf[t < kDBReg ? t : 0][ks][0], Bf[t < kDBReg ? t : 0][ks][1]);
+              MmaD<T>::run(acc[1], A[tp.a][tp.b][ks], Bf[t < kDBReg ? t : 0][ks][2], Bf[t < kDBReg ? t : 0][ks][3]);
+            } else {
+              uint32_t B[4];   // b0 / b1 of ci 0-7, b0 / b1 of ci 8-15
+              ldsm_x4(B, ws_u + (uint32_t)((tp.ky * 3 + tp.kx) * kCi * kWP + ks * 32) + b_lane);
+              MmaD<T>::run(acc[0], A[tp.a][tp.b][ks], B[0], B[1]);
+              MmaD<T>::run(acc[1], A[tp.a][tp.b][ks], B[2], B[3]);
+            }
+          }
         }
+        // matrices (n-tile, pixel half): lane l addresses row l % 8 of matrix l / 8 = staged pixel 2 * (8 * half + row) + dx
+        const int dy = c >> 1, dx = c & 1;
+        stsm_x4(st_u + (uint32_t)(dy * (32 * kSP) + (2 * (8 * ((lane >> 3) & 1) + (lane & 7)) + dx) * kSP + (lane >> 4) * 16),
+                MmaD<T>::pack(acc[0][0], acc[0][1]), MmaD<T>::pack(acc[0][2], acc[0][3]), MmaD<T>::pack(acc[1][0], acc[1][1]),
+                MmaD<T>::pack(acc[1][2], acc[1][3]));
       }
       __syncwarp();
       unsigned char* orow = reinterpret_cast<unsigned char*>(gx) + (((size_t)b * H + 2 * (py0 + pr)) * W + 2 * px0) * (kCi * 2);
@@ -196,9 +216,20 @@ __global__ void __launch_bounds__(kFThreads, 2) conv3_fwd_s2_kernel(const T* __r
   const uint32_t b_lane = (uint32_t)(((lane & 7) + ((lane & 16) ? 8 : 0)) * kFWP + ((lane & 8) ? 16 : 0));
   unsigned char* st = stage + (size_t)warp * (16 * kFSP);
   const int gpr = Wo / 16;
+  // The weight fragments live in registers for the whole kernel (9 taps x 2 x 4 registers): re-reading them per 16-pixel group
+  // was 18 of the 27 ldmatrix per group, and ncu showed the kernel stalled on the shared-memory pipe (mio_throttle /
+  // short_scoreboard), not on HMMA (26 % of its rate) or DRAM (30 %)
+  __syncthreads();
+  constexpr int kBReg = 6;   // taps whose fragments fit next to the accumulators under the 2-CTAs-per-SM register budget (102)
+  uint32_t Bf[kBReg][2][4];
+#pragma unroll
+  for (int t = 0; t < kBReg; ++t) {
+    ldsm_x4(Bf[t][0], ws_u + (uint32_t)((t * kOc) * kFWP) + b_lane);          // oc 0-15: b0/b1 of n-tiles 0, 1
+    ldsm_x4(Bf[t][1], ws_u + (uint32_t)((t * kOc + 16) * kFWP) + b_lane);     // oc 16-31: n-tiles 2, 3
+  }
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int b = tile / tiles_per_img, oy0 = (tile - b * tiles_per_img) * kFR;
-    __syncthreads();   // previous tile consumed (first pass: weights / zero pixels written)
+    __syncthreads();   // previous tile consumed
 #pragma unroll
     for (int i = 0; i < IR; ++i) {
       const int iy = 2 * oy0 - 1 + i;
@@ -218,14 +249,22 @@ __global__ void __launch_bounds__(kFThreads, 2) conv3_fwd_s2_kernel(const T* __r
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int ky = t / 3, kx = t - ky * 3;
-        uint32_t A[4], B0[4], B1[4];
+        uint32_t A[4];
         ldsm_x4(A, xs_u + (uint32_t)((2 * orow + ky) * RPB + og * 1024) + a_off[kx]);
-        ldsm_x4(B0, ws_u + (uint32_t)((t * kOc) * kFWP) + b_lane);          // oc 0-15: b0/b1 of n-tiles 0, 1
-        ldsm_x4(B1, ws_u + (uint32_t)((t * kOc + 16) * kFWP) + b_lane);     // oc 16-31: n-tiles 2, 3
-        MmaD<T>::run(acc[0], A, B0[0], B0[1]);
-        MmaD<T>::run(acc[1], A, B0[2], B0[3]);
-        MmaD<T>::run(acc[2], A, B1[0], B1[1]);
-        MmaD<T>::run(acc[3], A, B1[2], B1[3]);
+        if (t < kBReg) {
+          MmaD<T>::run(acc[0], A, Bf[t < kBReg ? t : 0][0][0], Bf[t < kBReg ? t : 0][0][1]);
+          MmaD<T>::run(acc[1], A, Bf[t < kBReg ? t : 0][0][2], Bf[t < kBReg ? t : 0][0][3]);
+          MmaD<T>::run(acc[2], A, Bf[t < kBReg ? t : 0][1][0], Bf[t < kBReg ? t : 0][1][1]);
+          MmaD<T>::run(acc[3], A, Bf[t < kBReg ? t : 0][1][2], Bf[t < kBReg ? t : 0][1][3]);
+        } else {
+          uint32_t B0[4], B1[4];
+          ldsm_x4(B0, ws_u + (uint32_t)((t * kOc) * kFWP) + b_lane);
+          ldsm_x4(B1, ws_u + (uint32_t)((t * kOc + 16) * kFWP) + b_lane);
+          MmaD<T>::run(acc[0], A, B0[0], B0[1]);
+          MmaD<T>::run(acc[1], A, B0[2], B0[3]);
+          MmaD<T>::run(acc[2], A, B1[0], B1[1]);
+          MmaD<T>::run(acc[3], A, B1[2], B1[3]);
+        }
       }
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
