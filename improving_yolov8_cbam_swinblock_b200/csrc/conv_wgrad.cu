@@ -46,10 +46,14 @@ __global__ void __launch_bounds__(WarpPlan<OC>::NW * 32, 2) conv3_wgrad_kernel(c
   pdl_enter();
   using WP = WarpPlan<OC>;
   constexpr int R = TileRows<S>::R, IR = TileRows<S>::IR, MT = OC / 16, NT = kCin / 8, PB = kCin * 2, NTH = WP::NW * 32, TPW = WP::TPW;
+  // shared-memory pixel pitches: 16 bytes of padding per pixel, so that the eight 16-byte rows of an ldmatrix tile (consecutive pixels,
+  // or every second one at stride 2) fall into different banks -- at the dense pitches (32 / 64 bytes) every ldmatrix was a 2- to 4-way
+  // bank conflict and ncu showed the kernel waiting on shared memory (short_scoreboard 5-8 warps per issue)
+  constexpr int PBP = PB + 16, GP = OC * 2 + 16;
   extern __shared__ __align__(16) unsigned char smem[];
-  const int pitch = (W + 2) * PB;
+  const int pitch = (W + 2) * PBP;
   unsigned char* xs = smem;                          // IR input rows: [zero pixel | W pixels | zero pixel] x 16 channels
-  unsigned char* gs = smem + (size_t)IR * pitch;     // R rows of gy: [R][Wo][OC]
+  unsigned char* gs = smem + (size_t)IR * pitch;     // R rows of gy: [R][Wo][GP bytes]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q = lane & 3, r = lane >> 2;
   const int ts = warp % WP::TS, ps = warp / WP::TS;  // tap set, pixel-group split
   const int lm_pix = (lane & 7) + ((lane & 16) ? 8 : 0), lm_c = (lane & 8) ? 8 : 0;
@@ -61,9 +65,9 @@ __global__ void __launch_bounds__(WarpPlan<OC>::NW * 32, 2) conv3_wgrad_kernel(c
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) acc[t][mt][nt][0] = acc[t][mt][nt][1] = acc[t][mt][nt][2] = acc[t][mt][nt][3] = 0.f;
-  const int vpr = pitch / 16, vpp = PB / 16;
-  const uint32_t xs_lane = smem_u32(xs) + (uint32_t)(S * lm_pix * PB + lm_c * 2);
-  const uint32_t gs_lane = smem_u32(gs) + (uint32_t)((lm_pix * OC + lm_c) * 2);
+  const int vpr = (W + 2) * (PB / 16), vpp = PB / 16;   // 16-byte chunks of data per staged input row / per pixel
+  const uint32_t xs_lane = smem_u32(xs) + (uint32_t)(S * lm_pix * PBP + lm_c * 2);
+  const uint32_t gs_lane = smem_u32(gs) + (uint32_t)(lm_pix * GP + lm_c * 2);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int b = tile / tiles_per_img, oy0 = (tile - b * tiles_per_img) * R;
     const int rows = min(R, Ho - oy0);
@@ -78,12 +82,14 @@ __global__ void __launch_bounds__(WarpPlan<OC>::NW * 32, 2) conv3_wgrad_kernel(c
         unsigned char* rdst = xs + (size_t)i * pitch;
         for (int v = threadIdx.x; v < vpr; v += NTH) {
           const bool ok = row_ok && v >= vpp && v < vpr - vpp;
-          cp_async16(rdst + (size_t)v * 16, ok ? rsrc + (size_t)(v - vpp) * 16 : xb, ok);
+          const int px = v / vpp, ch = v - px * vpp;   // vpp is a power of two (kCin = 16: 2)
+          cp_async16(rdst + (size_t)px * PBP + ch * 16, ok ? rsrc + (size_t)(v - vpp) * 16 : xb, ok);
         }
       }
       const int vecs = rows * Wo * OC * 2 / 16;
       const unsigned char* src = reinterpret_cast<const unsigned char*>(gy) + ((size_t)(b * Ho + oy0) * Wo) * OC * 2;
-      for (int v = threadIdx.x; v < vecs; v += NTH) cp_async16(gs + (size_t)v * 16, src + (size_t)v * 16, true);
+      constexpr int cpp = OC * 2 / 16;   // 16-byte chunks per gy pixel
+      for (int v = threadIdx.x; v < vecs; v += NTH) cp_async16(gs + (size_t)(v / cpp) * GP + (v % cpp) * 16, src + (size_t)v * 16, true);
       cp_async_wait_all();
     }
     __syncthreads();
@@ -94,13 +100,13 @@ __global__ void __launch_bounds__(WarpPlan<OC>::NW * 32, 2) conv3_wgrad_kernel(c
       uint32_t a[MT][4];
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)   // a0 = (oc 0-7, pix 0-7), a1 = (oc 8-15, pix 0-7), a2 = (oc 0-7, pix 8-15), a3 = (oc 8-15, pix 8-15)
-        ldsm_x4_t(a[mt], gs_lane + (uint32_t)(((orow * Wo + ox0) * OC + mt * 16) * 2));
-      const uint32_t xg = xs_lane + (uint32_t)(S * orow * pitch + S * ox0 * PB);
+        ldsm_x4_t(a[mt], gs_lane + (uint32_t)((orow * Wo + ox0) * GP + mt * 32));
+      const uint32_t xg = xs_lane + (uint32_t)(S * orow * pitch + S * ox0 * PBP);
 #pragma unroll
       for (int t = 0; t < TPW; ++t) {
         const int tap = ts * TPW + t, ky = tap / 3, kx = tap - ky * 3;
         uint32_t bb[4];   // b0(c 0-7), b0(c 8-15), b1(c 0-7), b1(c 8-15)
-        ldsm_x4_t(bb, xg + (uint32_t)(ky * pitch + kx * PB));
+        ldsm_x4_t(bb, xg + (uint32_t)(ky * pitch + kx * PBP));
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           MmaW<T>::run(acc[t][mt][0], a[mt], bb[0], bb[2]);
@@ -155,7 +161,7 @@ bool wgrad_shape_ok(int H, int W, int cin, int oc, int stride, int dtype) {
   if (H <= 0 || W <= 0 || (stride == 2 && ((H | W) & 1))) return false;
   const int Wo = W / stride;
   const int R = stride == 1 ? 4 : 2, IR = stride * (R - 1) + 3;
-  const size_t smem = (size_t)IR * (W + 2) * cin * 2 + (size_t)R * Wo * oc * 2;
+  const size_t smem = (size_t)IR * (W + 2) * (cin * 2 + 16) + (size_t)R * Wo * (oc * 2 + 16);
   return Wo % 16 == 0 && smem <= (size_t)max_smem_optin();
 }
 
@@ -163,7 +169,7 @@ template <typename T, int OC, int S>
 int launch_wgrad(const void* gy, const void* x, float* gw, float* part, int n_ctas_max, int B, int H, int W, cudaStream_t st) {
   constexpr int R = TileRows<S>::R, IR = TileRows<S>::IR, NTH = WarpPlan<OC>::NW * 32;
   const int Ho = H / S, Wo = W / S, tpi = (Ho + R - 1) / R, n_tiles = B * tpi;
-  const size_t smem_tile = (size_t)IR * (W + 2) * kCin * 2 + (size_t)R * Wo * OC * 2, smem_red = (size_t)9 * OC * kCin * 4;
+  const size_t smem_tile = (size_t)IR * (W + 2) * (kCin * 2 + 16) + (size_t)R * Wo * (OC * 2 + 16), smem_red = (size_t)9 * OC * kCin * 4;
   const size_t smem = smem_tile > smem_red ? smem_tile : smem_red;
   auto kern = conv3_wgrad_kernel<T, OC, S>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
