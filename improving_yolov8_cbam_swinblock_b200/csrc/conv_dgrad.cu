@@ -65,6 +65,9 @@ __device__ __forceinline__ void stsm_x4(uint32_t addr, uint32_t r0, uint32_t r1,
 }
 
 struct WStride { long long oc, ci, ky, kx; };
+// L2 prefetch of a row segment the NEXT tile will stage (one 128-byte line per call): after the shared-memory work ncu showed these
+// kernels waiting on the global loads of the tile staging (long_scoreboard / wait); a persistent CTA knows its next tile
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 // tap -> (A tile: row offset a, pixel offset b) and parity class (dy * 2 + dx); see the header
 struct Tap { int ky, kx, a, b, cls; };
@@ -119,6 +122,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv3_dgrad_s2_kernel(const T* __
     }
     cp_async_wait_all();
     __syncthreads();
+    if (tile + (int)gridDim.x < n_tiles) {   // pull the next tile's gy rows into L2 while this one is multiplied
+      const int nt_ = tile + gridDim.x, nb = nt_ / tiles_per_img, npy = (nt_ - nb * tiles_per_img) * kR;
+      const int rows_n = min(kR + 1, Ho - npy), bytes = rows_n * Wo * (kOc * 2);   // the rows of a tile are contiguous in gy
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(gy) + ((size_t)(nb * Ho + npy) * Wo) * (kOc * 2);
+      for (int o = tid * 128; o < bytes; o += kThreads * 128) prefetch_l2(src + o);
+    }
     for (int g = warp; g < kR * gpr; g += kWarps) {
       const int pr = g / gpr, px0 = (g - pr * gpr) * 16;
       if (py0 + pr >= Ho) break;
@@ -240,6 +249,12 @@ __global__ void __launch_bounds__(kFThreads, 2) conv3_fwd_s2_kernel(const T* __r
     }
     cp_async_wait_all();
     __syncthreads();
+    if (tile + (int)gridDim.x < n_tiles) {   // pull the next tile's input rows into L2 while this one is multiplied
+      const int nt_ = tile + gridDim.x, nb = nt_ / tiles_per_img, noy = (nt_ - nb * tiles_per_img) * kFR;
+      const int iy0 = max(2 * noy - 1, 0), iy1 = min(2 * noy - 1 + IR, H), bytes = (iy1 - iy0) * W * (kCi * 2);   // contiguous rows of x
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(x) + ((size_t)(nb * H + iy0) * W) * (kCi * 2);
+      for (int o = tid * 128; o < bytes; o += kFThreads * 128) prefetch_l2(src + o);
+    }
     for (int g = warp; g < kFR * gpr; g += kFWarps) {
       const int orow = g / gpr, og = g - orow * gpr;
       if (oy0 + orow >= Ho) break;
